@@ -1,0 +1,197 @@
+"""ctypes wrapper around oracle/_build/libvgi_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs, never by the product package. PARITY UNPINNED (see vgi_oracle.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from vk_voxel_cone_tracing_b200 import structs as S
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libvgi_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("vgi_oracle.c", "vgi_oracle_svo.inc", "vgi_oracle.h", "Makefile")]
+    srcs.append(os.path.join(_HERE, "..", "include", "vgi.h"))
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+class Tris(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("pos", C.c_void_p), ("nrm", C.c_void_p), ("mat", C.c_void_p)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.vgo_atlas_bytes.restype = C.c_size_t
+        _lib.vgo_scene_triangle_count.restype = C.c_uint32
+        _lib.vgo_voxelize_level.restype = C.c_uint64
+        _lib.vgo_voxelization_pass.restype = C.c_uint64
+        _lib.vgo_svo_fragments.restype = C.c_uint32
+        _lib.vgo_svo_build.restype = C.c_uint32
+        _lib.vgo_svo_canonicalize.restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class OracleScene:
+    """World-space triangle soup of a synth.Scene (vgo_scene_triangles)."""
+
+    def __init__(self, scene):
+        self.scene = scene
+        d = scene.desc()
+        n = lib().vgo_scene_triangle_count(C.byref(d))
+        self.pos = np.zeros((n, 3, 3), dtype=np.float32)
+        self.nrm = np.zeros((n, 3, 3), dtype=np.float32)
+        self.mat = np.zeros(n, dtype=np.int32)
+        lib().vgo_scene_triangles(C.byref(d), _p(self.pos), _p(self.nrm), _p(self.mat))
+        self.tris = Tris(n, self.pos.ctypes.data, self.nrm.ctypes.data, self.mat.ctypes.data)
+        self.materials = np.ascontiguousarray(scene.materials)
+
+
+def regions(cfg, cam_pos):
+    out = (S.ClipRegion * cfg.level_count)()
+    cam = (C.c_float * 3)(*[float(x) for x in cam_pos])
+    lib().vgo_regions(C.byref(cfg), cam, out)
+    return out
+
+
+def new_atlas(cfg):
+    return np.zeros(S.atlas_shape(cfg), dtype=np.uint8)
+
+
+def voxelization_pass(cfg, regs, osc, opacity):
+    return lib().vgo_voxelization_pass(C.byref(cfg), regs, C.byref(osc.tris), _p(opacity))
+
+
+def voxelize_level(cfg, regs, level, osc, opacity):
+    return lib().vgo_voxelize_level(C.byref(cfg), regs, C.c_uint32(level), C.byref(osc.tris), _p(opacity))
+
+
+def injection_pass(cfg, regs, osc, light, shadow, shadow_depth, frame_index, opacity, radiance):
+    h, w = shadow_depth.shape
+    lib().vgo_injection_pass(C.byref(cfg), regs, C.byref(osc.tris), _p(osc.materials), C.byref(light),
+                             C.byref(shadow), _p(shadow_depth), C.c_uint32(w), C.c_uint32(h),
+                             C.c_uint32(frame_index), _p(opacity), _p(radiance))
+
+
+def inject_level(cfg, regs, level, osc, light, shadow, shadow_depth, radiance):
+    h, w = shadow_depth.shape
+    lib().vgo_inject_level(C.byref(cfg), regs, C.c_uint32(level), C.byref(osc.tris), _p(osc.materials),
+                           C.byref(light), C.byref(shadow), _p(shadow_depth), C.c_uint32(w), C.c_uint32(h),
+                           _p(radiance))
+
+
+def clear_region(cfg, atlas, min_corner, extent, level):
+    lib().vgo_clear_region(C.byref(cfg), _p(atlas), (C.c_int32 * 3)(*min_corner), (C.c_uint32 * 3)(*extent),
+                           C.c_uint32(level))
+
+
+def copy_alpha(cfg, level, dst, src):
+    lib().vgo_copy_alpha(C.byref(cfg), C.c_uint32(level), _p(dst), _p(src))
+
+
+def downsample(cfg, regs, level, atlas, which):
+    lib().vgo_downsample(C.byref(cfg), regs, C.c_uint32(level), _p(atlas), C.c_int(which))
+
+
+def wrap_border(cfg, atlas, literal=False):
+    lib().vgo_wrap_border(C.byref(cfg), _p(atlas), C.c_int(1 if literal else 0))
+
+
+def build_clipmap(cfg, regs, osc, light, shadow, shadow_depth, frame_index=0, opacity=None, radiance=None):
+    """VoxelizationPass::render followed by RadianceInjectionPass::render (Application.cpp:178,192)."""
+    opacity = new_atlas(cfg) if opacity is None else opacity
+    radiance = new_atlas(cfg) if radiance is None else radiance
+    pairs = voxelization_pass(cfg, regs, osc, opacity)
+    injection_pass(cfg, regs, osc, light, shadow, shadow_depth, frame_index, opacity, radiance)
+    return opacity, radiance, pairs
+
+
+class HostGBuffer:
+    def __init__(self, diffuse, normal, specular, emission, depth):
+        self.diffuse, self.normal, self.specular, self.emission, self.depth = diffuse, normal, specular, emission, depth
+        self.height, self.width = depth.shape
+
+    def struct(self):
+        g = S.GBuffer()
+        g.diffuse_rgba8 = self.diffuse.ctypes.data
+        g.normal_rgba16f = self.normal.ctypes.data
+        g.specular_rgba8 = self.specular.ctypes.data
+        g.emission_rgba16f = self.emission.ctypes.data
+        g.depth_f32 = self.depth.ctypes.data
+        g.width, g.height = self.width, self.height
+        return g
+
+
+def cone_trace(cfg, cam, gbuf, prm, light, shadow, shadow_depth, radiance, rows=None):
+    h, w = gbuf.height, gbuf.width
+    out_d = np.zeros((h, w, 4), dtype=np.float32)
+    out_s = np.zeros((h, w, 4), dtype=np.float32)
+    taps = C.c_uint64(0)
+    y0, y1 = rows if rows is not None else (0, h)
+    sh, sw = shadow_depth.shape
+    g = gbuf.struct()
+    lib().vgo_cone_trace(C.byref(cfg), C.byref(cam), C.byref(g), C.byref(prm), C.byref(light), C.byref(shadow),
+                         _p(shadow_depth), C.c_uint32(sw), C.c_uint32(sh), _p(radiance), _p(out_d), _p(out_s),
+                         C.c_uint32(y0), C.c_uint32(y1), C.byref(taps))
+    return out_d, out_s, taps.value
+
+
+# ---- SVO ------------------------------------------------------------------------------------------
+
+def svo_fragments(level, bb_min, bb_max, osc, light, shadow, shadow_depth, mode_flags=0):
+    sh, sw = shadow_depth.shape
+    args = (C.c_uint32(level), (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)),
+            C.byref(osc.tris), _p(osc.materials), C.byref(light), C.byref(shadow), _p(shadow_depth),
+            C.c_uint32(sw), C.c_uint32(sh), C.c_uint32(mode_flags))
+    n = lib().vgo_svo_fragments(*args, C.c_void_p(0))
+    frags = np.zeros((n, 2), dtype=np.uint32)
+    lib().vgo_svo_fragments(*args, _p(frags))
+    return frags
+
+
+def svo_build(level, frags, capacity=None, mode_flags=0):
+    n = frags.shape[0]
+    if capacity is None:
+        capacity = min(max(1000000, n << 3), 500000000)
+    nodes = np.zeros((capacity, 2), dtype=np.uint32)
+    cnt = lib().vgo_svo_build(C.c_uint32(level), _p(frags), C.c_uint32(n), _p(nodes), C.c_uint32(capacity),
+                              C.c_uint32(mode_flags))
+    return nodes[:cnt].copy()
+
+
+def svo_canonicalize(nodes):
+    out = np.zeros_like(nodes)
+    n = lib().vgo_svo_canonicalize(_p(nodes), C.c_uint32(nodes.shape[0]), _p(out))
+    return out[:n].copy()
+
+
+def svo_cone_trace(cam, gbuf, prm, light, shadow, shadow_depth, nodes, bb_min, bb_max, clip_level_count=6,
+                   rows=None):
+    h, w = gbuf.height, gbuf.width
+    out_d = np.zeros((h, w, 4), dtype=np.float32)
+    out_s = np.zeros((h, w, 4), dtype=np.float32)
+    y0, y1 = rows if rows is not None else (0, h)
+    sh, sw = shadow_depth.shape
+    g = gbuf.struct()
+    lib().vgo_svo_cone_trace(C.byref(cam), C.byref(g), C.byref(prm), C.byref(light), C.byref(shadow),
+                             _p(shadow_depth), C.c_uint32(sw), C.c_uint32(sh), _p(nodes),
+                             (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)),
+                             C.c_uint32(clip_level_count), _p(out_d), _p(out_s), C.c_uint32(y0), C.c_uint32(y1))
+    return out_d, out_s

@@ -1,0 +1,117 @@
+/*
+ * vgi_oracle.h — CPU restatement ("oracle") of the reference's voxel-GI shaders.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing in the product path (vk_voxel_cone_tracing_b200/, libvgi.so)
+ * may include, link or call this. Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
+ *  and its GLSL cannot be executed here (no Vulkan ICD / GLSL compiler).
+ * The oracle follows the shader text line by line (citations on every function) and is pinned
+ * by analytic known-answer tests in tests/test_oracle_kat.py plus glm golden matrices generated
+ * from the reference's vendored glm (oracle/ref_glm/).
+ *
+ * Arithmetic contract: IEEE-754 binary32, round-to-nearest-even, NO fused multiply-add
+ * (build with -ffp-contract=off), expressions evaluated left to right as written in the GLSL.
+ * The CUDA kernels follow the same contract wherever results are quantised (occupancy, RGBA8).
+ *
+ * All atlases here are in the REFERENCE image layout (ref: Voxelizer.h:40-52, Voxelizer.cpp:153-174):
+ * RGBA8, x fastest, W=(R+2)*6, H=(R+2)*L, D=R+2; texel of voxel (x,y,z), face f, level l is
+ * (1+x+f*(R+2), 1+y+l*(R+2), 1+z) (ref: msaaVoxelizer.frag:43-55).
+ */
+#ifndef VGI_ORACLE_H
+#define VGI_ORACLE_H
+
+#include "../include/vgi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* world-space triangle soup produced by vgo_scene_triangles */
+typedef struct vgo_tris {
+    uint32_t count;
+    float*   pos;   /* count*9: p0 p1 p2 (world) */
+    float*   nrm;   /* count*9: world normals (itModel * n), NOT normalised */
+    int32_t* mat;   /* count: material index */
+} vgo_tris;
+
+size_t vgo_atlas_bytes(const vgi_config* cfg);
+
+/* ref: Application.cpp:116-128, VoxelizationPass.cpp:335-357, 438-448 */
+void vgo_regions(const vgi_config* cfg, const float cam[3], vgi_clip_region* out);
+
+/* ref: msaaVoxelizer.vert:31-36 (model / itModel transform), GLTFScene.cpp:457-490 (draw order) */
+uint32_t vgo_scene_triangle_count(const vgi_scene_desc* s);
+void     vgo_scene_triangles(const vgi_scene_desc* s, float* pos, float* nrm, int32_t* mat);
+
+/* ref: VoxelizationPass.cpp:104-126 (vkCmdClearColorImage) */
+void vgo_clear_atlas(const vgi_config* cfg, uint8_t* atlas);
+/* ref: msaaVoxelizer.geom:27-49, msaaVoxelizer.frag:43-73 with canonical conservative coverage (Q3).
+ * returns number of (triangle,voxel) pairs */
+uint64_t vgo_voxelize_level(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,
+                            const vgo_tris* tris, uint8_t* opacity);
+/* ref: clipmapCleaning.comp:17-31 */
+void vgo_clear_region(const vgi_config* cfg, uint8_t* atlas, const int32_t min_corner[3],
+                      const uint32_t extent[3], uint32_t level);
+/* ref: msaaInjectRadiance.frag:68-155,162-216 + shadow.glsl:8-36, canonical exact-mean accumulation (Q10) */
+void vgo_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,
+                      const vgo_tris* tris, const vgi_material* materials,
+                      const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                      const float* shadow_depth, uint32_t sw, uint32_t sh, uint8_t* radiance);
+/* ref: copyAlphaImage.comp:16-29 */
+void vgo_copy_alpha(const vgi_config* cfg, uint32_t level, uint8_t* dst, const uint8_t* src);
+/* ref: opacityDownSample.comp:28-138 (which=0), radianceDownSample.comp:28-139 with Q6 repaired (which=1) */
+void vgo_downsample(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,
+                    uint8_t* atlas, int which);
+/* ref: borderWrapping.comp:14-37; literal!=0 reproduces the 16-group dispatch (Q4) */
+void vgo_wrap_border(const vgi_config* cfg, uint8_t* atlas, int literal);
+
+/* ref: VoxelizationPass.cpp:74-212 (clear, voxelize all levels, opacity mips, border wrap) */
+uint64_t vgo_voxelization_pass(const vgi_config* cfg, const vgi_clip_region* regions,
+                               const vgo_tris* tris, uint8_t* opacity);
+/* ref: RadianceInjectionPass.cpp:64-159 (cadence clear, inject, copy alpha, radiance mips) */
+void vgo_injection_pass(const vgi_config* cfg, const vgi_clip_region* regions, const vgo_tris* tris,
+                        const vgi_material* materials, const vgi_dir_light* light,
+                        const vgi_dir_light_shadow* shadow, const float* shadow_depth,
+                        uint32_t sw, uint32_t sh, uint32_t frame_index,
+                        const uint8_t* opacity, uint8_t* radiance);
+
+/* ref: voxelConeTracing.frag:143-414, brdf.glsl:30-78, shadow.glsl:8-36. HOST pointers in gbuf.
+ * taps (may be NULL) receives the number of trilinear taps executed (SURVEY 8d A_cone).
+ * rows [y0,y1). */
+void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuffer* gbuf,
+                    const vgi_vct_params* prm, const vgi_dir_light* light,
+                    const vgi_dir_light_shadow* shadow, const float* shadow_depth,
+                    uint32_t sw, uint32_t sh, const uint8_t* radiance,
+                    float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1,
+                    uint64_t* taps);
+
+/* ---- SVO (vgi_oracle_svo.inc, compiled as part of vgi_oracle.c) ---- */
+/* ref: voxelizer.vert:37-48, voxelizer.geom:39-56, voxelizer.frag:48-103. Fragments are emitted
+ * in (triangle, z, y, x) order. frags may be NULL to count only. returns count. */
+uint32_t vgo_svo_fragments(uint32_t level, const float bb_min[3], const float bb_max[3],
+                           const vgo_tris* tris, const vgi_material* materials,
+                           const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                           const float* shadow_depth, uint32_t sw, uint32_t sh,
+                           uint32_t mode_flags, uint32_t* frags);
+/* ref: OctreeBuilder.cpp:213-345 + octreeNode{Init,Flag,Alloc,ModifyArg,LeafWrite,MipmapWrite}.comp,
+ * invocations executed sequentially in gl_GlobalInvocationID order. nodes: capacity*2 u32.
+ * returns number of nodes allocated (allocBegin+allocNum after the last level). */
+uint32_t vgo_svo_build(uint32_t level, const uint32_t* frags, uint32_t nfrag, uint32_t* nodes,
+                       uint32_t capacity, uint32_t mode_flags);
+/* canonical child ordering: rewrites the pool breadth-first so that equal trees compare equal
+ * regardless of allocation order. returns node count. */
+uint32_t vgo_svo_canonicalize(const uint32_t* nodes, uint32_t nnodes, uint32_t* out);
+/* ref: voxelConeTracing_Octree.frag:148-409 */
+void vgo_svo_cone_trace(const vgi_camera* cam, const vgi_gbuffer* gbuf, const vgi_vct_params* prm,
+                        const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                        const float* shadow_depth, uint32_t sw, uint32_t sh,
+                        const uint32_t* nodes, const float bb_min[3], const float bb_max[3],
+                        uint32_t clip_level_count,
+                        float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

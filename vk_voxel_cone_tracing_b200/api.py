@@ -1,0 +1,189 @@
+"""ctypes binding of libvgi.so (include/vgi.h) — the call a Python user makes.
+
+torch is used for device memory and streams only (plumbing); all compute is in the hand-written
+CUDA kernels behind the C ABI. There is no CPU fallback: importing the library without the built
+extension, or creating a context without a CUDA device, raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from . import structs as S
+
+_lib = None
+
+
+class VgiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvgi error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load csrc/libvgi.so (built in-tree by build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.LIBVGI):
+            raise ImportError(
+                f"{_build.LIBVGI} is missing: build it with `python -m vk_voxel_cone_tracing_b200.build` "
+                "(libvgi has no CPU fallback)")
+        _lib = C.CDLL(_build.LIBVGI)
+        _lib.vgi_last_error.restype = C.c_char_p
+        _lib.vgi_last_error.argtypes = [C.c_void_p]
+        _lib.vgi_atlas_bytes.restype = C.c_size_t
+        _lib.vgi_atlas_bytes.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _stream(stream=None):
+    if stream is not None:
+        return C.c_void_p(int(stream))
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class VoxelGI:
+    """One vgi_ctx: the voxel-GI hot path on one GPU."""
+
+    def __init__(self, cfg=None, device=None):
+        import torch
+        self._torch = torch
+        self.cfg = cfg if cfg is not None else S.default_config()
+        if device is not None:
+            self.cfg.device = int(device)
+        self._h = C.c_void_p()
+        self._keep = {}
+        rc = lib().vgi_create(C.byref(self.cfg), C.byref(self._h))
+        if rc != S.VGI_OK:
+            raise VgiError(rc, lib().vgi_last_error(None).decode())
+        self.device = torch.device("cuda", self.cfg.device if self.cfg.device >= 0 else torch.cuda.current_device())
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc != S.VGI_OK:
+            raise VgiError(rc, lib().vgi_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().vgi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs
+    def set_scene(self, scene):
+        d = scene.desc()
+        self._ck(lib().vgi_set_scene(self._h, C.byref(d)))
+        self.scene = scene
+
+    def set_light(self, light, shadow, shadow_depth):
+        """shadow_depth: numpy (H,W) float32 (copied) or a CUDA torch tensor (borrowed)."""
+        torch = self._torch
+        if isinstance(shadow_depth, np.ndarray):
+            shadow_depth = torch.from_numpy(np.ascontiguousarray(shadow_depth, dtype=np.float32)).to(self.device)
+        assert shadow_depth.is_cuda and shadow_depth.dtype == torch.float32 and shadow_depth.is_contiguous()
+        self._keep["shadow"] = shadow_depth
+        h, w = shadow_depth.shape
+        self._ck(lib().vgi_set_light(self._h, C.byref(light), C.byref(shadow), C.c_void_p(shadow_depth.data_ptr()),
+                                     C.c_uint32(w), C.c_uint32(h), C.c_int(0)))
+        self.light, self.shadow = light, shadow
+
+    def update_regions(self, camera_pos):
+        self._ck(lib().vgi_update_regions(self._h, _f3(camera_pos)))
+
+    def set_regions(self, regions):
+        self._ck(lib().vgi_set_regions(self._h, regions, C.c_uint32(len(regions))))
+
+    def regions(self):
+        out = (S.ClipRegion * self.cfg.level_count)()
+        self._ck(lib().vgi_get_regions(self._h, out, C.c_uint32(self.cfg.level_count)))
+        return out
+
+    # -- clipmap build
+    def voxelize_opacity(self, stream=None):
+        self._ck(lib().vgi_voxelize_opacity(self._h, _stream(stream)))
+
+    def inject_radiance(self, frame_index=0, stream=None):
+        self._ck(lib().vgi_inject_radiance(self._h, C.c_uint32(frame_index), _stream(stream)))
+
+    def build_clipmap(self, frame_index=0, stream=None):
+        self._ck(lib().vgi_build_clipmap(self._h, C.c_uint32(frame_index), _stream(stream)))
+
+    def export_atlas(self, which, out=None, stream=None):
+        """which: 0 opacity, 1 radiance -> uint8 tensor (D, H, W, 4) in the reference image layout."""
+        torch = self._torch
+        shape = S.atlas_shape(self.cfg)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        self._ck(lib().vgi_export_atlas(self._h, C.c_int(which), C.c_void_p(out.data_ptr()), _stream(stream)))
+        return out
+
+    def voxel_store(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(lib().vgi_get_voxel_store(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def bind_voxel_store(self, tensor):
+        self._keep["store"] = tensor
+        self._ck(lib().vgi_bind_voxel_store(self._h, C.c_void_p(tensor.data_ptr()), C.c_size_t(tensor.numel() * tensor.element_size())))
+
+    def set_slab(self, z0, z1):
+        self._ck(lib().vgi_set_slab(self._h, C.c_uint32(z0), C.c_uint32(z1)))
+
+    def stats(self):
+        st = S.Stats()
+        self._ck(lib().vgi_get_stats(self._h, C.byref(st)))
+        return st
+
+    # -- cone tracing
+    def default_vct_params(self, rendering_mode=8):
+        p = S.VctParams()
+        self._ck(lib().vgi_default_vct_params(self._h, C.byref(p)))
+        p.rendering_mode = rendering_mode
+        return p
+
+    def upload_gbuffer(self, gb):
+        """dict of numpy arrays (raster.gbuffer) -> dict of CUDA tensors."""
+        torch = self._torch
+        out = {}
+        for k, v in gb.items():
+            a = np.ascontiguousarray(v)
+            if a.dtype == np.uint16:
+                t = torch.from_numpy(a.view(np.int16)).to(self.device)
+            else:
+                t = torch.from_numpy(a).to(self.device)
+            out[k] = t
+        return out
+
+    @staticmethod
+    def gbuffer_struct(gb):
+        g = S.GBuffer()
+        g.diffuse_rgba8 = gb["diffuse"].data_ptr()
+        g.normal_rgba16f = gb["normal"].data_ptr()
+        g.specular_rgba8 = gb["specular"].data_ptr()
+        g.emission_rgba16f = gb["emission"].data_ptr()
+        g.depth_f32 = gb["depth"].data_ptr()
+        g.height, g.width = gb["depth"].shape
+        return g
+
+    def cone_trace(self, camera, gbuffer, params, out=None, rows=None, stream=None):
+        """gbuffer: dict of CUDA tensors. Returns (diffuse, specular) float32 (H, W, 4) CUDA tensors."""
+        torch = self._torch
+        g = self.gbuffer_struct(gbuffer)
+        if out is None:
+            out = (torch.zeros((g.height, g.width, 4), dtype=torch.float32, device=self.device),
+                   torch.zeros((g.height, g.width, 4), dtype=torch.float32, device=self.device))
+        y0, y1 = rows if rows is not None else (0, g.height)
+        self._ck(lib().vgi_cone_trace_rows(self._h, C.byref(camera), C.byref(g), C.byref(params),
+                                          C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                          C.c_uint32(y0), C.c_uint32(y1), _stream(stream)))
+        return out

@@ -1,0 +1,225 @@
+/*
+ * synth_raster.c — host-side producers of the cone tracer's INPUTS for headless runs:
+ * the shadow-map depth image and the G-buffer that the reference renders with Vulkan
+ * (ref: VFS/Shaders/shadowPass.vert:33, gBufferPass.vert:45, gBufferPass.frag:62-116;
+ * formats ref: VFS/RenderPass/GBufferPass.cpp:177-194). They are NOT part of the hot path
+ * (SURVEY.md section 2 rows 15-16 are out of scope) and are never timed; tests and bench.py use them to
+ * build identical inputs for the CUDA path and the CPU oracle. Plain C + OpenMP, no CUDA.
+ *
+ * Rasterisation: pixel-centre sampling, depth test LESS with ties broken by the lower triangle
+ * index, triangles with a vertex at w <= 1e-4 are skipped (synthetic cameras sit in open space),
+ * fragments with z outside [0,1] are clipped. Factor-only materials (texture indices -1).
+ */
+#include "../../include/vgi.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static uint16_t float_to_half(float f)
+{
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+    uint32_t man = x & 0x7fffffu;
+    if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+    if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        const int shift = 14 - exp;
+        uint32_t h = man >> shift;
+        const uint32_t rem = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (h & 1))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+}
+
+static uint8_t to_unorm8(float x)
+{
+    if (!(x > 0.0f)) return 0;
+    if (x > 1.0f) x = 1.0f;
+    return (uint8_t)(x * 255.0f + 0.5f);
+}
+
+typedef struct tri_world {
+    float p[3][3];
+    float n[3][3];
+    int32_t mat;
+} tri_world;
+
+static void xform_point(const float* m, const float* v, float* o)
+{
+    for (int r = 0; r < 3; ++r) o[r] = ((m[r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2]) + m[12 + r];
+}
+static void xform_dir(const float* m, const float* v, float* o)
+{
+    for (int r = 0; r < 3; ++r) o[r] = (m[r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2];
+}
+
+static tri_world* world_tris(const vgi_scene_desc* s, uint32_t* count)
+{
+    uint64_t n = 0;
+    for (uint32_t p = 0; p < s->primitive_count; ++p) n += s->primitives[p].index_count / 3;
+    tri_world* out = (tri_world*)malloc((n ? n : 1) * sizeof(tri_world));
+    size_t t = 0;
+    for (uint32_t p = 0; p < s->primitive_count; ++p) {
+        const vgi_primitive* pr = &s->primitives[p];
+        const vgi_node_matrix* nm = &s->nodes[pr->node_index];
+        for (uint32_t i = 0; i + 2 < pr->index_count; i += 3, ++t) {
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t vi = s->indices[pr->first_index + i + k] + pr->vertex_offset;
+                xform_point(nm->model, s->positions + 3 * (size_t)vi, out[t].p[k]);
+                xform_dir(nm->it_model, s->normals + 3 * (size_t)vi, out[t].n[k]);
+            }
+            out[t].mat = pr->material_index;
+        }
+    }
+    *count = (uint32_t)n;
+    return out;
+}
+
+typedef struct proj_tri {
+    double x[3], y[3], z[3], iw[3]; /* pixel coords, ndc depth, 1/w */
+    int ok;
+} proj_tri;
+
+static void project(const float* M, const tri_world* t, uint32_t w, uint32_t h, proj_tri* o)
+{
+    o->ok = 1;
+    for (int k = 0; k < 3; ++k) {
+        const float* p = t->p[k];
+        double c[4];
+        for (int r = 0; r < 4; ++r)
+            c[r] = (double)M[r] * p[0] + (double)M[4 + r] * p[1] + (double)M[8 + r] * p[2] + (double)M[12 + r];
+        if (c[3] <= 1e-4) { o->ok = 0; return; }
+        o->iw[k] = 1.0 / c[3];
+        o->x[k] = (c[0] * o->iw[k] * 0.5 + 0.5) * (double)w;
+        o->y[k] = (c[1] * o->iw[k] * 0.5 + 0.5) * (double)h;
+        o->z[k] = c[2] * o->iw[k];
+    }
+}
+
+/* depth + winning triangle id per pixel */
+static void raster_ids(const float* M, const tri_world* tris, uint32_t ntri, uint32_t w, uint32_t h,
+                       float* depth, int32_t* ids)
+{
+    for (size_t i = 0; i < (size_t)w * h; ++i) { depth[i] = 1.0f; ids[i] = -1; }
+    proj_tri* pt = (proj_tri*)malloc((ntri ? ntri : 1) * sizeof(proj_tri));
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < (int64_t)ntri; ++t) project(M, &tris[t], w, h, &pt[t]);
+
+    const int band = 16;
+    const int nbands = (int)((h + band - 1) / band);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nbands; ++b) {
+        const int by0 = b * band, by1 = (by0 + band < (int)h) ? by0 + band : (int)h;
+        for (uint32_t t = 0; t < ntri; ++t) {
+            const proj_tri* q = &pt[t];
+            if (!q->ok) continue;
+            const double ymin = fmin(q->y[0], fmin(q->y[1], q->y[2])), ymax = fmax(q->y[0], fmax(q->y[1], q->y[2]));
+            if (ymax < by0 || ymin > by1) continue;
+            const double xmin = fmin(q->x[0], fmin(q->x[1], q->x[2])), xmax = fmax(q->x[0], fmax(q->x[1], q->x[2]));
+            if (xmax < 0 || xmin > w) continue;
+            const double area = (q->x[1] - q->x[0]) * (q->y[2] - q->y[0]) - (q->x[2] - q->x[0]) * (q->y[1] - q->y[0]);
+            if (area == 0.0) continue;
+            int x0 = (int)floor(xmin - 0.5), x1 = (int)ceil(xmax - 0.5);
+            int y0 = (int)floor(ymin - 0.5), y1 = (int)ceil(ymax - 0.5);
+            if (x0 < 0) x0 = 0;
+            if (x1 > (int)w - 1) x1 = (int)w - 1;
+            if (y0 < by0) y0 = by0;
+            if (y1 > by1 - 1) y1 = by1 - 1;
+            for (int y = y0; y <= y1; ++y)
+                for (int x = x0; x <= x1; ++x) {
+                    const double px = x + 0.5, py = y + 0.5;
+                    const double w0 = ((q->x[1] - px) * (q->y[2] - py) - (q->x[2] - px) * (q->y[1] - py)) / area;
+                    const double w1 = ((q->x[2] - px) * (q->y[0] - py) - (q->x[0] - px) * (q->y[2] - py)) / area;
+                    const double w2 = 1.0 - w0 - w1;
+                    if (w0 < 0 || w1 < 0 || w2 < 0) continue;
+                    const double z = w0 * q->z[0] + w1 * q->z[1] + w2 * q->z[2];
+                    if (z < 0.0 || z > 1.0) continue;
+                    const float zf = (float)z;
+                    const size_t pi = (size_t)y * w + x;
+                    if (zf < depth[pi]) { depth[pi] = zf; ids[pi] = (int32_t)t; }
+                }
+        }
+    }
+    free(pt);
+}
+
+/* ref: shadowPass.vert:33 — depth-only render of the scene with proj*view; clear 1.0 */
+int vgs_shadow_depth(const vgi_scene_desc* scene, const vgi_dir_light_shadow* sh, uint32_t w, uint32_t h, float* depth)
+{
+    uint32_t ntri;
+    tri_world* tris = world_tris(scene, &ntri);
+    float M[16];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += (double)sh->proj[k * 4 + r] * sh->view[c * 4 + k];
+            M[c * 4 + r] = (float)s;
+        }
+    int32_t* ids = (int32_t*)malloc((size_t)w * h * sizeof(int32_t));
+    raster_ids(M, tris, ntri, w, h, depth, ids);
+    free(ids);
+    free(tris);
+    return 0;
+}
+
+/* ref: gBufferPass.frag:62-116 for factor-only materials */
+int vgs_gbuffer(const vgi_scene_desc* scene, const vgi_camera* cam, uint32_t w, uint32_t h,
+                uint8_t* diffuse, uint16_t* normal, uint8_t* specular, uint16_t* emission, float* depth)
+{
+    uint32_t ntri;
+    tri_world* tris = world_tris(scene, &ntri);
+    int32_t* ids = (int32_t*)malloc((size_t)w * h * sizeof(int32_t));
+    raster_ids(cam->view_proj, tris, ntri, w, h, depth, ids);
+#pragma omp parallel for schedule(static)
+    for (int64_t y = 0; y < (int64_t)h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const size_t pi = (size_t)y * w + x;
+            memset(diffuse + pi * 4, 0, 4);
+            memset(specular + pi * 4, 0, 4);
+            memset(normal + pi * 4, 0, 8);
+            memset(emission + pi * 4, 0, 8);
+            if (ids[pi] < 0) continue;
+            const tri_world* t = &tris[ids[pi]];
+            proj_tri q;
+            project(cam->view_proj, t, w, h, &q);
+            const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
+            const double px = x + 0.5, py = y + 0.5;
+            double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
+            double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
+            double b2 = 1.0 - b0 - b1;
+            /* perspective-correct attribute interpolation */
+            b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2];
+            const double bs = b0 + b1 + b2;
+            b0 /= bs; b1 /= bs; b2 /= bs;
+            double n[3];
+            for (int k = 0; k < 3; ++k) n[k] = b0 * t->n[0][k] + b1 * t->n[1][k] + b2 * t->n[2][k];
+            const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            const vgi_material* m = &scene->materials[t->mat];
+            float rough = m->roughness_factor, metal = m->metallic_factor;
+            rough = rough < 0.04f ? 0.04f : (rough > 1.0f ? 1.0f : rough); /* MIN_ROUGHNESS clamp, untextured */
+            metal = metal < 0.0f ? 0.0f : (metal > 1.0f ? 1.0f : metal);
+            for (int k = 0; k < 3; ++k) {
+                const float base = m->base_color_factor[k];
+                diffuse[pi * 4 + k] = to_unorm8(base * (1.0f - 0.04f) * (1.0f - metal));
+                specular[pi * 4 + k] = to_unorm8(0.04f * (1.0f - metal) + base * metal);
+                normal[pi * 4 + k] = float_to_half((float)((ln > 0 ? n[k] / ln : 0.0) * 0.5 + 0.5));
+                emission[pi * 4 + k] = float_to_half(m->emissive_factor[k]);
+            }
+            diffuse[pi * 4 + 3] = to_unorm8(rough);
+            specular[pi * 4 + 3] = to_unorm8(metal);
+            normal[pi * 4 + 3] = float_to_half(1.0f);
+            emission[pi * 4 + 3] = float_to_half(1.0f);
+        }
+    free(ids);
+    free(tris);
+    return 0;
+}

@@ -1,0 +1,568 @@
+// vgi_api.cpp — the C ABI of libvgi.so (include/vgi.h): context, inputs, orchestration.
+// Host-side float arithmetic that feeds quantised results (regions, world-space vertices) follows the
+// same IEEE binary32 / no-FMA / left-to-right contract as the kernels (built with -ffp-contract=off).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "vgi_internal.h"
+
+static thread_local std::string g_err;
+
+static int fail(vgi_ctx* c, int code, const std::string& msg)
+{
+    g_err = msg;
+    if (c) c->err = msg;
+    return code;
+}
+#define CK(ctx, call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? VGI_E_NOMEM : VGI_E_CUDA,                     \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                                  \
+    } while (0)
+
+static int ilog2(uint32_t v) { int l = 0; while ((1u << l) < v) ++l; return l; }
+
+extern "C" {
+
+int vgi_version(void) { return VGI_VERSION; }
+
+void vgi_default_config(vgi_config* cfg)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(vgi_config);
+    cfg->resolution = 128;       // DEFAULT_VOXEL_RESOLUTION
+    cfg->level_count = 6;        // DEFAULT_CLIP_REGION_COUNT
+    cfg->downsample_band = 10;   // DEFAULT_DOWNSAMPLE_REGION_SIZE
+    cfg->extent_level0 = 16.0f;  // DEFAULT_VOXEL_EXTENT_L0
+    const uint32_t mc[6] = { 2, 2, 2, 2, 2, 1 }; // VoxelizationPass.h:57
+    for (int i = 0; i < VGI_MAX_LEVELS; ++i) cfg->clip_min_change[i] = i < 6 ? mc[i] : 1;
+    cfg->device = -1;
+}
+
+const char* vgi_last_error(const vgi_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+static void free_scene(vgi_ctx* c)
+{
+    cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials);
+    cudaFree(c->pairs); cudaFree(c->large); cudaFree(c->acc);
+    c->tri_pos = c->tri_nrm = nullptr; c->materials = nullptr; c->pairs = nullptr; c->large = nullptr; c->acc = nullptr;
+    c->ntri = 0;
+}
+
+int vgi_create(const vgi_config* cfg, vgi_ctx** out)
+{
+    if (!cfg || !out) return fail(nullptr, VGI_E_INVALID, "vgi_create: null argument");
+    if (cfg->struct_size != sizeof(vgi_config)) return fail(nullptr, VGI_E_INVALID, "vgi_create: struct_size mismatch");
+    const uint32_t R = cfg->resolution, L = cfg->level_count;
+    if (R < 16 || R > 512 || (R & (R - 1))) return fail(nullptr, VGI_E_INVALID, "vgi_create: resolution must be a power of two in [16,512]");
+    if (L < 1 || L > VGI_MAX_LEVELS) return fail(nullptr, VGI_E_INVALID, "vgi_create: level_count out of range");
+    if (!(cfg->extent_level0 > 0.0f)) return fail(nullptr, VGI_E_INVALID, "vgi_create: extent_level0 must be positive");
+    for (uint32_t i = 0; i < L; ++i)
+        if (cfg->clip_min_change[i] == 0) return fail(nullptr, VGI_E_INVALID, "vgi_create: clip_min_change must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, VGI_E_CUDA, "vgi_create: no CUDA device (libvgi has no CPU fallback)");
+    vgi_ctx* c = new (std::nothrow) vgi_ctx();
+    if (!c) return fail(nullptr, VGI_E_NOMEM, "vgi_create: out of host memory");
+    c->cfg = *cfg;
+    if (cfg->device >= 0) { CK(c, cudaSetDevice(cfg->device)); }
+    CK(c, cudaGetDevice(&c->device));
+    memset(&c->light, 0, sizeof(c->light));
+    const size_t nvox = (size_t)R * R * R;
+    const size_t nwords = (nvox >> 5) * L;
+    c->store_bytes = nvox * L * sizeof(VoxelRecord);
+    CK(c, cudaMalloc(&c->store, c->store_bytes));
+    c->store_owned = true;
+    CK(c, cudaMemset(c->store, 0, c->store_bytes));
+    CK(c, cudaMalloc(&c->occ, nwords * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->occ_prefix, nwords * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->block_sums, ((nwords + 4095) / 4096 + 1) * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->counters, sizeof(Counters)));
+    CK(c, cudaMemset(c->counters, 0, sizeof(Counters)));
+    CK(c, cudaMallocHost(&c->h_counters, sizeof(Counters)));
+    memset(c->h_counters, 0, sizeof(Counters));
+    c->z0 = 0;
+    c->z1 = (int)R;
+    // default regions: camera at the origin
+    const float origin[3] = { 0.f, 0.f, 0.f };
+    *out = c;
+    vgi_update_regions(c, origin);
+    return VGI_OK;
+}
+
+int vgi_destroy(vgi_ctx* c)
+{
+    if (!c) return VGI_OK;
+    cudaDeviceSynchronize();
+    free_scene(c);
+    if (c->store_owned) cudaFree(c->store);
+    cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
+    cudaFree(c->brick_mask); cudaFree(c->spec_list); cudaFree(c->shadow_owned);
+    cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
+    cudaFreeHost(c->h_counters);
+    delete c;
+    return VGI_OK;
+}
+
+int vgi_get_stats(vgi_ctx* c, vgi_stats* out)
+{
+    if (!c || !out) return fail(c, VGI_E_INVALID, "vgi_get_stats: null argument");
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    CK(c, cudaMemcpy(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    out->triangles = c->ntri;
+    out->clip_pairs = c->h_counters->pairs;
+    out->occupied_voxels = c->h_counters->occ_total;
+    out->svo_fragments = c->svo_nfrag;
+    out->svo_nodes = c->svo_nnodes;
+    out->kernel_launches = c->launches;
+    if (c->h_counters->overflow) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device list overflow (mask 0x%x): pairs=%u/%u occupied=%u/%u — raise vgi_config.max_fragments",
+                 c->h_counters->overflow, c->h_counters->pairs, c->max_pairs, c->h_counters->occ_total, c->max_occ);
+        return fail(c, VGI_E_OVERFLOW, buf);
+    }
+    return VGI_OK;
+}
+
+// ---- inputs -----------------------------------------------------------------------------------------
+
+static inline void xform_point(const float* m, const float* v, float* o)
+{
+    for (int r = 0; r < 3; ++r) o[r] = ((m[r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2]) + m[12 + r];
+}
+static inline void xform_dir(const float* m, const float* v, float* o)
+{
+    for (int r = 0; r < 3; ++r) o[r] = (m[r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2];
+}
+
+int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
+{
+    if (!c || !s) return fail(c, VGI_E_INVALID, "vgi_set_scene: null argument");
+    if (!s->positions || !s->normals || !s->indices || !s->primitives || !s->nodes || !s->materials)
+        return fail(c, VGI_E_INVALID, "vgi_set_scene: missing buffer");
+    for (uint32_t m = 0; m < s->material_count; ++m) {
+        const vgi_material& mt = s->materials[m];
+        if (mt.base_color_texture > -1 || mt.emissive_texture > -1 || mt.occlusion_texture > -1)
+            return fail(c, VGI_E_UNSUPPORTED, "vgi_set_scene: textured materials are outside the hot path (factor-only materials)");
+    }
+    uint64_t ntri = 0;
+    for (uint32_t p = 0; p < s->primitive_count; ++p) {
+        const vgi_primitive& pr = s->primitives[p];
+        if (pr.node_index >= s->node_count || pr.material_index < 0 || (uint32_t)pr.material_index >= s->material_count ||
+            (uint64_t)pr.first_index + pr.index_count > s->index_count)
+            return fail(c, VGI_E_INVALID, "vgi_set_scene: primitive out of range");
+        ntri += pr.index_count / 3;
+    }
+    if (ntri > 0x7fffffffull) return fail(c, VGI_E_INVALID, "vgi_set_scene: too many triangles");
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    free_scene(c);
+    std::vector<float4> pos(ntri * 3), nrm(ntri * 3);
+    float bbmin[3] = { INFINITY, INFINITY, INFINITY }, bbmax[3] = { -INFINITY, -INFINITY, -INFINITY };
+    size_t t = 0;
+    // world transform: ref msaaVoxelizer.vert:31-36; draw order: GLTFScene.cpp:457-490
+    for (uint32_t p = 0; p < s->primitive_count; ++p) {
+        const vgi_primitive& pr = s->primitives[p];
+        const vgi_node_matrix& nm = s->nodes[pr.node_index];
+        for (uint32_t i = 0; i + 2 < pr.index_count; i += 3, ++t) {
+            for (int k = 0; k < 3; ++k) {
+                const uint64_t vi = (uint64_t)s->indices[pr.first_index + i + k] + pr.vertex_offset;
+                if (vi >= s->vertex_count) return fail(c, VGI_E_INVALID, "vgi_set_scene: vertex index out of range");
+                float w[3], n[3];
+                xform_point(nm.model, s->positions + 3 * vi, w);
+                xform_dir(nm.it_model, s->normals + 3 * vi, n);
+                int32_t mat = pr.material_index;
+                float matf;
+                memcpy(&matf, &mat, 4);
+                pos[t * 3 + k] = make_float4(w[0], w[1], w[2], matf);
+                nrm[t * 3 + k] = make_float4(n[0], n[1], n[2], 0.f);
+                for (int a = 0; a < 3; ++a) {
+                    bbmin[a] = w[a] < bbmin[a] ? w[a] : bbmin[a];
+                    bbmax[a] = w[a] > bbmax[a] ? w[a] : bbmax[a];
+                }
+            }
+        }
+    }
+    c->ntri = (uint32_t)ntri;
+    memcpy(c->scene_bb_min, bbmin, sizeof bbmin);
+    memcpy(c->scene_bb_max, bbmax, sizeof bbmax);
+    c->nmat = s->material_count;
+    if (ntri) {
+        CK(c, cudaMalloc(&c->tri_pos, pos.size() * sizeof(float4)));
+        CK(c, cudaMalloc(&c->tri_nrm, nrm.size() * sizeof(float4)));
+        CK(c, cudaMemcpy(c->tri_pos, pos.data(), pos.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->tri_nrm, nrm.data(), nrm.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    CK(c, cudaMalloc(&c->materials, (s->material_count ? s->material_count : 1) * sizeof(vgi_material)));
+    CK(c, cudaMemcpy(c->materials, s->materials, s->material_count * sizeof(vgi_material), cudaMemcpyHostToDevice));
+
+    const uint32_t R = c->cfg.resolution, L = c->cfg.level_count;
+    uint64_t maxPairs = c->cfg.max_fragments;
+    if (!maxPairs) {
+        maxPairs = ntri * 48;
+        if (maxPairs < (1ull << 22)) maxPairs = 1ull << 22;
+        if (maxPairs > (1ull << 27)) maxPairs = 1ull << 27;
+    }
+    c->max_pairs = (uint32_t)maxPairs;
+    uint64_t maxOcc = maxPairs / 2;
+    const uint64_t allVox = (uint64_t)R * R * R * L;
+    if (maxOcc > allVox) maxOcc = allVox;
+    if (maxOcc < 1024) maxOcc = 1024;
+    c->max_occ = (uint32_t)maxOcc;
+    c->max_large = (uint32_t)((ntri ? ntri : 1) * L);
+    CK(c, cudaMalloc(&c->pairs, (size_t)c->max_pairs * sizeof(vgi_pair_t)));
+    CK(c, cudaMalloc(&c->large, (size_t)c->max_large * sizeof(uint2)));
+    CK(c, cudaMalloc(&c->acc, (size_t)c->max_occ * 24 * sizeof(uint32_t)));
+    c->voxelized = c->built = false;
+    return VGI_OK;
+}
+
+int vgi_set_light(vgi_ctx* c, const vgi_dir_light* light, const vgi_dir_light_shadow* sh, const float* depth,
+                  uint32_t w, uint32_t h, int is_host)
+{
+    if (!c || !light || !sh || !depth || !w || !h) return fail(c, VGI_E_INVALID, "vgi_set_light: null argument");
+    LightParams& lp = c->light;
+    memcpy(lp.view, sh->view, sizeof lp.view);
+    memcpy(lp.proj, sh->proj, sizeof lp.proj);
+    // normalize(-direction), ref msaaInjectRadiance.frag:139
+    const float d[3] = { -light->direction[0], -light->direction[1], -light->direction[2] };
+    const float len = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    for (int k = 0; k < 3; ++k) { lp.dir_to_light[k] = d[k] / len; lp.color[k] = light->color[k]; }
+    lp.intensity = light->intensity;
+    lp.z_near = sh->z_near;
+    lp.z_far = sh->z_far;
+    lp.sw = (int)w;
+    lp.sh = (int)h;
+    if (is_host) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->shadow_owned);
+        c->shadow_owned = nullptr;
+        CK(c, cudaMalloc(&c->shadow_owned, (size_t)w * h * sizeof(float)));
+        CK(c, cudaMemcpy(c->shadow_owned, depth, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice));
+        lp.depth = c->shadow_owned;
+    } else {
+        lp.depth = depth;
+    }
+    c->light_set = true;
+    return VGI_OK;
+}
+
+// ref: Application.cpp:116-128 + VoxelizationPass.cpp:335-357, 438-448
+int vgi_update_regions(vgi_ctx* c, const float cam[3])
+{
+    if (!c || !cam) return fail(c, VGI_E_INVALID, "vgi_update_regions: null argument");
+    const uint32_t R = c->cfg.resolution;
+    for (uint32_t i = 0; i < c->cfg.level_count; ++i) {
+        vgi_clip_region& r = c->regions[i];
+        const float voxelSize = (c->cfg.extent_level0 * (float)(1u << i)) / (float)R;
+        const float halfSize = (c->cfg.extent_level0 * 0.5f) * (float)(1u << i);
+        const int32_t mc = (int32_t)c->cfg.clip_min_change[i];
+        const float minChange = voxelSize * (float)mc;
+        for (int k = 0; k < 3; ++k) {
+            const int32_t minCorner = -(int32_t)(R >> 1);
+            const float bbMin = cam[k] - halfSize;
+            const float deltaW = bbMin - ((float)minCorner * voxelSize);
+            const int32_t delta = (int32_t)truncf(deltaW / minChange) * mc;
+            r.min_corner[k] = minCorner + delta;
+            r.extent[k] = R;
+        }
+        r.voxel_size = voxelSize;
+    }
+    c->regions_set = true;
+    return VGI_OK;
+}
+
+int vgi_set_regions(vgi_ctx* c, const vgi_clip_region* regions, uint32_t count)
+{
+    if (!c || !regions || count != c->cfg.level_count) return fail(c, VGI_E_INVALID, "vgi_set_regions: bad argument");
+    for (uint32_t i = 0; i < count; ++i) {
+        if (regions[i].extent[0] != c->cfg.resolution || !(regions[i].voxel_size > 0.0f))
+            return fail(c, VGI_E_INVALID, "vgi_set_regions: extent must equal the resolution");
+        c->regions[i] = regions[i];
+    }
+    c->regions_set = true;
+    return VGI_OK;
+}
+
+int vgi_get_regions(vgi_ctx* c, vgi_clip_region* out, uint32_t count)
+{
+    if (!c || !out || count > c->cfg.level_count) return fail(c, VGI_E_INVALID, "vgi_get_regions: bad argument");
+    memcpy(out, c->regions, count * sizeof(vgi_clip_region));
+    return VGI_OK;
+}
+
+} // extern "C"
+
+void build_params_from_ctx(const vgi_ctx* c, uint32_t frame_index, BuildParams* bp)
+{
+    memset(bp, 0, sizeof(*bp));
+    bp->R = (int)c->cfg.resolution;
+    bp->L = (int)c->cfg.level_count;
+    bp->logR = ilog2(c->cfg.resolution);
+    bp->band = (int)c->cfg.downsample_band;
+    bp->ntri = c->ntri;
+    bp->max_pairs = c->max_pairs;
+    bp->max_occ = c->max_occ;
+    bp->max_large = c->max_large;
+    bp->z0 = c->z0;
+    bp->z1 = c->z1;
+    bp->shadow_compare = (c->cfg.mode_flags & VGI_MODE_SHADOW_COMPARE) ? 1 : 0;
+    uint32_t mask = 0;
+    for (int l = 0; l < bp->L; ++l) {
+        for (int k = 0; k < 3; ++k) bp->lv[l].min_corner[k] = c->regions[l].min_corner[k];
+        bp->lv[l].voxel_size = c->regions[l].voxel_size;
+        if (frame_index % (1u << l) == 0) mask |= 1u << l; // ref: RadianceInjectionPass.cpp:36-38,75
+    }
+    bp->level_mask = mask;
+}
+
+extern "C" {
+
+static int check_launch(vgi_ctx* c, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, VGI_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return VGI_OK;
+}
+
+int vgi_voxelize_opacity(vgi_ctx* c, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_voxelize_opacity: null ctx");
+    if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_voxelize_opacity: call vgi_set_scene first");
+    CK(c, cudaSetDevice(c->device));
+    BuildParams bp;
+    build_params_from_ctx(c, 0, &bp);
+    cudaStream_t s = (cudaStream_t)stream;
+    c->launches += vgi_launch_voxelize(c, bp, s);
+    c->last_stream = s;
+    c->voxelized = true;
+    return check_launch(c, "vgi_voxelize_opacity");
+}
+
+int vgi_inject_radiance(vgi_ctx* c, uint32_t frame_index, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_inject_radiance: null ctx");
+    if (!c->voxelized) return fail(c, VGI_E_STATE, "vgi_inject_radiance: call vgi_voxelize_opacity first");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_inject_radiance: call vgi_set_light first");
+    CK(c, cudaSetDevice(c->device));
+    BuildParams bp;
+    build_params_from_ctx(c, frame_index, &bp);
+    cudaStream_t s = (cudaStream_t)stream;
+    c->launches += vgi_launch_inject_finalize(c, bp, s);
+    c->last_stream = s;
+    c->voxelized = false; // the pair list is consumed: the next frame re-voxelizes (Q8/Q9)
+    c->built = true;
+    return check_launch(c, "vgi_inject_radiance");
+}
+
+int vgi_build_clipmap(vgi_ctx* c, uint32_t frame_index, void* stream)
+{
+    int r = vgi_voxelize_opacity(c, stream);
+    if (r != VGI_OK) return r;
+    return vgi_inject_radiance(c, frame_index, stream);
+}
+
+size_t vgi_atlas_bytes(const vgi_ctx* c)
+{
+    if (!c) return 0;
+    const size_t rb = c->cfg.resolution + 2;
+    return rb * 6 * rb * c->cfg.level_count * rb * 4;
+}
+
+int vgi_export_atlas(vgi_ctx* c, int which, void* dst, void* stream)
+{
+    if (!c || !dst || (which != 0 && which != 1)) return fail(c, VGI_E_INVALID, "vgi_export_atlas: bad argument");
+    if (!c->built) return fail(c, VGI_E_STATE, "vgi_export_atlas: nothing built yet");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_export(c, which, (uint8_t*)dst, (c->cfg.mode_flags & VGI_MODE_BORDER_LITERAL) ? 1 : 0, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_export_atlas");
+}
+
+int vgi_get_voxel_store(vgi_ctx* c, void** dev_ptr, size_t* bytes)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_get_voxel_store: null ctx");
+    if (dev_ptr) *dev_ptr = c->store;
+    if (bytes) *bytes = c->store_bytes;
+    return VGI_OK;
+}
+
+int vgi_bind_voxel_store(vgi_ctx* c, void* dev_ptr, size_t bytes)
+{
+    if (!c || !dev_ptr) return fail(c, VGI_E_INVALID, "vgi_bind_voxel_store: null argument");
+    if (bytes < c->store_bytes) return fail(c, VGI_E_INVALID, "vgi_bind_voxel_store: buffer too small");
+    if (((uintptr_t)dev_ptr) & 31u) return fail(c, VGI_E_INVALID, "vgi_bind_voxel_store: buffer must be 32-byte aligned");
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    if (c->store_owned) cudaFree(c->store);
+    c->store = (VoxelRecord*)dev_ptr;
+    c->store_owned = false;
+    return VGI_OK;
+}
+
+int vgi_set_slab(vgi_ctx* c, uint32_t z0, uint32_t z1)
+{
+    if (!c || z0 >= z1 || z1 > c->cfg.resolution) return fail(c, VGI_E_INVALID, "vgi_set_slab: bad range");
+    c->z0 = (int)z0;
+    c->z1 = (int)z1;
+    return VGI_OK;
+}
+
+// ---- cone tracing -----------------------------------------------------------------------------------
+
+int vgi_default_vct_params(vgi_ctx* c, vgi_vct_params* p)
+{
+    if (!c || !p) return fail(c, VGI_E_INVALID, "vgi_default_vct_params: null argument");
+    const vgi_clip_region& r0 = c->regions[0];
+    // ref: VoxelConeTracingPass.cpp:88-93
+    for (int k = 0; k < 3; ++k)
+        p->volume_center[k] = ((float)r0.min_corner[k] * r0.voxel_size) + ((float)r0.extent[k] * r0.voxel_size) * 0.5f;
+    p->rendering_mode = 8;                 // CombinedGI, VoxelConeTracingPass.h:75
+    p->voxel_size = r0.voxel_size;
+    p->volume_dimension = (float)c->cfg.resolution;
+    p->trace_start_offset = 1.0f;          // VoxelConeTracingPass.h:76-82
+    p->indirect_diffuse_intensity = 8.0f;
+    p->ambient_occlusion_factor = 0.5f;
+    p->min_trace_step_factor = 1.0f;
+    p->indirect_specular_intensity = 3.0f;
+    p->occlusion_decay = 2.0f;
+    p->enable_32_cones = 0;
+    return VGI_OK;
+}
+
+int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                        void* out_diffuse, void* out_specular, uint32_t y0, uint32_t y1, void* stream)
+{
+    if (!c || !cam || !g || !prm || !out_diffuse || !out_specular) return fail(c, VGI_E_INVALID, "vgi_cone_trace: null argument");
+    if (!g->diffuse_rgba8 || !g->normal_rgba16f || !g->specular_rgba8 || !g->emission_rgba16f || !g->depth_f32 || !g->width || !g->height)
+        return fail(c, VGI_E_INVALID, "vgi_cone_trace: incomplete G-buffer");
+    if (y0 > y1 || y1 > g->height) return fail(c, VGI_E_INVALID, "vgi_cone_trace: bad row range");
+    if (prm->rendering_mode > 8) return fail(c, VGI_E_INVALID, "vgi_cone_trace: rendering_mode out of range");
+    if (!c->built) return fail(c, VGI_E_STATE, "vgi_cone_trace: build the clipmap first");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_cone_trace: call vgi_set_light first");
+    if ((uint32_t)prm->volume_dimension != c->cfg.resolution)
+        return fail(c, VGI_E_INVALID, "vgi_cone_trace: volume_dimension must equal the clipmap resolution");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t need = (size_t)g->width * g->height + 1;
+    if (c->spec_capacity < need) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->spec_list);
+        c->spec_list = nullptr;
+        CK(c, cudaMalloc(&c->spec_list, need * sizeof(uint32_t)));
+        c->spec_capacity = need;
+    }
+    TraceParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.p = *prm;
+    memcpy(tp.view_proj_inv, cam->view_proj_inv, sizeof tp.view_proj_inv);
+    memcpy(tp.eye, cam->eye_pos, sizeof tp.eye);
+    tp.R = (int)c->cfg.resolution;
+    tp.L = (int)c->cfg.level_count;
+    tp.logR = ilog2(c->cfg.resolution);
+    tp.store = c->store;
+    tp.brick_mask = nullptr;
+    tp.diffuse = g->diffuse_rgba8; tp.normal = g->normal_rgba16f; tp.specular = g->specular_rgba8;
+    tp.emission = g->emission_rgba16f; tp.depth = g->depth_f32;
+    tp.width = (int)g->width; tp.height = (int)g->height; tp.y0 = (int)y0; tp.y1 = (int)y1;
+    tp.out_diffuse = (float4*)out_diffuse;
+    tp.out_specular = (float4*)out_specular;
+    tp.light = c->light;
+    tp.shadow_compare = (c->cfg.mode_flags & VGI_MODE_SHADOW_COMPARE) ? 1 : 0;
+    tp.spec_list = c->spec_list + 1;
+    tp.spec_count = c->spec_list;
+    // ref: voxelConeTracing.frag:80,117,344 — coneCoefficient = 2 tan(aperture / 2)
+    tp.diffuse_aperture = prm->enable_32_cones ? 0.628319f : 0.872665f;
+    tp.cone_coeff_diffuse = 2.0f * tanf(tp.diffuse_aperture * 0.5f);
+    c->launches += vgi_launch_trace(c, tp, s);
+    c->last_stream = s;
+    return check_launch(c, "vgi_cone_trace");
+}
+
+int vgi_cone_trace(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                   void* out_diffuse, void* out_specular, void* stream)
+{
+    if (!g) return fail(c, VGI_E_INVALID, "vgi_cone_trace: null G-buffer");
+    return vgi_cone_trace_rows(c, cam, g, prm, out_diffuse, out_specular, 0, g->height, stream);
+}
+
+// ---- Vulkan interop (VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd) --------------------
+
+int vgi_import_vk_memory(vgi_ctx* c, int fd, size_t size, void** dev_ptr, void** handle)
+{
+    if (!c || !dev_ptr || !handle || fd < 0 || !size) return fail(c, VGI_E_INVALID, "vgi_import_vk_memory: bad argument");
+    CK(c, cudaSetDevice(c->device));
+    cudaExternalMemoryHandleDesc hd;
+    memset(&hd, 0, sizeof hd);
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = size;
+    cudaExternalMemory_t em;
+    CK(c, cudaImportExternalMemory(&em, &hd));
+    cudaExternalMemoryBufferDesc bd;
+    memset(&bd, 0, sizeof bd);
+    bd.offset = 0;
+    bd.size = size;
+    void* p = nullptr;
+    cudaError_t e = cudaExternalMemoryGetMappedBuffer(&p, em, &bd);
+    if (e != cudaSuccess) {
+        cudaDestroyExternalMemory(em);
+        return fail(c, VGI_E_CUDA, std::string("cudaExternalMemoryGetMappedBuffer: ") + cudaGetErrorString(e));
+    }
+    *dev_ptr = p;
+    *handle = (void*)em;
+    return VGI_OK;
+}
+
+int vgi_release_vk_memory(vgi_ctx* c, void* handle)
+{
+    if (!c || !handle) return fail(c, VGI_E_INVALID, "vgi_release_vk_memory: bad argument");
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    CK(c, cudaDestroyExternalMemory((cudaExternalMemory_t)handle));
+    return VGI_OK;
+}
+
+int vgi_import_vk_semaphore(vgi_ctx* c, int fd, void** handle)
+{
+    if (!c || !handle || fd < 0) return fail(c, VGI_E_INVALID, "vgi_import_vk_semaphore: bad argument");
+    CK(c, cudaSetDevice(c->device));
+    cudaExternalSemaphoreHandleDesc sd;
+    memset(&sd, 0, sizeof sd);
+    sd.type = cudaExternalSemaphoreHandleTypeOpaqueFd;
+    sd.handle.fd = fd;
+    cudaExternalSemaphore_t sem;
+    CK(c, cudaImportExternalSemaphore(&sem, &sd));
+    *handle = (void*)sem;
+    return VGI_OK;
+}
+
+int vgi_wait_vk_semaphore(vgi_ctx* c, void* handle, void* stream)
+{
+    if (!c || !handle) return fail(c, VGI_E_INVALID, "vgi_wait_vk_semaphore: bad argument");
+    cudaExternalSemaphore_t sem = (cudaExternalSemaphore_t)handle;
+    cudaExternalSemaphoreWaitParams wp;
+    memset(&wp, 0, sizeof wp);
+    CK(c, cudaWaitExternalSemaphoresAsync(&sem, &wp, 1, (cudaStream_t)stream));
+    return VGI_OK;
+}
+
+int vgi_signal_vk_semaphore(vgi_ctx* c, void* handle, void* stream)
+{
+    if (!c || !handle) return fail(c, VGI_E_INVALID, "vgi_signal_vk_semaphore: bad argument");
+    cudaExternalSemaphore_t sem = (cudaExternalSemaphore_t)handle;
+    cudaExternalSemaphoreSignalParams sp;
+    memset(&sp, 0, sizeof sp);
+    CK(c, cudaSignalExternalSemaphoresAsync(&sem, &sp, 1, (cudaStream_t)stream));
+    return VGI_OK;
+}
+
+int vgi_release_vk_semaphore(vgi_ctx* c, void* handle)
+{
+    if (!c || !handle) return fail(c, VGI_E_INVALID, "vgi_release_vk_semaphore: bad argument");
+    CK(c, cudaDestroyExternalSemaphore((cudaExternalSemaphore_t)handle));
+    return VGI_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,766 @@
+// vgi_build.cu — clipmap build kernels for sm_100a: conservative voxelization, radiance injection,
+// record finalisation, opacity/radiance down-sampling, atlas export.
+//
+// Compiled with -fmad=false: everything here that feeds a quantised result (occupancy bits, RGBA8
+// texels) follows the IEEE binary32, no-FMA, left-to-right contract of DESIGN.md "numerics", so the
+// results are bit-identical to the CPU oracle. Reference citations ("ref:") are relative to the
+// reference checkout; this file restates behaviour, it does not share code with the GLSL.
+#include "vgi_internal.h"
+
+#define DEVFN static __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+DEVFN float f_min(float a, float b) { return a < b ? a : b; }
+DEVFN float f_max(float a, float b) { return a > b ? a : b; }
+DEVFN float f_clamp(float x, float lo, float hi) { return f_min(f_max(x, lo), hi); }
+DEVFN float f_mix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+DEVFN float dot3(const float* a, const float* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+DEVFN float unorm8_to_f(uint32_t c) { return (float)c / 255.0f; }
+DEVFN uint32_t f_to_unorm8(float x)
+{
+    if (!(x > 0.0f)) return 0u;
+    if (x > 1.0f) x = 1.0f;
+    return (uint32_t)(x * 255.0f + 0.5f);
+}
+DEVFN unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Conservative triangle/voxel coverage (DESIGN.md "canonical coverage"; Schwarz-Seidel test in voxel
+// units). ref: msaaVoxelizer.geom:27-49 / msaaVoxelizer.frag:43-73 with the raster coverage (Q3)
+// replaced by exact overlap.
+struct TriSetup {
+    float n[3], d1, d2;
+    float ne[3][3][2];
+    float de[3][3];
+    int lo[3], hi[3];
+    bool valid;
+};
+
+// cross(p1-p0, p2-p0) and dominant axis (ref: msaaVoxelizer.geom:27-32: ties -> z, then y)
+DEVFN int cross_and_axis(const float p[9], float N[3])
+{
+    const float a0 = p[3] - p[0], a1 = p[4] - p[1], a2 = p[5] - p[2];
+    const float b0 = p[6] - p[0], b1 = p[7] - p[1], b2 = p[8] - p[2];
+    N[0] = a1 * b2 - a2 * b1;
+    N[1] = a2 * b0 - a0 * b2;
+    N[2] = a0 * b1 - a1 * b0;
+    const float ax = fabsf(N[0]), ay = fabsf(N[1]), az = fabsf(N[2]);
+    return (ax > ay && ax > az) ? 0 : ((ay > az) ? 1 : 2);
+}
+
+DEVFN void tri_setup_grid(TriSetup& ts, const float q[3][3], const float N[3], const int clipLo[3], const int clipHi[3])
+{
+    float e[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e[i][k] = q[(i + 1) % 3][k] - q[i][k];
+    float* n = ts.n;
+    n[0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+    n[1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+    n[2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+    bool valid = !((n[0] == 0.0f && n[1] == 0.0f && n[2] == 0.0f) || (N[0] == 0.0f && N[1] == 0.0f && N[2] == 0.0f));
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (!(fabsf(q[i][k]) < 1.0e9f)) valid = false;
+    ts.valid = valid;
+    if (!valid) return;
+
+    const float c0 = n[0] > 0.0f ? 1.0f : 0.0f, c1 = n[1] > 0.0f ? 1.0f : 0.0f, c2 = n[2] > 0.0f ? 1.0f : 0.0f;
+    ts.d1 = (n[0] * (c0 - q[0][0]) + n[1] * (c1 - q[0][1])) + n[2] * (c2 - q[0][2]);
+    ts.d2 = (n[0] * ((1.0f - c0) - q[0][0]) + n[1] * ((1.0f - c1) - q[0][1])) + n[2] * ((1.0f - c2) - q[0][2]);
+    // plane 0: xy (sign n.z), plane 1: yz (sign n.x), plane 2: zx (sign n.y)
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const int U = pl, V = (pl + 1) % 3, S = (pl + 2) % 3;
+        const float s = n[S] >= 0.0f ? 1.0f : -1.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float nx = -e[i][V] * s;
+            const float ny = e[i][U] * s;
+            ts.ne[pl][i][0] = nx;
+            ts.ne[pl][i][1] = ny;
+            ts.de[pl][i] = (-(nx * q[i][U] + ny * q[i][V]) + f_max(0.0f, nx)) + f_max(0.0f, ny);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float mn = f_min(q[0][k], f_min(q[1][k], q[2][k]));
+        const float mx = f_max(q[0][k], f_max(q[1][k], q[2][k]));
+        const int lo = (int)floorf(mn), hi = (int)floorf(mx);
+        ts.lo[k] = lo > clipLo[k] ? lo : clipLo[k];
+        ts.hi[k] = hi < clipHi[k] ? hi : clipHi[k];
+    }
+}
+
+DEVFN void tri_setup_level(TriSetup& ts, const float p[9], const float N[3], const LevelParams& lv, int R)
+{
+    float q[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[i][k] = p[i * 3 + k] / lv.voxel_size;
+    const int lo[3] = { lv.min_corner[0], lv.min_corner[1], lv.min_corner[2] };
+    const int hi[3] = { lv.min_corner[0] + R - 1, lv.min_corner[1] + R - 1, lv.min_corner[2] + R - 1 };
+    tri_setup_grid(ts, q, N, lo, hi);
+}
+
+DEVFN bool tri_overlaps_voxel(const TriSetup& ts, int vx, int vy, int vz)
+{
+    const float f[3] = { (float)vx, (float)vy, (float)vz };
+    const float np = (ts.n[0] * f[0] + ts.n[1] * f[1]) + ts.n[2] * f[2];
+    if ((np + ts.d1) * (np + ts.d2) > 0.0f) return false;
+    bool ok = true;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const int U = pl, V = (pl + 1) % 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if ((ts.ne[pl][i][0] * f[U] + ts.ne[pl][i][1] * f[V]) + ts.de[pl][i] < 0.0f) ok = false;
+    }
+    return ok;
+}
+
+DEVFN void load_tri(const float4* __restrict__ tri_pos, uint32_t t, float p[9], int* mat)
+{
+    const float4 a = __ldg(tri_pos + 3 * (size_t)t), b = __ldg(tri_pos + 3 * (size_t)t + 1), c = __ldg(tri_pos + 3 * (size_t)t + 2);
+    p[0] = a.x; p[1] = a.y; p[2] = a.z;
+    p[3] = b.x; p[4] = b.y; p[5] = b.z;
+    p[6] = c.x; p[7] = c.y; p[8] = c.z;
+    if (mat) *mat = __float_as_int(a.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: voxelize — occupancy bits + (triangle, level, texel) pair list
+// ---------------------------------------------------------------------------------------------------
+#define SMALL_BOX_MAX 64
+
+DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
+                     Counters* __restrict__ cnt, uint32_t tri, int level, int vx, int vy, int vz)
+{
+    const int Rm = bp.R - 1;
+    const uint32_t x = vx & Rm, y = vy & Rm, z = vz & Rm;
+    const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
+    const size_t w = (size_t)level * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
+    const uint32_t bit = 1u << (x & 31u);
+    if (!(occ[w] & bit)) atomicOr(&occ[w], bit);
+    // warp-aggregated append
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    const unsigned rank = __popc(m & ((1u << lane_id()) - 1u));
+    uint32_t base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(&cnt->pairs, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t slot = base + rank;
+    if (slot < bp.max_pairs)
+        pairs[slot] = ((vgi_pair_t)tri << 32) | ((vgi_pair_t)level << 27) | ((vgi_pair_t)z << 18) | ((vgi_pair_t)y << 9) | x;
+    else
+        atomicOr(&cnt->overflow, 1u);
+}
+
+__global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* __restrict__ tri_pos,
+                                                   uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
+                                                   uint2* __restrict__ large, Counters* __restrict__ cnt)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bp.ntri) return;
+    float p[9], N[3];
+    load_tri(tri_pos, t, p, nullptr);
+    cross_and_axis(p, N);
+    for (int l = 0; l < bp.L; ++l) {
+        TriSetup ts;
+        tri_setup_level(ts, p, N, bp.lv[l], bp.R);
+        if (!ts.valid) continue;
+        if (ts.lo[0] > ts.hi[0] || ts.lo[1] > ts.hi[1] || ts.lo[2] > ts.hi[2]) continue;
+        const long long vol = (long long)(ts.hi[0] - ts.lo[0] + 1) * (ts.hi[1] - ts.lo[1] + 1) * (ts.hi[2] - ts.lo[2] + 1);
+        if (vol > SMALL_BOX_MAX) {
+            const uint32_t slot = atomicAdd(&cnt->large, 1u);
+            if (slot < bp.max_large) large[slot] = make_uint2(t, (uint32_t)l);
+            else atomicOr(&cnt->overflow, 2u);
+            continue;
+        }
+        for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
+            for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
+                for (int x = ts.lo[0]; x <= ts.hi[0]; ++x)
+                    if (tri_overlaps_voxel(ts, x, y, z)) emit_pair(bp, occ, pairs, cnt, t, l, x, y, z);
+    }
+}
+
+// one warp per big (triangle, level) item; lanes stride over the clipped bounding box
+__global__ void __launch_bounds__(256) k_voxelize_large(BuildParams bp, const float4* __restrict__ tri_pos,
+                                                         uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
+                                                         const uint2* __restrict__ large, Counters* __restrict__ cnt)
+{
+    const uint32_t nitems = min(cnt->large, bp.max_large);
+    const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += warpsPerGrid) {
+        const uint2 it = large[item];
+        float p[9], N[3];
+        load_tri(tri_pos, it.x, p, nullptr);
+        cross_and_axis(p, N);
+        TriSetup ts;
+        tri_setup_level(ts, p, N, bp.lv[it.y], bp.R);
+        const int nx = ts.hi[0] - ts.lo[0] + 1, ny = ts.hi[1] - ts.lo[1] + 1, nz = ts.hi[2] - ts.lo[2] + 1;
+        const long long vol = (long long)nx * ny * nz;
+        for (long long base = 0; base < vol; base += 32) {
+            const long long i = base + lane_id();
+            if (i < vol) {
+                const int x = ts.lo[0] + (int)(i % nx);
+                const int y = ts.lo[1] + (int)((i / nx) % ny);
+                const int z = ts.lo[2] + (int)(i / ((long long)nx * ny));
+                if (tri_overlaps_voxel(ts, x, y, z)) emit_pair(bp, occ, pairs, cnt, it.x, (int)it.y, x, y, z);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: exclusive prefix sum of the occupancy popcounts (compact accumulator index per occupied voxel)
+// ---------------------------------------------------------------------------------------------------
+#define SCAN_BLOCK 1024
+#define SCAN_ITEMS 4  // words per thread -> 4096 words per block
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block_sums(const uint32_t* __restrict__ occ, size_t nwords,
+                                                                 uint32_t* __restrict__ block_sums)
+{
+    __shared__ uint32_t warp_sums[SCAN_BLOCK / 32];
+    const size_t base = ((size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    uint32_t s = 0;
+    if (base + SCAN_ITEMS <= nwords) {
+        const uint4 v = *reinterpret_cast<const uint4*>(occ + base);
+        s = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    } else {
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < nwords) s += __popc(occ[base + i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane_id() == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = warp_sums[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+    }
+}
+
+// single block: exclusive scan of block sums in place, total -> counters->occ_total
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ block_sums, uint32_t nblocks, Counters* __restrict__ cnt)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane_id() >= o) inc += n;
+        }
+        if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_tot[threadIdx.x], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+                if ((int)lane_id() >= o) winc += n;
+            }
+            warp_tot[threadIdx.x] = winc - w; // exclusive
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + (inc - v);
+        if (i < nblocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cnt->occ_total = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_final(const uint32_t* __restrict__ occ, size_t nwords,
+                                                            const uint32_t* __restrict__ block_sums,
+                                                            uint32_t* __restrict__ prefix)
+{
+    __shared__ uint32_t warp_tot[SCAN_BLOCK / 32];
+    const size_t base = ((size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        c[i] = (base + i < nwords) ? __popc(occ[base + i]) : 0u;
+        s += c[i];
+    }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane_id() >= o) inc += n;
+    }
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_tot[threadIdx.x], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if ((int)lane_id() >= o) winc += n;
+        }
+        warp_tot[threadIdx.x] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = block_sums[blockIdx.x] + warp_tot[threadIdx.x >> 5] + (inc - s);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < nwords) prefix[base + i] = run;
+        run += c[i];
+    }
+}
+
+__global__ void k_zero_acc(uint32_t* __restrict__ acc, const Counters* __restrict__ cnt, uint32_t max_occ)
+{
+    const size_t n = (size_t)min(cnt->occ_total, max_occ) * 24;
+    uint4* a4 = reinterpret_cast<uint4*>(acc);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x)
+        a4[i] = make_uint4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: radiance injection — one thread per (triangle, voxel) pair.
+// ref: msaaInjectRadiance.frag:68-155 (shading), :176-183 (faces from -normal), shadow.glsl:8-36.
+// Canonical accumulation (Q10): 16.16 fixed-point integer sums + count, order independent.
+// ---------------------------------------------------------------------------------------------------
+DEVFN void xform_point(const float* m, const float* v, float* o)
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[r] = ((m[r] * v[0] + m[4 + r] * v[1]) + m[8 + r] * v[2]) + m[12 + r];
+}
+
+DEVFN float shadow_texel(const LightParams& lp, int x, int y)
+{
+    if (x < 0 || y < 0 || x >= lp.sw || y >= lp.sh) return 0.0f; // CLAMP_TO_BORDER, opaque black
+    return __ldg(lp.depth + (size_t)y * lp.sw + x);
+}
+
+DEVFN float shadow_bilinear(const LightParams& lp, float u, float v, bool compare, float cmpz)
+{
+    const float x = u * (float)lp.sw - 0.5f, y = v * (float)lp.sh - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float a = x - fx, b = y - fy;
+    const int ix = (int)f_clamp(fx, -4.0f, (float)lp.sw + 4.0f), iy = (int)f_clamp(fy, -4.0f, (float)lp.sh + 4.0f);
+    float t00 = shadow_texel(lp, ix, iy), t10 = shadow_texel(lp, ix + 1, iy);
+    float t01 = shadow_texel(lp, ix, iy + 1), t11 = shadow_texel(lp, ix + 1, iy + 1);
+    if (compare) {
+        t00 = t00 >= cmpz ? 1.0f : 0.0f; t10 = t10 >= cmpz ? 1.0f : 0.0f;
+        t01 = t01 >= cmpz ? 1.0f : 0.0f; t11 = t11 >= cmpz ? 1.0f : 0.0f;
+    }
+    return (t00 * (1.0f - a) + t10 * a) * (1.0f - b) + (t01 * (1.0f - a) + t11 * a) * b;
+}
+
+// ref: shadow.glsl:28-36 + :14-26 (literal Q1: mean of 16 bilinear raw-depth taps)
+DEVFN float calc_visibility(const LightParams& lp, const float* worldPos, bool compare)
+{
+    float l[3];
+    xform_point(lp.view, worldPos, l);
+    const float* P = lp.proj;
+    float px = ((P[0] * l[0] + P[4] * l[1]) + P[8] * 0.0f) + P[12];
+    float py = ((P[1] * l[0] + P[5] * l[1]) + P[9] * 0.0f) + P[13];
+    px = px * 0.5f + 0.5f;
+    py = py * 0.5f + 0.5f;
+    float cmpz = 0.0f;
+    if (compare) cmpz = (P[10] * l[2] + P[14]) - 0.002f;
+    const float sx = 1.0f / (float)lp.sw, sy = 1.0f / (float)lp.sh;
+    float sum = 0.0f;
+    for (int j = 0; j < 4; ++j) {
+        const float oy = -1.5f + (float)j;
+        for (int i = 0; i < 4; ++i) {
+            const float ox = -1.5f + (float)i;
+            sum += shadow_bilinear(lp, px + ox * sx, py + oy * sy, compare, cmpz);
+        }
+    }
+    return sum * 0.0625f;
+}
+
+// voxel centre projected along the dominant axis onto the triangle plane, clamped into the triangle
+DEVFN bool inject_sample_at(int a, const float N[3], const float p[9], const float n9[9], float c[3],
+                            float pos[3], float nrm[3])
+{
+    const float Na = N[a];
+    if (Na == 0.0f) return false;
+    const float d[3] = { c[0] - p[0], c[1] - p[1], c[2] - p[2] };
+    const float t = dot3(N, d) / Na;
+    c[a] = c[a] - t;
+    const int u = (a == 0) ? 1 : 0;
+    const int v = (a == 2) ? 1 : 2;
+    const float e1u = p[3 + u] - p[u], e1v = p[3 + v] - p[v];
+    const float e2u = p[6 + u] - p[u], e2v = p[6 + v] - p[v];
+    const float cu = c[u] - p[u], cv = c[v] - p[v];
+    const float den = e1u * e2v - e2u * e1v;
+    if (den == 0.0f) return false;
+    float b1 = (cu * e2v - e2u * cv) / den;
+    float b2 = (e1u * cv - cu * e1v) / den;
+    float b0 = (1.0f - b1) - b2;
+    b0 = f_max(b0, 0.0f); b1 = f_max(b1, 0.0f); b2 = f_max(b2, 0.0f);
+    const float sum = (b0 + b1) + b2;
+    b0 = b0 / sum; b1 = b1 / sum; b2 = b2 / sum;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pos[k] = (p[k] * b0 + p[3 + k] * b1) + p[6 + k] * b2;
+        nrm[k] = (n9[k] * b0 + n9[3 + k] * b1) + n9[6 + k] * b2;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_inject(BuildParams bp, LightParams lp, const float4* __restrict__ tri_pos,
+                                                 const float4* __restrict__ tri_nrm, const vgi_material* __restrict__ materials,
+                                                 const vgi_pair_t* __restrict__ pairs, const uint32_t* __restrict__ occ,
+                                                 const uint32_t* __restrict__ occ_prefix, uint32_t* __restrict__ acc,
+                                                 Counters* __restrict__ cnt)
+{
+    const uint32_t npairs = min(cnt->pairs, bp.max_pairs);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const vgi_pair_t pr = pairs[i];
+        const uint32_t tri = (uint32_t)(pr >> 32);
+        const int level = (int)((pr >> 27) & 7u);
+        if (!((bp.level_mask >> level) & 1u)) continue;
+        const int tx = (int)(pr & 511u), ty = (int)((pr >> 9) & 511u), tz = (int)((pr >> 18) & 511u);
+        const LevelParams& lv = bp.lv[level];
+        const int Rm = bp.R - 1;
+        // unwrap the texel back to the voxel inside the region
+        const int vx = lv.min_corner[0] + ((tx - lv.min_corner[0]) & Rm);
+        const int vy = lv.min_corner[1] + ((ty - lv.min_corner[1]) & Rm);
+        const int vz = lv.min_corner[2] + ((tz - lv.min_corner[2]) & Rm);
+
+        float p[9], n9[9], N[3];
+        int mat;
+        load_tri(tri_pos, tri, p, &mat);
+        {
+            const float4 a = __ldg(tri_nrm + 3 * (size_t)tri), b = __ldg(tri_nrm + 3 * (size_t)tri + 1), c = __ldg(tri_nrm + 3 * (size_t)tri + 2);
+            n9[0] = a.x; n9[1] = a.y; n9[2] = a.z; n9[3] = b.x; n9[4] = b.y; n9[5] = b.z; n9[6] = c.x; n9[7] = c.y; n9[8] = c.z;
+        }
+        const int axis = cross_and_axis(p, N);
+        float c[3] = { ((float)vx + 0.5f) * lv.voxel_size, ((float)vy + 0.5f) * lv.voxel_size, ((float)vz + 0.5f) * lv.voxel_size };
+        float pos[3], nrm[3];
+        if (!inject_sample_at(axis, N, p, n9, c, pos, nrm)) continue;
+
+        const vgi_material* m = materials + mat;
+        int faces[6];
+        uint32_t q[6][3];
+        int nf = 0;
+        const float e0 = m->emissive_factor[0], e1 = m->emissive_factor[1], e2 = m->emissive_factor[2];
+        if (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f) {
+            const uint32_t q0 = (uint32_t)(f_clamp(e0, 0.0f, 1.0f) * 65536.0f + 0.5f);
+            const uint32_t q1 = (uint32_t)(f_clamp(e1, 0.0f, 1.0f) * 65536.0f + 0.5f);
+            const uint32_t q2 = (uint32_t)(f_clamp(e2, 0.0f, 1.0f) * 65536.0f + 0.5f);
+#pragma unroll
+            for (int f = 0; f < 6; ++f) { faces[f] = f; q[f][0] = q0; q[f][1] = q1; q[f][2] = q2; }
+            nf = 6;
+        } else {
+            const float len2 = dot3(nrm, nrm);
+            if (!(len2 > 0.0f)) continue;
+            const float len = sqrtf(len2);
+            const float n[3] = { nrm[0] / len, nrm[1] / len, nrm[2] / len };
+            const float NdotL = f_clamp(dot3(n, lp.dir_to_light), 0.001f, 1.0f);
+            const float vis = calc_visibility(lp, pos, bp.shadow_compare != 0);
+            float lc[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) lc[k] = ((NdotL * vis) * lp.color[k]) * lp.intensity;
+            if (lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f) continue;
+            float rad[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                rad[k] = f_clamp((lc[k] * m->base_color_factor[k]) * m->base_color_factor[3], 0.0f, 1.0f);
+            faces[0] = (-n[0] > 0.0f) ? 0 : 1;
+            faces[1] = (-n[1] > 0.0f) ? 2 : 3;
+            faces[2] = (-n[2] > 0.0f) ? 4 : 5;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const float w = fabsf(n[f]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) q[f][k] = (uint32_t)((rad[k] * w) * 65536.0f + 0.5f);
+            }
+            nf = 3;
+        }
+        const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
+        const size_t w = (size_t)level * wordsPerLevel + (((((size_t)tz << bp.logR) + ty) << bp.logR) + tx) / 32;
+        const uint32_t idx = occ_prefix[w] + __popc(occ[w] & ((1u << (tx & 31)) - 1u));
+        if (idx >= bp.max_occ) { atomicOr(&cnt->overflow, 4u); continue; }
+        uint32_t* a = acc + (size_t)idx * 24;
+        for (int f = 0; f < nf; ++f) {
+            uint32_t* af = a + faces[f] * 4;
+            atomicAdd(af + 0, q[f][0]);
+            atomicAdd(af + 1, q[f][1]);
+            atomicAdd(af + 2, q[f][2]);
+            atomicAdd(af + 3, 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: finalize — one thread per voxel writes its 32-byte record. Fuses the reference's clears
+// (A4 VoxelizationPass.cpp:104-126, A7 clipmapCleaning.comp), the raw opacity store
+// (msaaVoxelizer.frag:69-73), the radiance average (msaaInjectRadiance.frag:185-201, canonical mean)
+// and copy-alpha (A9 copyAlphaImage.comp:16-29).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(BuildParams bp, int level, const uint32_t* __restrict__ occ,
+                                                   const uint32_t* __restrict__ occ_prefix,
+                                                   const uint32_t* __restrict__ acc, VoxelRecord* __restrict__ store)
+{
+    const size_t nvox = (size_t)bp.R * bp.R * bp.R;
+    const size_t v = (size_t)bp.z0 * bp.R * bp.R + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (size_t)bp.z1 * bp.R * bp.R) return;
+    const size_t w = (size_t)level * (nvox >> 5) + (v >> 5);
+    const uint32_t word = __ldg(occ + w);
+    const uint32_t bit = (uint32_t)(v & 31u);
+    const bool raw = (word >> bit) & 1u;
+    const bool inject = (bp.level_mask >> level) & 1u;
+    uint4* dst = reinterpret_cast<uint4*>(store + (size_t)level * nvox + v);
+    uint4 lo, hi;
+    if (inject) {
+        uint32_t rad[6] = { 0, 0, 0, 0, 0, 0 };
+        if (raw) {
+            const uint32_t idx = __ldg(occ_prefix + w) + __popc(word & ((1u << bit) - 1u));
+            if (idx < bp.max_occ) {
+                const uint4* a = reinterpret_cast<const uint4*>(acc + (size_t)idx * 24);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    const uint4 s = a[f];
+                    uint32_t r = 0, g = 0, b = 0;
+                    if (s.w) {
+                        r = (uint32_t)(((unsigned long long)s.x * 255ull) >> 16) / s.w;
+                        g = (uint32_t)(((unsigned long long)s.y * 255ull) >> 16) / s.w;
+                        b = (uint32_t)(((unsigned long long)s.z * 255ull) >> 16) / s.w;
+                        r = r > 255u ? 255u : r; g = g > 255u ? 255u : g; b = b > 255u ? 255u : b;
+                    }
+                    rad[f] = r | (g << 8) | (b << 16) | 0xff000000u; // copy-alpha: opacity.a of an occupied voxel = 1
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < 6; ++f) rad[f] = 0xff000000u;
+            }
+        }
+        lo = make_uint4(rad[0], rad[1], rad[2], rad[3]);
+        hi.x = rad[4];
+        hi.y = rad[5];
+    } else {
+        // off-cadence level: the radiance texels (including their alpha) keep last frame's values
+        lo = dst[0];
+        const uint4 old = dst[1];
+        hi.x = old.x;
+        hi.y = old.y;
+    }
+    hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
+    hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
+    dst[0] = lo;
+    dst[1] = hi;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: down-sample level-1 -> level (centre half of `level`), both atlases in one pass.
+// ref: opacityDownSample.comp:28-138 and radianceDownSample.comp:28-139 (Q6 repaired). One thread
+// per coarse voxel; the eight children are two 64-byte reads per (dy,dz) row.
+// ---------------------------------------------------------------------------------------------------
+__constant__ int c_ds_pair[6][4][2] = {
+    { {0,1},{2,3},{4,5},{6,7} }, { {1,0},{3,2},{5,4},{7,6} },
+    { {0,2},{1,3},{4,6},{5,7} }, { {2,0},{3,1},{6,4},{7,5} },
+    { {0,4},{1,5},{2,6},{3,7} }, { {4,0},{5,1},{6,2},{7,3} } };
+
+__global__ void __launch_bounds__(128) k_downsample(BuildParams bp, int level, VoxelRecord* __restrict__ store)
+{
+    const int R = bp.R, half = R >> 1;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y, gz = blockIdx.z;
+    if (gx >= half) return;
+    const int g[3] = { gx, gy, gz };
+    const int* prevMin = bp.lv[level - 1].min_corner;
+    int cur[3], wpos[3], pstart[3];
+    float dist[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        cur[k] = (prevMin[k] >> 1) + g[k];
+        wpos[k] = cur[k] & (R - 1);
+        pstart[k] = (cur[k] << 1) & (R - 1);
+        const float center = (float)(prevMin[k] >> 1) + (float)((uint32_t)half >> 1);
+        dist[k] = fabsf(((float)cur[k] + 0.5f) - center) - 0.5f;
+    }
+    if (wpos[2] < bp.z0 || wpos[2] >= bp.z1) return;
+    const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)bp.band;
+    const float thr = (float)thrU;
+    const float invBand = 1.0f / ((float)bp.band + 1.0f);
+    float lerpFactor = 0.0f;
+    if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
+        lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
+        lerpFactor = lerpFactor * invBand;
+    }
+    const size_t nvox = (size_t)R * R * R;
+    const VoxelRecord* prev = store + (size_t)(level - 1) * nvox;
+    VoxelRecord* own = store + (size_t)level * nvox + ((((size_t)wpos[2] << bp.logR) + wpos[1]) << bp.logR) + wpos[0];
+
+    // children: index i = dx + 2*dy + 4*dz (OFFSETS order of the shader)
+    uint4 clo[8], chi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int x = pstart[0] + (i & 1), y = pstart[1] + ((i >> 1) & 1), z = pstart[2] + (i >> 2);
+        const uint4* src = reinterpret_cast<const uint4*>(prev + ((((size_t)z << bp.logR) + y) << bp.logR) + x);
+        clo[i] = src[0];
+        chi[i] = src[1];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(own);
+    uint4 olo = dst[0], ohi = dst[1];
+    const bool inject = (bp.level_mask >> level) & 1u;
+    const float ownRaw = ((ohi.w >> 16) & 0xffu) ? 1.0f : 0.0f; // opacity.r of this level (raw flag * 255 / 255)
+
+    uint32_t newOp[6], newRad[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        // child opacity alphas of face f: bytes 24+f
+        float ca[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t wsel = f < 4 ? chi[i].z : chi[i].w;
+            ca[i] = unorm8_to_f((wsel >> (8 * (f & 3))) & 0xffu);
+        }
+        float s = 0.0f;
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+            const float a0 = ca[c_ds_pair[f][pr][0]], a1 = ca[c_ds_pair[f][pr][1]];
+            s = s + a0;
+            s = s + (1.0f - a0) * a1;
+        }
+        const float dsOp = s * 0.25f;
+        const uint32_t aOp = f_to_unorm8(f_mix(dsOp, ownRaw, lerpFactor));
+        newOp[f] = aOp;
+
+        if (inject) {
+            uint32_t cw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                cw[i] = f == 0 ? clo[i].x : f == 1 ? clo[i].y : f == 2 ? clo[i].z : f == 3 ? clo[i].w : f == 4 ? chi[i].x : chi[i].y;
+            const uint32_t ow = f == 0 ? olo.x : f == 1 ? olo.y : f == 2 ? olo.z : f == 3 ? olo.w : f == 4 ? ohi.x : ohi.y;
+            // own texel: rgb as injected, alpha = this level's final opacity alpha (copy-alpha ran before the radiance mips)
+            const uint32_t ownTexel = (ow & 0x00ffffffu) | (aOp << 24);
+            uint32_t out = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float sc = 0.0f;
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    const uint32_t w0 = cw[c_ds_pair[f][pr][0]], w1 = cw[c_ds_pair[f][pr][1]];
+                    const float v0 = unorm8_to_f((w0 >> (8 * c)) & 0xffu);
+                    const float v0a = unorm8_to_f(w0 >> 24);
+                    const float v1 = unorm8_to_f((w1 >> (8 * c)) & 0xffu);
+                    sc = sc + v0;
+                    sc = sc + (1.0f - v0a) * v1;
+                }
+                const float ds = sc * 0.25f;
+                out |= f_to_unorm8(f_mix(ds, unorm8_to_f((ownTexel >> (8 * c)) & 0xffu), lerpFactor)) << (8 * c);
+            }
+            newRad[f] = out;
+        }
+    }
+    if (inject) {
+        olo = make_uint4(newRad[0], newRad[1], newRad[2], newRad[3]);
+        ohi.x = newRad[4];
+        ohi.y = newRad[5];
+    }
+    ohi.z = newOp[0] | (newOp[1] << 8) | (newOp[2] << 16) | (newOp[3] << 24);
+    ohi.w = (ohi.w & 0xffff0000u) | newOp[4] | (newOp[5] << 8);
+    dst[0] = olo;
+    dst[1] = ohi;
+}
+
+// On an injected level outside the centre half the radiance alpha is the raw opacity (copy-alpha);
+// k_finalize already wrote it. Off-cadence levels keep their radiance. Nothing else to do.
+
+// ---------------------------------------------------------------------------------------------------
+// export to the reference atlas layout (ref: Voxelizer.h:40-52; texel addressing msaaVoxelizer.frag:43-55;
+// border: borderWrapping.comp:14-37, canonical = both sides of both atlases, literal = Q4/Q5)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_export(int R, int L, int logR, int which, int literal,
+                                                 const VoxelRecord* __restrict__ store, uint32_t* __restrict__ dst)
+{
+    const int rb = R + 2;
+    const size_t W = (size_t)rb * 6, H = (size_t)rb * L, D = rb;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H * D) return;
+    const int ax = (int)(i % W), ay = (int)((i / W) % H), az = (int)(i / (W * H));
+    const int f = ax / rb, bx = ax % rb;
+    const int l = ay / rb, by = ay % rb;
+    const int bz = az;
+    const bool border = bx == 0 || by == 0 || bz == 0 || bx == R + 1 || by == R + 1 || bz == R + 1;
+    if (border && literal) {
+        const int lim = ((R + 2) >> 3) << 3; // BorderWrapper.cpp:139 dispatches (R+2)>>3 groups of 8
+        const bool written = which == 0 && bx < lim && by < lim && bz < lim && (bx == 0 || by == 0 || bz == 0);
+        if (!written) { dst[i] = 0u; return; }
+    }
+    const int x = (bx + R - 1) & (R - 1), y = (by + R - 1) & (R - 1), z = (bz + R - 1) & (R - 1);
+    const VoxelRecord* rec = store + (size_t)l * R * R * R + ((((size_t)z << logR) + y) << logR) + x;
+    uint32_t out;
+    if (which == 1) out = rec->radiance[f];
+    else {
+        const uint32_t raw = rec->raw ? 255u : 0u, a = rec->opacity[f];
+        out = raw | (a << 8) | (raw << 16) | (a << 24);
+    }
+    dst[i] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------------
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    int n = 0;
+    const size_t nwords = ((size_t)bp.R * bp.R * bp.R >> 5) * bp.L;
+    cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
+    cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
+    if (bp.ntri) {
+        k_voxelize<<<cdiv(bp.ntri, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters); ++n;
+        k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters); ++n;
+    }
+    const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
+    k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums); ++n;
+    k_scan_sums<<<1, 1024, 0, s>>>(c->block_sums, nblk, c->counters); ++n;
+    k_scan_final<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums, c->occ_prefix); ++n;
+    return n;
+}
+
+int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    int n = 0;
+    k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ); ++n;
+    if (bp.ntri && bp.level_mask) {
+        k_inject<<<148 * 16, 128, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs, c->occ,
+                                          c->occ_prefix, c->acc, c->counters); ++n;
+    }
+    const size_t slabVox = (size_t)(bp.z1 - bp.z0) * bp.R * bp.R;
+    for (int l = 0; l < bp.L; ++l) {
+        k_finalize<<<cdiv(slabVox, 256), 256, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->store); ++n;
+    }
+    for (int l = 1; l < bp.L; ++l) {
+        const int half = bp.R >> 1;
+        dim3 grid(cdiv(half, 128), half, half);
+        k_downsample<<<grid, min(half, 128), 0, s>>>(bp, l, c->store); ++n;
+    }
+    cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
+    return n;
+}
+
+int vgi_launch_export(vgi_ctx* c, int which, uint8_t* dst, int literal_border, cudaStream_t s)
+{
+    const int R = (int)c->cfg.resolution, L = (int)c->cfg.level_count;
+    int logR = 0;
+    while ((1 << logR) < R) ++logR;
+    const size_t n = (size_t)(R + 2) * 6 * (size_t)(R + 2) * L * (R + 2);
+    k_export<<<cdiv(n, 256), 256, 0, s>>>(R, L, logR, which, literal_border, c->store, reinterpret_cast<uint32_t*>(dst));
+    return 1;
+}

@@ -1,0 +1,160 @@
+// vgi_internal.h — shared between the C-ABI host code (vgi_api.cpp) and the CUDA translation units.
+// Not part of the public interface (include/vgi.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vgi.h"
+
+// ---- voxel store ---------------------------------------------------------------------------------
+// One 32-byte record per voxel, levels concatenated, x fastest, no border (filtering addresses
+// toroidally, which is what the reference's border texels emulate for the hardware sampler):
+//   bytes  0..23  radiance RGBA8 of faces 0..5 (+X,-X,+Y,-Y,+Z,-Z)      == "VoxelRadiance" texels
+//   bytes 24..29  opacity alpha of faces 0..5                             == "VoxelOpacity".a (= .g)
+//   byte  30      raw occupancy flag (0/1)                                == "VoxelOpacity".r (= .b) / 255
+//   byte  31      0
+struct alignas(32) VoxelRecord {
+    uint32_t radiance[6];
+    uint8_t  opacity[6];
+    uint8_t  raw;
+    uint8_t  pad;
+};
+static_assert(sizeof(VoxelRecord) == 32, "record size");
+
+// (triangle, level, texel) pair emitted by the voxelizer, consumed by the injection kernel.
+// bits 0..8 x, 9..17 y, 18..26 z (texel = voxel mod R), 27..29 level, 32..63 triangle.
+typedef unsigned long long vgi_pair_t;
+
+struct LevelParams {
+    int   min_corner[3];
+    float voxel_size;
+};
+
+struct BuildParams {
+    LevelParams lv[VGI_MAX_LEVELS];
+    int      R, L, logR;
+    int      band;
+    uint32_t ntri;
+    uint32_t max_pairs;
+    uint32_t max_occ;       // capacity of the accumulator table (occupied voxels)
+    uint32_t max_large;
+    uint32_t level_mask;    // levels whose radiance is (re)injected this frame (cadence)
+    int      z0, z1;        // slab of records this GPU writes
+    int      shadow_compare;
+};
+
+struct LightParams {
+    float view[16], proj[16];
+    float dir_to_light[3];  // normalize(-direction)
+    float color[3];
+    float intensity;
+    float z_near, z_far;
+    const float* depth;
+    int   sw, sh;
+};
+
+// device-side counters (one small buffer, zeroed at the start of each build)
+struct Counters {
+    uint32_t pairs;
+    uint32_t large;
+    uint32_t occ_total;
+    uint32_t overflow;      // bit 0 pairs, bit 1 large queue, bit 2 accumulators, bit 3 svo frags, bit 4 svo nodes
+    uint32_t spec_pixels;
+    uint32_t svo_frags;
+    uint32_t svo_counter;
+    uint32_t svo_alloc_begin;
+    uint32_t svo_alloc_num;
+    uint32_t pad[7];
+};
+
+struct TraceParams {
+    vgi_vct_params p;
+    float    view_proj_inv[16];
+    float    eye[3];
+    int      R, L, logR;
+    const VoxelRecord* store;
+    const uint32_t* brick_mask;   // 1 bit per 4^3 brick (incl. 1-texel halo), per level; may be null
+    const void* diffuse; const void* normal; const void* specular; const void* emission;
+    const float* depth;
+    int      width, height, y0, y1;
+    float4*  out_diffuse;
+    float4*  out_specular;
+    LightParams light;
+    int      shadow_compare;
+    uint32_t* spec_list;          // compacted pixels needing a specular cone
+    uint32_t* spec_count;
+    float    cone_coeff_diffuse;  // 2*tan(aperture/2), evaluated on the host
+    float    diffuse_aperture;
+};
+
+struct vgi_ctx {
+    vgi_config cfg;
+    int device = 0;
+    std::string err;
+    vgi_clip_region regions[VGI_MAX_LEVELS];
+    bool regions_set = false;
+
+    // scene (world space)
+    uint32_t ntri = 0;
+    float4*  tri_pos = nullptr;   // 3 per triangle; p0.w carries the material index bits
+    float4*  tri_nrm = nullptr;   // 3 per triangle
+    vgi_material* materials = nullptr;
+    uint32_t nmat = 0;
+    std::vector<float> h_tri_pos; // host copies for debugging / multi-GPU culling
+    float scene_bb_min[3], scene_bb_max[3];
+
+    // light
+    LightParams light;
+    float* shadow_owned = nullptr;
+    bool light_set = false;
+
+    // build state
+    VoxelRecord* store = nullptr;
+    bool store_owned = false;
+    size_t store_bytes = 0;
+    uint32_t* occ = nullptr;        // L * R^3/32 words
+    uint32_t* occ_prefix = nullptr; // exclusive prefix of popcounts per word
+    uint32_t* block_sums = nullptr;
+    uint32_t* acc = nullptr;        // max_occ * 24 u32: [voxel][face][r,g,b,count]
+    vgi_pair_t* pairs = nullptr;
+    uint2* large = nullptr;         // (triangle, level) work items for big triangles
+    uint32_t* brick_mask = nullptr;
+    Counters* counters = nullptr;
+    Counters* h_counters = nullptr; // pinned
+    uint32_t max_pairs = 0, max_occ = 0, max_large = 0;
+    int z0 = 0, z1 = 0;
+    bool voxelized = false, built = false;
+    uint32_t frame_of_voxelize = 0;
+    cudaStream_t last_stream = 0;
+    uint64_t launches = 0;
+
+    // cone trace scratch
+    uint32_t* spec_list = nullptr;
+    size_t spec_capacity = 0;
+
+    // svo
+    uint32_t svo_level = 0;
+    uint2* svo_frags = nullptr;
+    uint32_t svo_frag_capacity = 0;
+    uint2* svo_nodes = nullptr;
+    uint32_t svo_node_capacity = 0;
+    uint32_t svo_nfrag = 0, svo_nnodes = 0;
+    float svo_bb_min[3], svo_bb_max[3];
+    uint32_t* svo_scratch = nullptr;
+    size_t svo_scratch_words = 0;
+};
+
+// ---- launch wrappers implemented in the .cu files (return number of kernels launched) ------------
+int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
+int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
+int vgi_launch_export(vgi_ctx* c, int which, uint8_t* dst, int literal_border, cudaStream_t s);
+int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);
+int vgi_launch_atlas_clear(uint8_t* atlas, int R, int L, const int32_t* mc, const uint32_t* ext, int level, cudaStream_t s);
+int vgi_launch_atlas_copy_alpha(uint8_t* dst, const uint8_t* src, int R, int L, int level, cudaStream_t s);
+int vgi_launch_atlas_downsample(uint8_t* atlas, int R, int L, int band, const int32_t* prev_min, int level, int which, cudaStream_t s);
+int vgi_launch_atlas_wrap(uint8_t* atlas, int R, int L, int literal, cudaStream_t s);
+
+void build_params_from_ctx(const vgi_ctx* c, uint32_t frame_index, BuildParams* bp);

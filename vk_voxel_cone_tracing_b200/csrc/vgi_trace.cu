@@ -1,0 +1,422 @@
+// vgi_trace.cu — per-pixel voxel cone tracing through the clipmap voxel store (sm_100a).
+// ref: VFS/Shaders/voxelConeTracing.frag:143-414, brdf.glsl:30-78, shadow.glsl:8-36.
+//
+// Floating-point results here are judged with a tolerance (max abs 1e-3, PSNR >= 50 dB), so this
+// translation unit is compiled with FMA contraction on. The hardware texture unit is NOT used:
+// its 8-bit interpolation weights would break the tolerance against exact-weight filtering, and a
+// manual tri-linear fetch lets all six face texels of a voxel live in one 32-byte record
+// (DESIGN.md "data layout") so the three face taps of a cone share their sectors.
+#include <cuda_fp16.h>
+
+#include "vgi_internal.h"
+
+#define DEVFN static __device__ __forceinline__
+
+__constant__ float c_cones16[16][3] = { // ref: voxelConeTracing.frag:118-135
+    { 0.57735f, 0.57735f, 0.57735f }, { 0.57735f, -0.57735f, -0.57735f },
+    { -0.57735f, 0.57735f, -0.57735f }, { -0.57735f, -0.57735f, 0.57735f },
+    { -0.903007f, -0.182696f, -0.388844f }, { -0.903007f, 0.182696f, 0.388844f },
+    { 0.903007f, -0.182696f, 0.388844f }, { 0.903007f, 0.182696f, -0.388844f },
+    { -0.388844f, -0.903007f, -0.182696f }, { 0.388844f, -0.903007f, 0.182696f },
+    { 0.388844f, 0.903007f, -0.182696f }, { -0.388844f, 0.903007f, 0.182696f },
+    { -0.182696f, -0.388844f, -0.903007f }, { 0.182696f, 0.388844f, -0.903007f },
+    { -0.182696f, 0.388844f, 0.903007f }, { 0.182696f, -0.388844f, 0.903007f } };
+__constant__ float c_cones32[32][3] = { // ref: voxelConeTracing.frag:81-114
+    { 0.898904f, 0.435512f, 0.0479745f }, { 0.898904f, -0.435512f, -0.0479745f },
+    { 0.898904f, 0.0479745f, -0.435512f }, { 0.898904f, -0.0479745f, 0.435512f },
+    { -0.898904f, 0.435512f, -0.0479745f }, { -0.898904f, -0.435512f, 0.0479745f },
+    { -0.898904f, 0.0479745f, 0.435512f }, { -0.898904f, -0.0479745f, -0.435512f },
+    { 0.0479745f, 0.898904f, 0.435512f }, { -0.0479745f, 0.898904f, -0.435512f },
+    { -0.435512f, 0.898904f, 0.0479745f }, { 0.435512f, 0.898904f, -0.0479745f },
+    { -0.0479745f, -0.898904f, 0.435512f }, { 0.0479745f, -0.898904f, -0.435512f },
+    { 0.435512f, -0.898904f, 0.0479745f }, { -0.435512f, -0.898904f, -0.0479745f },
+    { 0.435512f, 0.0479745f, 0.898904f }, { -0.435512f, -0.0479745f, 0.898904f },
+    { 0.0479745f, -0.435512f, 0.898904f }, { -0.0479745f, 0.435512f, 0.898904f },
+    { 0.435512f, -0.0479745f, -0.898904f }, { -0.435512f, 0.0479745f, -0.898904f },
+    { 0.0479745f, 0.435512f, -0.898904f }, { -0.0479745f, -0.435512f, -0.898904f },
+    { 0.57735f, 0.57735f, 0.57735f }, { 0.57735f, 0.57735f, -0.57735f },
+    { 0.57735f, -0.57735f, 0.57735f }, { 0.57735f, -0.57735f, -0.57735f },
+    { -0.57735f, 0.57735f, 0.57735f }, { -0.57735f, 0.57735f, -0.57735f },
+    { -0.57735f, -0.57735f, 0.57735f }, { -0.57735f, -0.57735f, -0.57735f } };
+
+#define MIN_TRACE_STEP_FACTOR 0.2f
+#define MAX_TRACE_DISTANCE 30.0f
+#define MIN_SPECULAR_APERTURE 0.05f
+
+
+DEVFN float f_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+DEVFN float f_fract(float x) { return x - floorf(x); }
+DEVFN float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+DEVFN void normalize3(const float* v, float* o)
+{
+    const float inv = 1.0f / sqrtf(dot3(v, v));
+    o[0] = v[0] * inv; o[1] = v[1] * inv; o[2] = v[2] * inv;
+}
+
+// one clipmap level, three face-weighted tri-linear taps (ref: voxelConeTracing.frag:313-327).
+// Texel coordinate = fract(p / extent) * R - 0.5, indices wrapped modulo R: the toroidal addressing
+// that the reference obtains from REPEAT + wrapped border texels.
+DEVFN void sample_level(const TraceParams& tp, const float* pos, int level, int fsel, const float* weight, float* out)
+{
+    const int R = tp.R, Rm = R - 1;
+    const float extent = (tp.p.voxel_size * tp.p.volume_dimension) * exp2f((float)level);
+    const float inv = 1.0f / extent;
+    int i0[3], i1[3];
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float t = f_fract(pos[k] * inv) * (float)R - 0.5f;
+        const float fl = floorf(t);
+        w[k] = t - fl;
+        const int i = (int)fl;
+        i0[k] = i & Rm;
+        i1[k] = (i + 1) & Rm;
+    }
+    const VoxelRecord* base = tp.store + ((size_t)level << (3 * tp.logR));
+    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int x = (c & 1) ? i1[0] : i0[0], y = (c & 2) ? i1[1] : i0[1], z = (c & 4) ? i1[2] : i0[2];
+        const float wc = ((c & 1) ? w[0] : 1.0f - w[0]) * ((c & 2) ? w[1] : 1.0f - w[1]) * ((c & 4) ? w[2] : 1.0f - w[2]);
+        const uint4* rec = reinterpret_cast<const uint4*>(base + ((((size_t)z << tp.logR) + y) << tp.logR) + x);
+        const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+        const uint32_t tx = (fsel & 1) ? lo.y : lo.x;
+        const uint32_t ty = (fsel & 2) ? lo.w : lo.z;
+        const uint32_t tz = (fsel & 4) ? hi.y : hi.x;
+        if ((tx | ty | tz) == 0u) continue;
+        const float wxf = wc * weight[0], wyf = wc * weight[1], wzf = wc * weight[2];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            acc[ch] += wxf * (float)((tx >> (8 * ch)) & 0xffu);
+            acc[ch] += wyf * (float)((ty >> (8 * ch)) & 0xffu);
+            acc[ch] += wzf * (float)((tz >> (8 * ch)) & 0xffu);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) out[ch] = acc[ch] * (1.0f / 255.0f);
+}
+
+// ref: voxelConeTracing.frag:341-392
+DEVFN void trace_cone(const TraceParams& tp, const float* startPos_, const float* dir, float coneCoefficient, float maxDistance,
+                      float startLevel, float stepFactor, float* out)
+{
+    const vgi_vct_params& p = tp.p;
+    float result[4] = { 0.f, 0.f, 0.f, 0.f };
+    float curLevel = startLevel;
+    float voxelSize = p.voxel_size * exp2f(curLevel);
+    float startPos[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize * p.trace_start_offset * 0.5f;
+    float step = 0.0f;
+    float diameter = fmaxf(step * coneCoefficient, p.voxel_size);
+    float occlusion = 0.0f;
+    const int fsel = (dir[0] > 0.0f ? 0 : 1) | (dir[1] > 0.0f ? 0 : 2) | (dir[2] > 0.0f ? 0 : 4);
+    const float weight[3] = { dir[0] * dir[0], dir[1] * dir[1], dir[2] * dir[2] };
+    float curSegmentLength = voxelSize;
+    const float minRadius = p.voxel_size * p.volume_dimension * 0.5f;
+    const float invVoxel = 1.0f / p.voxel_size;
+    const float maxLevel = (float)(tp.L - 1);
+
+    while (step < maxDistance && occlusion < 1.0f) {
+        float position[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            position[k] = startPos[k] + dir[k] * step;
+            d[k] = p.volume_center[k] - position[k];
+        }
+        const float dist = sqrtf(dot3(d, d));
+        const float minLevel = ceilf(log2f(dist / minRadius));
+        curLevel = log2f(diameter * invVoxel);
+        curLevel = fminf(fmaxf(fmaxf(startLevel, curLevel), minLevel), maxLevel);
+
+        const float fl = floorf(curLevel);
+        const float fr = curLevel - fl;
+        float smp[4];
+        sample_level(tp, position, (int)fl, fsel, weight, smp);
+        if (fr > 0.0f) { // Q17: floor == ceil when the level is integral — the second fetch is identical
+            float up[4];
+            sample_level(tp, position, (int)fl + 1, fsel, weight, up);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
+        }
+        voxelSize = p.voxel_size * exp2f(curLevel);
+        const float correction = curSegmentLength / voxelSize;
+        float opacity = smp[3];
+        // 1 - pow(1 - a, correction)
+        opacity = f_clamp(1.0f - exp2f(correction * log2f(1.0f - opacity)), 0.0f, 1.0f);
+        if (smp[3] <= 0.0f) opacity = 0.0f;
+        const float k1 = f_clamp(1.0f - result[3], 0.0f, 1.0f);
+        result[0] += k1 * (smp[0] * correction);
+        result[1] += k1 * (smp[1] * correction);
+        result[2] += k1 * (smp[2] * correction);
+        result[3] += k1 * opacity;
+        occlusion += (1.0f - occlusion) * opacity / (1.0f + (step + voxelSize) * p.occlusion_decay);
+        const float prevStep = step;
+        step += fmaxf(diameter, p.voxel_size) * stepFactor;
+        curSegmentLength = step - prevStep;
+        diameter = step * coneCoefficient;
+    }
+    out[0] = result[0]; out[1] = result[1]; out[2] = result[2];
+    out[3] = 1.0f - occlusion;
+}
+
+// ref: voxelConeTracing.frag:394-414
+DEVFN float calc_min_level(const TraceParams& tp, const float* worldPos)
+{
+    const vgi_vct_params& p = tp.p;
+    const float d[3] = { p.volume_center[0] - worldPos[0], p.volume_center[1] - worldPos[1], p.volume_center[2] - worldPos[2] };
+    const float dist = sqrtf(dot3(d, d));
+    const float minRadius = p.voxel_size * p.volume_dimension * 0.5f;
+    const float minLevel = fmaxf(log2f(dist / minRadius), 0.0f);
+    const float radius = minRadius * exp2f(ceilf(minLevel));
+    const float f = dist / radius;
+    const float transitionStart = 0.5f;
+    const float c = 1.0f / (1.0f - transitionStart);
+    if (f > transitionStart) return ceilf(minLevel) + (f - transitionStart) * c;
+    return ceilf(minLevel);
+}
+
+// shadow.glsl:8-36 (literal Q1: mean of 16 bilinear raw-depth taps, CLAMP_TO_BORDER black)
+DEVFN float shadow_texel(const LightParams& lp, int x, int y)
+{
+    if (x < 0 || y < 0 || x >= lp.sw || y >= lp.sh) return 0.0f;
+    return __ldg(lp.depth + (size_t)y * lp.sw + x);
+}
+DEVFN float calc_visibility(const TraceParams& tp, const float* worldPos)
+{
+    const LightParams& lp = tp.light;
+    const float* V = lp.view;
+    const float* P = lp.proj;
+    float l[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) l[r] = V[r] * worldPos[0] + V[4 + r] * worldPos[1] + V[8 + r] * worldPos[2] + V[12 + r];
+    float px = P[0] * l[0] + P[4] * l[1] + P[12];
+    float py = P[1] * l[0] + P[5] * l[1] + P[13];
+    px = px * 0.5f + 0.5f;
+    py = py * 0.5f + 0.5f;
+    const bool compare = tp.shadow_compare != 0;
+    const float cmpz = (P[10] * l[2] + P[14]) - 0.002f;
+    const float sx = 1.0f / (float)lp.sw, sy = 1.0f / (float)lp.sh;
+    float sum = 0.0f;
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            const float u = px + (-1.5f + (float)i) * sx, v = py + (-1.5f + (float)j) * sy;
+            const float x = u * (float)lp.sw - 0.5f, y = v * (float)lp.sh - 0.5f;
+            const float fx = floorf(x), fy = floorf(y);
+            const float a = x - fx, b = y - fy;
+            const int ix = (int)f_clamp(fx, -4.0f, (float)lp.sw + 4.0f), iy = (int)f_clamp(fy, -4.0f, (float)lp.sh + 4.0f);
+            float t00 = shadow_texel(lp, ix, iy), t10 = shadow_texel(lp, ix + 1, iy);
+            float t01 = shadow_texel(lp, ix, iy + 1), t11 = shadow_texel(lp, ix + 1, iy + 1);
+            if (compare) {
+                t00 = t00 >= cmpz ? 1.f : 0.f; t10 = t10 >= cmpz ? 1.f : 0.f;
+                t01 = t01 >= cmpz ? 1.f : 0.f; t11 = t11 >= cmpz ? 1.f : 0.f;
+            }
+            sum += (t00 * (1.0f - a) + t10 * a) * (1.0f - b) + (t01 * (1.0f - a) + t11 * a) * b;
+        }
+    return sum * 0.0625f;
+}
+
+// ref: brdf.glsl:30-78
+DEVFN void microfacet_brdf(float NdotL, float NdotV, float NdotH, float VdotH, float alphaRoughness,
+                           const float* r0, float r90, const float* diffuseColor, float* o)
+{
+    const float PI_REF = 3.141592f;
+    const float x = f_clamp(1.0f - VdotH, 0.0f, 1.0f);
+    const float x2 = x * x;
+    const float fw = x2 * x2 * x;
+    const float r = alphaRoughness;
+    const float attL = 2.0f * NdotL / (NdotL + sqrtf(r * r + (1.0f - r * r) * (NdotL * NdotL)));
+    const float attV = 2.0f * NdotV / (NdotV + sqrtf(r * r + (1.0f - r * r) * (NdotV * NdotV)));
+    const float G = attL * attV;
+    const float rsq = r * r;
+    const float ff = (NdotH * rsq - NdotH) * NdotH + 1.0f;
+    const float Dm = rsq / (PI_REF * ff * ff);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float F = r0[k] + (r90 - r0[k]) * fw;
+        const float diffuseContrib = (1.0f - F) * (diffuseColor[k] / PI_REF);
+        const float specContrib = F * G * Dm / (4.0f * NdotL * NdotV);
+        o[k] = NdotL * (diffuseContrib + specContrib);
+    }
+}
+
+struct PixelSetup {
+    float worldPos[3], view[3], normal[3];
+    float diffuseColor[3], specularColor[3], emission[3];
+    float perceptualRoughness, metallic;
+    float minLevel;
+    float startPos[3];
+};
+
+DEVFN bool pixel_setup(const TraceParams& tp, int px, int py, PixelSetup& s)
+{
+    const size_t pi = (size_t)py * tp.width + px;
+    const float depth = __ldg(tp.depth + pi);
+    if (depth == 1.0f) return false; // discard
+    const float tcx = ((float)px + 0.5f) / (float)tp.width, tcy = ((float)py + 0.5f) / (float)tp.height;
+    {   // worldPosFromDepth :305-311 (no y flip, Q18)
+        const float v[4] = { tcx * 2.0f - 1.0f, tcy * 2.0f - 1.0f, depth, 1.0f };
+        const float* M = tp.view_proj_inv;
+        float o[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[r] = M[r] * v[0] + M[4 + r] * v[1] + M[8 + r] * v[2] + M[12 + r] * v[3];
+        s.worldPos[0] = o[0] / o[3]; s.worldPos[1] = o[1] / o[3]; s.worldPos[2] = o[2] / o[3];
+    }
+    {
+        const float d[3] = { tp.eye[0] - s.worldPos[0], tp.eye[1] - s.worldPos[1], tp.eye[2] - s.worldPos[2] };
+        normalize3(d, s.view);
+    }
+    const uchar4 dif = __ldg(reinterpret_cast<const uchar4*>(tp.diffuse) + pi);
+    const uchar4 spc = __ldg(reinterpret_cast<const uchar4*>(tp.specular) + pi);
+    const uint2 nrmw = __ldg(reinterpret_cast<const uint2*>(tp.normal) + pi);
+    const uint2 emiw = __ldg(reinterpret_cast<const uint2*>(tp.emission) + pi);
+    s.diffuseColor[0] = dif.x / 255.0f; s.diffuseColor[1] = dif.y / 255.0f; s.diffuseColor[2] = dif.z / 255.0f;
+    s.perceptualRoughness = dif.w / 255.0f;
+    s.specularColor[0] = spc.x / 255.0f; s.specularColor[1] = spc.y / 255.0f; s.specularColor[2] = spc.z / 255.0f;
+    s.metallic = spc.w / 255.0f;
+    {
+        const __half2 a = *reinterpret_cast<const __half2*>(&nrmw.x), b = *reinterpret_cast<const __half2*>(&nrmw.y);
+        const float n[3] = { __low2float(a) * 2.0f - 1.0f, __high2float(a) * 2.0f - 1.0f, __low2float(b) * 2.0f - 1.0f };
+        normalize3(n, s.normal);
+        const __half2 e0 = *reinterpret_cast<const __half2*>(&emiw.x), e1 = *reinterpret_cast<const __half2*>(&emiw.y);
+        s.emission[0] = __low2float(e0); s.emission[1] = __high2float(e0); s.emission[2] = __low2float(e1);
+    }
+    s.minLevel = calc_min_level(tp, s.worldPos);
+    const float voxelSize = tp.p.voxel_size * exp2f(s.minLevel);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s.startPos[k] = s.worldPos[k] + s.normal[k] * voxelSize * tp.p.trace_start_offset;
+    return true;
+}
+
+// main pass: diffuse cones + direct term + mode switch; pixels that need a specular cone are
+// appended to a compact list and finished by k_trace_specular (the specular march is up to two
+// orders of magnitude longer than a diffuse cone, Q12, and would stall whole warps).
+__global__ void __launch_bounds__(128) k_trace_main(const __grid_constant__ TraceParams tp)
+{
+    const int px = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int py = tp.y0 + blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (px >= tp.width || py >= tp.y1) return;
+    PixelSetup s;
+    if (!pixel_setup(tp, px, py, s)) return;
+    const size_t pi = (size_t)py * tp.width + px;
+    const uint32_t mode = tp.p.rendering_mode;
+    const bool needCones = mode == 4 || mode == 5 || mode == 7 || mode == 8;
+    const bool needDirect = mode == 4 || mode == 5 || mode == 8;
+    const bool needSpec = mode == 6 || mode == 8;
+
+    float indirect[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+    if (needCones) {
+        const int ncones = tp.p.enable_32_cones ? 32 : 16;
+        const float stepFactor = fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor);
+        for (int i = 0; i < ncones; ++i) {
+            float dir[3];
+            if (tp.p.enable_32_cones) { dir[0] = c_cones32[i][0]; dir[1] = c_cones32[i][1]; dir[2] = c_cones32[i][2]; }
+            else { dir[0] = c_cones16[i][0]; dir[1] = c_cones16[i][1]; dir[2] = c_cones16[i][2]; }
+            const float cosTheta = dot3(s.normal, dir);
+            if (cosTheta < 0.0f) continue;
+            float c[4];
+            trace_cone(tp, s.startPos, dir, tp.cone_coeff_diffuse, MAX_TRACE_DISTANCE, s.minLevel, stepFactor, c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) indirect[k] += c[k] * cosTheta;
+        }
+        const float invN = 1.0f / (float)ncones;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) indirect[k] *= invN;
+        indirect[3] *= tp.p.ambient_occlusion_factor;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) indirect[k] *= s.diffuseColor[k] * tp.p.indirect_diffuse_intensity;
+    }
+
+    if (needSpec && (s.specularColor[0] > 1e-6f || s.specularColor[1] > 1e-6f || s.specularColor[2] > 1e-6f) && s.metallic > 1e-6f) {
+        const uint32_t slot = atomicAdd(tp.spec_count, 1u);
+        tp.spec_list[slot] = (uint32_t)pi;
+    }
+
+    float direct[3] = { 0.f, 0.f, 0.f };
+    if (needDirect) {
+        if (s.emission[0] > 0.0f || s.emission[1] > 0.0f || s.emission[2] > 0.0f) {
+            direct[0] = s.emission[0]; direct[1] = s.emission[1]; direct[2] = s.emission[2];
+        } else {
+            const float alphaRoughness = s.perceptualRoughness * s.perceptualRoughness;
+            const float reflectance = fmaxf(fmaxf(s.specularColor[0], s.specularColor[1]), s.specularColor[2]);
+            const float r90 = f_clamp(reflectance * 50.0f, 0.0f, 1.0f);
+            const float* L = tp.light.dir_to_light;
+            float h[3];
+            {
+                const float t[3] = { L[0] + s.view[0], L[1] + s.view[1], L[2] + s.view[2] };
+                normalize3(t, h);
+            }
+            const float NdotL = f_clamp(dot3(s.normal, L), 0.001f, 1.0f);
+            const float NdotV = f_clamp(fabsf(dot3(s.normal, s.view)), 0.001f, 1.0f);
+            const float NdotH = f_clamp(dot3(s.normal, h), 0.0f, 1.0f);
+            const float VdotH = f_clamp(dot3(s.view, h), 0.0f, 1.0f);
+            float brdf[3];
+            microfacet_brdf(NdotL, NdotV, NdotH, VdotH, alphaRoughness, s.specularColor, r90, s.diffuseColor, brdf);
+            const float vis = calc_visibility(tp, s.worldPos);
+            direct[0] = brdf[0] * vis; direct[1] = brdf[1] * vis; direct[2] = brdf[2] * vis;
+        }
+    }
+
+    float4 dc = make_float4(0.f, 0.f, 0.f, 1.f);
+    switch (mode) {
+    case 0: dc = make_float4(s.diffuseColor[0], s.diffuseColor[1], s.diffuseColor[2], 1.f); break;
+    case 1: dc = make_float4(s.specularColor[0], s.specularColor[1], s.specularColor[2], 1.f); break;
+    case 2: dc = make_float4(s.normal[0] * 0.5f + 0.5f, s.normal[1] * 0.5f + 0.5f, s.normal[2] * 0.5f + 0.5f, 1.f); break;
+    case 3: {
+        const float colors[7][4] = { {1,0,0,1},{0,1,0,1},{0,0,1,1},{1,1,0,1},{0,1,1,1},{1,0,1,1},{1,1,1,1} };
+        int lower = (int)floorf(s.minLevel);
+        lower = lower < 0 ? 0 : (lower > 5 ? 5 : lower);
+        const float fr = f_fract(s.minLevel);
+        float o[4];
+        for (int k = 0; k < 4; ++k) o[k] = (colors[lower][k] * (1.0f - fr) + colors[lower + 1][k] * fr) * 0.5f;
+        dc = make_float4(o[0], o[1], o[2], o[3]);
+        break;
+    }
+    case 4: dc = make_float4(direct[0] * indirect[3], direct[1] * indirect[3], direct[2] * indirect[3], 1.f); break;
+    case 5:
+    case 8:
+        dc = make_float4(direct[0] * indirect[3] + indirect[0], direct[1] * indirect[3] + indirect[1],
+                         direct[2] * indirect[3] + indirect[2], 1.f);
+        break;
+    case 7: dc = make_float4(indirect[3], indirect[3], indirect[3], 1.f); break;
+    default: break;
+    }
+    tp.out_diffuse[pi] = dc;
+    tp.out_specular[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+
+// ref: voxelConeTracing.frag:205-216 (stepFactor = uVoxelSize, Q12)
+__global__ void __launch_bounds__(128) k_trace_specular(const __grid_constant__ TraceParams tp)
+{
+    const uint32_t n = *tp.spec_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pi = tp.spec_list[i];
+        const int px = (int)(pi % (uint32_t)tp.width), py = (int)(pi / (uint32_t)tp.width);
+        PixelSetup s;
+        if (!pixel_setup(tp, px, py, s)) continue;
+        // reflect(-view, normal) = I - 2 dot(N, I) N
+        const float I[3] = { -s.view[0], -s.view[1], -s.view[2] };
+        const float dn = dot3(s.normal, I);
+        const float dir[3] = { I[0] - 2.0f * dn * s.normal[0], I[1] - 2.0f * dn * s.normal[1], I[2] - 2.0f * dn * s.normal[2] };
+        const float aperture = fmaxf(s.perceptualRoughness, MIN_SPECULAR_APERTURE);
+        float c[4];
+        trace_cone(tp, s.startPos, dir, 2.0f * tanf(aperture * 0.5f), MAX_TRACE_DISTANCE, s.minLevel, tp.p.voxel_size, c);
+        float4 o = make_float4(c[0] * s.specularColor[0] * tp.p.indirect_specular_intensity,
+                               c[1] * s.specularColor[1] * tp.p.indirect_specular_intensity,
+                               c[2] * s.specularColor[2] * tp.p.indirect_specular_intensity, 1.0f);
+        tp.out_specular[pi] = o;
+    }
+}
+
+int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
+{
+    int n = 0;
+    cudaMemsetAsync(tp.spec_count, 0, sizeof(uint32_t), s);
+    const int rows = tp.y1 - tp.y0;
+    if (rows <= 0 || tp.width <= 0) return 0;
+    dim3 grid((tp.width + 15) / 16, (rows + 7) / 8);
+    k_trace_main<<<grid, 128, 0, s>>>(tp); ++n;
+    const uint32_t mode = tp.p.rendering_mode;
+    if (mode == 6 || mode == 8) { k_trace_specular<<<148 * 8, 128, 0, s>>>(tp); ++n; }
+    return n;
+}
