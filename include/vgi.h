@@ -186,6 +186,13 @@ int         vgi_create(const vgi_config* cfg, vgi_ctx** out);
 int         vgi_destroy(vgi_ctx* ctx);
 const char* vgi_last_error(const vgi_ctx* ctx);   /* ctx may be NULL: last global error */
 int         vgi_get_stats(vgi_ctx* ctx, vgi_stats* out); /* synchronises the ctx's last stream */
+/* Per-kernel device timing for roofline accounting: when enabled, CUDA events are recorded on the
+ * launching stream around every kernel. vgi_get_timings synchronises and returns, per kernel name,
+ * the accumulated milliseconds and launch count since the last vgi_reset_timings.
+ * names: array of `capacity` const char* (owned by the library). Returns the number of entries. */
+int         vgi_set_timing(vgi_ctx* ctx, int enable);
+int         vgi_get_timings(vgi_ctx* ctx, const char** names, double* ms, uint64_t* launches, uint32_t capacity);
+int         vgi_reset_timings(vgi_ctx* ctx);
 
 /* ---- inputs --------------------------------------------------------------------------------- */
 /* replaces: GLTFScene vertex/index/matrix/material uploads consumed by msaaVoxelizer.vert:31-36 */

@@ -104,6 +104,8 @@ int vgi_destroy(vgi_ctx* c)
     cudaFree(c->brick_mask); cudaFree(c->spec_list); cudaFree(c->shadow_owned);
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
     cudaFreeHost(c->h_counters);
+    c->timer.resolve();
+    for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
     delete c;
     return VGI_OK;
 }
@@ -125,6 +127,84 @@ int vgi_get_stats(vgi_ctx* c, vgi_stats* out)
                  c->h_counters->overflow, c->h_counters->pairs, c->max_pairs, c->h_counters->occ_total, c->max_occ);
         return fail(c, VGI_E_OVERFLOW, buf);
     }
+    return VGI_OK;
+}
+
+// ---- per-kernel timing ---------------------------------------------------------------------------
+} // extern "C"
+
+int KernelTimer::slot_of(const char* name)
+{
+    for (int i = 0; i < nslots; ++i)
+        if (names[i] == name || !strcmp(names[i], name)) return i;
+    if (nslots >= VGI_MAX_TIMED_KERNELS) return VGI_MAX_TIMED_KERNELS - 1;
+    names[nslots] = name;
+    return nslots++;
+}
+cudaEvent_t KernelTimer::get_event()
+{
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void KernelTimer::begin(const char* name, cudaStream_t s)
+{
+    if (!enabled) return;
+    Pending p{ slot_of(name), get_event(), get_event() };
+    cudaEventRecord(p.a, s);
+    pending.push_back(p);
+}
+void KernelTimer::end(cudaStream_t s)
+{
+    if (!enabled || pending.empty()) return;
+    cudaEventRecord(pending.back().b, s);
+}
+void KernelTimer::resolve()
+{
+    for (auto& p : pending) {
+        cudaEventSynchronize(p.b);
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) { ms[p.slot] += t; count[p.slot]++; }
+        pool.push_back(p.a);
+        pool.push_back(p.b);
+    }
+    pending.clear();
+}
+void KernelTimer::reset()
+{
+    resolve();
+    for (int i = 0; i < VGI_MAX_TIMED_KERNELS; ++i) { ms[i] = 0; count[i] = 0; }
+}
+
+extern "C" {
+
+int vgi_set_timing(vgi_ctx* c, int enable)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_set_timing: null ctx");
+    c->timer.resolve();
+    c->timer.enabled = enable != 0;
+    return VGI_OK;
+}
+
+int vgi_get_timings(vgi_ctx* c, const char** names, double* ms, uint64_t* launches, uint32_t capacity)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_get_timings: null ctx");
+    cudaStreamSynchronize(c->last_stream);
+    c->timer.resolve();
+    uint32_t n = 0;
+    for (int i = 0; i < c->timer.nslots && n < capacity; ++i, ++n) {
+        if (names) names[n] = c->timer.names[i];
+        if (ms) ms[n] = c->timer.ms[i];
+        if (launches) launches[n] = c->timer.count[i];
+    }
+    return (int)n;
+}
+
+int vgi_reset_timings(vgi_ctx* c)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_reset_timings: null ctx");
+    c->timer.reset();
     return VGI_OK;
 }
 

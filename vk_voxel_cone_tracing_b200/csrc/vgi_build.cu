@@ -716,6 +716,8 @@ __global__ void __launch_bounds__(256) k_export(int R, int L, int logR, int whic
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+// launch + optional per-kernel event timing (vgi_set_timing)
+#define LAUNCH(name, ...) do { c->timer.begin(name, s); __VA_ARGS__; c->timer.end(s); ++n; } while (0)
 
 int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
@@ -724,32 +726,32 @@ int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
     cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
     if (bp.ntri) {
-        k_voxelize<<<cdiv(bp.ntri, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters); ++n;
-        k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters); ++n;
+        LAUNCH("k_voxelize", k_voxelize<<<cdiv(bp.ntri, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
+        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
     }
     const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
-    k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums); ++n;
-    k_scan_sums<<<1, 1024, 0, s>>>(c->block_sums, nblk, c->counters); ++n;
-    k_scan_final<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums, c->occ_prefix); ++n;
+    LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));
+    LAUNCH("k_scan_sums", k_scan_sums<<<1, 1024, 0, s>>>(c->block_sums, nblk, c->counters));
+    LAUNCH("k_scan_final", k_scan_final<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums, c->occ_prefix));
     return n;
 }
 
 int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
     int n = 0;
-    k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ); ++n;
+    LAUNCH("k_zero_acc", k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ));
     if (bp.ntri && bp.level_mask) {
-        k_inject<<<148 * 16, 128, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs, c->occ,
-                                          c->occ_prefix, c->acc, c->counters); ++n;
+        LAUNCH("k_inject", k_inject<<<148 * 16, 128, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
+                                                             c->occ, c->occ_prefix, c->acc, c->counters));
     }
     const size_t slabVox = (size_t)(bp.z1 - bp.z0) * bp.R * bp.R;
     for (int l = 0; l < bp.L; ++l) {
-        k_finalize<<<cdiv(slabVox, 256), 256, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->store); ++n;
+        LAUNCH("k_finalize", k_finalize<<<cdiv(slabVox, 256), 256, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->store));
     }
     for (int l = 1; l < bp.L; ++l) {
         const int half = bp.R >> 1;
         dim3 grid(cdiv(half, 128), half, half);
-        k_downsample<<<grid, min(half, 128), 0, s>>>(bp, l, c->store); ++n;
+        LAUNCH("k_downsample", k_downsample<<<grid, min(half, 128), 0, s>>>(bp, l, c->store));
     }
     cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
     return n;

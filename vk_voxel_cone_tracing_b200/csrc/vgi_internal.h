@@ -90,8 +90,29 @@ struct TraceParams {
     float    diffuse_aperture;
 };
 
+// optional per-kernel CUDA-event timing (vgi_set_timing): events are recorded on the launching stream
+// around every kernel and resolved at the next vgi_get_timings().
+#define VGI_MAX_TIMED_KERNELS 32
+struct KernelTimer {
+    bool enabled = false;
+    struct Pending { int slot; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    const char* names[VGI_MAX_TIMED_KERNELS] = {};
+    double ms[VGI_MAX_TIMED_KERNELS] = {};
+    uint64_t count[VGI_MAX_TIMED_KERNELS] = {};
+    int nslots = 0;
+    int slot_of(const char* name);
+    cudaEvent_t get_event();
+    void begin(const char* name, cudaStream_t s);
+    void end(cudaStream_t s);
+    void resolve();
+    void reset();
+};
+
 struct vgi_ctx {
     vgi_config cfg;
+    KernelTimer timer;
     int device = 0;
     std::string err;
     vgi_clip_region regions[VGI_MAX_LEVELS];

@@ -415,8 +415,14 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     const int rows = tp.y1 - tp.y0;
     if (rows <= 0 || tp.width <= 0) return 0;
     dim3 grid((tp.width + 15) / 16, (rows + 7) / 8);
+    c->timer.begin("k_trace_main", s);
     k_trace_main<<<grid, 128, 0, s>>>(tp); ++n;
+    c->timer.end(s);
     const uint32_t mode = tp.p.rendering_mode;
-    if (mode == 6 || mode == 8) { k_trace_specular<<<148 * 8, 128, 0, s>>>(tp); ++n; }
+    if (mode == 6 || mode == 8) {
+        c->timer.begin("k_trace_specular", s);
+        k_trace_specular<<<148 * 8, 128, 0, s>>>(tp); ++n;
+        c->timer.end(s);
+    }
     return n;
 }
