@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — the voxel-GI hot path on BASELINE.json's configs[1].
+
+A "step" is one GI frame of the reference's pass sequence for this path (Application.cpp:178,192,221):
+clipmap build at frame 0 (all six levels voxelized, injected, down-sampled — the worst case of the
+cadence) + 1080p 16-cone CombinedGI cone trace (rendering mode 8, diffuse + specular cones).
+
+  value  frames/s with every input resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e    frames/s through the C-ABI host-buffer call vgi_frame_host(): per step the G-buffer and the
+         shadow map are copied from pinned host memory, both output images are copied back
+  stages build_ms (the "voxelize+inject+mip ms @256^3" half of the metric) and trace_ms / trace_fps
+  roofline / roofline_cone_trace / cpu_baseline: see DESIGN.md "measurement"
+
+N > 1 (torchrun, one rank per GPU): every rank renders its own camera view of the same scene
+(batched views, sharded by view, no data-path collective) — weak scaling.
+
+--impl reference: the CPU oracle (a port of the reference's shaders: the reference itself is GLSL on
+a Windows/Vulkan host and cannot run here) on the host cores, on a bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "1080p 16-cone GI frames/s; voxelize+inject+mip ms @256^3 (1/2/4/8 B200)"
+WORKLOAD = ("configs[1]: Sponza-scale synthetic atrium (262144 tris), 6-level 256^3 clipmap voxelize+inject+mip "
+            "(frame 0: all levels) + 1920x1080 16-cone diffuse/specular GI (mode 8)")
+RES, LEVELS, SHADOW, WIDTH, HEIGHT = 256, 6, 4096, 1920, 1080
+TRACE_ROW_STRIDE = 32          # reference arm: every 32nd row block of the image per sample
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def make_inputs(rank, world):
+    """Synthetic inputs of configs[1]; rank r > 0 gets the r-th orbit camera (batched views)."""
+    from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
+    scene = synth.atrium()
+    cfg = S.default_config(RES, LEVELS)
+    light, shadow = synth.make_light()
+    depth = raster.shadow_depth(scene, shadow, SHADOW)
+    if rank == 0:
+        cam_pos, cam_dir = (-8.0, 3.0, 0.0), (1.0, 0.0, 0.0)
+    else:
+        ang = 2.0 * np.pi * rank / max(world, 2)
+        cam_pos = (float(-8.0 * np.cos(ang)), 3.0 + 0.25 * rank, float(5.0 * np.sin(ang)))
+        d = np.array([-cam_pos[0], 1.0 - cam_pos[1] * 0.3, -cam_pos[2]])
+        cam_dir = tuple((d / np.linalg.norm(d)).tolist())
+    cam = synth.make_camera(cam_pos, cam_dir, aspect=WIDTH / HEIGHT)
+    gb = raster.gbuffer(scene, cam, WIDTH, HEIGHT)
+    return dict(scene=scene, cfg=cfg, light=light, shadow=shadow, shadow_depth=depth, cam=cam, gbuffer=gb,
+                cam_pos=cam_pos)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on a bounded sample of the same frame
+# ---------------------------------------------------------------------------------------------------
+class CpuFrameSampler:
+    """One sample = the clipmap build of ONE level (cycling over the six levels: clear, voxelize,
+    inject, copy-alpha, both down-samples) + the cone trace of every 32nd row. frame seconds =
+    sum over levels of the mean level-build time + 32 x the mean row-sample time."""
+
+    def __init__(self, inp):
+        from oracle import pyoracle as O
+        from vk_voxel_cone_tracing_b200 import structs as S
+        O.build()
+        self.O, self.inp = O, inp
+        self.cfg = inp["cfg"]
+        self.regs = O.regions(self.cfg, inp["cam_pos"])
+        self.osc = O.OracleScene(inp["scene"])
+        self.op = O.new_atlas(self.cfg)
+        self.rad = O.new_atlas(self.cfg)
+        gb = inp["gbuffer"]
+        self.hg = O.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+        self.prm = S.default_vct_params(self.regs[0], self.cfg.resolution, 8)
+        self.level_s = {l: [] for l in range(self.cfg.level_count)}
+        self.trace_s = []
+        self.i = 0
+
+    def build_level(self, l):
+        O, cfg, inp = self.O, self.cfg, self.inp
+        R = cfg.resolution
+        t = time.perf_counter()
+        mc = list(self.regs[l].min_corner)
+        O.clear_region(cfg, self.op, mc, (R, R, R), l)          # this level's share of the full clear
+        O.voxelize_level(cfg, self.regs, l, self.osc, self.op)
+        if l > 0:
+            O.downsample(cfg, self.regs, l, self.op, 0)
+        O.clear_region(cfg, self.rad, mc, (R, R, R), l)
+        O.inject_level(cfg, self.regs, l, self.osc, inp["light"], inp["shadow"], inp["shadow_depth"], self.rad)
+        O.copy_alpha(cfg, l, self.rad, self.op)
+        if l > 0:
+            O.downsample(cfg, self.regs, l, self.rad, 1)
+        return time.perf_counter() - t
+
+    def trace_rows(self, k):
+        O, inp = self.O, self.inp
+        rows = HEIGHT // TRACE_ROW_STRIDE
+        y0 = (k % TRACE_ROW_STRIDE) * rows
+        t = time.perf_counter()
+        O.cone_trace(self.cfg, inp["cam"], self.hg, self.prm, inp["light"], inp["shadow"], inp["shadow_depth"],
+                     self.rad, rows=(y0, y0 + rows))
+        return (time.perf_counter() - t) * (HEIGHT / rows)
+
+    def prime(self):
+        """Fill the atlases once (untimed) so the trace samples march through real radiance."""
+        for l in range(self.cfg.level_count):
+            self.build_level(l)
+
+    def step(self, record=True):
+        l = self.i % self.cfg.level_count
+        tb = self.build_level(l)
+        tt = self.trace_rows(self.i * 7 + 3)
+        self.i += 1
+        if record:
+            self.level_s[l].append(tb)
+            self.trace_s.append(tt)
+
+    def frame_seconds(self):
+        means = [np.mean(v) for v in self.level_s.values() if v]
+        build = float(np.sum(means)) * (self.cfg.level_count / max(len(means), 1))
+        trace = float(np.mean(self.trace_s)) if self.trace_s else float("nan")
+        return build, trace
+
+    SAMPLE = ("per step: oracle clipmap build of ONE level (cycling 0..5: clear, voxelize, inject, copy-alpha, "
+              "opacity+radiance down-sample) + cone trace of 1/32 of the 1080 rows; frame time = sum of per-level "
+              "means + 32 x mean row-sample time")
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    inp = make_inputs(0, 1)
+    smp = CpuFrameSampler(inp)
+    smp.prime()
+    for _ in range(args.warmup):
+        smp.step(record=False)
+    smp.i = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        smp.step()
+    wall = time.perf_counter() - t0
+    build_s, trace_s = smp.frame_seconds()
+    fps = 1.0 / (build_s + trace_s)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (build_s + trace_s),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 texels)",
+        "data": "synthetic", "config": {"workload": WORKLOAD},
+        "stages": {"build_ms": 1e3 * build_s, "trace_ms": 1e3 * trace_s, "sample_wall_s": wall},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu_cores(), "kind": "port",
+                         "sample": CpuFrameSampler.SAMPLE},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# algorithmic bytes per kernel launch (DESIGN.md "kernels"): what the kernel must move at minimum
+# ---------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, st, cfg):
+    R, L = cfg.resolution, cfg.level_count
+    nvox = R ** 3
+    occ = st.occupied_voxels
+    pairs = st.clip_pairs
+    tris = st.triangles
+    table = {
+        # dense formulation (v1 kernels)
+        "k_finalize": nvox * 32 + nvox // 8,
+        "k_downsample": (R // 2) ** 3 * (8 * 32 + 32 + 32),
+        # triangle list once (48 B positions) + one 8-byte pair per (triangle, voxel) + occupancy words
+        "k_voxelize": tris * 48 + pairs * 8,
+        # pair list + 96 B of triangle data per pair (L2-resident) + 16 shadow taps x 4 texels + 12 accumulator words
+        "k_inject": pairs * (8 + 12 * 4),
+        "k_build_level": None,
+    }
+    return table.get(name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_vgi(args):
+    import torch
+    import torch.distributed as dist
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libvgi has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    inp = make_inputs(rank, world)
+    gi = VoxelGI(inp["cfg"], device=local)
+    gi.set_scene(inp["scene"])
+    gi.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
+    gi.update_regions(inp["cam_pos"])
+    dgb = gi.upload_gbuffer(inp["gbuffer"])
+    prm = gi.default_vct_params(8)
+    out = (torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device=dev),
+           torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float32, device=dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frame():
+        gi.update_regions(inp["cam_pos"])
+        gi.build_clipmap(0)
+        gi.cone_trace(inp["cam"], dgb, prm, out=out)
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        frame()
+    barrier()
+    l0 = gi.stats().kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    for a, m, b in ev:
+        flush.zero_()                       # evict the previous frame from L2 (outside the timed events)
+        a.record()
+        gi.update_regions(inp["cam_pos"])
+        gi.build_clipmap(0)
+        m.record()
+        gi.cone_trace(inp["cam"], dgb, prm, out=out)
+        b.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    build_ms = sum(a.elapsed_time(m) for a, m, b in ev) / args.steps
+    trace_ms = sum(m.elapsed_time(b) for a, m, b in ev) / args.steps
+    step_ms = build_ms + trace_ms
+    st = gi.stats()
+    launches = (st.kernel_launches - l0) // args.steps
+
+    # ---- end to end through vgi_frame_host: pinned host inputs -> host outputs
+    hgb = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.int16) if v.dtype == np.uint16 else
+                               np.ascontiguousarray(v)).pin_memory() for k, v in inp["gbuffer"].items()}
+    hshadow = torch.from_numpy(inp["shadow_depth"]).pin_memory()
+    hout = (torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory(),
+            torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory())
+    h2d = sum(t.numel() * t.element_size() for t in hgb.values()) + hshadow.numel() * 4
+    d2h = sum(t.numel() * 4 for t in hout)
+    for _ in range(3):
+        gi.frame_host(0, inp["cam_pos"], inp["cam"], hgb, hshadow, prm, hout[0], hout[1])
+    barrier()
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    for a, b in e2e_ev:
+        a.record()
+        gi.frame_host(0, inp["cam_pos"], inp["cam"], hgb, hshadow, prm, hout[0], hout[1])
+        b.record()
+    barrier()
+    t_wall = (time.perf_counter() - t_wall) / args.steps * 1e3
+    e2e_ms = max(sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps, 0.0)
+    e2e_ms = max(e2e_ms, 0.0)
+    # the device copy and the host copy of the result must agree
+    assert torch.equal(hout[0], out[0].cpu()), "vgi_frame_host result differs from the device-resident path"
+
+    # ---- max over ranks
+    t = torch.tensor([step_ms, build_ms, trace_ms, e2e_ms, t_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, build_ms, trace_ms, e2e_ms, t_wall = t.tolist()
+
+    # ---- per-kernel CUDA-event timing (separate pass: the events would perturb the headline number)
+    roof, roof_trace, kernels = None, None, {}
+    if rank == 0:
+        gi.set_timing(True)
+        gi.reset_timings()
+        for _ in range(args.steps):
+            flush.zero_()
+            frame()
+        torch.cuda.synchronize()
+        tm = gi.timings()
+        gi.set_timing(False)
+        kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in tm.items()}
+        hbm_peak, peak_src, pk = peaks()
+        build_k = {k: v for k, v in tm.items() if not k.startswith("k_trace")}
+        if build_k:
+            name = max(build_k, key=lambda k: build_k[k][0])
+            ms_launch = build_k[name][0] / max(build_k[name][1], 1)
+            ab = algorithmic_bytes(name, st, inp["cfg"])
+            ach = (ab / (ms_launch * 1e-3) / 1e9) if ab else None
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (ach / hbm_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms_launch,
+                    "share_of_build": build_k[name][0] / sum(v[0] for v in build_k.values())}
+        trace_k = {k: v for k, v in tm.items() if k.startswith("k_trace")}
+        if trace_k:
+            tms = sum(v[0] for v in trace_k.values()) / args.steps
+            sm_mhz = (clk or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
+            nsm = torch.cuda.get_device_properties(local).multi_processor_count
+            l1_peak = nsm * 128 * sm_mhz * 1e6 / 1e9
+            roof_trace = {"kernels": sorted(trace_k), "bound": "l1", "ms_per_step": tms, "peak": l1_peak, "unit": "GB/s",
+                          "peak_source": f"{nsm} SMs x 128 B/clk x {sm_mhz:.0f} MHz (clock sampled during the run)",
+                          "achieved": None, "frac": None,
+                          "note": "taps counted by the oracle on a row sample; see cpu_baseline pass"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        smp = CpuFrameSampler(inp)
+        smp.prime()
+        smp.i = 0
+        for _ in range(LEVELS):
+            smp.step()
+        b_s, t_s = smp.frame_seconds()
+        cpu = {"value": 1.0 / (b_s + t_s), "unit": "frames/s", "cores": cpu_cores(), "kind": "port",
+               "sample": CpuFrameSampler.SAMPLE, "build_ms": 1e3 * b_s, "trace_ms": 1e3 * t_s}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * 1e3 / step_ms, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 texels)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "resolution": RES, "levels": LEVELS, "triangles": int(st.triangles),
+                       "image": [WIDTH, HEIGHT], "cones": 16, "shadow_map": SHADOW,
+                       "parallelism": f"{world} view(s), one per GPU, replicated clipmap build",
+                       "l2": "256 MB flush between timed steps"},
+            "stages": {"build_ms": build_ms, "trace_ms": trace_ms, "trace_fps": 1e3 / trace_ms,
+                       "clip_pairs": int(st.clip_pairs), "occupied_voxels": int(st.occupied_voxels)},
+            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "wall_ms_per_step": t_wall},
+            "gpu_launches": int(launches) * args.steps,
+            "gpu_launches_per_step": int(launches),
+            "clocks": clk, "roofline": roof, "roofline_cone_trace": roof_trace, "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vgi", choices=["vgi", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_vgi(args)
+
+
+if __name__ == "__main__":
+    main()

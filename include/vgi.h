@@ -245,6 +245,19 @@ int vgi_cone_trace_rows(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gbuffer* 
  * derived from the ctx's level-0 region (VoxelConeTracingPass.cpp:88-93). */
 int vgi_default_vct_params(vgi_ctx* ctx, vgi_vct_params* out);
 
+/* ---- whole frame with HOST buffers ---------------------------------------------------------- */
+/* replaces: one iteration of Application::run's pass sequence for this path (Application.cpp:178,192,221:
+ * "VoxelizationPass", "RadianceInjectionPass", "VoxelConeTracingPass") for a host that does not share
+ * memory with CUDA: every pointer in host_gbuf, host_shadow_depth (w*h f32 as given to vgi_set_light,
+ * NULL = keep the current one) and the two outputs (width*height float4 each) are HOST pointers
+ * (pinned memory recommended). The call uploads the inputs, updates the regions from camera_pos,
+ * builds the clipmap for frame_index, cone-traces, downloads both images and synchronises `stream`.
+ * params may be NULL (reference defaults, rendering mode 8). */
+int vgi_frame_host(vgi_ctx* ctx, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                   const vgi_gbuffer* host_gbuf, const float* host_shadow_depth,
+                   const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular,
+                   void* stream);
+
 /* ---- sparse voxel octree -------------------------------------------------------------------- */
 /* replaces: SparseVoxelizer::preVoxelize + cmdVoxelize (SparseVoxelizer.cpp:248-326) — one pass,
  * no host read-back. bb_min/bb_max: scene world bounding box (voxelizer.vert:42-47). */

@@ -1,0 +1,200 @@
+"""Analytic known-answer tests pinning the CPU oracle (the reference ships no tests or golden
+vectors for this path — SURVEY.md section 4 — so closed-form cases are the pins)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from vk_voxel_cone_tracing_b200 import structs as S, synth
+
+
+def _atlas_voxel(cfg, atlas, level, face, x, y, z):
+    rb = cfg.resolution + 2
+    return atlas[1 + z, 1 + y + level * rb, 1 + x + face * rb]
+
+
+def test_regions_origin_and_snapped(oracle):
+    cfg = S.default_config(128, 6)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    for l, r in enumerate(regs):
+        assert list(r.min_corner) == [-64, -64, -64]
+        assert list(r.extent) == [128, 128, 128]
+        assert r.voxel_size == np.float32(16.0 * 2 ** l / 128)
+    # camera moved +1 in x: level 0 voxel 0.125, snap 2 voxels = 0.25 -> 4 snaps = 8 voxels
+    regs = oracle.regions(cfg, (1.0, 0.0, 0.0))
+    assert list(regs[0].min_corner) == [-56, -64, -64]
+    # level 5: voxel 4.0, snap 1 voxel -> trunc(1/4) = 0
+    assert list(regs[5].min_corner) == [-64, -64, -64]
+    # negative moves truncate toward zero (VoxelizationPass.cpp:438-448 uses a float->int cast)
+    regs = oracle.regions(cfg, (-0.3, 0.0, 0.0))
+    assert list(regs[0].min_corner) == [-66, -64, -64]  # trunc(-0.3/0.25) = -1 -> -2 voxels
+
+
+def test_axis_aligned_quad_occupancy_closed_form(oracle):
+    """Quad in the plane z=0.3 covering [0.1,1.9]^2: per level l (voxel v=0.25*2^l) it must occupy
+    exactly ceil-span voxels in x,y and one z layer."""
+    cfg = S.default_config(64, 6)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    scene = synth.quad_scene([(0.1, 0.1, 0.3), (1.9, 0.1, 0.3), (1.9, 1.9, 0.3), (0.1, 1.9, 0.3)])
+    osc = oracle.OracleScene(scene)
+    op = oracle.new_atlas(cfg)
+    pairs = 0
+    for l in range(6):
+        pairs += oracle.voxelize_level(cfg, regs, l, osc, op)
+    rb = cfg.resolution + 2
+    for l in range(6):
+        v = 0.25 * 2 ** l
+        lo, hi = int(np.floor(0.1 / v)), int(np.floor(1.9 / v))
+        n = hi - lo + 1
+        lvl = op[1:-1, 1 + l * rb:1 + l * rb + 64, 1:65]  # face 0 interior
+        occ = lvl[..., 0] == 255
+        assert occ.sum() == n * n, (l, occ.sum(), n * n)
+        zz, yy, xx = np.nonzero(occ)
+        # toroidal texel = voxel mod R
+        assert set(zz) == {int(np.floor(0.3 / v)) % 64}
+        assert set(xx) == {i % 64 for i in range(lo, hi + 1)}
+        # the voxelizer stores (1,1,1,1) into all six faces (msaaVoxelizer.frag:69-73)
+        for f in range(6):
+            assert np.array_equal(op[1:-1, 1 + l * rb:1 + l * rb + 64, 1 + f * rb:65 + f * rb][occ],
+                                  np.full((n * n, 4), 255, np.uint8))
+    # the diagonal-shared voxels are hit by both triangles -> more pairs than voxels
+    assert pairs >= sum((int(np.floor(1.9 / (0.25 * 2 ** l))) - int(np.floor(0.1 / (0.25 * 2 ** l))) + 1) ** 2 for l in range(6))
+
+
+@pytest.mark.parametrize("a8", [255, 128, 51])
+def test_uniform_opacity_downsample_closed_form(oracle, a8):
+    """opacityDownSample.comp:97-138 on a uniform field: every directional pair gives a+(1-a)a, the
+    mean of four pairs is a(2-a); outside the blend band the result is round(255*a(2-a))."""
+    cfg = S.default_config(32, 2, downsample_band=2)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    at = oracle.new_atlas(cfg)
+    rb = cfg.resolution + 2
+    at[1:-1, 1:33, :, :] = 0
+    for f in range(6):
+        at[1:-1, 1:33, 1 + f * rb:33 + f * rb, :] = a8      # level 0 interior, all channels
+    oracle.downsample(cfg, regs, 1, at, 0)
+    a = np.float32(a8) / np.float32(255)
+    want_center = int(np.float32(a * (np.float32(2) - a)) * np.float32(255) + np.float32(0.5))
+    # level 0 (min corner -16, voxel 0.5) covers level-1 voxels -8..7; centre = (prevMin>>1) + R/4 = 0
+    for f in range(6):
+        t = _atlas_voxel(cfg, at, 1, f, 0, 0, 0)
+        assert abs(int(t[3]) - want_center) <= 1 and t[1] == t[3], (f, t, want_center)
+    # outermost covered voxel (-8): dist = |-8+0.5-0|-0.5 = 7, thr = R/4 - band = 6,
+    # lerp = (7 - 6 + 1) / (band + 1) = 2/3 toward the level's own raw flag (0 here)
+    t = _atlas_voxel(cfg, at, 1, 0, (-8) % 32, 0, 0)
+    f32 = np.float32
+    ds = f32(a * (f32(2) - a))
+    lf = f32(f32(2) * (f32(1) / f32(3)))
+    want_edge = int(f32(ds * (f32(1) - lf) + f32(0) * lf) * f32(255) + f32(0.5))
+    assert abs(int(t[3]) - want_edge) <= 1 and t[1] == t[3], (t, want_edge)
+    # one voxel further in (-7): dist 6 -> lerp 1/3
+    t = _atlas_voxel(cfg, at, 1, 0, (-7) % 32, 0, 0)
+    lf = f32(f32(1) * (f32(1) / f32(3)))
+    assert abs(int(t[3]) - int(f32(ds * (f32(1) - lf)) * f32(255) + f32(0.5))) <= 1
+    # and -6: dist 5 < thr -> no blending
+    assert abs(int(_atlas_voxel(cfg, at, 1, 0, (-6) % 32, 0, 0)[3]) - want_center) <= 1
+
+
+def test_empty_volume_cone_trace_closed_form(oracle):
+    """Empty radiance atlas: every cone returns (0,0,0,1) (voxelConeTracing.frag:391), so mode 7
+    (VXAO) is AOfactor * (1 + sum_{n.d>=0} n.d) / 16 (Q15 bias included)."""
+    cfg = S.default_config(32, 3)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    rad = oracle.new_atlas(cfg)
+    light, shadow = synth.make_light(origin=(0.0, 20.0, -3.5))
+    depth = np.ones((64, 64), dtype=np.float32)
+    cam = synth.make_camera((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), aspect=1.0)
+    n = np.array([0.0, 0.0, 1.0], dtype=np.float32)
+    W = H = 4
+    gb = dict(diffuse=np.full((H, W, 4), 255, np.uint8), specular=np.zeros((H, W, 4), np.uint8),
+              normal=np.tile((np.append(n * 0.5 + 0.5, 1.0)).astype(np.float16).view(np.uint16), (H, W, 1)),
+              emission=np.zeros((H, W, 4), np.uint16), depth=np.full((H, W), 0.995, np.float32))
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    prm = S.default_vct_params(regs[0], 32, 7)
+    d, s, taps = oracle.cone_trace(cfg, cam, hg, prm, light, shadow, depth, rad)
+    cones = np.array([
+        [0.57735, 0.57735, 0.57735], [0.57735, -0.57735, -0.57735], [-0.57735, 0.57735, -0.57735],
+        [-0.57735, -0.57735, 0.57735], [-0.903007, -0.182696, -0.388844], [-0.903007, 0.182696, 0.388844],
+        [0.903007, -0.182696, 0.388844], [0.903007, 0.182696, -0.388844], [-0.388844, -0.903007, -0.182696],
+        [0.388844, -0.903007, 0.182696], [0.388844, 0.903007, -0.182696], [-0.388844, 0.903007, 0.182696],
+        [-0.182696, -0.388844, -0.903007], [0.182696, 0.388844, -0.903007], [-0.182696, 0.388844, 0.903007],
+        [0.182696, -0.388844, 0.903007]])  # voxelConeTracing.frag:118-135
+    cos = cones @ n.astype(np.float64)
+    want = 0.5 * (1.0 + cos[cos >= 0].sum()) / 16.0
+    assert np.allclose(d[..., 0], want, atol=2e-6) and np.allclose(d[..., 3], 1.0)
+    assert np.allclose(d[..., 0], d[..., 1]) and np.allclose(d[..., 0], d[..., 2])
+    assert taps > 0
+
+
+def test_single_fragment_svo_path(oracle):
+    """One fragment -> exactly one flagged node per level, 8*level nodes, predicted child slots
+    (octreeNodeFlag.comp:28-46: position halved, slot = z | x<<1 | y<<2)."""
+    level = 5
+    px, py, pz = 21, 6, 27
+    frag = np.array([[px | (py << 12) | ((pz & 0xff) << 24), ((pz >> 8) << 28) | 0x0a0b0c0d & 0x0fffffff]], dtype=np.uint32)
+    nodes = oracle.svo_build(level, frag)
+    assert nodes.shape[0] == 8 * level
+    flagged = np.nonzero(nodes[:, 0] & 0x80000000)[0]
+    assert flagged.shape[0] == level
+    # walk the tree with the shader's descent
+    res = 1 << level
+    pos = np.array([px, py, pz]) >> 1
+    idx = 0
+    node_pos = np.zeros(3, dtype=np.int64)
+    for depth in range(level):
+        res >>= 1
+        cmp = (pos >= node_pos + res).astype(np.int64)
+        slot = int(cmp[2] | (cmp[0] << 1) | (cmp[1] << 2))
+        node_pos += cmp * res
+        n = idx + slot
+        assert nodes[n, 0] & 0x80000000, (depth, n)
+        if depth + 1 < level:
+            idx = int(nodes[n, 0] & 0x7fffffff)
+            assert idx == 8 * (depth + 1)  # children are allocated in level order
+    # leaf colour = the fragment's colour with alpha forced to 255 (canonical mean of one sample)
+    assert nodes[n, 1] == ((0x0a0b0c0d & 0x00ffffff) | 0xff000000)
+    # canonical ordering of an already breadth-first tree is the identity on the topology word
+    canon = oracle.svo_canonicalize(nodes)
+    assert np.array_equal(canon[:, 0], nodes[:, 0])
+
+
+def test_svo_canonicalize_is_allocation_order_independent(oracle):
+    rng = np.random.RandomState(3)
+    level = 6
+    p = rng.randint(0, 1 << level, size=(400, 3)).astype(np.uint32)
+    col = rng.randint(0, 1 << 24, size=400).astype(np.uint32)
+    frags = np.stack([p[:, 0] | (p[:, 1] << 12) | ((p[:, 2] & 0xff) << 24), ((p[:, 2] >> 8) << 28) | col], axis=1).astype(np.uint32)
+    a = oracle.svo_build(level, frags)
+    b = oracle.svo_build(level, frags[::-1].copy())
+    assert a.shape == b.shape
+    ca, cb = oracle.svo_canonicalize(a), oracle.svo_canonicalize(b)
+    assert np.array_equal(ca, cb)
+
+
+def test_injection_single_lit_quad(oracle):
+    """Upward-facing quad fully lit (shadow map cleared to 1.0 -> literal Q1 visibility = 1):
+    radiance = clamp(N.L,0.001,1) * albedo * |n_axis| into the faces selected by -n; for n = +y that is
+    face 3 (-Y travel) with weight 1 and faces 0/1, 4/5 with weight 0."""
+    cfg = S.default_config(32, 2)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    scene = synth.quad_scene([(0.3, 0.3, 0.3), (0.3, 0.3, 1.7), (1.7, 0.3, 1.7), (1.7, 0.3, 0.3)],
+                             normal=(0, 1, 0), base=(0.5, 0.25, 1.0, 1.0))
+    osc = oracle.OracleScene(scene)
+    light, shadow = synth.make_light(origin=(0.0, 20.0, -3.5), direction=(0.0, -1.0, 0.2))
+    depth = np.ones((256, 256), dtype=np.float32)
+    op, rad, pairs = oracle.build_clipmap(cfg, regs, osc, light, shadow, depth, 0)
+    # level 0 voxel 0.5: quad at y=0.3 -> y index 0; x,z indices 0..3
+    t = _atlas_voxel(cfg, rad, 0, 3, 1, 0, 1)
+    f32 = np.float32
+    ndl = f32(1.0) / f32(np.sqrt(f32(1.04)))               # n.L for L = normalize(0, 1, -0.2)
+    want = []
+    for base in (0.5, 0.25, 1.0):
+        q = int(f32(f32(ndl * f32(base)) * f32(65536.0)) + f32(0.5))   # 16.16 fixed point contribution
+        want.append((q * 255) >> 16)                                # canonical mean of identical samples
+    got = tuple(int(c) for c in t)
+    assert all(abs(g - w) <= 1 for g, w in zip(got[:3], want)) and got[3] == 255, (got, want)
+    assert abs(got[0] - 125) <= 1 and abs(got[2] - 250) <= 1
+    assert tuple(int(c) for c in _atlas_voxel(cfg, rad, 0, 2, 1, 0, 1))[:3] == (0, 0, 0)
+    t0 = _atlas_voxel(cfg, rad, 0, 0, 1, 0, 1)
+    assert tuple(int(c) for c in t0)[:3] == (0, 0, 0)
+    assert tuple(int(c) for c in _atlas_voxel(cfg, op, 0, 0, 1, 0, 1)) == (255, 255, 255, 255)

@@ -187,3 +187,41 @@ class VoxelGI:
                                           C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
                                           C.c_uint32(y0), C.c_uint32(y1), _stream(stream)))
         return out
+
+    # -- whole frame with host buffers (the e2e call)
+    def frame_host(self, frame_index, camera_pos, camera, host_gbuffer, host_shadow_depth, params,
+                   out_diffuse, out_specular, stream=None):
+        """host_gbuffer: dict of (pinned) CPU torch tensors or numpy arrays; out_*: (H, W, 4) float32
+        (pinned) CPU tensors / numpy arrays. Synchronous."""
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        g = S.GBuffer()
+        g.diffuse_rgba8 = ptr(host_gbuffer["diffuse"])
+        g.normal_rgba16f = ptr(host_gbuffer["normal"])
+        g.specular_rgba8 = ptr(host_gbuffer["specular"])
+        g.emission_rgba16f = ptr(host_gbuffer["emission"])
+        g.depth_f32 = ptr(host_gbuffer["depth"])
+        g.height, g.width = host_gbuffer["depth"].shape[:2]
+        sd = C.c_void_p(ptr(host_shadow_depth)) if host_shadow_depth is not None else C.c_void_p(0)
+        prm = C.byref(params) if params is not None else None
+        self._ck(lib().vgi_frame_host(self._h, C.c_uint32(frame_index), _f3(camera_pos), C.byref(camera), C.byref(g),
+                                      sd, prm, C.c_void_p(ptr(out_diffuse)), C.c_void_p(ptr(out_specular)),
+                                      _stream(stream)))
+
+    # -- per-kernel timing
+    def set_timing(self, enable=True):
+        self._ck(lib().vgi_set_timing(self._h, C.c_int(1 if enable else 0)))
+
+    def reset_timings(self):
+        self._ck(lib().vgi_reset_timings(self._h))
+
+    def timings(self):
+        """{kernel name: (total ms, launches)} since the last reset."""
+        cap = 32
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        n_l = (C.c_uint64 * cap)()
+        n = lib().vgi_get_timings(self._h, names, ms, n_l, C.c_uint32(cap))
+        if n < 0:
+            self._ck(n)
+        return {names[i].decode(): (ms[i], int(n_l[i])) for i in range(n)}

@@ -101,7 +101,7 @@ int vgi_destroy(vgi_ctx* c)
     free_scene(c);
     if (c->store_owned) cudaFree(c->store);
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
-    cudaFree(c->brick_mask); cudaFree(c->spec_list); cudaFree(c->shadow_owned);
+    cudaFree(c->brick_mask); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
@@ -321,6 +321,7 @@ int vgi_set_light(vgi_ctx* c, const vgi_dir_light* light, const vgi_dir_light_sh
         cudaFree(c->shadow_owned);
         c->shadow_owned = nullptr;
         CK(c, cudaMalloc(&c->shadow_owned, (size_t)w * h * sizeof(float)));
+        c->shadow_owned_bytes = (size_t)w * h * sizeof(float);
         CK(c, cudaMemcpy(c->shadow_owned, depth, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice));
         lp.depth = c->shadow_owned;
     } else {
@@ -566,6 +567,75 @@ int vgi_cone_trace(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, cons
 {
     if (!g) return fail(c, VGI_E_INVALID, "vgi_cone_trace: null G-buffer");
     return vgi_cone_trace_rows(c, cam, g, prm, out_diffuse, out_specular, 0, g->height, stream);
+}
+
+// ---- whole frame with host buffers ----------------------------------------------------------------
+
+int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                   const vgi_gbuffer* hg, const float* host_shadow_depth, const vgi_vct_params* params,
+                   void* host_out_diffuse, void* host_out_specular, void* stream)
+{
+    if (!c || !camera_pos || !cam || !hg || !host_out_diffuse || !host_out_specular)
+        return fail(c, VGI_E_INVALID, "vgi_frame_host: null argument");
+    if (!hg->diffuse_rgba8 || !hg->normal_rgba16f || !hg->specular_rgba8 || !hg->emission_rgba16f || !hg->depth_f32 ||
+        !hg->width || !hg->height)
+        return fail(c, VGI_E_INVALID, "vgi_frame_host: incomplete G-buffer");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_frame_host: call vgi_set_light first");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t npx = (size_t)hg->width * hg->height;
+    // staging layout: diffuse 4, specular 4, depth 4, normal 8, emission 8, out_diffuse 16, out_specular 16 B/pixel
+    const size_t need = npx * 60;
+    if (c->stage_bytes < need) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->stage);
+        c->stage = nullptr;
+        c->stage_bytes = 0;
+        CK(c, cudaMalloc(&c->stage, need));
+        c->stage_bytes = need;
+    }
+    uint8_t* d_out_d = c->stage;
+    uint8_t* d_out_s = d_out_d + npx * 16;
+    uint8_t* d_nrm = d_out_s + npx * 16;
+    uint8_t* d_emi = d_nrm + npx * 8;
+    uint8_t* d_dif = d_emi + npx * 8;
+    uint8_t* d_spc = d_dif + npx * 4;
+    uint8_t* d_dep = d_spc + npx * 4;
+    CK(c, cudaMemcpyAsync(d_nrm, hg->normal_rgba16f, npx * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_emi, hg->emission_rgba16f, npx * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_dif, hg->diffuse_rgba8, npx * 4, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_spc, hg->specular_rgba8, npx * 4, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_dep, hg->depth_f32, npx * 4, cudaMemcpyHostToDevice, s));
+    if (host_shadow_depth) {
+        const size_t sb = (size_t)c->light.sw * c->light.sh * sizeof(float);
+        if (!c->shadow_owned || c->shadow_owned_bytes < sb) {
+            CK(c, cudaStreamSynchronize(c->last_stream));
+            cudaFree(c->shadow_owned);
+            c->shadow_owned = nullptr;
+            CK(c, cudaMalloc(&c->shadow_owned, sb));
+            c->shadow_owned_bytes = sb;
+        }
+        CK(c, cudaMemcpyAsync(c->shadow_owned, host_shadow_depth, sb, cudaMemcpyHostToDevice, s));
+        c->light.depth = c->shadow_owned;
+    }
+    int r = vgi_update_regions(c, camera_pos);
+    if (r != VGI_OK) return r;
+    r = vgi_build_clipmap(c, frame_index, stream);
+    if (r != VGI_OK) return r;
+    vgi_vct_params prm;
+    if (params) prm = *params;
+    else vgi_default_vct_params(c, &prm);
+    vgi_gbuffer dg;
+    dg.diffuse_rgba8 = d_dif; dg.normal_rgba16f = d_nrm; dg.specular_rgba8 = d_spc; dg.emission_rgba16f = d_emi;
+    dg.depth_f32 = (const float*)d_dep; dg.width = hg->width; dg.height = hg->height;
+    // discarded pixels (depth == 1) are left untouched by the tracer: give them a defined value
+    CK(c, cudaMemsetAsync(d_out_d, 0, npx * 32, s));
+    r = vgi_cone_trace(c, cam, &dg, &prm, d_out_d, d_out_s, stream);
+    if (r != VGI_OK) return r;
+    CK(c, cudaMemcpyAsync(host_out_diffuse, d_out_d, npx * 16, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaMemcpyAsync(host_out_specular, d_out_s, npx * 16, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return VGI_OK;
 }
 
 // ---- Vulkan interop (VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd) --------------------

@@ -156,6 +156,11 @@ struct vgi_ctx {
     uint32_t* spec_list = nullptr;
     size_t spec_capacity = 0;
 
+    // vgi_frame_host staging (device copies of the host G-buffer and of both output images)
+    uint8_t* stage = nullptr;
+    size_t stage_bytes = 0;
+    size_t shadow_owned_bytes = 0;
+
     // svo
     uint32_t svo_level = 0;
     uint2* svo_frags = nullptr;

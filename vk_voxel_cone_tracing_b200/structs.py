@@ -44,12 +44,9 @@ def default_config(resolution=128, level_count=6, **kw):
     c.level_count = level_count
     c.downsample_band = 10
     c.extent_level0 = 16.0
+    # VoxelizationPass.h:57 {2,2,2,2,2,1}: every level snaps by 2 voxels, the coarsest by 1
     for i in range(VGI_MAX_LEVELS):
-        c.clip_min_change[i] = 2
-    c.clip_min_change[level_count - 1] = 1
-    if level_count == 6:
-        for i, v in enumerate((2, 2, 2, 2, 2, 1)):
-            c.clip_min_change[i] = v
+        c.clip_min_change[i] = 2 if i < level_count - 1 else 1
     c.max_fragments = 0
     c.mode_flags = 0
     c.device = -1
