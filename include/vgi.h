@@ -51,7 +51,7 @@ enum {
 /* ref: VFS/Util/EngineConfig.h:28-33 (compile-time constants there, runtime fields here). */
 typedef struct vgi_config {
     uint32_t struct_size;          /* = sizeof(vgi_config) */
-    uint32_t resolution;           /* R: DEFAULT_VOXEL_RESOLUTION (128); power of two, 16..512 */
+    uint32_t resolution;           /* R: DEFAULT_VOXEL_RESOLUTION (128); power of two, 32..512 */
     uint32_t level_count;          /* L: DEFAULT_CLIP_REGION_COUNT (6); 1..VGI_MAX_LEVELS */
     uint32_t downsample_band;      /* DEFAULT_DOWNSAMPLE_REGION_SIZE (10) */
     float    extent_level0;        /* DEFAULT_VOXEL_EXTENT_L0 (16) world units */

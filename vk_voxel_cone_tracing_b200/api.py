@@ -28,7 +28,8 @@ def lib():
             raise ImportError(
                 f"{_build.LIBVGI} is missing: build it with `python -m vk_voxel_cone_tracing_b200.build` "
                 "(libvgi has no CPU fallback)")
-        _lib = C.CDLL(_build.LIBVGI)
+        # VGI_LIBVGI_PATH: development override (e.g. the instrumented build made by tools/trace_stats.py)
+        _lib = C.CDLL(os.environ.get("VGI_LIBVGI_PATH", _build.LIBVGI))
         _lib.vgi_last_error.restype = C.c_char_p
         _lib.vgi_last_error.argtypes = [C.c_void_p]
         _lib.vgi_atlas_bytes.restype = C.c_size_t

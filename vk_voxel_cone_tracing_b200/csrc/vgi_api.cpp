@@ -58,7 +58,7 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
     if (!cfg || !out) return fail(nullptr, VGI_E_INVALID, "vgi_create: null argument");
     if (cfg->struct_size != sizeof(vgi_config)) return fail(nullptr, VGI_E_INVALID, "vgi_create: struct_size mismatch");
     const uint32_t R = cfg->resolution, L = cfg->level_count;
-    if (R < 16 || R > 512 || (R & (R - 1))) return fail(nullptr, VGI_E_INVALID, "vgi_create: resolution must be a power of two in [16,512]");
+    if (R < 32 || R > 512 || (R & (R - 1))) return fail(nullptr, VGI_E_INVALID, "vgi_create: resolution must be a power of two in [32,512]");
     if (L < 1 || L > VGI_MAX_LEVELS) return fail(nullptr, VGI_E_INVALID, "vgi_create: level_count out of range");
     if (!(cfg->extent_level0 > 0.0f)) return fail(nullptr, VGI_E_INVALID, "vgi_create: extent_level0 must be positive");
     for (uint32_t i = 0; i < L; ++i)
@@ -80,6 +80,16 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
     CK(c, cudaMemset(c->store, 0, c->store_bytes));
     CK(c, cudaMalloc(&c->occ, nwords * sizeof(uint32_t)));
     CK(c, cudaMalloc(&c->occ_prefix, nwords * sizeof(uint32_t)));
+    for (int k = 0; k < 2; ++k) {
+        CK(c, cudaMalloc(&c->nz[k], nwords * sizeof(uint32_t)));
+        CK(c, cudaMemset(c->nz[k], 0, nwords * sizeof(uint32_t)));
+    }
+    {
+        const size_t nb = (size_t)(R >> 2) * (R >> 2) * (R >> 5) * L;
+        CK(c, cudaMalloc(&c->brick_mask, nb));
+        CK(c, cudaMemset(c->brick_mask, 0, nb));
+        CK(c, cudaMalloc(&c->footprint, nvox * L));
+    }
     CK(c, cudaMalloc(&c->block_sums, ((nwords + 4095) / 4096 + 1) * sizeof(uint32_t)));
     CK(c, cudaMalloc(&c->counters, sizeof(Counters)));
     CK(c, cudaMemset(c->counters, 0, sizeof(Counters)));
@@ -101,7 +111,7 @@ int vgi_destroy(vgi_ctx* c)
     free_scene(c);
     if (c->store_owned) cudaFree(c->store);
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
-    cudaFree(c->brick_mask); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
+    cudaFree(c->brick_mask); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
@@ -480,6 +490,11 @@ int vgi_bind_voxel_store(vgi_ctx* c, void* dev_ptr, size_t bytes)
     if (c->store_owned) cudaFree(c->store);
     c->store = (VoxelRecord*)dev_ptr;
     c->store_owned = false;
+    // the sparse build only rewrites records its masks know about: start from an all-zero store
+    CK(c, cudaMemset(c->store, 0, c->store_bytes));
+    const size_t nwords = (((size_t)c->cfg.resolution * c->cfg.resolution * c->cfg.resolution) >> 5) * c->cfg.level_count;
+    for (int k = 0; k < 2; ++k) CK(c, cudaMemset(c->nz[k], 0, nwords * sizeof(uint32_t)));
+    c->built = false;
     return VGI_OK;
 }
 
@@ -544,7 +559,13 @@ int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g,
     tp.L = (int)c->cfg.level_count;
     tp.logR = ilog2(c->cfg.resolution);
     tp.store = c->store;
-    tp.brick_mask = nullptr;
+    tp.brick_mask = c->brick_mask;
+    tp.footprint = c->footprint;
+    for (int l = 0; l < VGI_MAX_LEVELS; ++l) {
+        // ref: voxelConeTracing.frag:315 — extent = voxelSize * volumeDimension * 2^level
+        const float extent = (prm->voxel_size * prm->volume_dimension) * exp2f((float)l);
+        tp.inv_extent[l] = 1.0f / extent;
+    }
     tp.diffuse = g->diffuse_rgba8; tp.normal = g->normal_rgba16f; tp.specular = g->specular_rgba8;
     tp.emission = g->emission_rgba16f; tp.depth = g->depth_f32;
     tp.width = (int)g->width; tp.height = (int)g->height; tp.y0 = (int)y0; tp.y1 = (int)y1;

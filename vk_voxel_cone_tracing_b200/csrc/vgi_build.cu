@@ -334,9 +334,7 @@ __global__ void k_zero_acc(uint32_t* __restrict__ acc, const Counters* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K3: radiance injection — one thread per (triangle, voxel) pair.
-// ref: msaaInjectRadiance.frag:68-155 (shading), :176-183 (faces from -normal), shadow.glsl:8-36.
-// Canonical accumulation (Q10): 16.16 fixed-point integer sums + count, order independent.
+// shading helpers shared by the injection kernel (ref: msaaInjectRadiance.frag:68-155, shadow.glsl:8-36)
 // ---------------------------------------------------------------------------------------------------
 DEVFN void xform_point(const float* m, const float* v, float* o)
 {
@@ -419,81 +417,227 @@ DEVFN bool inject_sample_at(int a, const float N[3], const float p[9], const flo
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_inject(BuildParams bp, LightParams lp, const float4* __restrict__ tri_pos,
+// Per-pair shading state produced by the lane-per-pair phase of k_inject.
+struct PairShade {
+    float px, py, cmpz;     // shadow-map uv of the sample, compare depth (shadow_compare mode)
+    float NdotL;
+    float n[3];
+    int   mat;
+    uint32_t cell;          // accumulator index of the voxel
+    int   kind;             // 0 = nothing, 1 = emissive (no visibility), 2 = lit (needs visibility)
+};
+
+// One bilinear tap exactly as shadow_bilinear() evaluates it, texels supplied by the caller.
+DEVFN float bilinear_mix(float t00, float t10, float t01, float t11, float a, float b)
+{
+    return (t00 * (1.0f - a) + t10 * a) * (1.0f - b) + (t01 * (1.0f - a) + t11 * a) * b;
+}
+
+// Visibility of 8 pairs per warp round: the four lanes of a quad own the four tap columns of one
+// pair (ref: shadow.glsl:14-26, 4x4 taps at -1.5..1.5 texels). The 16 bilinear footprints of a pair
+// tile a 5x5 texel block: lane i loads column i (5 texels) and one texel of column 4, neighbours are
+// exchanged by shuffles, so a pair costs 7 load instructions whose quad lanes share a 128-byte line
+// instead of 64 scattered loads. Every tap keeps its own (ix, iy, a, b) and the taps are summed in
+// the shader's order, so the result is bit-identical to calc_visibility(); pairs whose taps do not
+// tile the block (float rounding at a texel boundary) take the scalar path.
+DEVFN float quad_visibility(const LightParams& lp, float px, float py, bool compare, float cmpz, bool need)
+{
+    const unsigned lane = lane_id();
+    const int i = (int)(lane & 3u);
+    const unsigned qbase = lane & ~3u;
+    const float sx = 1.0f / (float)lp.sw, sy = 1.0f / (float)lp.sh;
+    // column i
+    const float ox = -1.5f + (float)i;
+    const float x = (px + ox * sx) * (float)lp.sw - 0.5f;
+    const float fx = floorf(x);
+    const float a = x - fx;
+    const int ix = (int)f_clamp(fx, -4.0f, (float)lp.sw + 4.0f);
+    float b[4];
+    int iy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float oy = -1.5f + (float)j;
+        const float y = (py + oy * sy) * (float)lp.sh - 0.5f;
+        const float fy = floorf(y);
+        b[j] = y - fy;
+        iy[j] = (int)f_clamp(fy, -4.0f, (float)lp.sh + 4.0f);
+    }
+    const int ix0 = __shfl_sync(0xffffffffu, ix, qbase);
+    const bool tiles = (ix == ix0 + i) && (iy[1] == iy[0] + 1) && (iy[2] == iy[0] + 2) && (iy[3] == iy[0] + 3);
+    const unsigned okmask = __ballot_sync(0xffffffffu, tiles || !need);
+    const bool quad_ok = ((okmask >> qbase) & 0xfu) == 0xfu;
+    float tap[4] = { 0.f, 0.f, 0.f, 0.f };
+    // block loads (all lanes run the shuffles; loads are predicated)
+    float c[5], e = 0.0f, e4 = 0.0f;
+    const bool ld = need && quad_ok;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c[k] = ld ? shadow_texel(lp, ix0 + i, iy[0] + k) : 0.0f;
+    if (ld) {
+        e = shadow_texel(lp, ix0 + 4, iy[0] + i);
+        e4 = shadow_texel(lp, ix0 + 4, iy[0] + 4);
+    }
+    if (compare) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) c[k] = c[k] >= cmpz ? 1.0f : 0.0f;
+        e = e >= cmpz ? 1.0f : 0.0f;
+        e4 = e4 >= cmpz ? 1.0f : 0.0f;
+    }
+    float r[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float right = __shfl_sync(0xffffffffu, c[k], (lane + 1u) & 31u);
+        const float edge = __shfl_sync(0xffffffffu, e, qbase + (unsigned)(k < 4 ? k : 3));
+        r[k] = (i < 3) ? right : (k < 4 ? edge : e4);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tap[j] = bilinear_mix(c[j], r[j], c[j + 1], r[j + 1], a, b[j]);
+    if (need && !quad_ok) {
+        // scalar path for this column's four taps
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t00 = shadow_texel(lp, ix, iy[j]), t10 = shadow_texel(lp, ix + 1, iy[j]);
+            float t01 = shadow_texel(lp, ix, iy[j] + 1), t11 = shadow_texel(lp, ix + 1, iy[j] + 1);
+            if (compare) {
+                t00 = t00 >= cmpz ? 1.0f : 0.0f; t10 = t10 >= cmpz ? 1.0f : 0.0f;
+                t01 = t01 >= cmpz ? 1.0f : 0.0f; t11 = t11 >= cmpz ? 1.0f : 0.0f;
+            }
+            tap[j] = bilinear_mix(t00, t10, t01, t11, a, b[j]);
+        }
+    }
+    // sum in the shader's order: rows j outer, columns i inner
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sum += __shfl_sync(0xffffffffu, tap[j], qbase + (unsigned)k);
+    return sum * 0.0625f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: radiance injection — one lane per (triangle, voxel) pair for the shading, one quad per pair for
+// the 16 shadow taps. ref: msaaInjectRadiance.frag:68-155 (shading), :176-183 (faces from -normal),
+// shadow.glsl:8-36. Canonical accumulation (Q10): 16.16 fixed-point integer sums + count, order
+// independent.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, const float4* __restrict__ tri_pos,
                                                  const float4* __restrict__ tri_nrm, const vgi_material* __restrict__ materials,
                                                  const vgi_pair_t* __restrict__ pairs, const uint32_t* __restrict__ occ,
                                                  const uint32_t* __restrict__ occ_prefix, uint32_t* __restrict__ acc,
                                                  Counters* __restrict__ cnt)
 {
     const uint32_t npairs = min(cnt->pairs, bp.max_pairs);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
-        const vgi_pair_t pr = pairs[i];
-        const uint32_t tri = (uint32_t)(pr >> 32);
-        const int level = (int)((pr >> 27) & 7u);
-        if (!((bp.level_mask >> level) & 1u)) continue;
-        const int tx = (int)(pr & 511u), ty = (int)((pr >> 9) & 511u), tz = (int)((pr >> 18) & 511u);
-        const LevelParams& lv = bp.lv[level];
-        const int Rm = bp.R - 1;
-        // unwrap the texel back to the voxel inside the region
-        const int vx = lv.min_corner[0] + ((tx - lv.min_corner[0]) & Rm);
-        const int vy = lv.min_corner[1] + ((ty - lv.min_corner[1]) & Rm);
-        const int vz = lv.min_corner[2] + ((tz - lv.min_corner[2]) & Rm);
-
-        float p[9], n9[9], N[3];
-        int mat;
-        load_tri(tri_pos, tri, p, &mat);
-        {
-            const float4 a = __ldg(tri_nrm + 3 * (size_t)tri), b = __ldg(tri_nrm + 3 * (size_t)tri + 1), c = __ldg(tri_nrm + 3 * (size_t)tri + 2);
-            n9[0] = a.x; n9[1] = a.y; n9[2] = a.z; n9[3] = b.x; n9[4] = b.y; n9[5] = b.z; n9[6] = c.x; n9[7] = c.y; n9[8] = c.z;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const unsigned lane = lane_id();
+    const bool compare = bp.shadow_compare != 0;
+    // warp-uniform trip count: the quad phase needs every lane of the warp
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < npairs; base += stride) {
+        const uint32_t i = base + lane;
+        PairShade ps;
+        ps.kind = 0;
+        ps.px = ps.py = ps.cmpz = 0.0f;
+        ps.NdotL = 0.0f;
+        ps.n[0] = ps.n[1] = ps.n[2] = 0.0f;
+        ps.mat = 0;
+        ps.cell = 0;
+        if (i < npairs) {
+            const vgi_pair_t pr = pairs[i];
+            const uint32_t tri = (uint32_t)(pr >> 32);
+            const int level = (int)((pr >> 27) & 7u);
+            if ((bp.level_mask >> level) & 1u) {
+                const int tx = (int)(pr & 511u), ty = (int)((pr >> 9) & 511u), tz = (int)((pr >> 18) & 511u);
+                const LevelParams& lv = bp.lv[level];
+                const int Rm = bp.R - 1;
+                // unwrap the texel back to the voxel inside the region
+                const int vx = lv.min_corner[0] + ((tx - lv.min_corner[0]) & Rm);
+                const int vy = lv.min_corner[1] + ((ty - lv.min_corner[1]) & Rm);
+                const int vz = lv.min_corner[2] + ((tz - lv.min_corner[2]) & Rm);
+                float p[9], n9[9], N[3];
+                load_tri(tri_pos, tri, p, &ps.mat);
+                {
+                    const float4 a = __ldg(tri_nrm + 3 * (size_t)tri), b = __ldg(tri_nrm + 3 * (size_t)tri + 1), c = __ldg(tri_nrm + 3 * (size_t)tri + 2);
+                    n9[0] = a.x; n9[1] = a.y; n9[2] = a.z; n9[3] = b.x; n9[4] = b.y; n9[5] = b.z; n9[6] = c.x; n9[7] = c.y; n9[8] = c.z;
+                }
+                const int axis = cross_and_axis(p, N);
+                float c[3] = { ((float)vx + 0.5f) * lv.voxel_size, ((float)vy + 0.5f) * lv.voxel_size, ((float)vz + 0.5f) * lv.voxel_size };
+                float pos[3], nrm[3];
+                if (inject_sample_at(axis, N, p, n9, c, pos, nrm)) {
+                    const vgi_material* m = materials + ps.mat;
+                    const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
+                    const size_t w = (size_t)level * wordsPerLevel + (((((size_t)tz << bp.logR) + ty) << bp.logR) + tx) / 32;
+                    ps.cell = occ_prefix[w] + __popc(occ[w] & ((1u << (tx & 31)) - 1u));
+                    if (m->emissive_factor[0] > 0.0f || m->emissive_factor[1] > 0.0f || m->emissive_factor[2] > 0.0f) {
+                        ps.kind = 1;
+                    } else {
+                        const float len2 = dot3(nrm, nrm);
+                        if (len2 > 0.0f) {
+                            const float len = sqrtf(len2);
+                            ps.n[0] = nrm[0] / len; ps.n[1] = nrm[1] / len; ps.n[2] = nrm[2] / len;
+                            ps.NdotL = f_clamp(dot3(ps.n, lp.dir_to_light), 0.001f, 1.0f);
+                            // ref: shadow.glsl:28-36 — light-space xy of the sample
+                            float l[3];
+                            xform_point(lp.view, pos, l);
+                            const float* P = lp.proj;
+                            float qx = ((P[0] * l[0] + P[4] * l[1]) + P[8] * 0.0f) + P[12];
+                            float qy = ((P[1] * l[0] + P[5] * l[1]) + P[9] * 0.0f) + P[13];
+                            ps.px = qx * 0.5f + 0.5f;
+                            ps.py = qy * 0.5f + 0.5f;
+                            if (compare) ps.cmpz = (P[10] * l[2] + P[14]) - 0.002f;
+                            ps.kind = 2;
+                        }
+                    }
+                    if (ps.kind && ps.cell >= bp.max_occ) { atomicOr(&cnt->overflow, 4u); ps.kind = 0; }
+                }
+            }
         }
-        const int axis = cross_and_axis(p, N);
-        float c[3] = { ((float)vx + 0.5f) * lv.voxel_size, ((float)vy + 0.5f) * lv.voxel_size, ((float)vz + 0.5f) * lv.voxel_size };
-        float pos[3], nrm[3];
-        if (!inject_sample_at(axis, N, p, n9, c, pos, nrm)) continue;
-
-        const vgi_material* m = materials + mat;
+        // quad phase: round r serves the pairs of lanes 8r..8r+7, quad q serves lane 8r+q
+        float vis = 0.0f;
+        const unsigned lit = __ballot_sync(0xffffffffu, ps.kind == 2);
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            if (!((lit >> (8 * r)) & 0xffu)) continue;
+            const unsigned src = 8u * (unsigned)r + (lane >> 2);
+            const float qpx = __shfl_sync(0xffffffffu, ps.px, src);
+            const float qpy = __shfl_sync(0xffffffffu, ps.py, src);
+            const float qcz = __shfl_sync(0xffffffffu, ps.cmpz, src);
+            const bool need = (lit >> src) & 1u;
+            const float v = quad_visibility(lp, qpx, qpy, compare, qcz, need);
+            // hand the result back to the owning lane: lane l (in round l/8) reads quad l%8
+            const float back = __shfl_sync(0xffffffffu, v, (lane & 7u) * 4u);
+            if ((int)(lane >> 3) == r) vis = back;
+        }
+        if (ps.kind == 0) continue;
+        const vgi_material* m = materials + ps.mat;
         int faces[6];
         uint32_t q[6][3];
         int nf = 0;
-        const float e0 = m->emissive_factor[0], e1 = m->emissive_factor[1], e2 = m->emissive_factor[2];
-        if (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f) {
-            const uint32_t q0 = (uint32_t)(f_clamp(e0, 0.0f, 1.0f) * 65536.0f + 0.5f);
-            const uint32_t q1 = (uint32_t)(f_clamp(e1, 0.0f, 1.0f) * 65536.0f + 0.5f);
-            const uint32_t q2 = (uint32_t)(f_clamp(e2, 0.0f, 1.0f) * 65536.0f + 0.5f);
+        if (ps.kind == 1) {
+            const uint32_t q0 = (uint32_t)(f_clamp(m->emissive_factor[0], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            const uint32_t q1 = (uint32_t)(f_clamp(m->emissive_factor[1], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            const uint32_t q2 = (uint32_t)(f_clamp(m->emissive_factor[2], 0.0f, 1.0f) * 65536.0f + 0.5f);
 #pragma unroll
             for (int f = 0; f < 6; ++f) { faces[f] = f; q[f][0] = q0; q[f][1] = q1; q[f][2] = q2; }
             nf = 6;
         } else {
-            const float len2 = dot3(nrm, nrm);
-            if (!(len2 > 0.0f)) continue;
-            const float len = sqrtf(len2);
-            const float n[3] = { nrm[0] / len, nrm[1] / len, nrm[2] / len };
-            const float NdotL = f_clamp(dot3(n, lp.dir_to_light), 0.001f, 1.0f);
-            const float vis = calc_visibility(lp, pos, bp.shadow_compare != 0);
             float lc[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) lc[k] = ((NdotL * vis) * lp.color[k]) * lp.intensity;
+            for (int k = 0; k < 3; ++k) lc[k] = ((ps.NdotL * vis) * lp.color[k]) * lp.intensity;
             if (lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f) continue;
             float rad[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 rad[k] = f_clamp((lc[k] * m->base_color_factor[k]) * m->base_color_factor[3], 0.0f, 1.0f);
-            faces[0] = (-n[0] > 0.0f) ? 0 : 1;
-            faces[1] = (-n[1] > 0.0f) ? 2 : 3;
-            faces[2] = (-n[2] > 0.0f) ? 4 : 5;
+            faces[0] = (-ps.n[0] > 0.0f) ? 0 : 1;
+            faces[1] = (-ps.n[1] > 0.0f) ? 2 : 3;
+            faces[2] = (-ps.n[2] > 0.0f) ? 4 : 5;
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
-                const float w = fabsf(n[f]);
+                const float w = fabsf(ps.n[f]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) q[f][k] = (uint32_t)((rad[k] * w) * 65536.0f + 0.5f);
             }
             nf = 3;
         }
-        const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
-        const size_t w = (size_t)level * wordsPerLevel + (((((size_t)tz << bp.logR) + ty) << bp.logR) + tx) / 32;
-        const uint32_t idx = occ_prefix[w] + __popc(occ[w] & ((1u << (tx & 31)) - 1u));
-        if (idx >= bp.max_occ) { atomicOr(&cnt->overflow, 4u); continue; }
-        uint32_t* a = acc + (size_t)idx * 24;
+        uint32_t* a = acc + (size_t)ps.cell * 24;
         for (int f = 0; f < nf; ++f) {
             uint32_t* af = a + faces[f] * 4;
             atomicAdd(af + 0, q[f][0]);
@@ -505,180 +649,335 @@ __global__ void __launch_bounds__(128) k_inject(BuildParams bp, LightParams lp, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4: finalize — one thread per voxel writes its 32-byte record. Fuses the reference's clears
-// (A4 VoxelizationPass.cpp:104-126, A7 clipmapCleaning.comp), the raw opacity store
-// (msaaVoxelizer.frag:69-73), the radiance average (msaaInjectRadiance.frag:185-201, canonical mean)
-// and copy-alpha (A9 copyAlphaImage.comp:16-29).
+// K4: k_build_level — one launch per clip level writes every record of the level that is, or was last
+// frame, non-zero; all other records are already zero and stay untouched. Per visited voxel it fuses
+//   the reference's clears (A4 VoxelizationPass.cpp:104-126, A7 clipmapCleaning.comp),
+//   the raw opacity store (msaaVoxelizer.frag:69-73),
+//   the radiance average (msaaInjectRadiance.frag:185-201, canonical mean) and copy-alpha (A9),
+//   the opacity and radiance down-sample of level-1 into the centre half
+//     (opacityDownSample.comp:28-138, radianceDownSample.comp:28-139 with Q6 repaired),
+// and writes the 32-byte record exactly once. The visit set comes from bit masks:
+//   occ[l]  raw occupancy of this frame (k_voxelize)
+//   nz[l]   superset of the non-zero records = occ[l] | centre-half(OR of the 2x2x2 children in nz[l-1])
+//   nzPrev  nz of the previous frame (records that may need clearing)
+// Warp layout: phase 1 lane = mask word (32 voxels along x), phase 2 lane = voxel of one word.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finalize(BuildParams bp, int level, const uint32_t* __restrict__ occ,
-                                                   const uint32_t* __restrict__ occ_prefix,
-                                                   const uint32_t* __restrict__ acc, VoxelRecord* __restrict__ store)
+// Child pair pr (0..3) of face f in the shader's OFFSETS order (child index = dx + 2 dy + 4 dz):
+// face 2a composites the low-side child over the high-side child along axis a, face 2a+1 the reverse
+// (ref: opacityDownSample.comp:97-138). Pure functions of compile-time loop indices, so the child
+// arrays stay in registers.
+DEVFN constexpr int ds_pair_base(int f, int pr)
 {
-    const size_t nvox = (size_t)bp.R * bp.R * bp.R;
-    const size_t v = (size_t)bp.z0 * bp.R * bp.R + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= (size_t)bp.z1 * bp.R * bp.R) return;
-    const size_t w = (size_t)level * (nvox >> 5) + (v >> 5);
-    const uint32_t word = __ldg(occ + w);
-    const uint32_t bit = (uint32_t)(v & 31u);
-    const bool raw = (word >> bit) & 1u;
+    return (f >> 1) == 0 ? (pr << 1) : ((f >> 1) == 1 ? ((pr & 1) | ((pr & 2) << 1)) : pr);
+}
+DEVFN constexpr int ds_pair_first(int f, int pr) { return ds_pair_base(f, pr) | ((f & 1) ? (1 << (f >> 1)) : 0); }
+DEVFN constexpr int ds_pair_second(int f, int pr) { return ds_pair_base(f, pr) | ((f & 1) ? 0 : (1 << (f >> 1))); }
+
+DEVFN uint32_t low_bits(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
+
+// bits b of a 32-texel word starting at texel x0 with ((x0 + b - start) mod R) < half
+DEVFN uint32_t centre_mask(int x0, int start, int R, int half)
+{
+    const int d0 = (x0 - start) & (R - 1);
+    const int e = R - d0;                       // bits until the wrap
+    const uint32_t first = low_bits(min(e, half - d0));
+    const uint32_t second = low_bits(e + half) & ~low_bits(e);
+    return first | second;
+}
+
+// keep the even bits of a 64-bit value: bit b of the result = bit 2b of v
+DEVFN uint32_t even_bits(unsigned long long v)
+{
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v >> 4)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v >> 8)) & 0x0000ffff0000ffffull;
+    v = (v | (v >> 16)) & 0x00000000ffffffffull;
+    return (uint32_t)v;
+}
+
+struct Rec { uint4 lo, hi; };
+
+DEVFN uint32_t rec_radiance(const Rec& r, int f)
+{
+    return f == 0 ? r.lo.x : f == 1 ? r.lo.y : f == 2 ? r.lo.z : f == 3 ? r.lo.w : f == 4 ? r.hi.x : r.hi.y;
+}
+
+__global__ void __launch_bounds__(256) k_build_level(BuildParams bp, int level, const uint32_t* __restrict__ occ,
+                                                      const uint32_t* __restrict__ occ_prefix,
+                                                      const uint32_t* __restrict__ acc, const uint32_t* __restrict__ nzPrev,
+                                                      uint32_t* __restrict__ nzCur, VoxelRecord* __restrict__ store)
+{
+    __shared__ float s_unorm[256];              // (float)c / 255.0f, exact
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = (float)i / 255.0f;
+    __syncthreads();
+
+    const int R = bp.R, Rm = R - 1, half = R >> 1, logR = bp.logR;
+    const int wpr = R >> 5;                     // mask words per x row
+    const size_t nvox = (size_t)R * R * R;
+    const uint32_t wordsPerLevel = (uint32_t)(nvox >> 5);
+    const uint32_t* occL = occ + (size_t)level * wordsPerLevel;
+    const uint32_t* prefL = occ_prefix + (size_t)level * wordsPerLevel;
+    const uint32_t* prevL = nzPrev + (size_t)level * wordsPerLevel;
+    uint32_t* curL = nzCur + (size_t)level * wordsPerLevel;
+    const uint32_t* fineL = nzCur + (size_t)(level - 1) * wordsPerLevel;   // valid for level > 0
     const bool inject = (bp.level_mask >> level) & 1u;
-    uint4* dst = reinterpret_cast<uint4*>(store + (size_t)level * nvox + v);
-    uint4 lo, hi;
-    if (inject) {
-        uint32_t rad[6] = { 0, 0, 0, 0, 0, 0 };
-        if (raw) {
-            const uint32_t idx = __ldg(occ_prefix + w) + __popc(word & ((1u << bit) - 1u));
-            if (idx < bp.max_occ) {
-                const uint4* a = reinterpret_cast<const uint4*>(acc + (size_t)idx * 24);
+    const bool mip = level > 0;
+    int pm[3] = { 0, 0, 0 };
+    if (mip) { pm[0] = bp.lv[level - 1].min_corner[0] >> 1; pm[1] = bp.lv[level - 1].min_corner[1] >> 1; pm[2] = bp.lv[level - 1].min_corner[2] >> 1; }
+    const unsigned lane = lane_id();
+    const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nchunks = wordsPerLevel >> 5;
+    VoxelRecord* storeL = store + (size_t)level * nvox;
+    const VoxelRecord* storeF = store + (size_t)(level - 1) * nvox;
+
+    for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warpsPerGrid) {
+        // ---- phase 1: lane = mask word
+        const uint32_t wi = chunk * 32u + lane;
+        const int xw = (int)(wi % (uint32_t)wpr);
+        const uint32_t row = wi / (uint32_t)wpr;
+        const int y = (int)(row & (uint32_t)Rm), z = (int)(row >> logR);
+        const uint32_t occw = __ldg(occL + wi);
+        const uint32_t prevw = __ldg(prevL + wi);
+        uint32_t nzw = occw;
+        if (mip) {
+            const bool in_yz = (((y - pm[1]) & Rm) < half) && (((z - pm[2]) & Rm) < half);
+            if (in_yz) {
+                const int fy = (2 * y) & Rm, fz = (2 * z) & Rm;
+                const int fxw = ((2 * xw * 32) & Rm) >> 5;
+                unsigned long long o = 0ull;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const size_t frow = ((size_t)(fz + (d >> 1)) << logR) + (size_t)(fy + (d & 1));
+                    const uint32_t a = fineL[frow * wpr + fxw];
+                    const uint32_t b = wpr > 1 ? fineL[frow * wpr + fxw + 1] : a;
+                    o |= ((unsigned long long)b << 32) | a;
+                }
+                nzw |= even_bits(o | (o >> 1)) & centre_mask(xw * 32, pm[0] & Rm, R, half);
+            }
+        }
+        if (!inject) nzw |= prevw;              // off-cadence: last frame's radiance stays in the records
+        curL[wi] = nzw;
+        const uint32_t visit = nzw | prevw;
+
+        // ---- phase 2: lane = voxel of one non-empty word
+        unsigned todo = __ballot_sync(0xffffffffu, visit != 0u);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t vword = __shfl_sync(0xffffffffu, visit, src);
+            const uint32_t oword = __shfl_sync(0xffffffffu, occw, src);
+            if (!((vword >> lane) & 1u)) continue;
+            const uint32_t wis = chunk * 32u + (uint32_t)src;
+            const int sxw = (int)(wis % (uint32_t)wpr);
+            const uint32_t srow = wis / (uint32_t)wpr;
+            const int vy = (int)(srow & (uint32_t)Rm), vz = (int)(srow >> logR);
+            const int vx = sxw * 32 + (int)lane;
+            VoxelRecord* dstp = storeL + ((((size_t)vz << logR) + vy) << logR) + vx;
+            uint4* dst = reinterpret_cast<uint4*>(dstp);
+            const bool raw = (oword >> lane) & 1u;
+
+            // -- finalize (k_finalize semantics)
+            Rec own;
+            if (inject) {
+                uint32_t rad[6] = { 0, 0, 0, 0, 0, 0 };
+                if (raw) {
+                    const uint32_t idx = __ldg(prefL + wis) + __popc(oword & ((1u << lane) - 1u));
+                    if (idx < bp.max_occ) {
+                        const uint4* a = reinterpret_cast<const uint4*>(acc + (size_t)idx * 24);
+#pragma unroll
+                        for (int f = 0; f < 6; ++f) {
+                            const uint4 s = a[f];
+                            uint32_t r = 0, g = 0, b = 0;
+                            if (s.w) {
+                                r = (uint32_t)(((unsigned long long)s.x * 255ull) >> 16) / s.w;
+                                g = (uint32_t)(((unsigned long long)s.y * 255ull) >> 16) / s.w;
+                                b = (uint32_t)(((unsigned long long)s.z * 255ull) >> 16) / s.w;
+                                r = r > 255u ? 255u : r; g = g > 255u ? 255u : g; b = b > 255u ? 255u : b;
+                            }
+                            rad[f] = r | (g << 8) | (b << 16) | 0xff000000u; // copy-alpha: opacity.a of an occupied voxel = 1
+                        }
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < 6; ++f) rad[f] = 0xff000000u;
+                    }
+                }
+                own.lo = make_uint4(rad[0], rad[1], rad[2], rad[3]);
+                own.hi.x = rad[4];
+                own.hi.y = rad[5];
+            } else {
+                // off-cadence level: the radiance texels (including their alpha) keep last frame's values
+                own.lo = dst[0];
+                const uint4 old = dst[1];
+                own.hi.x = old.x;
+                own.hi.y = old.y;
+            }
+            own.hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
+            own.hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
+
+            // -- down-sample of level-1 into the centre half (k_downsample semantics)
+            const int g0 = (vx - pm[0]) & Rm, g1 = (vy - pm[1]) & Rm, g2 = (vz - pm[2]) & Rm;
+            if (mip && g0 < half && g1 < half && g2 < half) {
+                const int g[3] = { g0, g1, g2 };
+                int pstart[3];
+                float dist[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int cur = pm[k] + g[k];
+                    pstart[k] = (cur << 1) & Rm;
+                    const float center = (float)pm[k] + (float)((uint32_t)half >> 1);
+                    dist[k] = fabsf(((float)cur + 0.5f) - center) - 0.5f;
+                }
+                const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)bp.band;
+                const float thr = (float)thrU;
+                const float invBand = 1.0f / ((float)bp.band + 1.0f);
+                float lerpFactor = 0.0f;
+                if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
+                    lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
+                    lerpFactor = lerpFactor * invBand;
+                }
+                // children: index i = dx + 2*dy + 4*dz; records whose nz bit is clear are zero
+                Rec ch[8];
+                uint32_t anyChild = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int cx = pstart[0] + (i & 1), cy = pstart[1] + ((i >> 1) & 1), cz = pstart[2] + (i >> 2);
+                    const size_t crow = ((size_t)cz << logR) + (size_t)cy;
+                    const uint32_t fw = fineL[crow * wpr + (cx >> 5)];
+                    ch[i].lo = make_uint4(0, 0, 0, 0);
+                    ch[i].hi = make_uint4(0, 0, 0, 0);
+                    if ((fw >> (cx & 31)) & 1u) {
+                        const uint4* srcp = reinterpret_cast<const uint4*>(storeF + (crow << logR) + cx);
+                        ch[i].lo = srcp[0];
+                        ch[i].hi = srcp[1];
+                        anyChild = 1u;
+                    }
+                }
+                const float ownRaw = raw ? 1.0f : 0.0f; // opacity.r of this level
+                uint32_t newOp[6], newRad[6];
 #pragma unroll
                 for (int f = 0; f < 6; ++f) {
-                    const uint4 s = a[f];
-                    uint32_t r = 0, g = 0, b = 0;
-                    if (s.w) {
-                        r = (uint32_t)(((unsigned long long)s.x * 255ull) >> 16) / s.w;
-                        g = (uint32_t)(((unsigned long long)s.y * 255ull) >> 16) / s.w;
-                        b = (uint32_t)(((unsigned long long)s.z * 255ull) >> 16) / s.w;
-                        r = r > 255u ? 255u : r; g = g > 255u ? 255u : g; b = b > 255u ? 255u : b;
+                    float s = 0.0f;
+                    if (anyChild) {
+#pragma unroll
+                        for (int pr = 0; pr < 4; ++pr) {
+                            const int i0 = ds_pair_first(f, pr), i1 = ds_pair_second(f, pr);
+                            const uint32_t w0 = f < 4 ? ch[i0].hi.z : ch[i0].hi.w;
+                            const uint32_t w1 = f < 4 ? ch[i1].hi.z : ch[i1].hi.w;
+                            const float a0 = s_unorm[(w0 >> (8 * (f & 3))) & 0xffu];
+                            const float a1 = s_unorm[(w1 >> (8 * (f & 3))) & 0xffu];
+                            s = s + a0;
+                            s = s + (1.0f - a0) * a1;
+                        }
                     }
-                    rad[f] = r | (g << 8) | (b << 16) | 0xff000000u; // copy-alpha: opacity.a of an occupied voxel = 1
-                }
-            } else {
+                    const float dsOp = s * 0.25f;
+                    const uint32_t aOp = f_to_unorm8(f_mix(dsOp, ownRaw, lerpFactor));
+                    newOp[f] = aOp;
+                    if (inject) {
+                        const uint32_t ow = rec_radiance(own, f);
+                        // own texel: rgb as injected, alpha = this level's final opacity alpha (copy-alpha ran before the radiance mips)
+                        const uint32_t ownTexel = (ow & 0x00ffffffu) | (aOp << 24);
+                        float sc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+                        if (anyChild) {
 #pragma unroll
-                for (int f = 0; f < 6; ++f) rad[f] = 0xff000000u;
+                            for (int pr = 0; pr < 4; ++pr) {
+                                const uint32_t w0 = rec_radiance(ch[ds_pair_first(f, pr)], f);
+                                const uint32_t w1 = rec_radiance(ch[ds_pair_second(f, pr)], f);
+                                if ((w0 | w1) == 0u) continue;      // adds exact zeros
+                                const float k1 = 1.0f - s_unorm[w0 >> 24];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    sc[c] = sc[c] + s_unorm[(w0 >> (8 * c)) & 0xffu];
+                                    sc[c] = sc[c] + k1 * s_unorm[(w1 >> (8 * c)) & 0xffu];
+                                }
+                            }
+                        }
+                        uint32_t out = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float ds = sc[c] * 0.25f;
+                            out |= f_to_unorm8(f_mix(ds, s_unorm[(ownTexel >> (8 * c)) & 0xffu], lerpFactor)) << (8 * c);
+                        }
+                        newRad[f] = out;
+                    }
+                }
+                if (inject) {
+                    own.lo = make_uint4(newRad[0], newRad[1], newRad[2], newRad[3]);
+                    own.hi.x = newRad[4];
+                    own.hi.y = newRad[5];
+                }
+                own.hi.z = newOp[0] | (newOp[1] << 8) | (newOp[2] << 16) | (newOp[3] << 24);
+                own.hi.w = (own.hi.w & 0xffff0000u) | newOp[4] | (newOp[5] << 8);
             }
+            dst[0] = own.lo;
+            dst[1] = own.hi;
         }
-        lo = make_uint4(rad[0], rad[1], rad[2], rad[3]);
-        hi.x = rad[4];
-        hi.y = rad[5];
-    } else {
-        // off-cadence level: the radiance texels (including their alpha) keep last frame's values
-        lo = dst[0];
-        const uint4 old = dst[1];
-        hi.x = old.x;
-        hi.y = old.y;
     }
-    hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
-    hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
-    dst[0] = lo;
-    dst[1] = hi;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K5: down-sample level-1 -> level (centre half of `level`), both atlases in one pass.
-// ref: opacityDownSample.comp:28-138 and radianceDownSample.comp:28-139 (Q6 repaired). One thread
-// per coarse voxel; the eight children are two 64-byte reads per (dy,dz) row.
+// K5: empty-space masks for the cone tracer, derived from the nz bits of this frame.
+//  brick     one bit per 4^3 brick, set when any record in voxels [4b, 4b+4] (per axis, toroidal; the +1
+//            covers the high corner of a tri-linear footprint whose low corner lies in the brick) may be
+//            non-zero. One byte per (brick row, nz word): bit k of byte [(bz*(R/4) + by)*wpr + xw] is
+//            brick bx = 8*xw + k.
+//  footprint one byte per voxel, written only for voxels of non-empty bricks: bit c = dx + 2 dy + 4 dz is
+//            the nz bit of record (x+dx, y+dy, z+dz), i.e. which of the 8 records of the footprint whose
+//            low corner is this voxel have to be fetched.
+// One thread per brick byte: 25 rows of 33 nz bits stay in registers.
 // ---------------------------------------------------------------------------------------------------
-__constant__ int c_ds_pair[6][4][2] = {
-    { {0,1},{2,3},{4,5},{6,7} }, { {1,0},{3,2},{5,4},{7,6} },
-    { {0,2},{1,3},{4,6},{5,7} }, { {2,0},{3,1},{6,4},{7,5} },
-    { {0,4},{1,5},{2,6},{3,7} }, { {4,0},{5,1},{6,2},{7,3} } };
-
-__global__ void __launch_bounds__(128) k_downsample(BuildParams bp, int level, VoxelRecord* __restrict__ store)
+__global__ void __launch_bounds__(128) k_brick_mask(int R, int L, int logR, const uint32_t* __restrict__ nz,
+                                                     uint8_t* __restrict__ brick, uint8_t* __restrict__ footprint)
 {
-    const int R = bp.R, half = R >> 1;
-    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gy = blockIdx.y, gz = blockIdx.z;
-    if (gx >= half) return;
-    const int g[3] = { gx, gy, gz };
-    const int* prevMin = bp.lv[level - 1].min_corner;
-    int cur[3], wpos[3], pstart[3];
-    float dist[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        cur[k] = (prevMin[k] >> 1) + g[k];
-        wpos[k] = cur[k] & (R - 1);
-        pstart[k] = (cur[k] << 1) & (R - 1);
-        const float center = (float)(prevMin[k] >> 1) + (float)((uint32_t)half >> 1);
-        dist[k] = fabsf(((float)cur[k] + 0.5f) - center) - 0.5f;
-    }
-    if (wpos[2] < bp.z0 || wpos[2] >= bp.z1) return;
-    const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)bp.band;
-    const float thr = (float)thrU;
-    const float invBand = 1.0f / ((float)bp.band + 1.0f);
-    float lerpFactor = 0.0f;
-    if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
-        lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
-        lerpFactor = lerpFactor * invBand;
-    }
+    const int wpr = R >> 5, nb = R >> 2, Rm = R - 1;
+    const size_t perLevel = (size_t)nb * nb * wpr;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= perLevel * L) return;
+    const int level = (int)(i / perLevel);
+    const size_t j = i % perLevel;
+    const int xw = (int)(j % wpr), by = (int)((j / wpr) % nb), bz = (int)(j / ((size_t)wpr * nb));
     const size_t nvox = (size_t)R * R * R;
-    const VoxelRecord* prev = store + (size_t)(level - 1) * nvox;
-    VoxelRecord* own = store + (size_t)level * nvox + ((((size_t)wpos[2] << bp.logR) + wpos[1]) << bp.logR) + wpos[0];
-
-    // children: index i = dx + 2*dy + 4*dz (OFFSETS order of the shader)
-    uint4 clo[8], chi[8];
+    const uint32_t* nzL = nz + (size_t)level * (nvox >> 5);
+    unsigned long long rows[5][5];
+    unsigned long long any = 0ull;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int x = pstart[0] + (i & 1), y = pstart[1] + ((i >> 1) & 1), z = pstart[2] + (i >> 2);
-        const uint4* src = reinterpret_cast<const uint4*>(prev + ((((size_t)z << bp.logR) + y) << bp.logR) + x);
-        clo[i] = src[0];
-        chi[i] = src[1];
-    }
-    uint4* dst = reinterpret_cast<uint4*>(own);
-    uint4 olo = dst[0], ohi = dst[1];
-    const bool inject = (bp.level_mask >> level) & 1u;
-    const float ownRaw = ((ohi.w >> 16) & 0xffu) ? 1.0f : 0.0f; // opacity.r of this level (raw flag * 255 / 255)
-
-    uint32_t newOp[6], newRad[6];
+    for (int dz = 0; dz < 5; ++dz)
 #pragma unroll
-    for (int f = 0; f < 6; ++f) {
-        // child opacity alphas of face f: bytes 24+f
-        float ca[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t wsel = f < 4 ? chi[i].z : chi[i].w;
-            ca[i] = unorm8_to_f((wsel >> (8 * (f & 3))) & 0xffu);
+        for (int dy = 0; dy < 5; ++dy) {
+            const size_t row = ((size_t)((bz * 4 + dz) & Rm) << logR) + (size_t)((by * 4 + dy) & Rm);
+            const uint32_t lo = __ldg(nzL + row * wpr + xw);
+            const uint32_t hi = __ldg(nzL + row * wpr + ((xw + 1) % wpr)) & 1u;
+            rows[dz][dy] = ((unsigned long long)hi << 32) | lo;
+            any |= rows[dz][dy];
         }
-        float s = 0.0f;
+    uint32_t out = 0u;
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-            const float a0 = ca[c_ds_pair[f][pr][0]], a1 = ca[c_ds_pair[f][pr][1]];
-            s = s + a0;
-            s = s + (1.0f - a0) * a1;
-        }
-        const float dsOp = s * 0.25f;
-        const uint32_t aOp = f_to_unorm8(f_mix(dsOp, ownRaw, lerpFactor));
-        newOp[f] = aOp;
-
-        if (inject) {
-            uint32_t cw[8];
+    for (int k = 0; k < 8; ++k)
+        if ((any >> (4 * k)) & 0x1full) out |= 1u << k;
+    brick[i] = (uint8_t)out;
+    if (!out) return;
+    uint8_t* fpL = footprint + (size_t)level * nvox;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                cw[i] = f == 0 ? clo[i].x : f == 1 ? clo[i].y : f == 2 ? clo[i].z : f == 3 ? clo[i].w : f == 4 ? chi[i].x : chi[i].y;
-            const uint32_t ow = f == 0 ? olo.x : f == 1 ? olo.y : f == 2 ? olo.z : f == 3 ? olo.w : f == 4 ? ohi.x : ohi.y;
-            // own texel: rgb as injected, alpha = this level's final opacity alpha (copy-alpha ran before the radiance mips)
-            const uint32_t ownTexel = (ow & 0x00ffffffu) | (aOp << 24);
-            uint32_t out = 0;
+    for (int z = 0; z < 4; ++z)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float sc = 0.0f;
+        for (int y = 0; y < 4; ++y) {
+            const unsigned long long r00 = rows[z][y], r10 = rows[z][y + 1], r01 = rows[z + 1][y], r11 = rows[z + 1][y + 1];
+            uint32_t* dst = reinterpret_cast<uint32_t*>(fpL + ((((size_t)(bz * 4 + z) << logR) + (size_t)(by * 4 + y)) << logR) + (size_t)xw * 32);
+            for (int k = 0; k < 8; ++k) {
+                if (!((out >> k) & 1u)) continue;
+                const uint32_t a = (uint32_t)(r00 >> (4 * k)) & 0x1fu, b = (uint32_t)(r10 >> (4 * k)) & 0x1fu;
+                const uint32_t c = (uint32_t)(r01 >> (4 * k)) & 0x1fu, d = (uint32_t)(r11 >> (4 * k)) & 0x1fu;
+                uint32_t word = 0u;
 #pragma unroll
-                for (int pr = 0; pr < 4; ++pr) {
-                    const uint32_t w0 = cw[c_ds_pair[f][pr][0]], w1 = cw[c_ds_pair[f][pr][1]];
-                    const float v0 = unorm8_to_f((w0 >> (8 * c)) & 0xffu);
-                    const float v0a = unorm8_to_f(w0 >> 24);
-                    const float v1 = unorm8_to_f((w1 >> (8 * c)) & 0xffu);
-                    sc = sc + v0;
-                    sc = sc + (1.0f - v0a) * v1;
+                for (int x = 0; x < 4; ++x) {
+                    const uint32_t byte = ((a >> x) & 3u) | (((b >> x) & 3u) << 2) | (((c >> x) & 3u) << 4) | (((d >> x) & 3u) << 6);
+                    word |= byte << (8 * x);
                 }
-                const float ds = sc * 0.25f;
-                out |= f_to_unorm8(f_mix(ds, unorm8_to_f((ownTexel >> (8 * c)) & 0xffu), lerpFactor)) << (8 * c);
+                dst[k] = word;
             }
-            newRad[f] = out;
         }
-    }
-    if (inject) {
-        olo = make_uint4(newRad[0], newRad[1], newRad[2], newRad[3]);
-        ohi.x = newRad[4];
-        ohi.y = newRad[5];
-    }
-    ohi.z = newOp[0] | (newOp[1] << 8) | (newOp[2] << 16) | (newOp[3] << 24);
-    ohi.w = (ohi.w & 0xffff0000u) | newOp[4] | (newOp[5] << 8);
-    dst[0] = olo;
-    dst[1] = ohi;
 }
-
-// On an injected level outside the centre half the radiance alpha is the raw opacity (copy-alpha);
-// k_finalize already wrote it. Off-cadence levels keep their radiance. Nothing else to do.
 
 // ---------------------------------------------------------------------------------------------------
 // export to the reference atlas layout (ref: Voxelizer.h:40-52; texel addressing msaaVoxelizer.frag:43-55;
@@ -741,18 +1040,19 @@ int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s
     int n = 0;
     LAUNCH("k_zero_acc", k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ));
     if (bp.ntri && bp.level_mask) {
-        LAUNCH("k_inject", k_inject<<<148 * 16, 128, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
-                                                             c->occ, c->occ_prefix, c->acc, c->counters));
+        LAUNCH("k_inject", k_inject<<<148 * 8, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
+                                                            c->occ, c->occ_prefix, c->acc, c->counters));
     }
-    const size_t slabVox = (size_t)(bp.z1 - bp.z0) * bp.R * bp.R;
+    // nz masks ping-pong between frames: nz[cur] is written by this build, nz[cur ^ 1] is last frame's
+    const int cur = c->nz_cur ^ 1;
+    const uint32_t chunks = (uint32_t)((((size_t)bp.R * bp.R * bp.R) >> 5) >> 5);
+    const unsigned grid = min(cdiv(chunks, 8), 148u * 16u);
     for (int l = 0; l < bp.L; ++l) {
-        LAUNCH("k_finalize", k_finalize<<<cdiv(slabVox, 256), 256, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->store));
+        LAUNCH("k_build_level", k_build_level<<<grid, 256, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur ^ 1], c->nz[cur], c->store));
     }
-    for (int l = 1; l < bp.L; ++l) {
-        const int half = bp.R >> 1;
-        dim3 grid(cdiv(half, 128), half, half);
-        LAUNCH("k_downsample", k_downsample<<<grid, min(half, 128), 0, s>>>(bp, l, c->store));
-    }
+    const size_t nbytes = (size_t)(bp.R >> 2) * (bp.R >> 2) * (bp.R >> 5) * bp.L;
+    LAUNCH("k_brick_mask", k_brick_mask<<<cdiv(nbytes, 128), 128, 0, s>>>(bp.R, bp.L, bp.logR, c->nz[cur], c->brick_mask, c->footprint));
+    c->nz_cur = cur;
     cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
     return n;
 }

@@ -76,7 +76,9 @@ struct TraceParams {
     float    eye[3];
     int      R, L, logR;
     const VoxelRecord* store;
-    const uint32_t* brick_mask;   // 1 bit per 4^3 brick (incl. 1-texel halo), per level; may be null
+    const uint8_t* brick_mask;    // 1 bit per 4^3 brick (dilated by one voxel on the high side), see k_brick_mask
+    const uint8_t* footprint;     // per voxel of a non-empty brick: which of the 8 footprint records may be non-zero
+    float    inv_extent[VGI_MAX_LEVELS]; // 1 / (voxel_size * R * 2^level)
     const void* diffuse; const void* normal; const void* specular; const void* emission;
     const float* depth;
     int      width, height, y0, y1;
@@ -142,7 +144,10 @@ struct vgi_ctx {
     uint32_t* acc = nullptr;        // max_occ * 24 u32: [voxel][face][r,g,b,count]
     vgi_pair_t* pairs = nullptr;
     uint2* large = nullptr;         // (triangle, level) work items for big triangles
-    uint32_t* brick_mask = nullptr;
+    uint32_t* nz[2] = { nullptr, nullptr }; // non-zero-record masks, ping-pong between frames (L * R^3/32 words each)
+    int nz_cur = 0;
+    uint8_t* brick_mask = nullptr;
+    uint8_t* footprint = nullptr;   // L * R^3 bytes, valid where the brick bit is set
     Counters* counters = nullptr;
     Counters* h_counters = nullptr; // pinned
     uint32_t max_pairs = 0, max_occ = 0, max_large = 0;

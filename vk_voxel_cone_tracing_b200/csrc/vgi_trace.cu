@@ -39,6 +39,23 @@ __constant__ float c_cones32[32][3] = { // ref: voxelConeTracing.frag:81-114
     { -0.57735f, 0.57735f, 0.57735f }, { -0.57735f, 0.57735f, -0.57735f },
     { -0.57735f, -0.57735f, 0.57735f }, { -0.57735f, -0.57735f, -0.57735f } };
 
+// development aid (VGI_TRACE_STATS=1): [0] steps, [1] level samples, [2] skipped by brick mask,
+// [3] footprints loaded but all-zero, [4] corners loaded, [5] corners with any of the 3 face texels non-zero
+__device__ unsigned long long g_trace_stats[8];
+#ifdef VGI_TRACE_STATS_BUILD
+#define STAT(i, n) atomicAdd(&g_trace_stats[i], (unsigned long long)(n))
+extern "C" void vgi_debug_trace_stats(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_trace_stats, sizeof(g_trace_stats));
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_trace_stats, z, sizeof z); }
+}
+#else
+#define STAT(i, n) ((void)0)
+#endif
+
+__constant__ float c_level_colors[7][4] = { {1,0,0,1},{0,1,0,1},{0,0,1,1},{1,1,0,1},{0,1,1,1},{1,0,1,1},{1,1,1,1} }; // ref: voxelConeTracing.frag:270-278
+
 #define MIN_TRACE_STEP_FACTOR 0.2f
 #define MAX_TRACE_DISTANCE 30.0f
 #define MIN_SPECULAR_APERTURE 0.05f
@@ -53,47 +70,82 @@ DEVFN void normalize3(const float* v, float* o)
     o[0] = v[0] * inv; o[1] = v[1] * inv; o[2] = v[2] * inv;
 }
 
+// byte k of a packed RGBA8 texel as an exact float: PRMT builds the bit pattern of 2^23 + byte, the
+// packed add removes the 2^23 (both on the full-rate pipes; an I2F would go through the quarter-rate one)
+DEVFN float2 unpack2(uint32_t t, uint32_t selLo, uint32_t selHi)
+{
+    const float2 m = make_float2(__uint_as_float(__byte_perm(t, 0x4B000000u, selLo)),
+                                 __uint_as_float(__byte_perm(t, 0x4B000000u, selHi)));
+    return __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+}
+
 // one clipmap level, three face-weighted tri-linear taps (ref: voxelConeTracing.frag:313-327).
 // Texel coordinate = fract(p / extent) * R - 0.5, indices wrapped modulo R: the toroidal addressing
 // that the reference obtains from REPEAT + wrapped border texels.
-DEVFN void sample_level(const TraceParams& tp, const float* pos, int level, int fsel, const float* weight, float* out)
+// Empty space is skipped in two steps: the 4^3 brick bit (k_brick_mask), then the footprint byte
+// (k_brick_mask writes, for every voxel of a non-empty brick, which of the 8 records of the footprint
+// whose low corner is that voxel may be non-zero); only those records are loaded and filtered.
+// Returns false (out = 0) when all eight records of the footprint are zero.
+DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, int fsel, const float* weight, float* out)
 {
-    const int R = tp.R, Rm = R - 1;
-    const float extent = (tp.p.voxel_size * tp.p.volume_dimension) * exp2f((float)level);
-    const float inv = 1.0f / extent;
-    int i0[3], i1[3];
+    const int R = tp.R, Rm = R - 1, logR = tp.logR;
+    const float inv = tp.inv_extent[level];
+    int i0[3];
     float w[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float t = f_fract(pos[k] * inv) * (float)R - 0.5f;
         const float fl = floorf(t);
         w[k] = t - fl;
-        const int i = (int)fl;
-        i0[k] = i & Rm;
-        i1[k] = (i + 1) & Rm;
+        i0[k] = (int)fl & Rm;
     }
-    const VoxelRecord* base = tp.store + ((size_t)level << (3 * tp.logR));
-    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int x = (c & 1) ? i1[0] : i0[0], y = (c & 2) ? i1[1] : i0[1], z = (c & 4) ? i1[2] : i0[2];
+    STAT(1, 1);
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    const int wpr = R >> 5, nb = R >> 2;
+    const uint8_t bbyte = __ldg(tp.brick_mask + ((size_t)level * nb + (i0[2] >> 2)) * nb * wpr + (size_t)(i0[1] >> 2) * wpr + (i0[0] >> 5));
+    if (!((bbyte >> ((i0[0] >> 2) & 7)) & 1u)) {
+        STAT(2, 1);
+        return false;
+    }
+    const size_t vox = ((size_t)level << (3 * logR)) + ((((size_t)i0[2] << logR) + i0[1]) << logR) + i0[0];
+    uint32_t m = __ldg(tp.footprint + vox);
+    if (!m) {
+        STAT(3, 1);
+        return false;
+    }
+    const VoxelRecord* base = tp.store + vox;
+    // record offsets of the +1 neighbours (toroidal)
+    const int dx = (i0[0] == Rm) ? -Rm : 1;
+    const int dy = ((i0[1] == Rm) ? -Rm : 1) << logR;
+    const int dz = ((i0[2] == Rm) ? -Rm : 1) << (2 * logR);
+    float2 aX0 = make_float2(0.f, 0.f), aX1 = aX0, aY0 = aX0, aY1 = aX0, aZ0 = aX0, aZ1 = aX0;
+    STAT(4, __popc(m));
+    do {
+        const int c = __ffs(m) - 1;
+        m &= m - 1;
+        const int off = ((c & 1) ? dx : 0) + ((c & 2) ? dy : 0) + ((c & 4) ? dz : 0);
         const float wc = ((c & 1) ? w[0] : 1.0f - w[0]) * ((c & 2) ? w[1] : 1.0f - w[1]) * ((c & 4) ? w[2] : 1.0f - w[2]);
-        const uint4* rec = reinterpret_cast<const uint4*>(base + ((((size_t)z << tp.logR) + y) << tp.logR) + x);
-        const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+        const uint4* rec = reinterpret_cast<const uint4*>(base + off);
+        const uint4 lo = __ldg(rec);
+        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(rec + 1));
         const uint32_t tx = (fsel & 1) ? lo.y : lo.x;
         const uint32_t ty = (fsel & 2) ? lo.w : lo.z;
         const uint32_t tz = (fsel & 4) ? hi.y : hi.x;
-        if ((tx | ty | tz) == 0u) continue;
-        const float wxf = wc * weight[0], wyf = wc * weight[1], wzf = wc * weight[2];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            acc[ch] += wxf * (float)((tx >> (8 * ch)) & 0xffu);
-            acc[ch] += wyf * (float)((ty >> (8 * ch)) & 0xffu);
-            acc[ch] += wzf * (float)((tz >> (8 * ch)) & 0xffu);
-        }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) out[ch] = acc[ch] * (1.0f / 255.0f);
+        const float2 w2 = make_float2(wc, wc);
+        aX0 = __ffma2_rn(w2, unpack2(tx, 0x7540u, 0x7541u), aX0);
+        aX1 = __ffma2_rn(w2, unpack2(tx, 0x7542u, 0x7543u), aX1);
+        aY0 = __ffma2_rn(w2, unpack2(ty, 0x7540u, 0x7541u), aY0);
+        aY1 = __ffma2_rn(w2, unpack2(ty, 0x7542u, 0x7543u), aY1);
+        aZ0 = __ffma2_rn(w2, unpack2(tz, 0x7540u, 0x7541u), aZ0);
+        aZ1 = __ffma2_rn(w2, unpack2(tz, 0x7542u, 0x7543u), aZ1);
+        STAT(5, (tx | ty | tz) != 0u);
+    } while (m);
+    const float kx = weight[0] * (1.0f / 255.0f), ky = weight[1] * (1.0f / 255.0f), kz = weight[2] * (1.0f / 255.0f);
+    out[0] = aX0.x * kx + aY0.x * ky + aZ0.x * kz;
+    out[1] = aX0.y * kx + aY0.y * ky + aZ0.y * kz;
+    out[2] = aX1.x * kx + aY1.x * ky + aZ1.x * kz;
+    out[3] = aX1.y * kx + aY1.y * ky + aZ1.y * kz;
+    return true;
 }
 
 // ref: voxelConeTracing.frag:341-392
@@ -118,6 +170,7 @@ DEVFN void trace_cone(const TraceParams& tp, const float* startPos_, const float
     const float maxLevel = (float)(tp.L - 1);
 
     while (step < maxDistance && occlusion < 1.0f) {
+        STAT(0, 1);
         float position[3], d[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -132,14 +185,21 @@ DEVFN void trace_cone(const TraceParams& tp, const float* startPos_, const float
         const float fl = floorf(curLevel);
         const float fr = curLevel - fl;
         float smp[4];
-        sample_level(tp, position, (int)fl, fsel, weight, smp);
+        bool any = sample_level(tp, position, (int)fl, fsel, weight, smp);
         if (fr > 0.0f) { // Q17: floor == ceil when the level is integral — the second fetch is identical
             float up[4];
-            sample_level(tp, position, (int)fl + 1, fsel, weight, up);
+            any |= sample_level(tp, position, (int)fl + 1, fsel, weight, up);
 #pragma unroll
             for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
         }
         voxelSize = p.voxel_size * exp2f(curLevel);
+        if (!any) { // empty footprints: the accumulators receive exact zeros, only the march advances
+            const float prevStep0 = step;
+            step += fmaxf(diameter, p.voxel_size) * stepFactor;
+            curSegmentLength = step - prevStep0;
+            diameter = step * coneCoefficient;
+            continue;
+        }
         const float correction = curSegmentLength / voxelSize;
         float opacity = smp[3];
         // 1 - pow(1 - a, correction)
@@ -363,12 +423,11 @@ __global__ void __launch_bounds__(128) k_trace_main(const __grid_constant__ Trac
     case 1: dc = make_float4(s.specularColor[0], s.specularColor[1], s.specularColor[2], 1.f); break;
     case 2: dc = make_float4(s.normal[0] * 0.5f + 0.5f, s.normal[1] * 0.5f + 0.5f, s.normal[2] * 0.5f + 0.5f, 1.f); break;
     case 3: {
-        const float colors[7][4] = { {1,0,0,1},{0,1,0,1},{0,0,1,1},{1,1,0,1},{0,1,1,1},{1,0,1,1},{1,1,1,1} };
         int lower = (int)floorf(s.minLevel);
         lower = lower < 0 ? 0 : (lower > 5 ? 5 : lower);
         const float fr = f_fract(s.minLevel);
         float o[4];
-        for (int k = 0; k < 4; ++k) o[k] = (colors[lower][k] * (1.0f - fr) + colors[lower + 1][k] * fr) * 0.5f;
+        for (int k = 0; k < 4; ++k) o[k] = (c_level_colors[lower][k] * (1.0f - fr) + c_level_colors[lower + 1][k] * fr) * 0.5f;
         dc = make_float4(o[0], o[1], o[2], o[3]);
         break;
     }
