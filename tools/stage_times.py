@@ -53,6 +53,16 @@ def main():
     med = lambda v: sorted(v)[len(v) // 2]
     print(f"pairs={st.clip_pairs} occupied={st.occupied_voxels} launches={st.kernel_launches}")
     print(f"voxelize {med(vox):.3f} ms | inject+finalize+mip {med(inj):.3f} ms | trace {med(trc):.3f} ms")
+    gi.set_timing(True)
+    gi.reset_timings()
+    for i in range(a.iters):
+        gi.voxelize_opacity()
+        gi.inject_radiance(0)
+        gi.cone_trace(inp["cam"], gb, prm, out=out)
+    torch.cuda.synchronize()
+    for k, (ms, n) in gi.timings().items():
+        print(f"  {k:20s} {ms / a.iters * 1e3:9.1f} us/frame  ({n // a.iters} launches)")
+    gi.set_timing(False)
     d = out[0]
     print("diffuse mean", float(d[..., :3].mean()), "spec mean", float(out[1][..., :3].mean()))
 

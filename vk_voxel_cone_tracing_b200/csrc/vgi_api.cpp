@@ -566,6 +566,26 @@ int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g,
         const float extent = (prm->voxel_size * prm->volume_dimension) * exp2f((float)l);
         tp.inv_extent[l] = 1.0f / extent;
     }
+    {
+        // ref: voxelConeTracing.frag:366-368 — minLevel = ceil(log2(dist / minRadius)), clamped to L-1 by the
+        // tracer: ceil(log2 x) > k  <=>  x > 2^k. x(dd) = sqrtf(dd) / minRadius is monotone in the squared
+        // distance dd, so bisect the largest dd (over binary32 bit patterns) with x(dd) <= 2^k.
+        const float minRadius = prm->voxel_size * prm->volume_dimension * 0.5f;
+        for (int k = 0; k < VGI_MAX_LEVELS; ++k) {
+            if (k >= (int)c->cfg.level_count - 1) { tp.min_level_dd[k] = INFINITY; continue; }
+            const float bound = exp2f((float)k);
+            uint32_t lo = 0u, hi = 0x7f7fffffu; // invariant: x(lo) <= bound; answer = largest such pattern
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo + 1u) / 2u;
+                float dd;
+                memcpy(&dd, &mid, 4);
+                const volatile float dist = sqrtf(dd);
+                const volatile float x = dist / minRadius;
+                if (x <= bound) lo = mid; else hi = mid - 1u;
+            }
+            memcpy(&tp.min_level_dd[k], &lo, 4);
+        }
+    }
     tp.diffuse = g->diffuse_rgba8; tp.normal = g->normal_rgba16f; tp.specular = g->specular_rgba8;
     tp.emission = g->emission_rgba16f; tp.depth = g->depth_f32;
     tp.width = (int)g->width; tp.height = (int)g->height; tp.y0 = (int)y0; tp.y1 = (int)y1;

@@ -148,76 +148,133 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, int 
     return true;
 }
 
-// ref: voxelConeTracing.frag:341-392
+// ceil(log2(dist / minRadius)) of voxelConeTracing.frag:367 clamped to [0, L-1], without sqrt / divide /
+// log2: tp.min_level_dd[k] is the largest squared distance whose sqrtf(dd) / minRadius is still <= 2^k
+// (bisected on the host over the same binary32 operations), so the level is a count of passed thresholds.
+DEVFN float min_level_from_dd(const TraceParams& tp, float dd)
+{
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < VGI_MAX_LEVELS - 1; ++k) n += (dd > tp.min_level_dd[k]) ? 1 : 0;
+    return (float)n;
+}
+
+// One marching step of voxelConeTracing.frag:361-389 at `step` (position, level selection, one or two
+// level samples, front-to-back accumulation). lod = log2(diameter / voxelSize0).
+struct ConeState {
+    float result[4];
+    float occlusion;
+};
+
+DEVFN void cone_step(const TraceParams& tp, ConeState& cs, const float* startPos, const float* dir, int fsel, const float* weight,
+                     float startLevel, float step, float lod, float curSegmentLength)
+{
+    const vgi_vct_params& p = tp.p;
+    STAT(0, 1);
+    float position[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        position[k] = startPos[k] + dir[k] * step;
+        d[k] = p.volume_center[k] - position[k];
+    }
+    const float minLevel = min_level_from_dd(tp, dot3(d, d));
+    const float curLevel = fminf(fmaxf(fmaxf(startLevel, lod), minLevel), (float)(tp.L - 1));
+    const float fl = floorf(curLevel);
+    const float fr = curLevel - fl;
+    float smp[4];
+    bool any = sample_level(tp, position, (int)fl, fsel, weight, smp);
+    if (fr > 0.0f) { // Q17: floor == ceil when the level is integral — the second fetch is identical
+        float up[4];
+        any |= sample_level(tp, position, (int)fl + 1, fsel, weight, up);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
+    }
+    if (!any) return; // empty footprints: the accumulators would receive exact zeros
+    const float voxelSize = p.voxel_size * exp2f(curLevel);
+    const float correction = __fdividef(curSegmentLength, voxelSize);
+    float opacity = 0.0f;
+    if (smp[3] > 0.0f) // 1 - pow(1 - a, correction)
+        opacity = f_clamp(1.0f - exp2f(correction * __log2f(1.0f - smp[3])), 0.0f, 1.0f);
+    const float k1 = f_clamp(1.0f - cs.result[3], 0.0f, 1.0f) ;
+    cs.result[0] += k1 * (smp[0] * correction);
+    cs.result[1] += k1 * (smp[1] * correction);
+    cs.result[2] += k1 * (smp[2] * correction);
+    cs.result[3] += k1 * opacity;
+    cs.occlusion += __fdividef((1.0f - cs.occlusion) * opacity, 1.0f + (step + voxelSize) * p.occlusion_decay);
+}
+
+// ref: voxelConeTracing.frag:341-392 — generic march (specular cone: per-pixel aperture)
 DEVFN void trace_cone(const TraceParams& tp, const float* startPos_, const float* dir, float coneCoefficient, float maxDistance,
                       float startLevel, float stepFactor, float* out)
 {
     const vgi_vct_params& p = tp.p;
-    float result[4] = { 0.f, 0.f, 0.f, 0.f };
-    float curLevel = startLevel;
-    float voxelSize = p.voxel_size * exp2f(curLevel);
+    ConeState cs = { { 0.f, 0.f, 0.f, 0.f }, 0.0f };
+    const float voxelSize0 = p.voxel_size * exp2f(startLevel);
     float startPos[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize * p.trace_start_offset * 0.5f;
+    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
     float step = 0.0f;
     float diameter = fmaxf(step * coneCoefficient, p.voxel_size);
-    float occlusion = 0.0f;
     const int fsel = (dir[0] > 0.0f ? 0 : 1) | (dir[1] > 0.0f ? 0 : 2) | (dir[2] > 0.0f ? 0 : 4);
     const float weight[3] = { dir[0] * dir[0], dir[1] * dir[1], dir[2] * dir[2] };
-    float curSegmentLength = voxelSize;
-    const float minRadius = p.voxel_size * p.volume_dimension * 0.5f;
+    float curSegmentLength = voxelSize0;
     const float invVoxel = 1.0f / p.voxel_size;
-    const float maxLevel = (float)(tp.L - 1);
-
-    while (step < maxDistance && occlusion < 1.0f) {
-        STAT(0, 1);
-        float position[3], d[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            position[k] = startPos[k] + dir[k] * step;
-            d[k] = p.volume_center[k] - position[k];
-        }
-        const float dist = sqrtf(dot3(d, d));
-        const float minLevel = ceilf(log2f(dist / minRadius));
-        curLevel = log2f(diameter * invVoxel);
-        curLevel = fminf(fmaxf(fmaxf(startLevel, curLevel), minLevel), maxLevel);
-
-        const float fl = floorf(curLevel);
-        const float fr = curLevel - fl;
-        float smp[4];
-        bool any = sample_level(tp, position, (int)fl, fsel, weight, smp);
-        if (fr > 0.0f) { // Q17: floor == ceil when the level is integral — the second fetch is identical
-            float up[4];
-            any |= sample_level(tp, position, (int)fl + 1, fsel, weight, up);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
-        }
-        voxelSize = p.voxel_size * exp2f(curLevel);
-        if (!any) { // empty footprints: the accumulators receive exact zeros, only the march advances
-            const float prevStep0 = step;
-            step += fmaxf(diameter, p.voxel_size) * stepFactor;
-            curSegmentLength = step - prevStep0;
-            diameter = step * coneCoefficient;
-            continue;
-        }
-        const float correction = curSegmentLength / voxelSize;
-        float opacity = smp[3];
-        // 1 - pow(1 - a, correction)
-        opacity = f_clamp(1.0f - exp2f(correction * log2f(1.0f - opacity)), 0.0f, 1.0f);
-        if (smp[3] <= 0.0f) opacity = 0.0f;
-        const float k1 = f_clamp(1.0f - result[3], 0.0f, 1.0f);
-        result[0] += k1 * (smp[0] * correction);
-        result[1] += k1 * (smp[1] * correction);
-        result[2] += k1 * (smp[2] * correction);
-        result[3] += k1 * opacity;
-        occlusion += (1.0f - occlusion) * opacity / (1.0f + (step + voxelSize) * p.occlusion_decay);
+    while (step < maxDistance && cs.occlusion < 1.0f) {
+        cone_step(tp, cs, startPos, dir, fsel, weight, startLevel, step, __log2f(diameter * invVoxel), curSegmentLength);
         const float prevStep = step;
         step += fmaxf(diameter, p.voxel_size) * stepFactor;
         curSegmentLength = step - prevStep;
         diameter = step * coneCoefficient;
     }
-    out[0] = result[0]; out[1] = result[1]; out[2] = result[2];
-    out[3] = 1.0f - occlusion;
+    out[0] = cs.result[0]; out[1] = cs.result[1]; out[2] = cs.result[2];
+    out[3] = 1.0f - cs.occlusion;
+}
+
+// Diffuse cones share aperture and step factor, so their step / diameter sequence is the same for every
+// pixel and cone (it does not depend on the position): the block tabulates it once.
+#define MAX_TABLE_STEPS 160   // 30 / (0.2 * voxelSize0-limited start) never needs more for stepFactor >= 0.2
+struct StepTable {
+    float step[MAX_TABLE_STEPS];
+    float lod[MAX_TABLE_STEPS];
+    int   n;
+};
+
+DEVFN void build_step_table(const TraceParams& tp, StepTable& t, float coneCoefficient, float stepFactor)
+{
+    const vgi_vct_params& p = tp.p;
+    const float invVoxel = 1.0f / p.voxel_size;
+    float step = 0.0f;
+    float diameter = fmaxf(step * coneCoefficient, p.voxel_size);
+    int n = 0;
+    while (step < MAX_TRACE_DISTANCE && n < MAX_TABLE_STEPS) {
+        t.step[n] = step;
+        t.lod[n] = __log2f(diameter * invVoxel);
+        ++n;
+        step += fmaxf(diameter, p.voxel_size) * stepFactor;
+        diameter = step * coneCoefficient;
+    }
+    t.n = (step < MAX_TRACE_DISTANCE) ? -1 : n; // -1: table too small, callers fall back to trace_cone
+}
+
+DEVFN void trace_cone_table(const TraceParams& tp, const StepTable& t, const float* startPos_, const float* dir, float startLevel, float* out)
+{
+    const vgi_vct_params& p = tp.p;
+    ConeState cs = { { 0.f, 0.f, 0.f, 0.f }, 0.0f };
+    const float voxelSize0 = p.voxel_size * exp2f(startLevel);
+    float startPos[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
+    const int fsel = (dir[0] > 0.0f ? 0 : 1) | (dir[1] > 0.0f ? 0 : 2) | (dir[2] > 0.0f ? 0 : 4);
+    const float weight[3] = { dir[0] * dir[0], dir[1] * dir[1], dir[2] * dir[2] };
+    float prevStep = 0.0f;
+    for (int k = 0; k < t.n && cs.occlusion < 1.0f; ++k) {
+        const float step = t.step[k];
+        const float seg = k == 0 ? voxelSize0 : step - prevStep;
+        cone_step(tp, cs, startPos, dir, fsel, weight, startLevel, step, t.lod[k], seg);
+        prevStep = step;
+    }
+    out[0] = cs.result[0]; out[1] = cs.result[1]; out[2] = cs.result[2];
+    out[3] = 1.0f - cs.occlusion;
 }
 
 // ref: voxelConeTracing.frag:394-414
@@ -351,35 +408,111 @@ DEVFN bool pixel_setup(const TraceParams& tp, int px, int py, PixelSetup& s)
 // main pass: diffuse cones + direct term + mode switch; pixels that need a specular cone are
 // appended to a compact list and finished by k_trace_specular (the specular march is up to two
 // orders of magnitude longer than a diffuse cone, Q12, and would stall whole warps).
+//
+// One block = one 8x8 pixel tile. Phase 1: one thread per pixel reconstructs the surface point.
+// Phase 2: the (cone, pixel) pairs that pass the hemisphere test (voxelConeTracing.frag:175-184) are
+// compacted cone-major, so every lane of a warp marches a real cone and neighbouring lanes march the
+// same direction from neighbouring pixels. Phase 3: one thread per pixel adds its cones in the
+// shader's order and finishes the pixel.
+#define TILE_W 8
+#define TILE_H 8
+#define TILE_PIX (TILE_W * TILE_H)
+
+template <int NCONES>
 __global__ void __launch_bounds__(128) k_trace_main(const __grid_constant__ TraceParams tp)
 {
-    const int px = blockIdx.x * 16 + (threadIdx.x & 15);
-    const int py = tp.y0 + blockIdx.y * 8 + (threadIdx.x >> 4);
-    if (px >= tp.width || py >= tp.y1) return;
-    PixelSetup s;
-    if (!pixel_setup(tp, px, py, s)) return;
-    const size_t pi = (size_t)py * tp.width + px;
+    __shared__ float s_pix[8][TILE_PIX];            // startPos xyz, normal xyz, minLevel, valid
+    __shared__ float4 s_res[NCONES][TILE_PIX];      // cone result * cos(theta)
+    __shared__ uint16_t s_list[NCONES * TILE_PIX];
+    __shared__ int s_warp_count[4];
+    __shared__ StepTable s_table;
+
+    const int tid = threadIdx.x;
+    const int tilesX = (tp.width + TILE_W - 1) / TILE_W;
+    const int tx0 = (blockIdx.x % tilesX) * TILE_W, ty0 = tp.y0 + (blockIdx.x / tilesX) * TILE_H;
     const uint32_t mode = tp.p.rendering_mode;
     const bool needCones = mode == 4 || mode == 5 || mode == 7 || mode == 8;
     const bool needDirect = mode == 4 || mode == 5 || mode == 8;
     const bool needSpec = mode == 6 || mode == 8;
+    const float (*cones)[3] = NCONES == 32 ? c_cones32 : c_cones16;
 
+    // ---- phase 1 (the full PixelSetup is rebuilt in phase 3 rather than kept live across the march)
+    const int px = tx0 + (tid & (TILE_W - 1)), py = ty0 + ((tid / TILE_W) & (TILE_H - 1));
+    if (tid < TILE_PIX) {
+        PixelSetup s;
+        bool valid = false;
+        if (px < tp.width && py < tp.y1) valid = pixel_setup(tp, px, py, s);
+        s_pix[0][tid] = s.startPos[0]; s_pix[1][tid] = s.startPos[1]; s_pix[2][tid] = s.startPos[2];
+        s_pix[3][tid] = s.normal[0]; s_pix[4][tid] = s.normal[1]; s_pix[5][tid] = s.normal[2];
+        s_pix[6][tid] = s.minLevel;
+        s_pix[7][tid] = valid ? 1.0f : 0.0f;
+    } else if (tid == 127 && needCones) {
+        build_step_table(tp, s_table, tp.cone_coeff_diffuse, fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor));
+    }
+    __syncthreads();
+
+    if (needCones) {
+        // ---- phase 2a: cone-major compaction; warp w owns slots [w * S/4, (w+1) * S/4)
+        constexpr int SLOTS = NCONES * TILE_PIX, PER_WARP = SLOTS / 4;
+        const int warp = tid >> 5, lane = tid & 31;
+        float cosT[PER_WARP / 32];
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < PER_WARP / 32; ++k) {
+            const int slot = warp * PER_WARP + k * 32 + lane;
+            const int cone = slot / TILE_PIX, pix = slot % TILE_PIX;
+            const float c = s_pix[3][pix] * cones[cone][0] + s_pix[4][pix] * cones[cone][1] + s_pix[5][pix] * cones[cone][2];
+            const bool act = s_pix[7][pix] != 0.0f && !(c < 0.0f);
+            cosT[k] = act ? c : -1.0f;
+            cnt += __popc(__ballot_sync(0xffffffffu, act));
+        }
+        if (lane == 0) s_warp_count[warp] = cnt;
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (w < warp) base += s_warp_count[w];
+            total += s_warp_count[w];
+        }
+#pragma unroll
+        for (int k = 0; k < PER_WARP / 32; ++k) {
+            const int slot = warp * PER_WARP + k * 32 + lane;
+            const bool act = cosT[k] >= 0.0f;
+            const unsigned b = __ballot_sync(0xffffffffu, act);
+            if (act) s_list[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)slot;
+            else s_res[slot / TILE_PIX][slot % TILE_PIX] = make_float4(0.f, 0.f, 0.f, 0.f);
+            base += __popc(b);
+        }
+        __syncthreads();
+        // ---- phase 2b: march
+        for (int i = tid; i < total; i += 128) {
+            const int slot = s_list[i];
+            const int cone = slot / TILE_PIX, pix = slot % TILE_PIX;
+            const float dir[3] = { cones[cone][0], cones[cone][1], cones[cone][2] };
+            const float sp[3] = { s_pix[0][pix], s_pix[1][pix], s_pix[2][pix] };
+            const float cosTheta = s_pix[3][pix] * dir[0] + s_pix[4][pix] * dir[1] + s_pix[5][pix] * dir[2];
+            float c[4];
+            if (s_table.n >= 0) trace_cone_table(tp, s_table, sp, dir, s_pix[6][pix], c);
+            else trace_cone(tp, sp, dir, tp.cone_coeff_diffuse, MAX_TRACE_DISTANCE, s_pix[6][pix],
+                            fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor), c);
+            s_res[cone][pix] = make_float4(c[0] * cosTheta, c[1] * cosTheta, c[2] * cosTheta, c[3] * cosTheta);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3
+    if (tid >= TILE_PIX || s_pix[7][tid] == 0.0f) return;
+    PixelSetup s;
+    pixel_setup(tp, px, py, s);
+    const size_t pi = (size_t)py * tp.width + px;
     float indirect[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
     if (needCones) {
-        const int ncones = tp.p.enable_32_cones ? 32 : 16;
-        const float stepFactor = fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor);
-        for (int i = 0; i < ncones; ++i) {
-            float dir[3];
-            if (tp.p.enable_32_cones) { dir[0] = c_cones32[i][0]; dir[1] = c_cones32[i][1]; dir[2] = c_cones32[i][2]; }
-            else { dir[0] = c_cones16[i][0]; dir[1] = c_cones16[i][1]; dir[2] = c_cones16[i][2]; }
-            const float cosTheta = dot3(s.normal, dir);
-            if (cosTheta < 0.0f) continue;
-            float c[4];
-            trace_cone(tp, s.startPos, dir, tp.cone_coeff_diffuse, MAX_TRACE_DISTANCE, s.minLevel, stepFactor, c);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) indirect[k] += c[k] * cosTheta;
+#pragma unroll 4
+        for (int i = 0; i < NCONES; ++i) {
+            const float4 r = s_res[i][tid];
+            indirect[0] += r.x; indirect[1] += r.y; indirect[2] += r.z; indirect[3] += r.w;
         }
-        const float invN = 1.0f / (float)ncones;
+        const float invN = 1.0f / (float)NCONES;
 #pragma unroll
         for (int k = 0; k < 4; ++k) indirect[k] *= invN;
         indirect[3] *= tp.p.ambient_occlusion_factor;
@@ -473,9 +606,11 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     cudaMemsetAsync(tp.spec_count, 0, sizeof(uint32_t), s);
     const int rows = tp.y1 - tp.y0;
     if (rows <= 0 || tp.width <= 0) return 0;
-    dim3 grid((tp.width + 15) / 16, (rows + 7) / 8);
+    const unsigned grid = (unsigned)(((tp.width + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H));
     c->timer.begin("k_trace_main", s);
-    k_trace_main<<<grid, 128, 0, s>>>(tp); ++n;
+    if (tp.p.enable_32_cones) k_trace_main<32><<<grid, 128, 0, s>>>(tp);
+    else k_trace_main<16><<<grid, 128, 0, s>>>(tp);
+    ++n;
     c->timer.end(s);
     const uint32_t mode = tp.p.rendering_mode;
     if (mode == 6 || mode == 8) {
