@@ -21,7 +21,7 @@ GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 CU_STRICT = ["vgi_build.cu", "vgi_svo.cu"]
 CU_FAST = ["vgi_trace.cu"]
 CPP = ["vgi_api.cpp"]
-HEADERS = ["vgi_internal.h", os.path.join("..", "..", "include", "vgi.h")]
+HEADERS = ["vgi_internal.h", "vgi_device.cuh", os.path.join("..", "..", "include", "vgi.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-ccbin", GXX]

@@ -86,51 +86,70 @@ DEVFN float2 unpack2(uint32_t t, uint32_t selLo, uint32_t selHi)
 // (k_brick_mask writes, for every voxel of a non-empty brick, which of the 8 records of the footprint
 // whose low corner is that voxel may be non-zero); only those records are loaded and filtered.
 // Returns false (out = 0) when all eight records of the footprint are zero.
-DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, int fsel, const float* weight, float* out)
+// Per-cone constants of the three face taps (ref: voxelConeTracing.frag:296-303, 318-326): byte offset of
+// the selected face texel inside a 32-byte record and the squared direction weights (pre-divided by 255).
+struct ConeFaces {
+    uint32_t offX, offY, offZ;
+    float kx, ky, kz;
+};
+
+DEVFN ConeFaces cone_faces(const float* dir)
+{
+    ConeFaces f;
+    f.offX = dir[0] > 0.0f ? 0u : 4u;
+    f.offY = dir[1] > 0.0f ? 8u : 12u;
+    f.offZ = dir[2] > 0.0f ? 16u : 20u;
+    f.kx = (dir[0] * dir[0]) * (1.0f / 255.0f);
+    f.ky = (dir[1] * dir[1]) * (1.0f / 255.0f);
+    f.kz = (dir[2] * dir[2]) * (1.0f / 255.0f);
+    return f;
+}
+
+DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, const ConeFaces& cf, float* out)
 {
     const int R = tp.R, Rm = R - 1, logR = tp.logR;
     const float inv = tp.inv_extent[level];
-    int i0[3];
+    uint32_t i0[3];
     float w[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float t = f_fract(pos[k] * inv) * (float)R - 0.5f;
         const float fl = floorf(t);
         w[k] = t - fl;
-        i0[k] = (int)fl & Rm;
+        i0[k] = (uint32_t)((int)fl & Rm);
     }
     STAT(1, 1);
-    out[0] = out[1] = out[2] = out[3] = 0.0f;
-    const int wpr = R >> 5, nb = R >> 2;
-    const uint8_t bbyte = __ldg(tp.brick_mask + ((size_t)level * nb + (i0[2] >> 2)) * nb * wpr + (size_t)(i0[1] >> 2) * wpr + (i0[0] >> 5));
-    if (!((bbyte >> ((i0[0] >> 2) & 7)) & 1u)) {
+    // 32-bit index arithmetic: L * R^3 <= 8 * 512^3 = 2^30
+    const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
+    const uint32_t bidx = (((((uint32_t)level << nbShift) + (i0[2] >> 2)) << nbShift) + (i0[1] >> 2) << wprShift) + (i0[0] >> 5);
+    const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
+    if (!((bbyte >> ((i0[0] >> 2) & 7u)) & 1u)) {
         STAT(2, 1);
         return false;
     }
-    const size_t vox = ((size_t)level << (3 * logR)) + ((((size_t)i0[2] << logR) + i0[1]) << logR) + i0[0];
+    const uint32_t vox = ((((((uint32_t)level << logR) + i0[2]) << logR) + i0[1]) << logR) + i0[0];
     uint32_t m = __ldg(tp.footprint + vox);
     if (!m) {
         STAT(3, 1);
         return false;
     }
-    const VoxelRecord* base = tp.store + vox;
-    // record offsets of the +1 neighbours (toroidal)
-    const int dx = (i0[0] == Rm) ? -Rm : 1;
-    const int dy = ((i0[1] == Rm) ? -Rm : 1) << logR;
-    const int dz = ((i0[2] == Rm) ? -Rm : 1) << (2 * logR);
+    const char* base = reinterpret_cast<const char*>(tp.store + vox);
+    // byte offsets of the +1 neighbours (toroidal)
+    const int dx = ((i0[0] == (uint32_t)Rm) ? -Rm : 1) * 32;
+    const int dy = (((i0[1] == (uint32_t)Rm) ? -Rm : 1) << logR) * 32;
+    const int dz = (((i0[2] == (uint32_t)Rm) ? -Rm : 1) << (2 * logR)) * 32;
     float2 aX0 = make_float2(0.f, 0.f), aX1 = aX0, aY0 = aX0, aY1 = aX0, aZ0 = aX0, aZ1 = aX0;
     STAT(4, __popc(m));
     do {
         const int c = __ffs(m) - 1;
         m &= m - 1;
-        const int off = ((c & 1) ? dx : 0) + ((c & 2) ? dy : 0) + ((c & 4) ? dz : 0);
-        const float wc = ((c & 1) ? w[0] : 1.0f - w[0]) * ((c & 2) ? w[1] : 1.0f - w[1]) * ((c & 4) ? w[2] : 1.0f - w[2]);
-        const uint4* rec = reinterpret_cast<const uint4*>(base + off);
-        const uint4 lo = __ldg(rec);
-        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(rec + 1));
-        const uint32_t tx = (fsel & 1) ? lo.y : lo.x;
-        const uint32_t ty = (fsel & 2) ? lo.w : lo.z;
-        const uint32_t tz = (fsel & 4) ? hi.y : hi.x;
+        const bool bx = c & 1, by = c & 2, bz = c & 4;
+        const int off = (bx ? dx : 0) + (by ? dy : 0) + (bz ? dz : 0);
+        const float wc = (bx ? w[0] : 1.0f - w[0]) * (by ? w[1] : 1.0f - w[1]) * (bz ? w[2] : 1.0f - w[2]);
+        const char* rec = base + off;
+        const uint32_t tx = __ldg(reinterpret_cast<const uint32_t*>(rec + cf.offX));
+        const uint32_t ty = __ldg(reinterpret_cast<const uint32_t*>(rec + cf.offY));
+        const uint32_t tz = __ldg(reinterpret_cast<const uint32_t*>(rec + cf.offZ));
         const float2 w2 = make_float2(wc, wc);
         aX0 = __ffma2_rn(w2, unpack2(tx, 0x7540u, 0x7541u), aX0);
         aX1 = __ffma2_rn(w2, unpack2(tx, 0x7542u, 0x7543u), aX1);
@@ -140,11 +159,10 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, int 
         aZ1 = __ffma2_rn(w2, unpack2(tz, 0x7542u, 0x7543u), aZ1);
         STAT(5, (tx | ty | tz) != 0u);
     } while (m);
-    const float kx = weight[0] * (1.0f / 255.0f), ky = weight[1] * (1.0f / 255.0f), kz = weight[2] * (1.0f / 255.0f);
-    out[0] = aX0.x * kx + aY0.x * ky + aZ0.x * kz;
-    out[1] = aX0.y * kx + aY0.y * ky + aZ0.y * kz;
-    out[2] = aX1.x * kx + aY1.x * ky + aZ1.x * kz;
-    out[3] = aX1.y * kx + aY1.y * ky + aZ1.y * kz;
+    out[0] = aX0.x * cf.kx + aY0.x * cf.ky + aZ0.x * cf.kz;
+    out[1] = aX0.y * cf.kx + aY0.y * cf.ky + aZ0.y * cf.kz;
+    out[2] = aX1.x * cf.kx + aY1.x * cf.ky + aZ1.x * cf.kz;
+    out[3] = aX1.y * cf.kx + aY1.y * cf.ky + aZ1.y * cf.kz;
     return true;
 }
 
@@ -166,7 +184,7 @@ struct ConeState {
     float occlusion;
 };
 
-DEVFN void cone_step(const TraceParams& tp, ConeState& cs, const float* startPos, const float* dir, int fsel, const float* weight,
+DEVFN void cone_step(const TraceParams& tp, ConeState& cs, const float* startPos, const float* dir, const ConeFaces& cf,
                      float startLevel, float step, float lod, float curSegmentLength)
 {
     const vgi_vct_params& p = tp.p;
@@ -181,13 +199,15 @@ DEVFN void cone_step(const TraceParams& tp, ConeState& cs, const float* startPos
     const float curLevel = fminf(fmaxf(fmaxf(startLevel, lod), minLevel), (float)(tp.L - 1));
     const float fl = floorf(curLevel);
     const float fr = curLevel - fl;
-    float smp[4];
-    bool any = sample_level(tp, position, (int)fl, fsel, weight, smp);
+    float smp[4] = { 0.f, 0.f, 0.f, 0.f };
+    bool any = sample_level(tp, position, (int)fl, cf, smp);
     if (fr > 0.0f) { // Q17: floor == ceil when the level is integral — the second fetch is identical
-        float up[4];
-        any |= sample_level(tp, position, (int)fl + 1, fsel, weight, up);
+        float up[4] = { 0.f, 0.f, 0.f, 0.f };
+        const bool anyUp = sample_level(tp, position, (int)fl + 1, cf, up);
+        if (!(any | anyUp)) return;
 #pragma unroll
         for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
+        any = true;
     }
     if (!any) return; // empty footprints: the accumulators would receive exact zeros
     const float voxelSize = p.voxel_size * exp2f(curLevel);
@@ -215,12 +235,11 @@ DEVFN void trace_cone(const TraceParams& tp, const float* startPos_, const float
     for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
     float step = 0.0f;
     float diameter = fmaxf(step * coneCoefficient, p.voxel_size);
-    const int fsel = (dir[0] > 0.0f ? 0 : 1) | (dir[1] > 0.0f ? 0 : 2) | (dir[2] > 0.0f ? 0 : 4);
-    const float weight[3] = { dir[0] * dir[0], dir[1] * dir[1], dir[2] * dir[2] };
+    const ConeFaces cf = cone_faces(dir);
     float curSegmentLength = voxelSize0;
     const float invVoxel = 1.0f / p.voxel_size;
     while (step < maxDistance && cs.occlusion < 1.0f) {
-        cone_step(tp, cs, startPos, dir, fsel, weight, startLevel, step, __log2f(diameter * invVoxel), curSegmentLength);
+        cone_step(tp, cs, startPos, dir, cf, startLevel, step, __log2f(diameter * invVoxel), curSegmentLength);
         const float prevStep = step;
         step += fmaxf(diameter, p.voxel_size) * stepFactor;
         curSegmentLength = step - prevStep;
@@ -264,13 +283,12 @@ DEVFN void trace_cone_table(const TraceParams& tp, const StepTable& t, const flo
     float startPos[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
-    const int fsel = (dir[0] > 0.0f ? 0 : 1) | (dir[1] > 0.0f ? 0 : 2) | (dir[2] > 0.0f ? 0 : 4);
-    const float weight[3] = { dir[0] * dir[0], dir[1] * dir[1], dir[2] * dir[2] };
+    const ConeFaces cf = cone_faces(dir);
     float prevStep = 0.0f;
     for (int k = 0; k < t.n && cs.occlusion < 1.0f; ++k) {
         const float step = t.step[k];
         const float seg = k == 0 ? voxelSize0 : step - prevStep;
-        cone_step(tp, cs, startPos, dir, fsel, weight, startLevel, step, t.lod[k], seg);
+        cone_step(tp, cs, startPos, dir, cf, startLevel, step, t.lod[k], seg);
         prevStep = step;
     }
     out[0] = cs.result[0]; out[1] = cs.result[1]; out[2] = cs.result[2];
