@@ -37,6 +37,13 @@ def lib():
     return _lib
 
 
+class _DevView:
+    """Borrowed view of library-owned device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
 def _stream(stream=None):
     if stream is not None:
         return C.c_void_p(int(stream))
@@ -188,6 +195,57 @@ class VoxelGI:
                                           C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
                                           C.c_uint32(y0), C.c_uint32(y1), _stream(stream)))
         return out
+
+    # -- sparse voxel octree
+    def svo_voxelize(self, level, bb_min, bb_max, stream=None):
+        self._ck(lib().vgi_svo_voxelize(self._h, C.c_uint32(level), _f3(bb_min), _f3(bb_max), _stream(stream)))
+        self.svo_level = level
+
+    def svo_build(self, stream=None):
+        self._ck(lib().vgi_svo_build(self._h, _stream(stream)))
+
+    def _svo_view(self, getter):
+        torch = self._torch
+        p, n = C.c_void_p(), C.c_uint32()
+        self._ck(getter(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return torch.zeros((0, 2), dtype=torch.int32, device=self.device)
+        # library-owned device memory, copied so that the result survives the next build
+        return torch.as_tensor(_DevView(p.value, (n.value, 2), "<i4"), device=self.device).clone()
+
+    def svo_fragments(self):
+        """(N, 2) int32 CUDA tensor of packed uvec2 fragments (voxelizer.frag:99-100)."""
+        return self._svo_view(lib().vgi_svo_get_fragments)
+
+    def svo_nodes(self):
+        """(N, 2) int32 CUDA tensor of uvec2 nodes {flag | child index, RGBA8}."""
+        return self._svo_view(lib().vgi_svo_get_nodes)
+
+    def svo_cone_trace(self, camera, gbuffer, params, out=None, stream=None):
+        torch = self._torch
+        g = self.gbuffer_struct(gbuffer)
+        if out is None:
+            out = (torch.zeros((g.height, g.width, 4), dtype=torch.float32, device=self.device),
+                   torch.zeros((g.height, g.width, 4), dtype=torch.float32, device=self.device))
+        self._ck(lib().vgi_svo_cone_trace(self._h, C.byref(camera), C.byref(g), C.byref(params),
+                                         C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), _stream(stream)))
+        return out
+
+    # -- helper passes on caller-owned reference-layout atlases (uint8 CUDA tensors of atlas_shape)
+    def atlas_clear_region(self, atlas, min_corner, extent, level, stream=None):
+        self._ck(lib().vgi_atlas_clear_region(self._h, C.c_void_p(atlas.data_ptr()), (C.c_int32 * 3)(*min_corner),
+                                              (C.c_uint32 * 3)(*extent), C.c_uint32(level), _stream(stream)))
+
+    def atlas_copy_alpha(self, dst, src, level, stream=None):
+        self._ck(lib().vgi_atlas_copy_alpha(self._h, C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()),
+                                            C.c_uint32(level), _stream(stream)))
+
+    def atlas_downsample(self, atlas, which, level, stream=None):
+        self._ck(lib().vgi_atlas_downsample(self._h, C.c_void_p(atlas.data_ptr()), C.c_int(which), C.c_uint32(level),
+                                            _stream(stream)))
+
+    def atlas_wrap_border(self, atlas, stream=None):
+        self._ck(lib().vgi_atlas_wrap_border(self._h, C.c_void_p(atlas.data_ptr()), _stream(stream)))
 
     # -- whole frame with host buffers (the e2e call)
     def frame_host(self, frame_index, camera_pos, camera, host_gbuffer, host_shadow_depth, params,

@@ -528,29 +528,9 @@ int vgi_default_vct_params(vgi_ctx* c, vgi_vct_params* p)
     return VGI_OK;
 }
 
-int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
-                        void* out_diffuse, void* out_specular, uint32_t y0, uint32_t y1, void* stream)
+static int fill_trace_params(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                             void* out_diffuse, void* out_specular, uint32_t y0, uint32_t y1, TraceParams& tp)
 {
-    if (!c || !cam || !g || !prm || !out_diffuse || !out_specular) return fail(c, VGI_E_INVALID, "vgi_cone_trace: null argument");
-    if (!g->diffuse_rgba8 || !g->normal_rgba16f || !g->specular_rgba8 || !g->emission_rgba16f || !g->depth_f32 || !g->width || !g->height)
-        return fail(c, VGI_E_INVALID, "vgi_cone_trace: incomplete G-buffer");
-    if (y0 > y1 || y1 > g->height) return fail(c, VGI_E_INVALID, "vgi_cone_trace: bad row range");
-    if (prm->rendering_mode > 8) return fail(c, VGI_E_INVALID, "vgi_cone_trace: rendering_mode out of range");
-    if (!c->built) return fail(c, VGI_E_STATE, "vgi_cone_trace: build the clipmap first");
-    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_cone_trace: call vgi_set_light first");
-    if ((uint32_t)prm->volume_dimension != c->cfg.resolution)
-        return fail(c, VGI_E_INVALID, "vgi_cone_trace: volume_dimension must equal the clipmap resolution");
-    CK(c, cudaSetDevice(c->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t need = (size_t)g->width * g->height + 1;
-    if (c->spec_capacity < need) {
-        CK(c, cudaStreamSynchronize(c->last_stream));
-        cudaFree(c->spec_list);
-        c->spec_list = nullptr;
-        CK(c, cudaMalloc(&c->spec_list, need * sizeof(uint32_t)));
-        c->spec_capacity = need;
-    }
-    TraceParams tp;
     memset(&tp, 0, sizeof tp);
     tp.p = *prm;
     memcpy(tp.view_proj_inv, cam->view_proj_inv, sizeof tp.view_proj_inv);
@@ -598,9 +578,70 @@ int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g,
     // ref: voxelConeTracing.frag:80,117,344 — coneCoefficient = 2 tan(aperture / 2)
     tp.diffuse_aperture = prm->enable_32_cones ? 0.628319f : 0.872665f;
     tp.cone_coeff_diffuse = 2.0f * tanf(tp.diffuse_aperture * 0.5f);
+    return VGI_OK;
+}
+
+static int check_trace_args(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                            void* out_diffuse, void* out_specular, uint32_t y0, uint32_t y1, const char* who)
+{
+    if (!c || !cam || !g || !prm || !out_diffuse || !out_specular) return fail(c, VGI_E_INVALID, std::string(who) + ": null argument");
+    if (!g->diffuse_rgba8 || !g->normal_rgba16f || !g->specular_rgba8 || !g->emission_rgba16f || !g->depth_f32 || !g->width || !g->height)
+        return fail(c, VGI_E_INVALID, std::string(who) + ": incomplete G-buffer");
+    if (y0 > y1 || y1 > g->height) return fail(c, VGI_E_INVALID, std::string(who) + ": bad row range");
+    if (prm->rendering_mode > 8) return fail(c, VGI_E_INVALID, std::string(who) + ": rendering_mode out of range");
+    if (!c->light_set) return fail(c, VGI_E_STATE, std::string(who) + ": call vgi_set_light first");
+    return VGI_OK;
+}
+
+int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                        void* out_diffuse, void* out_specular, uint32_t y0, uint32_t y1, void* stream)
+{
+    int r = check_trace_args(c, cam, g, prm, out_diffuse, out_specular, y0, y1, "vgi_cone_trace");
+    if (r != VGI_OK) return r;
+    if (!c->built) return fail(c, VGI_E_STATE, "vgi_cone_trace: build the clipmap first");
+    if ((uint32_t)prm->volume_dimension != c->cfg.resolution)
+        return fail(c, VGI_E_INVALID, "vgi_cone_trace: volume_dimension must equal the clipmap resolution");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t need = (size_t)g->width * g->height + 1;
+    if (c->spec_capacity < need) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->spec_list);
+        c->spec_list = nullptr;
+        CK(c, cudaMalloc(&c->spec_list, need * sizeof(uint32_t)));
+        c->spec_capacity = need;
+    }
+    TraceParams tp;
+    fill_trace_params(c, cam, g, prm, out_diffuse, out_specular, y0, y1, tp);
     c->launches += vgi_launch_trace(c, tp, s);
     c->last_stream = s;
     return check_launch(c, "vgi_cone_trace");
+}
+
+// replaces: OctreeVoxelConeTracing::onUpdate (OctreeVoxelConeTracing.cpp:74-104) + voxelConeTracing_Octree.frag
+int vgi_svo_cone_trace(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                       void* out_diffuse, void* out_specular, void* stream)
+{
+    int r = check_trace_args(c, cam, g, prm, out_diffuse, out_specular, 0, g ? g->height : 0, "vgi_svo_cone_trace");
+    if (r != VGI_OK) return r;
+    if (!c->svo_built) return fail(c, VGI_E_STATE, "vgi_svo_cone_trace: call vgi_svo_build first");
+    if ((uint32_t)prm->volume_dimension != (1u << c->svo_level))
+        return fail(c, VGI_E_INVALID, "vgi_svo_cone_trace: volume_dimension must equal 2^level of the octree");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TraceParams tp;
+    fill_trace_params(c, cam, g, prm, out_diffuse, out_specular, 0, g->height, tp);
+    tp.svo_nodes = c->svo_nodes;
+    {   // ref: voxelizer.vert:42-47 — the grid of the fragment voxelizer
+        const float ex = c->svo_bb_max[0] - c->svo_bb_min[0], ey = c->svo_bb_max[1] - c->svo_bb_min[1], ez = c->svo_bb_max[2] - c->svo_bb_min[2];
+        const float m = ex > ey ? (ex > ez ? ex : ez) : (ey > ez ? ey : ez);
+        tp.svo_extent = m * 0.5f;
+        for (int k = 0; k < 3; ++k) tp.svo_center[k] = (c->svo_bb_min[k] + c->svo_bb_max[k]) * 0.5f;
+        tp.svo_max_level = (float)((int)c->cfg.level_count - 1);
+    }
+    c->launches += vgi_launch_trace_svo(c, tp, s);
+    c->last_stream = s;
+    return check_launch(c, "vgi_svo_cone_trace");
 }
 
 int vgi_cone_trace(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
@@ -608,6 +649,52 @@ int vgi_cone_trace(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, cons
 {
     if (!g) return fail(c, VGI_E_INVALID, "vgi_cone_trace: null G-buffer");
     return vgi_cone_trace_rows(c, cam, g, prm, out_diffuse, out_specular, 0, g->height, stream);
+}
+
+// ---- helper passes on caller-owned reference-layout atlases --------------------------------------
+
+int vgi_atlas_clear_region(vgi_ctx* c, void* atlas, const int32_t min_corner[3], const uint32_t extent[3], uint32_t level, void* stream)
+{
+    if (!c || !atlas || !min_corner || !extent) return fail(c, VGI_E_INVALID, "vgi_atlas_clear_region: null argument");
+    if (level >= c->cfg.level_count) return fail(c, VGI_E_INVALID, "vgi_atlas_clear_region: level out of range");
+    for (int k = 0; k < 3; ++k)
+        if (extent[k] > c->cfg.resolution) return fail(c, VGI_E_INVALID, "vgi_atlas_clear_region: extent exceeds the resolution");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_atlas_clear((uint8_t*)atlas, (int)c->cfg.resolution, (int)c->cfg.level_count, min_corner, extent, (int)level, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_atlas_clear_region");
+}
+
+int vgi_atlas_copy_alpha(vgi_ctx* c, void* dst_atlas, const void* src_atlas, uint32_t level, void* stream)
+{
+    if (!c || !dst_atlas || !src_atlas) return fail(c, VGI_E_INVALID, "vgi_atlas_copy_alpha: null argument");
+    if (level >= c->cfg.level_count) return fail(c, VGI_E_INVALID, "vgi_atlas_copy_alpha: level out of range");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_atlas_copy_alpha((uint8_t*)dst_atlas, (const uint8_t*)src_atlas, (int)c->cfg.resolution, (int)c->cfg.level_count, (int)level, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_atlas_copy_alpha");
+}
+
+int vgi_atlas_downsample(vgi_ctx* c, void* atlas, int which, uint32_t level, void* stream)
+{
+    if (!c || !atlas || (which != 0 && which != 1)) return fail(c, VGI_E_INVALID, "vgi_atlas_downsample: bad argument");
+    if (level < 1 || level >= c->cfg.level_count) return fail(c, VGI_E_INVALID, "vgi_atlas_downsample: level must be in [1, L)");
+    if (c->cfg.downsample_band > c->cfg.resolution / 4) return fail(c, VGI_E_INVALID, "vgi_atlas_downsample: band exceeds R/4");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_atlas_downsample((uint8_t*)atlas, (int)c->cfg.resolution, (int)c->cfg.level_count, (int)c->cfg.downsample_band,
+                                               c->regions[level - 1].min_corner, (int)level, which, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_atlas_downsample");
+}
+
+int vgi_atlas_wrap_border(vgi_ctx* c, void* atlas, void* stream)
+{
+    if (!c || !atlas) return fail(c, VGI_E_INVALID, "vgi_atlas_wrap_border: null argument");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_atlas_wrap((uint8_t*)atlas, (int)c->cfg.resolution, (int)c->cfg.level_count,
+                                         (c->cfg.mode_flags & VGI_MODE_BORDER_LITERAL) ? 1 : 0, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_atlas_wrap_border");
 }
 
 // ---- whole frame with host buffers ----------------------------------------------------------------

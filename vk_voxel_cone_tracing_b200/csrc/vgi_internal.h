@@ -89,6 +89,8 @@ struct TraceParams {
     int      shadow_compare;
     uint32_t* spec_list;          // compacted pixels needing a specular cone
     uint32_t* spec_count;
+    const uint2* svo_nodes;       // SVO tracer: node pool, grid of the fragment voxelizer
+    float    svo_center[3], svo_extent, svo_max_level;
     float    cone_coeff_diffuse;  // 2*tan(aperture/2), evaluated on the host
     float    diffuse_aperture;
 };
@@ -174,6 +176,7 @@ struct vgi_ctx {
     uint2* svo_nodes = nullptr;
     uint32_t svo_node_capacity = 0;
     uint32_t svo_nfrag = 0, svo_nnodes = 0;
+    bool svo_voxelized = false, svo_built = false;
     float svo_bb_min[3], svo_bb_max[3];
     uint32_t* svo_scratch = nullptr;
     size_t svo_scratch_words = 0;
@@ -184,6 +187,7 @@ int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_export(vgi_ctx* c, int which, uint8_t* dst, int literal_border, cudaStream_t s);
 int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);
+int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);
 int vgi_launch_atlas_clear(uint8_t* atlas, int R, int L, const int32_t* mc, const uint32_t* ext, int level, cudaStream_t s);
 int vgi_launch_atlas_copy_alpha(uint8_t* dst, const uint8_t* src, int R, int L, int level, cudaStream_t s);
 int vgi_launch_atlas_downsample(uint8_t* atlas, int R, int L, int band, const int32_t* prev_min, int level, int which, cudaStream_t s);
