@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--mode", type=int, default=8)
+    ap.add_argument("--svo", type=int, default=0, help="also time the SVO path at this octree level")
     a = ap.parse_args()
     t0 = time.time()
     if a.scene == "atrium":
@@ -63,6 +64,28 @@ def main():
     for k, (ms, n) in gi.timings().items():
         print(f"  {k:20s} {ms / a.iters * 1e3:9.1f} us/frame  ({n // a.iters} launches)")
     gi.set_timing(False)
+    if a.svo:
+        lo, hi = inp["scene"].world_bbox()
+        sprm = gi.default_vct_params(a.mode)
+        sprm.volume_dimension = float(1 << a.svo)
+        sprm.voxel_size = float((hi - lo).max() / (1 << a.svo))
+        sprm.indirect_diffuse_intensity = 15.0
+        sprm.occlusion_decay = 3.0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        sv, sb, stc = [], [], []
+        for i in range(a.iters + 2):
+            ev[0].record()
+            gi.svo_voxelize(a.svo, lo, hi)
+            ev[1].record()
+            gi.svo_build()
+            ev[2].record()
+            so = gi.svo_cone_trace(inp["cam"], gb, sprm)
+            ev[3].record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                sv.append(ev[0].elapsed_time(ev[1])); sb.append(ev[1].elapsed_time(ev[2])); stc.append(ev[2].elapsed_time(ev[3]))
+        st = gi.stats()
+        print(f"SVO level {a.svo}: fragments={st.svo_fragments} nodes={st.svo_nodes} | voxelize {med(sv):.3f} ms | build {med(sb):.3f} ms | trace {med(stc):.3f} ms")
     d = out[0]
     print("diffuse mean", float(d[..., :3].mean()), "spec mean", float(out[1][..., :3].mean()))
 

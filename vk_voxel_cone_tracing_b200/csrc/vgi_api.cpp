@@ -111,7 +111,7 @@ int vgi_destroy(vgi_ctx* c)
     free_scene(c);
     if (c->store_owned) cudaFree(c->store);
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
-    cudaFree(c->brick_mask); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
+    cudaFree(c->brick_mask); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
@@ -306,6 +306,11 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     CK(c, cudaMalloc(&c->pairs, (size_t)c->max_pairs * sizeof(vgi_pair_t)));
     CK(c, cudaMalloc(&c->large, (size_t)c->max_large * sizeof(uint2)));
     CK(c, cudaMalloc(&c->acc, (size_t)c->max_occ * 24 * sizeof(uint32_t)));
+    // visit list per level: this frame's and last frame's non-zero records (each at most occupied + mip-derived)
+    cudaFree(c->visit_list);
+    c->visit_list = nullptr;
+    c->visit_cap = c->max_occ;
+    CK(c, cudaMalloc(&c->visit_list, (size_t)c->visit_cap * L * sizeof(uint32_t)));
     c->voxelized = c->built = false;
     return VGI_OK;
 }

@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4: k_build_level — one launch per clip level writes every record of the level that is, or was last
-// frame, non-zero; all other records are already zero and stay untouched. Per visited voxel it fuses
+// K4: k_level_masks + k_level_records — per clip level, write every record of the level that is, or was
+// last frame, non-zero; all other records are already zero and stay untouched. k_level_masks derives the
+// masks below and a compact work list of the visited voxels; k_level_records (one thread per list entry, so
+// every lane works) fuses per visited voxel
 //   the reference's clears (A4 VoxelizationPass.cpp:104-126, A7 clipmapCleaning.comp),
 //   the raw opacity store (msaaVoxelizer.frag:69-73),
 //   the radiance average (msaaInjectRadiance.frag:185-201, canonical mean) and copy-alpha (A9),
@@ -246,7 +248,8 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
 //   occ[l]  raw occupancy of this frame (k_voxelize)
 //   nz[l]   superset of the non-zero records = occ[l] | centre-half(OR of the 2x2x2 children in nz[l-1])
 //   nzPrev  nz of the previous frame (records that may need clearing)
-// Warp layout: phase 1 lane = mask word (32 voxels along x), phase 2 lane = voxel of one word.
+// k_level_masks: lane = mask word (32 voxels along x); the levels run fine to coarse (nz[l] needs nz[l-1]).
+// k_level_records: levels run fine to coarse as well (the children of level l are the records of l-1).
 // ---------------------------------------------------------------------------------------------------
 // Child pair pr (0..3) of face f in the shader's OFFSETS order (child index = dx + 2 dy + 4 dz):
 // face 2a composites the low-side child over the high-side child along axis a, face 2a+1 the reverse
@@ -290,21 +293,15 @@ DEVFN uint32_t rec_radiance(const Rec& r, int f)
     return f == 0 ? r.lo.x : f == 1 ? r.lo.y : f == 2 ? r.lo.z : f == 3 ? r.lo.w : f == 4 ? r.hi.x : r.hi.y;
 }
 
-__global__ void __launch_bounds__(256) k_build_level(BuildParams bp, int level, const uint32_t* __restrict__ occ,
-                                                      const uint32_t* __restrict__ occ_prefix,
-                                                      const uint32_t* __restrict__ acc, const uint32_t* __restrict__ nzPrev,
-                                                      uint32_t* __restrict__ nzCur, VoxelRecord* __restrict__ store)
+__global__ void __launch_bounds__(256) k_level_masks(BuildParams bp, int level, const uint32_t* __restrict__ occ,
+                                                      const uint32_t* __restrict__ nzPrev, uint32_t* __restrict__ nzCur,
+                                                      uint32_t* __restrict__ visitList, uint32_t listCap, Counters* __restrict__ cnt)
 {
-    __shared__ float s_unorm[256];              // (float)c / 255.0f, exact
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = (float)i / 255.0f;
-    __syncthreads();
-
     const int R = bp.R, Rm = R - 1, half = R >> 1, logR = bp.logR;
     const int wpr = R >> 5;                     // mask words per x row
     const size_t nvox = (size_t)R * R * R;
     const uint32_t wordsPerLevel = (uint32_t)(nvox >> 5);
     const uint32_t* occL = occ + (size_t)level * wordsPerLevel;
-    const uint32_t* prefL = occ_prefix + (size_t)level * wordsPerLevel;
     const uint32_t* prevL = nzPrev + (size_t)level * wordsPerLevel;
     uint32_t* curL = nzCur + (size_t)level * wordsPerLevel;
     const uint32_t* fineL = nzCur + (size_t)(level - 1) * wordsPerLevel;   // valid for level > 0
@@ -315,8 +312,7 @@ __global__ void __launch_bounds__(256) k_build_level(BuildParams bp, int level, 
     const unsigned lane = lane_id();
     const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nchunks = wordsPerLevel >> 5;
-    VoxelRecord* storeL = store + (size_t)level * nvox;
-    const VoxelRecord* storeF = store + (size_t)(level - 1) * nvox;
+    uint32_t* list = visitList + (size_t)level * listCap;
 
     for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warpsPerGrid) {
         // ---- phase 1: lane = mask word
@@ -347,158 +343,197 @@ __global__ void __launch_bounds__(256) k_build_level(BuildParams bp, int level, 
         curL[wi] = nzw;
         const uint32_t visit = nzw | prevw;
 
-        // ---- phase 2: lane = voxel of one non-empty word
-        unsigned todo = __ballot_sync(0xffffffffu, visit != 0u);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t vword = __shfl_sync(0xffffffffu, visit, src);
-            const uint32_t oword = __shfl_sync(0xffffffffu, occw, src);
-            if (!((vword >> lane) & 1u)) continue;
-            const uint32_t wis = chunk * 32u + (uint32_t)src;
-            const int sxw = (int)(wis % (uint32_t)wpr);
-            const uint32_t srow = wis / (uint32_t)wpr;
-            const int vy = (int)(srow & (uint32_t)Rm), vz = (int)(srow >> logR);
-            const int vx = sxw * 32 + (int)lane;
-            VoxelRecord* dstp = storeL + ((((size_t)vz << logR) + vy) << logR) + vx;
-            uint4* dst = reinterpret_cast<uint4*>(dstp);
-            const bool raw = (oword >> lane) & 1u;
-
-            // -- finalize (k_finalize semantics)
-            Rec own;
-            if (inject) {
-                uint32_t rad[6] = { 0, 0, 0, 0, 0, 0 };
-                if (raw) {
-                    const uint32_t idx = __ldg(prefL + wis) + __popc(oword & ((1u << lane) - 1u));
-                    if (idx < bp.max_occ) {
-                        const uint4* a = reinterpret_cast<const uint4*>(acc + (size_t)idx * 24);
+        // ---- append the visited voxels (texel index inside the level) to this level's work list
+        const uint32_t n = (uint32_t)__popc(visit);
+        uint32_t incl = n;
 #pragma unroll
-                        for (int f = 0; f < 6; ++f) {
-                            const uint4 s = a[f];
-                            uint32_t r = 0, g = 0, b = 0;
-                            if (s.w) {
-                                r = (uint32_t)(((unsigned long long)s.x * 255ull) >> 16) / s.w;
-                                g = (uint32_t)(((unsigned long long)s.y * 255ull) >> 16) / s.w;
-                                b = (uint32_t)(((unsigned long long)s.z * 255ull) >> 16) / s.w;
-                                r = r > 255u ? 255u : r; g = g > 255u ? 255u : g; b = b > 255u ? 255u : b;
-                            }
-                            rad[f] = r | (g << 8) | (b << 16) | 0xff000000u; // copy-alpha: opacity.a of an occupied voxel = 1
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!total) continue;
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(&cnt->visit[level], total);
+        base = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
+        for (uint32_t v = visit; v; v &= v - 1) {
+            if (base < listCap) list[base] = wi * 32u + (uint32_t)(__ffs(v) - 1);
+            else atomicOr(&cnt->overflow, 4u);
+            ++base;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level, const uint32_t* __restrict__ occ,
+                                                        const uint32_t* __restrict__ occ_prefix,
+                                                        const uint32_t* __restrict__ acc, const uint32_t* __restrict__ nzCur,
+                                                        const uint32_t* __restrict__ visitList, uint32_t listCap,
+                                                        const Counters* __restrict__ cnt, VoxelRecord* __restrict__ store)
+{
+    __shared__ float s_unorm[256];              // (float)c / 255.0f, exact
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = (float)i / 255.0f;
+    __syncthreads();
+
+    const int R = bp.R, Rm = R - 1, half = R >> 1, logR = bp.logR;
+    const int wpr = R >> 5;
+    const size_t nvox = (size_t)R * R * R;
+    const uint32_t wordsPerLevel = (uint32_t)(nvox >> 5);
+    const uint32_t* occL = occ + (size_t)level * wordsPerLevel;
+    const uint32_t* prefL = occ_prefix + (size_t)level * wordsPerLevel;
+    const uint32_t* fineL = nzCur + (size_t)(level - 1) * wordsPerLevel;   // valid for level > 0
+    const bool inject = (bp.level_mask >> level) & 1u;
+    const bool mip = level > 0;
+    int pm[3] = { 0, 0, 0 };
+    if (mip) { pm[0] = bp.lv[level - 1].min_corner[0] >> 1; pm[1] = bp.lv[level - 1].min_corner[1] >> 1; pm[2] = bp.lv[level - 1].min_corner[2] >> 1; }
+    VoxelRecord* storeL = store + (size_t)level * nvox;
+    const VoxelRecord* storeF = store + (size_t)(level - 1) * nvox;
+    const uint32_t* list = visitList + (size_t)level * listCap;
+    const uint32_t n = min(cnt->visit[level], listCap);
+
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t vid = list[i];
+        const int vx = (int)(vid & (uint32_t)Rm), vy = (int)((vid >> logR) & (uint32_t)Rm), vz = (int)(vid >> (2 * logR));
+        const uint32_t wis = vid >> 5;
+        const uint32_t lane = vid & 31u;
+        const uint32_t oword = __ldg(occL + wis);
+        VoxelRecord* dstp = storeL + ((((size_t)vz << logR) + vy) << logR) + vx;
+        uint4* dst = reinterpret_cast<uint4*>(dstp);
+        const bool raw = (oword >> lane) & 1u;
+
+        // -- finalize (k_finalize semantics)
+        Rec own;
+        if (inject) {
+            uint32_t rad[6] = { 0, 0, 0, 0, 0, 0 };
+            if (raw) {
+                const uint32_t idx = __ldg(prefL + wis) + __popc(oword & ((1u << lane) - 1u));
+                if (idx < bp.max_occ) {
+                    const uint4* a = reinterpret_cast<const uint4*>(acc + (size_t)idx * 24);
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        const uint4 s = a[f];
+                        uint32_t r = 0, g = 0, b = 0;
+                        if (s.w) {
+                            r = (uint32_t)(((unsigned long long)s.x * 255ull) >> 16) / s.w;
+                            g = (uint32_t)(((unsigned long long)s.y * 255ull) >> 16) / s.w;
+                            b = (uint32_t)(((unsigned long long)s.z * 255ull) >> 16) / s.w;
+                            r = r > 255u ? 255u : r; g = g > 255u ? 255u : g; b = b > 255u ? 255u : b;
                         }
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < 6; ++f) rad[f] = 0xff000000u;
+                        rad[f] = r | (g << 8) | (b << 16) | 0xff000000u; // copy-alpha: opacity.a of an occupied voxel = 1
                     }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) rad[f] = 0xff000000u;
                 }
-                own.lo = make_uint4(rad[0], rad[1], rad[2], rad[3]);
-                own.hi.x = rad[4];
-                own.hi.y = rad[5];
-            } else {
-                // off-cadence level: the radiance texels (including their alpha) keep last frame's values
-                own.lo = dst[0];
-                const uint4 old = dst[1];
-                own.hi.x = old.x;
-                own.hi.y = old.y;
             }
-            own.hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
-            own.hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
+            own.lo = make_uint4(rad[0], rad[1], rad[2], rad[3]);
+            own.hi.x = rad[4];
+            own.hi.y = rad[5];
+        } else {
+            // off-cadence level: the radiance texels (including their alpha) keep last frame's values
+            own.lo = dst[0];
+            const uint4 old = dst[1];
+            own.hi.x = old.x;
+            own.hi.y = old.y;
+        }
+        own.hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
+        own.hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
 
-            // -- down-sample of level-1 into the centre half (k_downsample semantics)
-            const int g0 = (vx - pm[0]) & Rm, g1 = (vy - pm[1]) & Rm, g2 = (vz - pm[2]) & Rm;
-            if (mip && g0 < half && g1 < half && g2 < half) {
-                const int g[3] = { g0, g1, g2 };
-                int pstart[3];
-                float dist[3];
+        // -- down-sample of level-1 into the centre half (k_downsample semantics)
+        const int g0 = (vx - pm[0]) & Rm, g1 = (vy - pm[1]) & Rm, g2 = (vz - pm[2]) & Rm;
+        if (mip && g0 < half && g1 < half && g2 < half) {
+            const int g[3] = { g0, g1, g2 };
+            int pstart[3];
+            float dist[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int cur = pm[k] + g[k];
-                    pstart[k] = (cur << 1) & Rm;
-                    const float center = (float)pm[k] + (float)((uint32_t)half >> 1);
-                    dist[k] = fabsf(((float)cur + 0.5f) - center) - 0.5f;
-                }
-                const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)bp.band;
-                const float thr = (float)thrU;
-                const float invBand = 1.0f / ((float)bp.band + 1.0f);
-                float lerpFactor = 0.0f;
-                if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
-                    lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
-                    lerpFactor = lerpFactor * invBand;
-                }
-                // children: index i = dx + 2*dy + 4*dz; records whose nz bit is clear are zero
-                Rec ch[8];
-                uint32_t anyChild = 0u;
+            for (int k = 0; k < 3; ++k) {
+                const int cur = pm[k] + g[k];
+                pstart[k] = (cur << 1) & Rm;
+                const float center = (float)pm[k] + (float)((uint32_t)half >> 1);
+                dist[k] = fabsf(((float)cur + 0.5f) - center) - 0.5f;
+            }
+            const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)bp.band;
+            const float thr = (float)thrU;
+            const float invBand = 1.0f / ((float)bp.band + 1.0f);
+            float lerpFactor = 0.0f;
+            if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
+                lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
+                lerpFactor = lerpFactor * invBand;
+            }
+            // children: index i = dx + 2*dy + 4*dz; records whose nz bit is clear are zero
+            Rec ch[8];
+            uint32_t anyChild = 0u;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int cx = pstart[0] + (i & 1), cy = pstart[1] + ((i >> 1) & 1), cz = pstart[2] + (i >> 2);
-                    const size_t crow = ((size_t)cz << logR) + (size_t)cy;
-                    const uint32_t fw = fineL[crow * wpr + (cx >> 5)];
-                    ch[i].lo = make_uint4(0, 0, 0, 0);
-                    ch[i].hi = make_uint4(0, 0, 0, 0);
-                    if ((fw >> (cx & 31)) & 1u) {
-                        const uint4* srcp = reinterpret_cast<const uint4*>(storeF + (crow << logR) + cx);
-                        ch[i].lo = srcp[0];
-                        ch[i].hi = srcp[1];
-                        anyChild = 1u;
+            for (int i = 0; i < 8; ++i) {
+                const int cx = pstart[0] + (i & 1), cy = pstart[1] + ((i >> 1) & 1), cz = pstart[2] + (i >> 2);
+                const size_t crow = ((size_t)cz << logR) + (size_t)cy;
+                const uint32_t fw = fineL[crow * wpr + (cx >> 5)];
+                ch[i].lo = make_uint4(0, 0, 0, 0);
+                ch[i].hi = make_uint4(0, 0, 0, 0);
+                if ((fw >> (cx & 31)) & 1u) {
+                    const uint4* srcp = reinterpret_cast<const uint4*>(storeF + (crow << logR) + cx);
+                    ch[i].lo = srcp[0];
+                    ch[i].hi = srcp[1];
+                    anyChild = 1u;
+                }
+            }
+            const float ownRaw = raw ? 1.0f : 0.0f; // opacity.r of this level
+            uint32_t newOp[6], newRad[6];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+                float s = 0.0f;
+                if (anyChild) {
+#pragma unroll
+                    for (int pr = 0; pr < 4; ++pr) {
+                        const int i0 = ds_pair_first(f, pr), i1 = ds_pair_second(f, pr);
+                        const uint32_t w0 = f < 4 ? ch[i0].hi.z : ch[i0].hi.w;
+                        const uint32_t w1 = f < 4 ? ch[i1].hi.z : ch[i1].hi.w;
+                        const float a0 = s_unorm[(w0 >> (8 * (f & 3))) & 0xffu];
+                        const float a1 = s_unorm[(w1 >> (8 * (f & 3))) & 0xffu];
+                        s = s + a0;
+                        s = s + (1.0f - a0) * a1;
                     }
                 }
-                const float ownRaw = raw ? 1.0f : 0.0f; // opacity.r of this level
-                uint32_t newOp[6], newRad[6];
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    float s = 0.0f;
+                const float dsOp = s * 0.25f;
+                const uint32_t aOp = f_to_unorm8(f_mix(dsOp, ownRaw, lerpFactor));
+                newOp[f] = aOp;
+                if (inject) {
+                    const uint32_t ow = rec_radiance(own, f);
+                    // own texel: rgb as injected, alpha = this level's final opacity alpha (copy-alpha ran before the radiance mips)
+                    const uint32_t ownTexel = (ow & 0x00ffffffu) | (aOp << 24);
+                    float sc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
                     if (anyChild) {
 #pragma unroll
                         for (int pr = 0; pr < 4; ++pr) {
-                            const int i0 = ds_pair_first(f, pr), i1 = ds_pair_second(f, pr);
-                            const uint32_t w0 = f < 4 ? ch[i0].hi.z : ch[i0].hi.w;
-                            const uint32_t w1 = f < 4 ? ch[i1].hi.z : ch[i1].hi.w;
-                            const float a0 = s_unorm[(w0 >> (8 * (f & 3))) & 0xffu];
-                            const float a1 = s_unorm[(w1 >> (8 * (f & 3))) & 0xffu];
-                            s = s + a0;
-                            s = s + (1.0f - a0) * a1;
-                        }
-                    }
-                    const float dsOp = s * 0.25f;
-                    const uint32_t aOp = f_to_unorm8(f_mix(dsOp, ownRaw, lerpFactor));
-                    newOp[f] = aOp;
-                    if (inject) {
-                        const uint32_t ow = rec_radiance(own, f);
-                        // own texel: rgb as injected, alpha = this level's final opacity alpha (copy-alpha ran before the radiance mips)
-                        const uint32_t ownTexel = (ow & 0x00ffffffu) | (aOp << 24);
-                        float sc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-                        if (anyChild) {
+                            const uint32_t w0 = rec_radiance(ch[ds_pair_first(f, pr)], f);
+                            const uint32_t w1 = rec_radiance(ch[ds_pair_second(f, pr)], f);
+                            if ((w0 | w1) == 0u) continue;      // adds exact zeros
+                            const float k1 = 1.0f - s_unorm[w0 >> 24];
 #pragma unroll
-                            for (int pr = 0; pr < 4; ++pr) {
-                                const uint32_t w0 = rec_radiance(ch[ds_pair_first(f, pr)], f);
-                                const uint32_t w1 = rec_radiance(ch[ds_pair_second(f, pr)], f);
-                                if ((w0 | w1) == 0u) continue;      // adds exact zeros
-                                const float k1 = 1.0f - s_unorm[w0 >> 24];
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    sc[c] = sc[c] + s_unorm[(w0 >> (8 * c)) & 0xffu];
-                                    sc[c] = sc[c] + k1 * s_unorm[(w1 >> (8 * c)) & 0xffu];
-                                }
+                            for (int c = 0; c < 4; ++c) {
+                                sc[c] = sc[c] + s_unorm[(w0 >> (8 * c)) & 0xffu];
+                                sc[c] = sc[c] + k1 * s_unorm[(w1 >> (8 * c)) & 0xffu];
                             }
                         }
-                        uint32_t out = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float ds = sc[c] * 0.25f;
-                            out |= f_to_unorm8(f_mix(ds, s_unorm[(ownTexel >> (8 * c)) & 0xffu], lerpFactor)) << (8 * c);
-                        }
-                        newRad[f] = out;
                     }
+                    uint32_t out = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float ds = sc[c] * 0.25f;
+                        out |= f_to_unorm8(f_mix(ds, s_unorm[(ownTexel >> (8 * c)) & 0xffu], lerpFactor)) << (8 * c);
+                    }
+                    newRad[f] = out;
                 }
-                if (inject) {
-                    own.lo = make_uint4(newRad[0], newRad[1], newRad[2], newRad[3]);
-                    own.hi.x = newRad[4];
-                    own.hi.y = newRad[5];
-                }
-                own.hi.z = newOp[0] | (newOp[1] << 8) | (newOp[2] << 16) | (newOp[3] << 24);
-                own.hi.w = (own.hi.w & 0xffff0000u) | newOp[4] | (newOp[5] << 8);
             }
-            dst[0] = own.lo;
-            dst[1] = own.hi;
+            if (inject) {
+                own.lo = make_uint4(newRad[0], newRad[1], newRad[2], newRad[3]);
+                own.hi.x = newRad[4];
+                own.hi.y = newRad[5];
+            }
+            own.hi.z = newOp[0] | (newOp[1] << 8) | (newOp[2] << 16) | (newOp[3] << 24);
+            own.hi.w = (own.hi.w & 0xffff0000u) | newOp[4] | (newOp[5] << 8);
         }
+        dst[0] = own.lo;
+        dst[1] = own.hi;
     }
 }
 
@@ -633,9 +668,10 @@ int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s
     const int cur = c->nz_cur ^ 1;
     const uint32_t chunks = (uint32_t)((((size_t)bp.R * bp.R * bp.R) >> 5) >> 5);
     const unsigned grid = min(cdiv(chunks, 8), 148u * 16u);
-    for (int l = 0; l < bp.L; ++l) {
-        LAUNCH("k_build_level", k_build_level<<<grid, 256, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur ^ 1], c->nz[cur], c->store));
-    }
+    for (int l = 0; l < bp.L; ++l)
+        LAUNCH("k_level_masks", k_level_masks<<<grid, 256, 0, s>>>(bp, l, c->occ, c->nz[cur ^ 1], c->nz[cur], c->visit_list, c->visit_cap, c->counters));
+    for (int l = 0; l < bp.L; ++l)
+        LAUNCH("k_level_records", k_level_records<<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store));
     const size_t nbytes = (size_t)(bp.R >> 2) * (bp.R >> 2) * (bp.R >> 5) * bp.L;
     LAUNCH("k_brick_mask", k_brick_mask<<<cdiv(nbytes, 128), 128, 0, s>>>(bp.R, bp.L, bp.logR, c->nz[cur], c->brick_mask, c->footprint));
     c->nz_cur = cur;

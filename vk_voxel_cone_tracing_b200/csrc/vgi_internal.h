@@ -67,6 +67,7 @@ struct Counters {
     uint32_t svo_counter;
     uint32_t svo_alloc_begin;
     uint32_t svo_alloc_num;
+    uint32_t visit[VGI_MAX_LEVELS]; // entries in each level's visit list (k_level_masks)
     uint32_t pad[7];
 };
 
@@ -150,6 +151,8 @@ struct vgi_ctx {
     uint32_t* nz[2] = { nullptr, nullptr }; // non-zero-record masks, ping-pong between frames (L * R^3/32 words each)
     int nz_cur = 0;
     uint8_t* brick_mask = nullptr;
+    uint32_t* visit_list = nullptr;  // L segments of visit_cap voxel ids (records to rewrite this frame)
+    uint32_t visit_cap = 0;
     uint8_t* footprint = nullptr;   // L * R^3 bytes, valid where the brick bit is set
     Counters* counters = nullptr;
     Counters* h_counters = nullptr; // pinned
