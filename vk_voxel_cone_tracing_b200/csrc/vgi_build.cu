@@ -176,60 +176,58 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
             }
         }
         // quad phase: round r serves the pairs of lanes 8r..8r+7, quad q serves lane 8r+q
-        float vis = 0.0f;
         const unsigned lit = __ballot_sync(0xffffffffu, ps.kind == 2);
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            if (!((lit >> (8 * r)) & 0xffu)) continue;
-            const unsigned src = 8u * (unsigned)r + (lane >> 2);
-            const float qpx = __shfl_sync(0xffffffffu, ps.px, src);
-            const float qpy = __shfl_sync(0xffffffffu, ps.py, src);
-            const float qcz = __shfl_sync(0xffffffffu, ps.cmpz, src);
-            const bool need = (lit >> src) & 1u;
-            const float v = quad_visibility(lp, qpx, qpy, compare, qcz, need);
-            // hand the result back to the owning lane: lane l (in round l/8) reads quad l%8
-            const float back = __shfl_sync(0xffffffffu, v, (lane & 7u) * 4u);
-            if ((int)(lane >> 3) == r) vis = back;
-        }
-        if (ps.kind == 0) continue;
+        const float vis = warp_visibility(lp, ps.px, ps.py, ps.cmpz, compare, lit);
+        // contribution of this lane: up to 6 faces x (r, g, b) in 16.16 fixed point
         const vgi_material* m = materials + ps.mat;
-        int faces[6];
-        uint32_t q[6][3];
-        int nf = 0;
+        uint32_t q[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+        uint32_t fcode = 0u;            // lit: sign bits of the three faces; emissive: 8
+        bool contrib = false;
         if (ps.kind == 1) {
-            const uint32_t q0 = (uint32_t)(f_clamp(m->emissive_factor[0], 0.0f, 1.0f) * 65536.0f + 0.5f);
-            const uint32_t q1 = (uint32_t)(f_clamp(m->emissive_factor[1], 0.0f, 1.0f) * 65536.0f + 0.5f);
-            const uint32_t q2 = (uint32_t)(f_clamp(m->emissive_factor[2], 0.0f, 1.0f) * 65536.0f + 0.5f);
-#pragma unroll
-            for (int f = 0; f < 6; ++f) { faces[f] = f; q[f][0] = q0; q[f][1] = q1; q[f][2] = q2; }
-            nf = 6;
-        } else {
+            q[0][0] = (uint32_t)(f_clamp(m->emissive_factor[0], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            q[0][1] = (uint32_t)(f_clamp(m->emissive_factor[1], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            q[0][2] = (uint32_t)(f_clamp(m->emissive_factor[2], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            fcode = 8u;
+            contrib = true;
+        } else if (ps.kind == 2) {
             float lc[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) lc[k] = ((ps.NdotL * vis) * lp.color[k]) * lp.intensity;
-            if (lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f) continue;
-            float rad[3];
+            if (!(lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f)) {
+                float rad[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                rad[k] = f_clamp((lc[k] * m->base_color_factor[k]) * m->base_color_factor[3], 0.0f, 1.0f);
-            faces[0] = (-ps.n[0] > 0.0f) ? 0 : 1;
-            faces[1] = (-ps.n[1] > 0.0f) ? 2 : 3;
-            faces[2] = (-ps.n[2] > 0.0f) ? 4 : 5;
+                for (int k = 0; k < 3; ++k)
+                    rad[k] = f_clamp((lc[k] * m->base_color_factor[k]) * m->base_color_factor[3], 0.0f, 1.0f);
+                // faces selected by -normal (ref: msaaInjectRadiance.frag:152-153): 0/1 = +X/-X, ...
+                fcode = ((-ps.n[0] > 0.0f) ? 0u : 1u) | ((-ps.n[1] > 0.0f) ? 0u : 2u) | ((-ps.n[2] > 0.0f) ? 0u : 4u);
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    const float w = fabsf(ps.n[f]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) q[f][k] = (uint32_t)((rad[k] * w) * 65536.0f + 0.5f);
+                }
+                contrib = true;
+            }
+        }
+        if (!contrib) continue;
+        // two 32-bit sums per 64-bit reduction: {r, g} and {b, count} of a face are adjacent words, and a sum
+        // cannot carry into its neighbour before it would overflow its own 32 bits
+        unsigned long long* a = reinterpret_cast<unsigned long long*>(acc + (size_t)ps.cell * 24);
+        if (fcode == 8u) {
+            const unsigned long long rg = ((unsigned long long)q[0][1] << 32) | q[0][0];
+            const unsigned long long bn = (1ull << 32) | q[0][2];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+                atomicAdd(a + f * 2 + 0, rg);
+                atomicAdd(a + f * 2 + 1, bn);
+            }
+        } else {
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
-                const float w = fabsf(ps.n[f]);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) q[f][k] = (uint32_t)((rad[k] * w) * 65536.0f + 0.5f);
+                unsigned long long* af = a + (2 * f + ((fcode >> f) & 1u)) * 2;
+                atomicAdd(af + 0, ((unsigned long long)q[f][1] << 32) | q[f][0]);
+                atomicAdd(af + 1, (1ull << 32) | q[f][2]);
             }
-            nf = 3;
-        }
-        uint32_t* a = acc + (size_t)ps.cell * 24;
-        for (int f = 0; f < nf; ++f) {
-            uint32_t* af = a + faces[f] * 4;
-            atomicAdd(af + 0, q[f][0]);
-            atomicAdd(af + 1, q[f][1]);
-            atomicAdd(af + 2, q[f][2]);
-            atomicAdd(af + 3, 1u);
         }
     }
 }

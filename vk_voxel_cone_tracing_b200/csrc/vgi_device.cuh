@@ -189,16 +189,20 @@ DEVFN float calc_visibility(const LightParams& lp, const float* worldPos, bool c
 DEVFN bool inject_sample_at(int a, const float N[3], const float p[9], const float n9[9], float c[3],
                             float pos[3], float nrm[3])
 {
-    const float Na = N[a];
+    // component selects instead of dynamic indexing keep the vertex arrays in registers
+#define SEL3(arr, base, i) ((i) == 0 ? (arr)[(base)] : ((i) == 1 ? (arr)[(base) + 1] : (arr)[(base) + 2]))
+    const float Na = SEL3(N, 0, a);
     if (Na == 0.0f) return false;
     const float d[3] = { c[0] - p[0], c[1] - p[1], c[2] - p[2] };
     const float t = dot3(N, d) / Na;
-    c[a] = c[a] - t;
+    if (a == 0) c[0] = c[0] - t; else if (a == 1) c[1] = c[1] - t; else c[2] = c[2] - t;
     const int u = (a == 0) ? 1 : 0;
     const int v = (a == 2) ? 1 : 2;
-    const float e1u = p[3 + u] - p[u], e1v = p[3 + v] - p[v];
-    const float e2u = p[6 + u] - p[u], e2v = p[6 + v] - p[v];
-    const float cu = c[u] - p[u], cv = c[v] - p[v];
+    const float p0u = SEL3(p, 0, u), p0v = SEL3(p, 0, v);
+    const float e1u = SEL3(p, 3, u) - p0u, e1v = SEL3(p, 3, v) - p0v;
+    const float e2u = SEL3(p, 6, u) - p0u, e2v = SEL3(p, 6, v) - p0v;
+    const float cu = SEL3(c, 0, u) - p0u, cv = SEL3(c, 0, v) - p0v;
+#undef SEL3
     const float den = e1u * e2v - e2u * e1v;
     if (den == 0.0f) return false;
     float b1 = (cu * e2v - e2u * cv) / den;
@@ -238,68 +242,90 @@ DEVFN float bilinear_mix(float t00, float t10, float t01, float t11, float a, fl
 // instead of 64 scattered loads. Every tap keeps its own (ix, iy, a, b) and the taps are summed in
 // the shader's order, so the result is bit-identical to calc_visibility(); pairs whose taps do not
 // tile the block (float rounding at a texel boundary) take the scalar path.
-DEVFN float quad_visibility(const LightParams& lp, float px, float py, bool compare, float cmpz, bool need)
+// Split in two so that a caller can issue the loads of several rounds before consuming any of them.
+struct QuadTexels {
+    float c[5], e, e4;
+    bool quad_ok;
+};
+
+struct QuadCoords {
+    float a, b[4];
+    int ix, iy[4];
+};
+
+DEVFN void quad_coords(const LightParams& lp, float px, float py, QuadCoords& q)
 {
-    const unsigned lane = lane_id();
-    const int i = (int)(lane & 3u);
-    const unsigned qbase = lane & ~3u;
+    const int i = (int)(lane_id() & 3u);
     const float sx = 1.0f / (float)lp.sw, sy = 1.0f / (float)lp.sh;
-    // column i
     const float ox = -1.5f + (float)i;
     const float x = (px + ox * sx) * (float)lp.sw - 0.5f;
     const float fx = floorf(x);
-    const float a = x - fx;
-    const int ix = (int)f_clamp(fx, -4.0f, (float)lp.sw + 4.0f);
-    float b[4];
-    int iy[4];
+    q.a = x - fx;
+    q.ix = (int)f_clamp(fx, -4.0f, (float)lp.sw + 4.0f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float oy = -1.5f + (float)j;
         const float y = (py + oy * sy) * (float)lp.sh - 0.5f;
         const float fy = floorf(y);
-        b[j] = y - fy;
-        iy[j] = (int)f_clamp(fy, -4.0f, (float)lp.sh + 4.0f);
+        q.b[j] = y - fy;
+        q.iy[j] = (int)f_clamp(fy, -4.0f, (float)lp.sh + 4.0f);
     }
-    const int ix0 = __shfl_sync(0xffffffffu, ix, qbase);
-    const bool tiles = (ix == ix0 + i) && (iy[1] == iy[0] + 1) && (iy[2] == iy[0] + 2) && (iy[3] == iy[0] + 3);
+}
+
+// stage 1: issue the block loads of this quad's pair (all lanes of the warp must call)
+DEVFN void quad_visibility_load(const LightParams& lp, float px, float py, bool need, QuadTexels& t)
+{
+    const unsigned lane = lane_id();
+    const int i = (int)(lane & 3u);
+    const unsigned qbase = lane & ~3u;
+    QuadCoords q;
+    quad_coords(lp, px, py, q);
+    const int ix0 = __shfl_sync(0xffffffffu, q.ix, qbase);
+    const bool tiles = (q.ix == ix0 + i) && (q.iy[1] == q.iy[0] + 1) && (q.iy[2] == q.iy[0] + 2) && (q.iy[3] == q.iy[0] + 3);
     const unsigned okmask = __ballot_sync(0xffffffffu, tiles || !need);
-    const bool quad_ok = ((okmask >> qbase) & 0xfu) == 0xfu;
-    float tap[4] = { 0.f, 0.f, 0.f, 0.f };
-    // block loads (all lanes run the shuffles; loads are predicated)
-    float c[5], e = 0.0f, e4 = 0.0f;
-    const bool ld = need && quad_ok;
+    t.quad_ok = ((okmask >> qbase) & 0xfu) == 0xfu;
+    const bool ld = need && t.quad_ok;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) c[k] = ld ? shadow_texel(lp, ix0 + i, iy[0] + k) : 0.0f;
-    if (ld) {
-        e = shadow_texel(lp, ix0 + 4, iy[0] + i);
-        e4 = shadow_texel(lp, ix0 + 4, iy[0] + 4);
-    }
+    for (int k = 0; k < 5; ++k) t.c[k] = ld ? shadow_texel(lp, ix0 + i, q.iy[0] + k) : 0.0f;
+    t.e = ld ? shadow_texel(lp, ix0 + 4, q.iy[0] + i) : 0.0f;
+    t.e4 = ld ? shadow_texel(lp, ix0 + 4, q.iy[0] + 4) : 0.0f;
+}
+
+// stage 2: exchange, filter and sum (all lanes of the warp must call)
+DEVFN float quad_visibility_finish(const LightParams& lp, float px, float py, bool compare, float cmpz, bool need, QuadTexels& t)
+{
+    const unsigned lane = lane_id();
+    const int i = (int)(lane & 3u);
+    const unsigned qbase = lane & ~3u;
+    QuadCoords q;
+    quad_coords(lp, px, py, q);
     if (compare) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) c[k] = c[k] >= cmpz ? 1.0f : 0.0f;
-        e = e >= cmpz ? 1.0f : 0.0f;
-        e4 = e4 >= cmpz ? 1.0f : 0.0f;
+        for (int k = 0; k < 5; ++k) t.c[k] = t.c[k] >= cmpz ? 1.0f : 0.0f;
+        t.e = t.e >= cmpz ? 1.0f : 0.0f;
+        t.e4 = t.e4 >= cmpz ? 1.0f : 0.0f;
     }
     float r[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const float right = __shfl_sync(0xffffffffu, c[k], (lane + 1u) & 31u);
-        const float edge = __shfl_sync(0xffffffffu, e, qbase + (unsigned)(k < 4 ? k : 3));
-        r[k] = (i < 3) ? right : (k < 4 ? edge : e4);
+        const float right = __shfl_sync(0xffffffffu, t.c[k], (lane + 1u) & 31u);
+        const float edge = __shfl_sync(0xffffffffu, t.e, qbase + (unsigned)(k < 4 ? k : 3));
+        r[k] = (i < 3) ? right : (k < 4 ? edge : t.e4);
     }
+    float tap[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) tap[j] = bilinear_mix(c[j], r[j], c[j + 1], r[j + 1], a, b[j]);
-    if (need && !quad_ok) {
+    for (int j = 0; j < 4; ++j) tap[j] = bilinear_mix(t.c[j], r[j], t.c[j + 1], r[j + 1], q.a, q.b[j]);
+    if (need && !t.quad_ok) {
         // scalar path for this column's four taps
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float t00 = shadow_texel(lp, ix, iy[j]), t10 = shadow_texel(lp, ix + 1, iy[j]);
-            float t01 = shadow_texel(lp, ix, iy[j] + 1), t11 = shadow_texel(lp, ix + 1, iy[j] + 1);
+            float t00 = shadow_texel(lp, q.ix, q.iy[j]), t10 = shadow_texel(lp, q.ix + 1, q.iy[j]);
+            float t01 = shadow_texel(lp, q.ix, q.iy[j] + 1), t11 = shadow_texel(lp, q.ix + 1, q.iy[j] + 1);
             if (compare) {
                 t00 = t00 >= cmpz ? 1.0f : 0.0f; t10 = t10 >= cmpz ? 1.0f : 0.0f;
                 t01 = t01 >= cmpz ? 1.0f : 0.0f; t11 = t11 >= cmpz ? 1.0f : 0.0f;
             }
-            tap[j] = bilinear_mix(t00, t10, t01, t11, a, b[j]);
+            tap[j] = bilinear_mix(t00, t10, t01, t11, q.a, q.b[j]);
         }
     }
     // sum in the shader's order: rows j outer, columns i inner
@@ -309,6 +335,41 @@ DEVFN float quad_visibility(const LightParams& lp, float px, float py, bool comp
 #pragma unroll
         for (int k = 0; k < 4; ++k) sum += __shfl_sync(0xffffffffu, tap[j], qbase + (unsigned)k);
     return sum * 0.0625f;
+}
+
+DEVFN float quad_visibility(const LightParams& lp, float px, float py, bool compare, float cmpz, bool need)
+{
+    QuadTexels t;
+    quad_visibility_load(lp, px, py, need, t);
+    return quad_visibility_finish(lp, px, py, compare, cmpz, need, t);
+}
+
+// Visibility of the 32 pairs of a warp (one per lane, kind == lit where `lit` has the lane's bit): four
+// rounds of eight quads; the loads of all rounds are issued before the first is consumed.
+DEVFN float warp_visibility(const LightParams& lp, float px, float py, float cmpz, bool compare, unsigned lit)
+{
+    const unsigned lane = lane_id();
+    float vis = 0.0f;
+    if (!lit) return vis;
+    QuadTexels t[4];
+    float qpx[4], qpy[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned src = 8u * (unsigned)r + (lane >> 2);
+        qpx[r] = __shfl_sync(0xffffffffu, px, src);
+        qpy[r] = __shfl_sync(0xffffffffu, py, src);
+        quad_visibility_load(lp, qpx[r], qpy[r], (lit >> src) & 1u, t[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned src = 8u * (unsigned)r + (lane >> 2);
+        const float qcz = __shfl_sync(0xffffffffu, cmpz, src);
+        const float v = quad_visibility_finish(lp, qpx[r], qpy[r], compare, qcz, (lit >> src) & 1u, t[r]);
+        // hand the result back to the owning lane: lane l (in round l/8) reads quad l%8
+        const float back = __shfl_sync(0xffffffffu, v, (lane & 7u) * 4u);
+        if ((int)(lane >> 3) == r) vis = back;
+    }
+    return vis;
 }
 
 // ---------------------------------------------------------------------------------------------------

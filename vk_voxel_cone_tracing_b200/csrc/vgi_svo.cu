@@ -189,20 +189,8 @@ __global__ void __launch_bounds__(256) k_svo_shade(SvoGrid g, LightParams lp, in
                 }
             }
         }
-        float vis = 0.0f;
         const unsigned lit = __ballot_sync(0xffffffffu, kind == 2);
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            if (!((lit >> (8 * r)) & 0xffu)) continue;
-            const unsigned src = 8u * (unsigned)r + (lane >> 2);
-            const float qpx = __shfl_sync(0xffffffffu, spx, src);
-            const float qpy = __shfl_sync(0xffffffffu, spy, src);
-            const float qcz = __shfl_sync(0xffffffffu, scz, src);
-            const bool need = (lit >> src) & 1u;
-            const float v = quad_visibility(lp, qpx, qpy, compare, qcz, need);
-            const float back = __shfl_sync(0xffffffffu, v, (lane & 7u) * 4u);
-            if ((int)(lane >> 3) == r) vis = back;
-        }
+        const float vis = warp_visibility(lp, spx, spy, scz, compare, lit);
         float radiance[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
         bool emit = kind != 0;
         if (kind == 1) {
