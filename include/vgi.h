@@ -231,6 +231,24 @@ int    vgi_bind_voxel_store(vgi_ctx* ctx, void* dev_ptr, size_t bytes);
 /* Restrict vgi_build_clipmap's record writes to z in [z0,z1) (slab sharding); default [0,R). */
 int    vgi_set_slab(vgi_ctx* ctx, uint32_t z0, uint32_t z1);
 
+/* ---- slab-sharded clipmap build (one ctx per GPU; the collectives stay with the caller) --------
+ * GPU g owns the texel planes z in [z0,z1) of every level (vgi_set_slab); the z-slowest layout makes a slab
+ * of the occupancy words one contiguous range per level. Sequence per frame, identical on every rank:
+ *   vgi_slab_build_begin   voxelize + inject the own slab
+ *   all-gather of the occupancy words in place (vgi_get_occupancy; e.g. ncclAllGather per level)
+ *   vgi_slab_finalize      masks of the whole volume, own-slab records written and packed for exchange
+ *   all-gather of the packed records (vgi_get_slab_pack), vgi_slab_unpack for every other rank's buffer
+ *   vgi_slab_build_end     opacity + radiance mips (replicated) and the tracer's empty-space masks
+ * The result equals vgi_build_clipmap on one GPU bit for bit. */
+int vgi_slab_build_begin(vgi_ctx* ctx, uint32_t frame_index, void* stream);
+/* occupancy words: level l at dev_ptr + l * bytes_per_level; planes [z0,z1) = bytes [z0*R*R/8, z1*R*R/8) */
+int vgi_get_occupancy(vgi_ctx* ctx, void** dev_ptr, size_t* bytes_per_level);
+int vgi_slab_finalize(vgi_ctx* ctx, uint32_t frame_index, void* stream);
+/* ids: count x u32 (level << 27 | texel index), recs: count x 32-byte records; synchronises the stream */
+int vgi_get_slab_pack(vgi_ctx* ctx, void** ids, void** recs, uint32_t* count);
+int vgi_slab_unpack(vgi_ctx* ctx, const void* ids, const void* recs, uint32_t count, void* stream);
+int vgi_slab_build_end(vgi_ctx* ctx, uint32_t frame_index, void* stream);
+
 /* ---- cone tracing --------------------------------------------------------------------------- */
 /* replaces: VoxelConeTracingPass::onUpdate (VoxelConeTracingPass.cpp:75-106) + voxelConeTracing.frag.
  * out_diffuse / out_specular: width*height float4 (R32G32B32A32_SFLOAT, VoxelConeTracingPass.cpp:141-144).

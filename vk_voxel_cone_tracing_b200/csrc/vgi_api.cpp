@@ -111,7 +111,7 @@ int vgi_destroy(vgi_ctx* c)
     free_scene(c);
     if (c->store_owned) cudaFree(c->store);
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
-    cudaFree(c->brick_mask); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
+    cudaFree(c->brick_mask); cudaFree(c->slab_ids); cudaFree(c->slab_recs); cudaFree(c->slab_count); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
@@ -509,6 +509,92 @@ int vgi_set_slab(vgi_ctx* c, uint32_t z0, uint32_t z1)
     c->z0 = (int)z0;
     c->z1 = (int)z1;
     return VGI_OK;
+}
+
+// ---- slab-sharded build ----------------------------------------------------------------------------
+
+int vgi_slab_build_begin(vgi_ctx* c, uint32_t frame_index, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_slab_build_begin: null ctx");
+    if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_slab_build_begin: call vgi_set_scene first");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_slab_build_begin: call vgi_set_light first");
+    CK(c, cudaSetDevice(c->device));
+    if (!c->slab_ids) {
+        c->slab_cap = c->max_occ;
+        CK(c, cudaMalloc(&c->slab_ids, (size_t)c->slab_cap * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&c->slab_recs, (size_t)c->slab_cap * 2 * sizeof(uint4)));
+        CK(c, cudaMalloc(&c->slab_count, sizeof(uint32_t)));
+    }
+    BuildParams bp;
+    build_params_from_ctx(c, frame_index, &bp);
+    cudaStream_t s = (cudaStream_t)stream;
+    c->launches += vgi_launch_slab_begin(c, bp, s);
+    c->last_stream = s;
+    c->slab_phase = 1;
+    return check_launch(c, "vgi_slab_build_begin");
+}
+
+int vgi_get_occupancy(vgi_ctx* c, void** dev_ptr, size_t* bytes_per_level)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_get_occupancy: null ctx");
+    if (dev_ptr) *dev_ptr = c->occ;
+    if (bytes_per_level) *bytes_per_level = ((size_t)c->cfg.resolution * c->cfg.resolution * c->cfg.resolution) >> 3;
+    return VGI_OK;
+}
+
+int vgi_slab_finalize(vgi_ctx* c, uint32_t frame_index, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_slab_finalize: null ctx");
+    if (c->slab_phase != 1) return fail(c, VGI_E_STATE, "vgi_slab_finalize: call vgi_slab_build_begin first");
+    CK(c, cudaSetDevice(c->device));
+    BuildParams bp;
+    build_params_from_ctx(c, frame_index, &bp);
+    cudaStream_t s = (cudaStream_t)stream;
+    c->launches += vgi_launch_slab_finalize(c, bp, s);
+    c->last_stream = s;
+    c->slab_phase = 2;
+    return check_launch(c, "vgi_slab_finalize");
+}
+
+int vgi_get_slab_pack(vgi_ctx* c, void** ids, void** recs, uint32_t* count)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_get_slab_pack: null ctx");
+    if (c->slab_phase != 2) return fail(c, VGI_E_STATE, "vgi_get_slab_pack: call vgi_slab_finalize first");
+    uint32_t n = 0;
+    CK(c, cudaMemcpyAsync(&n, c->slab_count, sizeof n, cudaMemcpyDeviceToHost, c->last_stream));
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    if (n > c->slab_cap || (c->h_counters->overflow & 4u))
+        return fail(c, VGI_E_OVERFLOW, "vgi_get_slab_pack: exchange buffer overflow — raise vgi_config.max_fragments");
+    if (ids) *ids = c->slab_ids;
+    if (recs) *recs = c->slab_recs;
+    if (count) *count = n;
+    return VGI_OK;
+}
+
+int vgi_slab_unpack(vgi_ctx* c, const void* ids, const void* recs, uint32_t count, void* stream)
+{
+    if (!c || (count && (!ids || !recs))) return fail(c, VGI_E_INVALID, "vgi_slab_unpack: null argument");
+    if (c->slab_phase != 2) return fail(c, VGI_E_STATE, "vgi_slab_unpack: call vgi_slab_finalize first");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_slab_unpack(c, (const uint32_t*)ids, (const uint4*)recs, count, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_slab_unpack");
+}
+
+int vgi_slab_build_end(vgi_ctx* c, uint32_t frame_index, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_slab_build_end: null ctx");
+    if (c->slab_phase != 2) return fail(c, VGI_E_STATE, "vgi_slab_build_end: call vgi_slab_finalize first");
+    CK(c, cudaSetDevice(c->device));
+    BuildParams bp;
+    build_params_from_ctx(c, frame_index, &bp);
+    cudaStream_t s = (cudaStream_t)stream;
+    c->launches += vgi_launch_slab_end(c, bp, s);
+    c->last_stream = s;
+    c->slab_phase = 0;
+    c->voxelized = false;
+    c->built = true;
+    return check_launch(c, "vgi_slab_build_end");
 }
 
 // ---- cone tracing -----------------------------------------------------------------------------------

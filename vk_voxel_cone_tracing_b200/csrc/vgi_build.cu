@@ -17,6 +17,7 @@ DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair
 {
     const int Rm = bp.R - 1;
     const uint32_t x = vx & Rm, y = vy & Rm, z = vz & Rm;
+    if ((int)z < bp.z0 || (int)z >= bp.z1) return;   // slab-sharded build: this GPU owns texel planes [z0, z1)
     const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
     const size_t w = (size_t)level * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
     const uint32_t bit = 1u << (x & 31u);
@@ -362,11 +363,22 @@ __global__ void __launch_bounds__(256) k_level_masks(BuildParams bp, int level, 
     }
 }
 
+// MODE 0: fused finalize + mip (single GPU). Slab-sharded build: MODE 1 finalizes the
+// records of this GPU's z slab only and appends them to the exchange buffer; MODE 2 runs the mips on the
+// gathered store (own record read back instead of recomputed).
+struct SlabPack {
+    uint32_t* ids;      // level << 27 | texel index
+    uint4*    recs;     // 2 x uint4 per record
+    uint32_t* count;
+    uint32_t  cap;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level, const uint32_t* __restrict__ occ,
                                                         const uint32_t* __restrict__ occ_prefix,
                                                         const uint32_t* __restrict__ acc, const uint32_t* __restrict__ nzCur,
                                                         const uint32_t* __restrict__ visitList, uint32_t listCap,
-                                                        const Counters* __restrict__ cnt, VoxelRecord* __restrict__ store)
+                                                        Counters* __restrict__ cnt, VoxelRecord* __restrict__ store, SlabPack pack)
 {
     __shared__ float s_unorm[256];              // (float)c / 255.0f, exact
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = (float)i / 255.0f;
@@ -393,14 +405,21 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
         const int vx = (int)(vid & (uint32_t)Rm), vy = (int)((vid >> logR) & (uint32_t)Rm), vz = (int)(vid >> (2 * logR));
         const uint32_t wis = vid >> 5;
         const uint32_t lane = vid & 31u;
+        if (MODE == 1 && (vz < bp.z0 || vz >= bp.z1)) continue;
         const uint32_t oword = __ldg(occL + wis);
         VoxelRecord* dstp = storeL + ((((size_t)vz << logR) + vy) << logR) + vx;
         uint4* dst = reinterpret_cast<uint4*>(dstp);
         const bool raw = (oword >> lane) & 1u;
+        const int g0 = (vx - pm[0]) & Rm, g1 = (vy - pm[1]) & Rm, g2 = (vz - pm[2]) & Rm;
+        const bool centre = mip && g0 < half && g1 < half && g2 < half;
+        if (MODE == 2 && !centre) continue;
 
         // -- finalize (k_finalize semantics)
         Rec own;
-        if (inject) {
+        if (MODE == 2) {
+            own.lo = dst[0];
+            own.hi = dst[1];
+        } else if (inject) {
             uint32_t rad[6] = { 0, 0, 0, 0, 0, 0 };
             if (raw) {
                 const uint32_t idx = __ldg(prefL + wis) + __popc(oword & ((1u << lane) - 1u));
@@ -433,12 +452,26 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
             own.hi.x = old.x;
             own.hi.y = old.y;
         }
-        own.hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
-        own.hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
+        if (MODE != 2) {
+            own.hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
+            own.hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
+        }
+        if (MODE == 1) {
+            dst[0] = own.lo;
+            dst[1] = own.hi;
+            const uint32_t slot = atomicAdd(pack.count, 1u);
+            if (slot < pack.cap) {
+                pack.ids[slot] = ((uint32_t)level << 27) | vid;
+                pack.recs[2 * (size_t)slot] = own.lo;
+                pack.recs[2 * (size_t)slot + 1] = own.hi;
+            } else {
+                atomicOr(&cnt->overflow, 4u);
+            }
+            continue;
+        }
 
         // -- down-sample of level-1 into the centre half (k_downsample semantics)
-        const int g0 = (vx - pm[0]) & Rm, g1 = (vy - pm[1]) & Rm, g2 = (vz - pm[2]) & Rm;
-        if (mip && g0 < half && g1 < half && g2 < half) {
+        if (centre) {
             const int g[3] = { g0, g1, g2 };
             int pstart[3];
             float dist[3];
@@ -654,7 +687,21 @@ int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
     return n;
 }
 
-int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+static void launch_masks(vgi_ctx* c, const BuildParams& bp, int cur, cudaStream_t s, int& n)
+{
+    const uint32_t chunks = (uint32_t)((((size_t)bp.R * bp.R * bp.R) >> 5) >> 5);
+    const unsigned grid = min(cdiv(chunks, 8), 148u * 16u);
+    for (int l = 0; l < bp.L; ++l)
+        LAUNCH("k_level_masks", k_level_masks<<<grid, 256, 0, s>>>(bp, l, c->occ, c->nz[cur ^ 1], c->nz[cur], c->visit_list, c->visit_cap, c->counters));
+}
+
+static void launch_brick(vgi_ctx* c, const BuildParams& bp, int cur, cudaStream_t s, int& n)
+{
+    const size_t nbytes = (size_t)(bp.R >> 2) * (bp.R >> 2) * (bp.R >> 5) * bp.L;
+    LAUNCH("k_brick_mask", k_brick_mask<<<cdiv(nbytes, 128), 128, 0, s>>>(bp.R, bp.L, bp.logR, c->nz[cur], c->brick_mask, c->footprint));
+}
+
+static int launch_inject(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
     int n = 0;
     LAUNCH("k_zero_acc", k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ));
@@ -662,18 +709,75 @@ int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s
         LAUNCH("k_inject", k_inject<<<148 * 8, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
                                                             c->occ, c->occ_prefix, c->acc, c->counters));
     }
+    return n;
+}
+
+int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    int n = launch_inject(c, bp, s);
     // nz masks ping-pong between frames: nz[cur] is written by this build, nz[cur ^ 1] is last frame's
     const int cur = c->nz_cur ^ 1;
-    const uint32_t chunks = (uint32_t)((((size_t)bp.R * bp.R * bp.R) >> 5) >> 5);
-    const unsigned grid = min(cdiv(chunks, 8), 148u * 16u);
+    launch_masks(c, bp, cur, s, n);
+    const SlabPack none = { nullptr, nullptr, nullptr, 0u };
     for (int l = 0; l < bp.L; ++l)
-        LAUNCH("k_level_masks", k_level_masks<<<grid, 256, 0, s>>>(bp, l, c->occ, c->nz[cur ^ 1], c->nz[cur], c->visit_list, c->visit_cap, c->counters));
-    for (int l = 0; l < bp.L; ++l)
-        LAUNCH("k_level_records", k_level_records<<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store));
-    const size_t nbytes = (size_t)(bp.R >> 2) * (bp.R >> 2) * (bp.R >> 5) * bp.L;
-    LAUNCH("k_brick_mask", k_brick_mask<<<cdiv(nbytes, 128), 128, 0, s>>>(bp.R, bp.L, bp.logR, c->nz[cur], c->brick_mask, c->footprint));
+        LAUNCH("k_level_records", k_level_records<0><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
+    launch_brick(c, bp, cur, s, n);
     c->nz_cur = cur;
     cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
+    return n;
+}
+
+// ---- slab-sharded build (multi-GPU) --------------------------------------------
+// records received from the other GPUs -> store
+__global__ void __launch_bounds__(256) k_slab_unpack(int R, const uint32_t* __restrict__ ids, const uint4* __restrict__ recs, uint32_t count,
+                                                      VoxelRecord* __restrict__ store)
+{
+    const size_t nvox = (size_t)R * R * R;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        uint4* dst = reinterpret_cast<uint4*>(store + (size_t)(id >> 27) * nvox + (id & 0x07ffffffu));
+        dst[0] = recs[2 * (size_t)i];
+        dst[1] = recs[2 * (size_t)i + 1];
+    }
+}
+
+int vgi_launch_slab_begin(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    int n = vgi_launch_voxelize(c, bp, s);
+    n += launch_inject(c, bp, s);
+    return n;
+}
+
+int vgi_launch_slab_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    int n = 0;
+    const int cur = c->nz_cur ^ 1;
+    cudaMemsetAsync(c->slab_count, 0, sizeof(uint32_t), s);
+    launch_masks(c, bp, cur, s, n);
+    const SlabPack pack = { c->slab_ids, c->slab_recs, c->slab_count, c->slab_cap };
+    for (int l = 0; l < bp.L; ++l)
+        LAUNCH("k_level_records_slab", k_level_records<1><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, pack));
+    cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
+    return n;
+}
+
+int vgi_launch_slab_unpack(vgi_ctx* c, const uint32_t* ids, const uint4* recs, uint32_t count, cudaStream_t s)
+{
+    int n = 0;
+    if (!count) return 0;
+    LAUNCH("k_slab_unpack", k_slab_unpack<<<min(cdiv(count, 256), 148u * 8u), 256, 0, s>>>((int)c->cfg.resolution, ids, recs, count, c->store));
+    return n;
+}
+
+int vgi_launch_slab_end(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    int n = 0;
+    const int cur = c->nz_cur ^ 1;
+    const SlabPack none = { nullptr, nullptr, nullptr, 0u };
+    for (int l = 1; l < bp.L; ++l)
+        LAUNCH("k_level_records_mip", k_level_records<2><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
+    launch_brick(c, bp, cur, s, n);
+    c->nz_cur = cur;
     return n;
 }
 

@@ -151,6 +151,12 @@ struct vgi_ctx {
     uint32_t* nz[2] = { nullptr, nullptr }; // non-zero-record masks, ping-pong between frames (L * R^3/32 words each)
     int nz_cur = 0;
     uint8_t* brick_mask = nullptr;
+    // slab-sharded build: exchange buffer of this GPU's finalized records
+    uint32_t* slab_ids = nullptr;
+    uint4*    slab_recs = nullptr;
+    uint32_t* slab_count = nullptr;
+    uint32_t  slab_cap = 0;
+    int       slab_phase = 0;        // 0 idle, 1 begun, 2 finalized
     uint32_t* visit_list = nullptr;  // L segments of visit_cap voxel ids (records to rewrite this frame)
     uint32_t visit_cap = 0;
     uint8_t* footprint = nullptr;   // L * R^3 bytes, valid where the brick bit is set
@@ -188,6 +194,10 @@ struct vgi_ctx {
 // ---- launch wrappers implemented in the .cu files (return number of kernels launched) ------------
 int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
+int vgi_launch_slab_begin(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
+int vgi_launch_slab_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
+int vgi_launch_slab_unpack(vgi_ctx* c, const uint32_t* ids, const uint4* recs, uint32_t count, cudaStream_t s);
+int vgi_launch_slab_end(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_export(vgi_ctx* c, int which, uint8_t* dst, int literal_border, cudaStream_t s);
 int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);
 int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);
