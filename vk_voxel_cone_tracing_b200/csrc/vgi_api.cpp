@@ -112,6 +112,7 @@ int vgi_destroy(vgi_ctx* c)
     if (c->store_owned) cudaFree(c->store);
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
     cudaFree(c->brick_mask); cudaFree(c->slab_ids); cudaFree(c->slab_recs); cudaFree(c->slab_count); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_inputs); cudaEventDestroy(c->ev_main_done); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_copy_done); }
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
@@ -664,8 +665,9 @@ static int fill_trace_params(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffe
     tp.out_specular = (float4*)out_specular;
     tp.light = c->light;
     tp.shadow_compare = (c->cfg.mode_flags & VGI_MODE_SHADOW_COMPARE) ? 1 : 0;
-    tp.spec_list = c->spec_list + 1;
+    tp.spec_list = c->spec_list + 2;
     tp.spec_count = c->spec_list;
+    tp.spec_cursor = c->spec_list + 1;
     // ref: voxelConeTracing.frag:80,117,344 — coneCoefficient = 2 tan(aperture / 2)
     tp.diffuse_aperture = prm->enable_32_cones ? 0.628319f : 0.872665f;
     tp.cone_coeff_diffuse = 2.0f * tanf(tp.diffuse_aperture * 0.5f);
@@ -694,7 +696,7 @@ int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g,
         return fail(c, VGI_E_INVALID, "vgi_cone_trace: volume_dimension must equal the clipmap resolution");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t need = (size_t)g->width * g->height + 1;
+    const size_t need = (size_t)g->width * g->height + 2;
     if (c->spec_capacity < need) {
         CK(c, cudaStreamSynchronize(c->last_stream));
         cudaFree(c->spec_list);
@@ -808,6 +810,7 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     if (c->stage_bytes < need) {
         CK(c, cudaStreamSynchronize(c->last_stream));
         cudaFree(c->stage);
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_inputs); cudaEventDestroy(c->ev_main_done); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_copy_done); }
         c->stage = nullptr;
         c->stage_bytes = 0;
         CK(c, cudaMalloc(&c->stage, need));
@@ -820,11 +823,19 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     uint8_t* d_dif = d_emi + npx * 8;
     uint8_t* d_spc = d_dif + npx * 4;
     uint8_t* d_dep = d_spc + npx * 4;
-    CK(c, cudaMemcpyAsync(d_nrm, hg->normal_rgba16f, npx * 8, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(d_emi, hg->emission_rgba16f, npx * 8, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(d_dif, hg->diffuse_rgba8, npx * 4, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(d_spc, hg->specular_rgba8, npx * 4, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(d_dep, hg->depth_f32, npx * 4, cudaMemcpyHostToDevice, s));
+    if (!c->copy_stream) {
+        CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_main_done, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = c->copy_stream;
+    // fork: the copy stream starts where the caller's stream is now
+    CK(c, cudaEventRecord(c->ev_fork, s));
+    CK(c, cudaStreamWaitEvent(cs, c->ev_fork, 0));
+    // main stream: shadow map (needed by the injection) then the build; copy stream: the G-buffer, which only the
+    // tracer needs, travels while the clipmap is built
     if (host_shadow_depth) {
         const size_t sb = (size_t)c->light.sw * c->light.sh * sizeof(float);
         if (!c->shadow_owned || c->shadow_owned_bytes < sb) {
@@ -837,6 +848,14 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
         CK(c, cudaMemcpyAsync(c->shadow_owned, host_shadow_depth, sb, cudaMemcpyHostToDevice, s));
         c->light.depth = c->shadow_owned;
     }
+    CK(c, cudaMemcpyAsync(d_nrm, hg->normal_rgba16f, npx * 8, cudaMemcpyHostToDevice, cs));
+    CK(c, cudaMemcpyAsync(d_emi, hg->emission_rgba16f, npx * 8, cudaMemcpyHostToDevice, cs));
+    CK(c, cudaMemcpyAsync(d_dif, hg->diffuse_rgba8, npx * 4, cudaMemcpyHostToDevice, cs));
+    CK(c, cudaMemcpyAsync(d_spc, hg->specular_rgba8, npx * 4, cudaMemcpyHostToDevice, cs));
+    CK(c, cudaMemcpyAsync(d_dep, hg->depth_f32, npx * 4, cudaMemcpyHostToDevice, cs));
+    // discarded pixels (depth == 1) are left untouched by the tracer: give them a defined value
+    CK(c, cudaMemsetAsync(d_out_d, 0, npx * 32, cs));
+    CK(c, cudaEventRecord(c->ev_inputs, cs));
     int r = vgi_update_regions(c, camera_pos);
     if (r != VGI_OK) return r;
     r = vgi_build_clipmap(c, frame_index, stream);
@@ -847,12 +866,18 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     vgi_gbuffer dg;
     dg.diffuse_rgba8 = d_dif; dg.normal_rgba16f = d_nrm; dg.specular_rgba8 = d_spc; dg.emission_rgba16f = d_emi;
     dg.depth_f32 = (const float*)d_dep; dg.width = hg->width; dg.height = hg->height;
-    // discarded pixels (depth == 1) are left untouched by the tracer: give them a defined value
-    CK(c, cudaMemsetAsync(d_out_d, 0, npx * 32, s));
+    CK(c, cudaStreamWaitEvent(s, c->ev_inputs, 0));
+    c->mark_main_done = c->ev_main_done;
     r = vgi_cone_trace(c, cam, &dg, &prm, d_out_d, d_out_s, stream);
+    c->mark_main_done = nullptr;
     if (r != VGI_OK) return r;
-    CK(c, cudaMemcpyAsync(host_out_diffuse, d_out_d, npx * 16, cudaMemcpyDeviceToHost, s));
+    // the diffuse image is final after the main kernel: it goes home while the specular cones march
+    CK(c, cudaStreamWaitEvent(cs, c->ev_main_done, 0));
+    CK(c, cudaMemcpyAsync(host_out_diffuse, d_out_d, npx * 16, cudaMemcpyDeviceToHost, cs));
+    CK(c, cudaEventRecord(c->ev_copy_done, cs));
     CK(c, cudaMemcpyAsync(host_out_specular, d_out_s, npx * 16, cudaMemcpyDeviceToHost, s));
+    // join: the caller's stream is complete only when the side copies are
+    CK(c, cudaStreamWaitEvent(s, c->ev_copy_done, 0));
     CK(c, cudaStreamSynchronize(s));
     return VGI_OK;
 }

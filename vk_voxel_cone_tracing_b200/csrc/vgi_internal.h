@@ -90,6 +90,7 @@ struct TraceParams {
     int      shadow_compare;
     uint32_t* spec_list;          // compacted pixels needing a specular cone
     uint32_t* spec_count;
+    uint32_t* spec_cursor;        // next unclaimed entry of spec_list (k_trace_specular)
     const uint2* svo_nodes;       // SVO tracer: node pool, grid of the fragment voxelizer
     float    svo_center[3], svo_extent, svo_max_level;
     float    cone_coeff_diffuse;  // 2*tan(aperture/2), evaluated on the host
@@ -173,6 +174,10 @@ struct vgi_ctx {
     uint32_t* spec_list = nullptr;
     size_t spec_capacity = 0;
 
+    // vgi_frame_host: second stream + events so that PCIe copies overlap the kernels
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_inputs = nullptr, ev_main_done = nullptr, ev_fork = nullptr, ev_copy_done = nullptr;
+    cudaEvent_t mark_main_done = nullptr; // when set, vgi_launch_trace records it after k_trace_main
     // vgi_frame_host staging (device copies of the host G-buffer and of both output images)
     uint8_t* stage = nullptr;
     size_t stage_bytes = 0;

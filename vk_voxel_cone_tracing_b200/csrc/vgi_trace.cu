@@ -436,8 +436,14 @@ DEVFN bool pixel_setup(const TraceParams& tp, int px, int py, PixelSetup& s)
 #define TILE_H 8
 #define TILE_PIX (TILE_W * TILE_H)
 
+#ifndef VGI_TRACE_MAIN_MINBLOCKS
+#define VGI_TRACE_MAIN_MINBLOCKS 1
+#endif
+#ifndef VGI_TRACE_SPEC_MINBLOCKS
+#define VGI_TRACE_SPEC_MINBLOCKS 1
+#endif
 template <int NCONES>
-__global__ void __launch_bounds__(128) k_trace_main(const __grid_constant__ TraceParams tp)
+__global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(const __grid_constant__ TraceParams tp)
 {
     __shared__ float s_pix[8][TILE_PIX];            // startPos xyz, normal xyz, minLevel, valid
     __shared__ float4 s_res[NCONES][TILE_PIX];      // cone result * cos(theta)
@@ -596,25 +602,78 @@ __global__ void __launch_bounds__(128) k_trace_main(const __grid_constant__ Trac
 }
 
 // ref: voxelConeTracing.frag:205-216 (stepFactor = uVoxelSize, Q12)
-__global__ void __launch_bounds__(128) k_trace_specular(const __grid_constant__ TraceParams tp)
+// Specular marches differ by two orders of magnitude in length (aperture from the roughness, early exit on
+// full occlusion), so pixels are not bound to lanes: a lane that finishes its cone immediately claims the
+// next pixel of the compacted list from a global cursor (warp-aggregated atomic), and every lane of a warp
+// executes one marching step per loop iteration.
+__global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specular(const __grid_constant__ TraceParams tp)
 {
     const uint32_t n = *tp.spec_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pi = tp.spec_list[i];
-        const int px = (int)(pi % (uint32_t)tp.width), py = (int)(pi / (uint32_t)tp.width);
-        PixelSetup s;
-        if (!pixel_setup(tp, px, py, s)) continue;
-        // reflect(-view, normal) = I - 2 dot(N, I) N
-        const float I[3] = { -s.view[0], -s.view[1], -s.view[2] };
-        const float dn = dot3(s.normal, I);
-        const float dir[3] = { I[0] - 2.0f * dn * s.normal[0], I[1] - 2.0f * dn * s.normal[1], I[2] - 2.0f * dn * s.normal[2] };
-        const float aperture = fmaxf(s.perceptualRoughness, MIN_SPECULAR_APERTURE);
-        float c[4];
-        trace_cone(tp, s.startPos, dir, 2.0f * tanf(aperture * 0.5f), MAX_TRACE_DISTANCE, s.minLevel, tp.p.voxel_size, c);
-        float4 o = make_float4(c[0] * s.specularColor[0] * tp.p.indirect_specular_intensity,
-                               c[1] * s.specularColor[1] * tp.p.indirect_specular_intensity,
-                               c[2] * s.specularColor[2] * tp.p.indirect_specular_intensity, 1.0f);
-        tp.out_specular[pi] = o;
+    const unsigned lane = threadIdx.x & 31u;
+    const vgi_vct_params& p = tp.p;
+    const float invVoxel = 1.0f / p.voxel_size;
+    const float stepFactor = p.voxel_size;
+    bool active = false, exhausted = false;
+    // per-lane cone state
+    ConeState cs = { { 0.f, 0.f, 0.f, 0.f }, 0.0f };
+    ConeFaces cf = { 0u, 8u, 16u, 0.f, 0.f, 0.f };
+    float startPos[3] = { 0.f, 0.f, 0.f }, dir[3] = { 0.f, 0.f, 1.f }, spec[3] = { 0.f, 0.f, 0.f };
+    float step = 0.0f, diameter = 0.0f, seg = 0.0f, startLevel = 0.0f, coneCoefficient = 0.0f;
+    uint32_t pi = 0u;
+    for (;;) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(0xffffffffu, !active && !exhausted);
+        if (idle) {
+            uint32_t base = 0u;
+            if (lane == (unsigned)(__ffs(idle) - 1)) base = atomicAdd(tp.spec_cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+            if (!active && !exhausted) {
+                const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
+                if (item >= n) {
+                    exhausted = true;
+                } else {
+                    pi = tp.spec_list[item];
+                    const int px = (int)(pi % (uint32_t)tp.width), py = (int)(pi / (uint32_t)tp.width);
+                    PixelSetup s;
+                    if (pixel_setup(tp, px, py, s)) {
+                        // reflect(-view, normal) = I - 2 dot(N, I) N
+                        const float I[3] = { -s.view[0], -s.view[1], -s.view[2] };
+                        const float dn = dot3(s.normal, I);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) dir[k] = I[k] - 2.0f * dn * s.normal[k];
+                        const float aperture = fmaxf(s.perceptualRoughness, MIN_SPECULAR_APERTURE);
+                        coneCoefficient = 2.0f * tanf(aperture * 0.5f);
+                        startLevel = s.minLevel;
+                        const float voxelSize0 = p.voxel_size * exp2f(startLevel);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            startPos[k] = s.startPos[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
+                            spec[k] = s.specularColor[k] * p.indirect_specular_intensity;
+                        }
+                        cf = cone_faces(dir);
+                        cs.result[0] = cs.result[1] = cs.result[2] = cs.result[3] = 0.0f;
+                        cs.occlusion = 0.0f;
+                        step = 0.0f;
+                        diameter = fmaxf(step * coneCoefficient, p.voxel_size);
+                        seg = voxelSize0;
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        // ---- one marching step per active lane
+        if (active) {
+            cone_step(tp, cs, startPos, dir, cf, startLevel, step, __log2f(diameter * invVoxel), seg);
+            const float prevStep = step;
+            step += fmaxf(diameter, p.voxel_size) * stepFactor;
+            seg = step - prevStep;
+            diameter = step * coneCoefficient;
+            if (!(step < MAX_TRACE_DISTANCE && cs.occlusion < 1.0f)) {
+                tp.out_specular[pi] = make_float4(cs.result[0] * spec[0], cs.result[1] * spec[1], cs.result[2] * spec[2], 1.0f);
+                active = false;
+            }
+        }
     }
 }
 
@@ -831,7 +890,7 @@ int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
 int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
 {
     int n = 0;
-    cudaMemsetAsync(tp.spec_count, 0, sizeof(uint32_t), s);
+    cudaMemsetAsync(tp.spec_count, 0, 2 * sizeof(uint32_t), s); // list length + work cursor
     const int rows = tp.y1 - tp.y0;
     if (rows <= 0 || tp.width <= 0) return 0;
     const unsigned grid = (unsigned)(((tp.width + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H));
@@ -840,10 +899,11 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     else k_trace_main<16><<<grid, 128, 0, s>>>(tp);
     ++n;
     c->timer.end(s);
+    if (c->mark_main_done) cudaEventRecord(c->mark_main_done, s); // the diffuse image is complete here
     const uint32_t mode = tp.p.rendering_mode;
     if (mode == 6 || mode == 8) {
         c->timer.begin("k_trace_specular", s);
-        k_trace_specular<<<148 * 8, 128, 0, s>>>(tp); ++n;
+        k_trace_specular<<<148 * 5, 128, 0, s>>>(tp); ++n;
         c->timer.end(s);
     }
     return n;
