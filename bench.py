@@ -28,6 +28,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# keep stdout for the one JSON line: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
@@ -135,6 +137,7 @@ class CpuFrameSampler:
         from oracle import pyoracle as O
         from vk_voxel_cone_tracing_b200 import structs as S
         O.build()
+        self.threads = O.set_threads(cpu_cores())   # torchrun exports OMP_NUM_THREADS=1: use every host core
         self.O, self.inp = O, inp
         self.cfg = inp["cfg"]
         self.regs = O.regions(self.cfg, inp["cam_pos"])
@@ -229,7 +232,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 texels)",
         "data": "synthetic", "config": {"workload": WORKLOAD},
         "stages": {"build_ms": 1e3 * build_s, "trace_ms": 1e3 * trace_s, "sample_wall_s": wall},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu_cores(), "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": smp.threads, "kind": "port",
                          "sample": CpuFrameSampler.SAMPLE},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -443,7 +446,7 @@ def run_vgi(args):
         for _ in range(LEVELS):
             smp.step()
         b_s, t_s = smp.frame_seconds()
-        cpu = {"value": 1.0 / (b_s + t_s), "unit": "frames/s", "cores": cpu_cores(), "kind": "port",
+        cpu = {"value": 1.0 / (b_s + t_s), "unit": "frames/s", "cores": smp.threads, "kind": "port",
                "sample": CpuFrameSampler.SAMPLE, "build_ms": 1e3 * b_s, "trace_ms": 1e3 * t_s}
         if roof_trace and smp.taps:
             taps = float(np.mean(smp.taps))

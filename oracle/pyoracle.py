@@ -45,6 +45,11 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """Use n OpenMP threads (0 = leave unchanged); returns the thread count in effect."""
+    return int(lib().vgo_set_threads(C.c_int(int(n))))
+
+
 def _p(a):
     return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
 

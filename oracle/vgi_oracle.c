@@ -11,6 +11,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ------------------------------------------------------------------------------------------------
  * small helpers
@@ -1047,4 +1050,16 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
 }
 
 /* SVO path: shares the helpers above (single translation unit). */
+/* thread count of the OpenMP loops (torchrun exports OMP_NUM_THREADS=1; the CPU baseline uses every core) */
+int vgo_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 #include "vgi_oracle_svo.inc"

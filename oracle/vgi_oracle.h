@@ -37,6 +37,8 @@ typedef struct vgo_tris {
 } vgo_tris;
 
 size_t vgo_atlas_bytes(const vgi_config* cfg);
+/* sets (n > 0) and returns the number of OpenMP threads the oracle loops use */
+int vgo_set_threads(int n);
 
 /* ref: Application.cpp:116-128, VoxelizationPass.cpp:335-357, 438-448 */
 void vgo_regions(const vgi_config* cfg, const float cam[3], vgi_clip_region* out);
