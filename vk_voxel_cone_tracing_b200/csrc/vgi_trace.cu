@@ -86,19 +86,19 @@ DEVFN float2 unpack2(uint32_t t, uint32_t selLo, uint32_t selHi)
 // (k_brick_mask writes, for every voxel of a non-empty brick, which of the 8 records of the footprint
 // whose low corner is that voxel may be non-zero); only those records are loaded and filtered.
 // Returns false (out = 0) when all eight records of the footprint are zero.
-// Per-cone constants of the three face taps (ref: voxelConeTracing.frag:296-303, 318-326): byte offset of
-// the selected face texel inside a 32-byte record and the squared direction weights (pre-divided by 255).
+// Per-cone constants of the three face taps (ref: voxelConeTracing.frag:296-303, 318-326): which face of
+// each +/- pair the cone reads and the squared direction weights (pre-divided by 255).
 struct ConeFaces {
-    uint32_t offX, offY, offZ;
+    bool negX, negY, negZ;      // travel direction negative -> odd face of the pair
     float kx, ky, kz;
 };
 
 DEVFN ConeFaces cone_faces(const float* dir)
 {
     ConeFaces f;
-    f.offX = dir[0] > 0.0f ? 0u : 4u;
-    f.offY = dir[1] > 0.0f ? 8u : 12u;
-    f.offZ = dir[2] > 0.0f ? 16u : 20u;
+    f.negX = !(dir[0] > 0.0f);
+    f.negY = !(dir[1] > 0.0f);
+    f.negZ = !(dir[2] > 0.0f);
     f.kx = (dir[0] * dir[0]) * (1.0f / 255.0f);
     f.ky = (dir[1] * dir[1]) * (1.0f / 255.0f);
     f.kz = (dir[2] * dir[2]) * (1.0f / 255.0f);
@@ -140,16 +140,23 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, cons
     const int dz = (((i0[2] == (uint32_t)Rm) ? -Rm : 1) << (2 * logR)) * 32;
     float2 aX0 = make_float2(0.f, 0.f), aX1 = aX0, aY0 = aX0, aY1 = aX0, aZ0 = aX0, aZ1 = aX0;
     STAT(4, __popc(m));
-    do {
-        const int c = __ffs(m) - 1;
-        m &= m - 1;
-        const bool bx = c & 1, by = c & 2, bz = c & 4;
-        const int off = (bx ? dx : 0) + (by ? dy : 0) + (bz ? dz : 0);
-        const float wc = (bx ? w[0] : 1.0f - w[0]) * (by ? w[1] : 1.0f - w[1]) * (bz ? w[2] : 1.0f - w[2]);
-        const char* rec = base + off;
-        const uint32_t tx = __ldg(reinterpret_cast<const uint32_t*>(rec + cf.offX));
-        const uint32_t ty = __ldg(reinterpret_cast<const uint32_t*>(rec + cf.offY));
-        const uint32_t tz = __ldg(reinterpret_cast<const uint32_t*>(rec + cf.offZ));
+    // eight statically addressed corner blocks (offsets and weights are compile-time combinations), each
+    // skipped when no lane of the warp needs it; the face pairs are fetched as three 8-byte loads at
+    // immediate offsets from one address and the cone's sign picks the half
+    const float wx0 = 1.0f - w[0], wy0 = 1.0f - w[1], wz0 = 1.0f - w[2];
+    const float wxy[4] = { wx0 * wy0, w[0] * wy0, wx0 * w[1], w[0] * w[1] };
+    const int oxy[4] = { 0, dx, dy, dx + dy };
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (!((m >> c) & 1u)) continue;
+        const int off = oxy[c & 3] + ((c & 4) ? dz : 0);
+        const float wc = wxy[c & 3] * ((c & 4) ? w[2] : wz0);
+        const uint2* rec = reinterpret_cast<const uint2*>(base + off);
+        const uint2 fx = __ldg(rec), fy = __ldg(rec + 1), fz = __ldg(rec + 2);
+        const uint32_t tx = cf.negX ? fx.y : fx.x;
+        const uint32_t ty = cf.negY ? fy.y : fy.x;
+        const uint32_t tz = cf.negZ ? fz.y : fz.x;
+        STAT(5, (tx | ty | tz) != 0u);
         const float2 w2 = make_float2(wc, wc);
         aX0 = __ffma2_rn(w2, unpack2(tx, 0x7540u, 0x7541u), aX0);
         aX1 = __ffma2_rn(w2, unpack2(tx, 0x7542u, 0x7543u), aX1);
@@ -157,8 +164,7 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, cons
         aY1 = __ffma2_rn(w2, unpack2(ty, 0x7542u, 0x7543u), aY1);
         aZ0 = __ffma2_rn(w2, unpack2(tz, 0x7540u, 0x7541u), aZ0);
         aZ1 = __ffma2_rn(w2, unpack2(tz, 0x7542u, 0x7543u), aZ1);
-        STAT(5, (tx | ty | tz) != 0u);
-    } while (m);
+    }
     out[0] = aX0.x * cf.kx + aY0.x * cf.ky + aZ0.x * cf.kz;
     out[1] = aX0.y * cf.kx + aY0.y * cf.ky + aZ0.y * cf.kz;
     out[2] = aX1.x * cf.kx + aY1.x * cf.ky + aZ1.x * cf.kz;
@@ -616,7 +622,7 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
     bool active = false, exhausted = false;
     // per-lane cone state
     ConeState cs = { { 0.f, 0.f, 0.f, 0.f }, 0.0f };
-    ConeFaces cf = { 0u, 8u, 16u, 0.f, 0.f, 0.f };
+    ConeFaces cf = { false, false, false, 0.f, 0.f, 0.f };
     float startPos[3] = { 0.f, 0.f, 0.f }, dir[3] = { 0.f, 0.f, 1.f }, spec[3] = { 0.f, 0.f, 0.f };
     float step = 0.0f, diameter = 0.0f, seg = 0.0f, startLevel = 0.0f, coneCoefficient = 0.0f;
     uint32_t pi = 0u;
