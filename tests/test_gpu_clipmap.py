@@ -170,3 +170,86 @@ def test_frame_host_matches_device_path(oracle):
     assert np.array_equal(od[covered], d.cpu().numpy()[covered])
     assert np.array_equal(os_[covered], s.cpu().numpy()[covered])
     assert (od[~covered] == 0).all()   # discarded pixels get a defined value on the host path
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6])
+def test_all_rendering_modes(oracle, mode):
+    """The nine output modes of voxelConeTracing.frag:258-293 (7 and 8 are covered above)."""
+    inp = common.cornell_inputs(64, 1024, 96, 96)
+    gi, regs, op, rad, pairs = _build_both(oracle, inp)
+    prm = gi.default_vct_params(mode)
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    ref_d, ref_s, _ = oracle.cone_trace(inp["cfg"], inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+    d, s = gi.cone_trace(inp["cam"], gi.upload_gbuffer(gb), prm)
+    covered = gb["depth"] < 1.0
+    assert np.abs(d.cpu().numpy() - ref_d)[covered].max() <= 1e-3
+    assert np.abs(s.cpu().numpy() - ref_s)[covered].max() <= 1e-3
+
+
+def test_32_cones_and_min_step_factor(oracle):
+    """enable32Cones (aperture 0.628319, voxelConeTracing.frag:79-114) and a smaller step factor (more steps
+    than the tabulated default sequence)."""
+    inp = common.cornell_inputs(64, 1024, 96, 96)
+    gi, regs, op, rad, pairs = _build_both(oracle, inp)
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    dgb = gi.upload_gbuffer(gb)
+    covered = gb["depth"] < 1.0
+    for cones32, step in ((1, 1.0), (0, 0.2), (1, 0.5)):
+        prm = gi.default_vct_params(8)
+        prm.enable_32_cones = cones32
+        prm.min_trace_step_factor = step
+        ref_d, ref_s, _ = oracle.cone_trace(inp["cfg"], inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+        d, s = gi.cone_trace(inp["cam"], dgb, prm)
+        assert np.abs(d.cpu().numpy() - ref_d)[covered].max() <= 1e-3, (cones32, step)
+        assert np.abs(s.cpu().numpy() - ref_s)[covered].max() <= 1e-3, (cones32, step)
+        assert common.psnr(d.cpu().numpy()[..., :3], ref_d[..., :3]) >= 50.0
+
+
+def test_shadow_compare_mode_bit_exact(oracle):
+    """VGI_MODE_SHADOW_COMPARE (the fixed Q1: depth comparison instead of averaged raw depth)."""
+    from vk_voxel_cone_tracing_b200 import structs as S
+    inp = dict(common.cornell_inputs(64, 1024, 96, 96))
+    inp["cfg"] = S.default_config(64, 6, mode_flags=S.VGI_MODE_SHADOW_COMPARE)
+    gi, regs, op, rad, pairs = _build_both(oracle, inp)
+    assert np.array_equal(gi.export_atlas(1).cpu().numpy(), rad)
+    prm = gi.default_vct_params(8)
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    ref_d, ref_s, _ = oracle.cone_trace(inp["cfg"], inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+    d, s = gi.cone_trace(inp["cam"], gi.upload_gbuffer(gb), prm)
+    covered = gb["depth"] < 1.0
+    assert np.abs(d.cpu().numpy() - ref_d)[covered].max() <= 1e-3
+
+
+def test_literal_border_export(oracle):
+    """VGI_MODE_BORDER_LITERAL: only the low opacity border is wrapped, the radiance border stays zero (Q4/Q5)."""
+    from vk_voxel_cone_tracing_b200 import structs as S
+    inp = dict(common.cornell_inputs(64, 1024, 96, 96))
+    inp["cfg"] = S.default_config(64, 6, mode_flags=S.VGI_MODE_BORDER_LITERAL)
+    gi, regs, op, rad, pairs = _build_both(oracle, inp)
+    assert np.array_equal(gi.export_atlas(0).cpu().numpy(), op)
+    assert np.array_equal(gi.export_atlas(1).cpu().numpy(), rad)
+
+
+def test_error_paths():
+    """Call-order and argument errors come back as codes, never as crashes (vgi.h conventions)."""
+    from vk_voxel_cone_tracing_b200 import structs as S
+    from vk_voxel_cone_tracing_b200.api import VgiError, VoxelGI
+    gi = VoxelGI(S.default_config(32, 2))
+    with pytest.raises(VgiError) as e:
+        gi.voxelize_opacity()
+    assert e.value.code == S.VGI_E_STATE
+    with pytest.raises(VgiError) as e:
+        gi.export_atlas(0)
+    assert e.value.code == S.VGI_E_STATE
+    with pytest.raises(VgiError) as e:
+        gi.set_slab(5, 3)
+    assert e.value.code == S.VGI_E_INVALID
+    with pytest.raises(VgiError) as e:
+        gi.svo_build()
+    assert e.value.code == S.VGI_E_STATE
+    with pytest.raises(VgiError) as e:
+        VoxelGI(S.default_config(100, 2))
+    assert e.value.code == S.VGI_E_INVALID
