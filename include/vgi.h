@@ -259,6 +259,11 @@ int vgi_cone_trace(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gbuffer* gbuf,
 int vgi_cone_trace_rows(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gbuffer* gbuf,
                         const vgi_vct_params* params, void* out_diffuse, void* out_specular,
                         uint32_t y0, uint32_t y1, void* stream);
+/* Same, restricted to the 8-row tile rows part, part + parts, part + 2*parts, ... of the image: the balanced way
+ * to shard ONE view across `parts` GPUs (contiguous row blocks put all the sky on one GPU). */
+int vgi_cone_trace_interleaved(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gbuffer* gbuf,
+                               const vgi_vct_params* params, void* out_diffuse, void* out_specular,
+                               uint32_t part, uint32_t parts, void* stream);
 /* Fill params with the reference defaults (VoxelConeTracingPass.h:75-82) and the volume fields
  * derived from the ctx's level-0 region (VoxelConeTracingPass.cpp:88-93). */
 int vgi_default_vct_params(vgi_ctx* ctx, vgi_vct_params* out);

@@ -63,6 +63,12 @@ def main():
     ok_trace = True
     for k in range(2):
         ok_trace = ok_trace and torch.equal(part[k][y0:y1], full[k][y0:y1])
+    # interleaved tile rows: the balanced single-view sharding
+    inter = shard.cone_trace(inp["cam"], gb, prm, part=(rank, world))
+    tile_rows = torch.arange(a.height, device="cuda") // 8
+    mine = (tile_rows % world) == rank
+    for k in range(2):
+        ok_trace = ok_trace and torch.equal(inter[k][mine], full[k][mine])
     flags = torch.tensor([int(ok_build), int(ok_trace)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 
@@ -71,7 +77,8 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for name, fn in (("replicated_build_ms", lambda: ref.build_clipmap(0)), ("slab_build_ms", lambda: sb.build(0)),
                          ("full_trace_ms", lambda: ref.cone_trace(inp["cam"], gb, prm, out=full)),
-                         ("row_sharded_trace_ms", lambda: shard.cone_trace(inp["cam"], gb, prm, out=part, rows=(y0, y1)))):
+                         ("row_sharded_trace_ms", lambda: shard.cone_trace(inp["cam"], gb, prm, out=part, rows=(y0, y1))),
+                         ("tile_interleaved_trace_ms", lambda: shard.cone_trace(inp["cam"], gb, prm, out=inter, part=(rank, world)))):
             for _ in range(3):
                 fn()
             dist.barrier()

@@ -183,13 +183,19 @@ class VoxelGI:
         g.height, g.width = gb["depth"].shape
         return g
 
-    def cone_trace(self, camera, gbuffer, params, out=None, rows=None, stream=None):
-        """gbuffer: dict of CUDA tensors. Returns (diffuse, specular) float32 (H, W, 4) CUDA tensors."""
+    def cone_trace(self, camera, gbuffer, params, out=None, rows=None, stream=None, part=None):
+        """gbuffer: dict of CUDA tensors. Returns (diffuse, specular) float32 (H, W, 4) CUDA tensors.
+        rows=(y0, y1): only that row block; part=(i, n): only the 8-row tile rows i, i+n, ... (multi-GPU)."""
         torch = self._torch
         g = self.gbuffer_struct(gbuffer)
         if out is None:
             out = (torch.zeros((g.height, g.width, 4), dtype=torch.float32, device=self.device),
                    torch.zeros((g.height, g.width, 4), dtype=torch.float32, device=self.device))
+        if part is not None:
+            self._ck(lib().vgi_cone_trace_interleaved(self._h, C.byref(camera), C.byref(g), C.byref(params),
+                                                     C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                                     C.c_uint32(part[0]), C.c_uint32(part[1]), _stream(stream)))
+            return out
         y0, y1 = rows if rows is not None else (0, g.height)
         self._ck(lib().vgi_cone_trace_rows(self._h, C.byref(camera), C.byref(g), C.byref(params),
                                           C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),

@@ -661,6 +661,7 @@ static int fill_trace_params(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffe
     tp.diffuse = g->diffuse_rgba8; tp.normal = g->normal_rgba16f; tp.specular = g->specular_rgba8;
     tp.emission = g->emission_rgba16f; tp.depth = g->depth_f32;
     tp.width = (int)g->width; tp.height = (int)g->height; tp.y0 = (int)y0; tp.y1 = (int)y1;
+    tp.tile_stride = 1; tp.tile_phase = 0;
     tp.out_diffuse = (float4*)out_diffuse;
     tp.out_specular = (float4*)out_specular;
     tp.light = c->light;
@@ -709,6 +710,34 @@ int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g,
     c->launches += vgi_launch_trace(c, tp, s);
     c->last_stream = s;
     return check_launch(c, "vgi_cone_trace");
+}
+
+int vgi_cone_trace_interleaved(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, const vgi_vct_params* prm,
+                               void* out_diffuse, void* out_specular, uint32_t part, uint32_t parts, void* stream)
+{
+    int r = check_trace_args(c, cam, g, prm, out_diffuse, out_specular, 0, g ? g->height : 0, "vgi_cone_trace_interleaved");
+    if (r != VGI_OK) return r;
+    if (!parts || part >= parts) return fail(c, VGI_E_INVALID, "vgi_cone_trace_interleaved: part must be < parts");
+    if (!c->built) return fail(c, VGI_E_STATE, "vgi_cone_trace_interleaved: build the clipmap first");
+    if ((uint32_t)prm->volume_dimension != c->cfg.resolution)
+        return fail(c, VGI_E_INVALID, "vgi_cone_trace_interleaved: volume_dimension must equal the clipmap resolution");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t need = (size_t)g->width * g->height + 2;
+    if (c->spec_capacity < need) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->spec_list);
+        c->spec_list = nullptr;
+        CK(c, cudaMalloc(&c->spec_list, need * sizeof(uint32_t)));
+        c->spec_capacity = need;
+    }
+    TraceParams tp;
+    fill_trace_params(c, cam, g, prm, out_diffuse, out_specular, 0, g->height, tp);
+    tp.tile_stride = (int)parts;
+    tp.tile_phase = (int)part;
+    c->launches += vgi_launch_trace(c, tp, s);
+    c->last_stream = s;
+    return check_launch(c, "vgi_cone_trace_interleaved");
 }
 
 // replaces: OctreeVoxelConeTracing::onUpdate (OctreeVoxelConeTracing.cpp:74-104) + voxelConeTracing_Octree.frag

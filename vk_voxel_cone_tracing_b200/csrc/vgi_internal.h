@@ -84,6 +84,7 @@ struct TraceParams {
     const void* diffuse; const void* normal; const void* specular; const void* emission;
     const float* depth;
     int      width, height, y0, y1;
+    int      tile_stride, tile_phase; // 8-row tile rows phase, phase+stride, ... of [y0,y1) (multi-GPU interleave)
     float4*  out_diffuse;
     float4*  out_specular;
     LightParams light;

@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
 
     const int tid = threadIdx.x;
     const int tilesX = (tp.width + TILE_W - 1) / TILE_W;
-    const int tx0 = (blockIdx.x % tilesX) * TILE_W, ty0 = tp.y0 + (blockIdx.x / tilesX) * TILE_H;
+    // tile rows are dealt round-robin when the image is sharded across GPUs (tile_stride > 1)
+    const int tx0 = (blockIdx.x % tilesX) * TILE_W, ty0 = tp.y0 + (tp.tile_phase + (int)(blockIdx.x / tilesX) * tp.tile_stride) * TILE_H;
     const uint32_t mode = tp.p.rendering_mode;
     const bool needCones = mode == 4 || mode == 5 || mode == 7 || mode == 8;
     const bool needDirect = mode == 4 || mode == 5 || mode == 8;
@@ -899,7 +900,10 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     cudaMemsetAsync(tp.spec_count, 0, 2 * sizeof(uint32_t), s); // list length + work cursor
     const int rows = tp.y1 - tp.y0;
     if (rows <= 0 || tp.width <= 0) return 0;
-    const unsigned grid = (unsigned)(((tp.width + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H));
+    const int tileRows = (rows + TILE_H - 1) / TILE_H;
+    const int myTileRows = tileRows > tp.tile_phase ? (tileRows - tp.tile_phase + tp.tile_stride - 1) / tp.tile_stride : 0;
+    if (myTileRows <= 0) return 0;
+    const unsigned grid = (unsigned)(((tp.width + TILE_W - 1) / TILE_W) * myTileRows);
     c->timer.begin("k_trace_main", s);
     if (tp.p.enable_32_cones) k_trace_main<32><<<grid, 128, 0, s>>>(tp);
     else k_trace_main<16><<<grid, 128, 0, s>>>(tp);
