@@ -40,27 +40,74 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
                                                    uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
                                                    uint2* __restrict__ large, Counters* __restrict__ cnt)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= bp.ntri) return;
-    float p[9], N[3];
-    load_tri(tri_pos, t, p, nullptr);
-    cross_and_axis(p, N);
-    for (int l = 0; l < bp.L; ++l) {
+    // One thread per (level, triangle), level-major: neighbouring lanes are neighbouring triangles at the same
+    // level. A thread first tests its (at most 64) candidate voxels into a 64-bit hit mask; then the warp
+    // reserves the space for all its pairs with ONE atomic (warp prefix sum of the popcounts) and every lane
+    // writes its pairs to consecutive slots. The single global pair counter is no longer hit once per voxel row.
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inRange = gid < bp.ntri * (uint32_t)bp.L;
+    const int l = inRange ? (int)(gid / bp.ntri) : 0;
+    const uint32_t t = inRange ? gid - (uint32_t)l * bp.ntri : 0u;
+    unsigned long long hits = 0ull;
+    int lo0 = 0, lo1 = 0, lo2 = 0, nx = 1, ny = 1;
+    if (inRange) {
+        float p[9], N[3];
+        load_tri(tri_pos, t, p, nullptr);
+        cross_and_axis(p, N);
         TriSetup ts;
         tri_setup_level(ts, p, N, bp.lv[l], bp.R);
-        if (!ts.valid) continue;
-        if (ts.lo[0] > ts.hi[0] || ts.lo[1] > ts.hi[1] || ts.lo[2] > ts.hi[2]) continue;
-        const long long vol = (long long)(ts.hi[0] - ts.lo[0] + 1) * (ts.hi[1] - ts.lo[1] + 1) * (ts.hi[2] - ts.lo[2] + 1);
-        if (vol > SMALL_BOX_MAX) {
-            const uint32_t slot = atomicAdd(&cnt->large, 1u);
-            if (slot < bp.max_large) large[slot] = make_uint2(t, (uint32_t)l);
-            else atomicOr(&cnt->overflow, 2u);
-            continue;
+        if (ts.valid && ts.lo[0] <= ts.hi[0] && ts.lo[1] <= ts.hi[1] && ts.lo[2] <= ts.hi[2]) {
+            nx = ts.hi[0] - ts.lo[0] + 1;
+            ny = ts.hi[1] - ts.lo[1] + 1;
+            const int nz = ts.hi[2] - ts.lo[2] + 1;
+            const long long vol = (long long)nx * ny * nz;
+            if (vol > SMALL_BOX_MAX) {
+                const uint32_t slot = atomicAdd(&cnt->large, 1u);
+                if (slot < bp.max_large) large[slot] = make_uint2(t, (uint32_t)l);
+                else atomicOr(&cnt->overflow, 2u);
+            } else {
+                lo0 = ts.lo[0]; lo1 = ts.lo[1]; lo2 = ts.lo[2];
+                int i = 0;
+                for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
+                    for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
+                        for (int x = ts.lo[0]; x <= ts.hi[0]; ++x, ++i)
+                            if (tri_overlaps_voxel(ts, x, y, z)) hits |= 1ull << i;
+            }
         }
-        for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
-            for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
-                for (int x = ts.lo[0]; x <= ts.hi[0]; ++x)
-                    if (tri_overlaps_voxel(ts, x, y, z)) emit_pair(bp, occ, pairs, cnt, t, l, x, y, z);
+    }
+    // drop the hits outside this GPU's slab (slab-sharded build) before reserving space
+    const int Rm = bp.R - 1;
+    if (bp.z0 > 0 || bp.z1 < bp.R) {
+        for (unsigned long long h = hits; h; h &= h - 1) {
+            const int i = __ffsll((long long)h) - 1;
+            const int z = (lo2 + i / (nx * ny)) & Rm;
+            if (z < bp.z0 || z >= bp.z1) hits &= ~(1ull << i);
+        }
+    }
+    const uint32_t n = (uint32_t)__popcll(hits);
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) return;
+    uint32_t base = 0u;
+    if (lane_id() == 31u) base = atomicAdd(&cnt->pairs, total);
+    uint32_t slot = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
+    const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
+    for (unsigned long long h = hits; h; h &= h - 1, ++slot) {
+        const int i = __ffsll((long long)h) - 1;
+        const int vx = lo0 + i % nx, vy = lo1 + (i / nx) % ny, vz = lo2 + i / (nx * ny);
+        const uint32_t x = vx & Rm, y = vy & Rm, z = vz & Rm;
+        const size_t w = (size_t)l * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
+        const uint32_t bit = 1u << (x & 31u);
+        if (!(occ[w] & bit)) atomicOr(&occ[w], bit);
+        if (slot < bp.max_pairs)
+            pairs[slot] = ((vgi_pair_t)t << 32) | ((vgi_pair_t)l << 27) | ((vgi_pair_t)z << 18) | ((vgi_pair_t)y << 9) | x;
+        else
+            atomicOr(&cnt->overflow, 1u);
     }
 }
 
@@ -677,7 +724,7 @@ int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
     cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
     if (bp.ntri) {
-        LAUNCH("k_voxelize", k_voxelize<<<cdiv(bp.ntri, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
+        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
         LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
     }
     const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
