@@ -129,6 +129,10 @@ int vgi_get_stats(vgi_ctx* c, vgi_stats* out)
     out->triangles = c->ntri;
     out->clip_pairs = c->h_counters->pairs;
     out->occupied_voxels = c->h_counters->occ_total;
+    if (c->svo_counters_fresh) { // the device counters still hold the SVO pass (no clipmap build since)
+        if (c->svo_voxelized) c->svo_nfrag = c->h_counters->svo_frags;
+        if (c->svo_built) c->svo_nnodes = c->h_counters->svo_counter;
+    }
     out->svo_fragments = c->svo_nfrag;
     out->svo_nodes = c->svo_nnodes;
     out->kernel_launches = c->launches;
@@ -435,6 +439,7 @@ int vgi_voxelize_opacity(vgi_ctx* c, void* stream)
     cudaStream_t s = (cudaStream_t)stream;
     c->launches += vgi_launch_voxelize(c, bp, s);
     c->last_stream = s;
+    c->svo_counters_fresh = false;
     c->voxelized = true;
     return check_launch(c, "vgi_voxelize_opacity");
 }
@@ -529,6 +534,7 @@ int vgi_slab_build_begin(vgi_ctx* c, uint32_t frame_index, void* stream)
     BuildParams bp;
     build_params_from_ctx(c, frame_index, &bp);
     cudaStream_t s = (cudaStream_t)stream;
+    c->svo_counters_fresh = false;
     c->launches += vgi_launch_slab_begin(c, bp, s);
     c->last_stream = s;
     c->slab_phase = 1;

@@ -191,7 +191,7 @@ struct vgi_ctx {
     uint2* svo_nodes = nullptr;
     uint32_t svo_node_capacity = 0;
     uint32_t svo_nfrag = 0, svo_nnodes = 0;
-    bool svo_voxelized = false, svo_built = false;
+    bool svo_voxelized = false, svo_built = false, svo_counters_fresh = false;
     float svo_bb_min[3], svo_bb_max[3];
     uint32_t* svo_scratch = nullptr;
     size_t svo_scratch_words = 0;

@@ -71,26 +71,52 @@ __global__ void __launch_bounds__(128) k_svo_voxelize(SvoGrid g, uint32_t ntri, 
                                                        svo_pair_t* __restrict__ pairs, uint32_t max_pairs,
                                                        uint2* __restrict__ large, uint32_t max_large, Counters* __restrict__ cnt)
 {
+    // same scheme as k_voxelize: 64-bit hit mask per thread, one reservation per warp
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntri) return;
-    float p[9], N[3];
-    int axis;
-    load_tri(tri_pos, t, p, nullptr);
-    TriSetup ts;
-    svo_setup(g, p, ts, N, &axis);
-    if (!ts.valid) return;
-    if (ts.lo[0] > ts.hi[0] || ts.lo[1] > ts.hi[1] || ts.lo[2] > ts.hi[2]) return;
-    const long long vol = (long long)(ts.hi[0] - ts.lo[0] + 1) * (ts.hi[1] - ts.lo[1] + 1) * (ts.hi[2] - ts.lo[2] + 1);
-    if (vol > SVO_SMALL_BOX_MAX) {
-        const uint32_t slot = atomicAdd(&cnt->large, 1u);
-        if (slot < max_large) large[slot] = make_uint2(t, 0u);
-        else atomicOr(&cnt->overflow, 2u);
-        return;
+    unsigned long long hits = 0ull;
+    int lo0 = 0, lo1 = 0, lo2 = 0, nx = 1, ny = 1;
+    if (t < ntri) {
+        float p[9], N[3];
+        int axis;
+        load_tri(tri_pos, t, p, nullptr);
+        TriSetup ts;
+        svo_setup(g, p, ts, N, &axis);
+        if (ts.valid && ts.lo[0] <= ts.hi[0] && ts.lo[1] <= ts.hi[1] && ts.lo[2] <= ts.hi[2]) {
+            nx = ts.hi[0] - ts.lo[0] + 1;
+            ny = ts.hi[1] - ts.lo[1] + 1;
+            const long long vol = (long long)nx * ny * (ts.hi[2] - ts.lo[2] + 1);
+            if (vol > SVO_SMALL_BOX_MAX) {
+                const uint32_t slot = atomicAdd(&cnt->large, 1u);
+                if (slot < max_large) large[slot] = make_uint2(t, 0u);
+                else atomicOr(&cnt->overflow, 2u);
+            } else {
+                lo0 = ts.lo[0]; lo1 = ts.lo[1]; lo2 = ts.lo[2];
+                int i = 0;
+                for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
+                    for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
+                        for (int x = ts.lo[0]; x <= ts.hi[0]; ++x, ++i)
+                            if (tri_overlaps_voxel(ts, x, y, z)) hits |= 1ull << i;
+            }
+        }
     }
-    for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
-        for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
-            for (int x = ts.lo[0]; x <= ts.hi[0]; ++x)
-                if (tri_overlaps_voxel(ts, x, y, z)) svo_emit_pair(pairs, cnt, max_pairs, t, x, y, z);
+    const uint32_t n = (uint32_t)__popcll(hits);
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) return;
+    uint32_t base = 0u;
+    if (lane_id() == 31u) base = atomicAdd(&cnt->pairs, total);
+    uint32_t slot = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
+    for (unsigned long long h = hits; h; h &= h - 1, ++slot) {
+        const int i = __ffsll((long long)h) - 1;
+        const uint32_t x = (uint32_t)(lo0 + i % nx), y = (uint32_t)(lo1 + (i / nx) % ny), z = (uint32_t)(lo2 + i / (nx * ny));
+        if (slot < max_pairs) pairs[slot] = ((svo_pair_t)t << 36) | ((svo_pair_t)z << 24) | ((svo_pair_t)y << 12) | x;
+        else atomicOr(&cnt->overflow, 1u);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_svo_voxelize_large(SvoGrid g, const float4* __restrict__ tri_pos,
@@ -507,6 +533,7 @@ int vgi_svo_voxelize(vgi_ctx* c, uint32_t level, const float bb_min[3], const fl
     c->voxelized = false; // the pair buffer was reused
     c->svo_voxelized = true;
     c->svo_built = false;
+    c->svo_counters_fresh = true;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return svo_fail(c, VGI_E_CUDA, std::string("vgi_svo_voxelize: ") + cudaGetErrorString(e));
     return VGI_OK;
