@@ -913,7 +913,16 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     const uint32_t mode = tp.p.rendering_mode;
     if (mode == 6 || mode == 8) {
         c->timer.begin("k_trace_specular", s);
-        k_trace_specular<<<148 * 5, 128, 0, s>>>(tp); ++n;
+        // persistent kernel: exactly as many blocks as fit on the device at once
+        static int specBlocks = 0;
+        if (!specBlocks) {
+            int perSm = 0, dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace_specular, 128, 0);
+            specBlocks = sms * (perSm > 0 ? perSm : 4);
+        }
+        k_trace_specular<<<specBlocks, 128, 0, s>>>(tp); ++n;
         c->timer.end(s);
     }
     return n;
