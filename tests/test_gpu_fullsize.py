@@ -118,3 +118,43 @@ def test_octree_level9_structure(full):
     for sh in (0, 8, 16, 24):
         want = ((nodes[kid_rows, 1] >> sh) & 0xff).sum(axis=1) >> 3
         assert np.array_equal((nodes[par, 1] >> sh) & 0xff, want)
+
+
+def test_max_resolution_512_single_level_vs_oracle(oracle):
+    """R = 512 (the largest supported resolution; configs[4]'s volume): atlases bit-exact and cone trace within
+    tolerance against the oracle. Guards the 32-bit index arithmetic at the upper size limit."""
+    import torch
+    from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    scene = synth.cornell_box(wall_quads=12, box_quads=4)
+    cfg = S.default_config(512, 1)
+    light, shadow = synth.make_light(origin=(0.0, 20.0, -3.5))
+    depth = raster.shadow_depth(scene, shadow, 512)
+    cam_pos = (0.3, 0.2, -0.1)
+    cam = synth.make_camera(cam_pos, (0.0, 0.0, -1.0), aspect=1.0)
+    gb = raster.gbuffer(scene, cam, 64, 64)
+    gi = VoxelGI(cfg)
+    gi.set_scene(scene)
+    gi.set_light(light, shadow, depth)
+    gi.update_regions(cam_pos)
+    gi.build_clipmap(0)
+    regs = oracle.regions(cfg, cam_pos)
+    op, rad, pairs = oracle.build_clipmap(cfg, regs, oracle.OracleScene(scene), light, shadow, depth, 0)
+    assert gi.stats().clip_pairs == pairs
+    for which, ref in ((0, op), (1, rad)):
+        got = gi.export_atlas(which)
+        assert torch.equal(got.cpu(), torch.from_numpy(ref)), f"atlas {which} differs"
+        del got
+    prm = gi.default_vct_params(8)
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    ref_d, ref_s, _ = oracle.cone_trace(cfg, cam, hg, prm, light, shadow, depth, rad)
+    d, s = gi.cone_trace(cam, gi.upload_gbuffer(gb), prm)
+    covered = gb["depth"] < 1.0
+    # a single 512^3 level makes the un-tonemapped sums reach ~11 (segment length / voxel size is large), where
+    # 1e-3 absolute is the binary32 noise floor of the accumulation: tolerance 1e-3 * max(1, |reference|)
+    tol_d = 1e-3 * np.maximum(1.0, np.abs(ref_d))[covered]
+    tol_s = 1e-3 * np.maximum(1.0, np.abs(ref_s))[covered]
+    ed, es = np.abs(d.cpu().numpy() - ref_d)[covered], np.abs(s.cpu().numpy() - ref_s)[covered]
+    assert (ed <= tol_d).all(), (float(ed.max()), float(np.abs(ref_d[covered]).max()))
+    assert (es <= tol_s).all(), (float(es.max()), float(np.abs(ref_s[covered]).max()))
+    assert np.abs(ed[np.abs(ref_d[covered]) <= 1.0]).max() <= 1e-3

@@ -133,11 +133,11 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, cons
         STAT(3, 1);
         return false;
     }
-    const char* base = reinterpret_cast<const char*>(tp.store + vox);
-    // byte offsets of the +1 neighbours (toroidal)
-    const int dx = ((i0[0] == (uint32_t)Rm) ? -Rm : 1) * 32;
-    const int dy = (((i0[1] == (uint32_t)Rm) ? -Rm : 1) << logR) * 32;
-    const int dz = (((i0[2] == (uint32_t)Rm) ? -Rm : 1) << (2 * logR)) * 32;
+    const VoxelRecord* base = tp.store + vox;
+    // record offsets of the +1 neighbours (toroidal); in records, not bytes: -(R-1) * R^2 * 32 overflows int at R = 512
+    const int dx = (i0[0] == (uint32_t)Rm) ? -Rm : 1;
+    const int dy = ((i0[1] == (uint32_t)Rm) ? -Rm : 1) << logR;
+    const int dz = ((i0[2] == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
     float2 aX0 = make_float2(0.f, 0.f), aX1 = aX0, aY0 = aX0, aY1 = aX0, aZ0 = aX0, aZ1 = aX0;
     STAT(4, __popc(m));
     // eight statically addressed corner blocks (offsets and weights are compile-time combinations), each
@@ -151,7 +151,7 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, cons
         if (!((m >> c) & 1u)) continue;
         const int off = oxy[c & 3] + ((c & 4) ? dz : 0);
         const float wc = wxy[c & 3] * ((c & 4) ? w[2] : wz0);
-        const uint2* rec = reinterpret_cast<const uint2*>(base + off);
+        const uint2* rec = reinterpret_cast<const uint2*>(base + off);   // base is a VoxelRecord*: off counts records
         const uint2 fx = __ldg(rec), fy = __ldg(rec + 1), fz = __ldg(rec + 2);
         const uint32_t tx = cf.negX ? fx.y : fx.x;
         const uint32_t ty = cf.negY ? fy.y : fy.x;
