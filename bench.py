@@ -105,6 +105,16 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+    (profiles/r1_ncu_traffic.json, written by the session that profiled these kernels); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        return json.load(open(p))["kernels"][kernel]["traffic"]
+    except Exception:
+        return None
+
+
 def make_inputs(rank, world):
     """Synthetic inputs of configs[1]; rank r > 0 gets the r-th orbit camera (batched views)."""
     from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
@@ -391,7 +401,7 @@ def run_vgi(args):
                                   "not DRAM utilisation (see profiles/ for dram__bytes)"}
             ach = (ab / (ms_launch * 1e-3) / 1e9) if ab else None
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (ach / hbm_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / hbm_peak) if ach else None, "traffic": ncu_traffic(name), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms_launch,
                     "share_of_build": build_k[name][0] / sum(v[0] for v in build_k.values())}
         trace_k = {k: v for k, v in tm.items() if k.startswith("k_trace")}
@@ -403,6 +413,7 @@ def run_vgi(args):
             roof_trace = {"kernels": sorted(trace_k), "bound": "l1", "ms_per_step": tms, "peak": l1_peak, "unit": "GB/s",
                           "peak_source": f"{nsm} SMs x 128 B/clk x {sm_mhz:.0f} MHz (clock sampled during the run)",
                           "achieved": None, "frac": None,
+                          "traffic": (ncu_traffic("k_trace_main") or 0) + (ncu_traffic("k_trace_specular") or 0) or None,
                           "note": "A_cone = 32 B x tri-linear taps (counted by the oracle on the sampled rows, scaled) + 60 B x pixels"}
 
     # ---- configs[2] beside it: 512^3 octree (level 9) fragment list + build + 1080p octree cone trace
