@@ -105,44 +105,59 @@ DEVFN ConeFaces cone_faces(const float* dir)
     return f;
 }
 
-DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, const ConeFaces& cf, float* out)
+// Where a tri-linear footprint lies: texel index of its low corner, the fractional weights and the mask of
+// the records that can be non-zero (0 = nothing to fetch).
+struct Footprint {
+    uint32_t vox;       // level << 3 logR | z << 2 logR | y << logR | x
+    uint32_t mask;
+    float    w[3];
+};
+
+// coordinates + the two emptiness tests (4^3 brick bit, per-voxel footprint byte)
+DEVFN void probe_level(const TraceParams& tp, const float* pos, int level, Footprint& fp)
 {
     const int R = tp.R, Rm = R - 1, logR = tp.logR;
     const float inv = tp.inv_extent[level];
     uint32_t i0[3];
-    float w[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float t = f_fract(pos[k] * inv) * (float)R - 0.5f;
         const float fl = floorf(t);
-        w[k] = t - fl;
+        fp.w[k] = t - fl;
         i0[k] = (uint32_t)((int)fl & Rm);
     }
     STAT(1, 1);
     // 32-bit index arithmetic: L * R^3 <= 8 * 512^3 = 2^30
     const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
     const uint32_t bidx = (((((uint32_t)level << nbShift) + (i0[2] >> 2)) << nbShift) + (i0[1] >> 2) << wprShift) + (i0[0] >> 5);
+    fp.vox = ((((((uint32_t)level << logR) + i0[2]) << logR) + i0[1]) << logR) + i0[0];
+    // both lookups are issued together (one memory latency instead of two in the dependent chain); the
+    // footprint byte is only meaningful where the brick bit is set
     const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
-    if (!((bbyte >> ((i0[0] >> 2) & 7u)) & 1u)) {
-        STAT(2, 1);
-        return false;
-    }
-    const uint32_t vox = ((((((uint32_t)level << logR) + i0[2]) << logR) + i0[1]) << logR) + i0[0];
-    uint32_t m = __ldg(tp.footprint + vox);
-    if (!m) {
-        STAT(3, 1);
-        return false;
-    }
-    const VoxelRecord* base = tp.store + vox;
+    const uint32_t m = __ldg(tp.footprint + fp.vox);
+    const bool brick = (bbyte >> ((i0[0] >> 2) & 7u)) & 1u;
+    if (!brick) STAT(2, 1);
+    else if (!m) STAT(3, 1);
+    fp.mask = brick ? m : 0u;
+}
+
+// the filtered fetch of the non-zero records of a footprint: three face-weighted tri-linear taps
+DEVFN void filter_footprint(const TraceParams& tp, const Footprint& fp, const ConeFaces& cf, float* out)
+{
+    const int R = tp.R, Rm = R - 1, logR = tp.logR;
+    const uint32_t m = fp.mask;
+    const uint32_t ix = fp.vox & (uint32_t)Rm, iy = (fp.vox >> logR) & (uint32_t)Rm, iz = (fp.vox >> (2 * logR)) & (uint32_t)Rm;
+    const VoxelRecord* base = tp.store + fp.vox;
     // record offsets of the +1 neighbours (toroidal); in records, not bytes: -(R-1) * R^2 * 32 overflows int at R = 512
-    const int dx = (i0[0] == (uint32_t)Rm) ? -Rm : 1;
-    const int dy = ((i0[1] == (uint32_t)Rm) ? -Rm : 1) << logR;
-    const int dz = ((i0[2] == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
+    const int dx = (ix == (uint32_t)Rm) ? -Rm : 1;
+    const int dy = ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
+    const int dz = ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
     float2 aX0 = make_float2(0.f, 0.f), aX1 = aX0, aY0 = aX0, aY1 = aX0, aZ0 = aX0, aZ1 = aX0;
     STAT(4, __popc(m));
     // eight statically addressed corner blocks (offsets and weights are compile-time combinations), each
     // skipped when no lane of the warp needs it; the face pairs are fetched as three 8-byte loads at
     // immediate offsets from one address and the cone's sign picks the half
+    const float* w = fp.w;
     const float wx0 = 1.0f - w[0], wy0 = 1.0f - w[1], wz0 = 1.0f - w[2];
     const float wxy[4] = { wx0 * wy0, w[0] * wy0, wx0 * w[1], w[0] * w[1] };
     const int oxy[4] = { 0, dx, dy, dx + dy };
@@ -169,7 +184,6 @@ DEVFN bool sample_level(const TraceParams& tp, const float* pos, int level, cons
     out[1] = aX0.y * cf.kx + aY0.y * cf.ky + aZ0.y * cf.kz;
     out[2] = aX1.x * cf.kx + aY1.x * cf.ky + aZ1.x * cf.kz;
     out[3] = aX1.y * cf.kx + aY1.y * cf.ky + aZ1.y * cf.kz;
-    return true;
 }
 
 // ceil(log2(dist / minRadius)) of voxelConeTracing.frag:367 clamped to [0, L-1], without sqrt / divide /
@@ -205,15 +219,19 @@ DEVFN void cone_step(const TraceParams& tp, ConeState& cs, const float* startPos
     const float curLevel = fminf(fmaxf(fmaxf(startLevel, lod), minLevel), (float)(tp.L - 1));
     const float fl = floorf(curLevel);
     const float fr = curLevel - fl;
+    // probe both levels first (their mask lookups overlap), then fetch and filter what is not empty
+    Footprint f0, f1;
+    probe_level(tp, position, (int)fl, f0);
+    f1.mask = 0u;
+    if (fr > 0.0f) probe_level(tp, position, (int)fl + 1, f1); // Q17: floor == ceil when the level is integral
+    const bool any = (f0.mask | f1.mask) != 0u;
     float smp[4] = { 0.f, 0.f, 0.f, 0.f };
-    bool any = sample_level(tp, position, (int)fl, cf, smp);
-    if (fr > 0.0f) { // Q17: floor == ceil when the level is integral — the second fetch is identical
+    if (f0.mask) filter_footprint(tp, f0, cf, smp);
+    if (fr > 0.0f && any) {
         float up[4] = { 0.f, 0.f, 0.f, 0.f };
-        const bool anyUp = sample_level(tp, position, (int)fl + 1, cf, up);
-        if (!(any | anyUp)) return;
+        if (f1.mask) filter_footprint(tp, f1, cf, up);
 #pragma unroll
         for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
-        any = true;
     }
     if (!any) return; // empty footprints: the accumulators would receive exact zeros
     const float voxelSize = p.voxel_size * exp2f(curLevel);
