@@ -447,6 +447,195 @@ DEVFN bool pixel_setup(const TraceParams& tp, int px, int py, PixelSetup& s)
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// SVO cone tracing. ref: voxelConeTracing_Octree.frag:148-409 (bbox parameterised, Q14; same >>1 as the
+// build, Q13). Samples are point descents through the node pool (no filtering), two per step.
+// ---------------------------------------------------------------------------------------------------
+DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t level, float* o)
+{
+    uint32_t resolution = (uint32_t)tp.p.volume_dimension;
+    uint32_t fp[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float scaled = (position[k] - tp.svo_center[k]) / tp.svo_extent;
+        float g = ((scaled + 1.0f) * 0.5f) * (float)resolution;
+        g = f_clamp(g, 0.0f, (float)resolution);
+        fp[k] = ((uint32_t)g) >> 1;
+    }
+    const uint32_t targetResolution = 1u << level;
+    uint32_t idx = 0, cur = 0;
+    do {
+        resolution >>= 1;
+        const uint32_t cx = fp[0] >= resolution, cy = fp[1] >= resolution, cz = fp[2] >= resolution;
+        idx = cur + (cz | (cx << 1) | (cy << 2));
+        cur = __ldg(&tp.svo_nodes[idx].x) & 0x7fffffffu;
+        fp[0] -= cx * resolution; fp[1] -= cy * resolution; fp[2] -= cz * resolution;
+    } while (cur != 0u && resolution > targetResolution);
+    const uint32_t y = __ldg(&tp.svo_nodes[idx].y);
+    o[0] = (float)(y & 0xffu) * (1.0f / 255.0f);
+    o[1] = (float)((y >> 8) & 0xffu) * (1.0f / 255.0f);
+    o[2] = (float)((y >> 16) & 0xffu) * (1.0f / 255.0f);
+    o[3] = (float)(y >> 24) * (1.0f / 255.0f);
+}
+
+DEVFN void svo_trace_cone(const TraceParams& tp, const float* startPos_, const float* dir, float coneCoefficient,
+                          float startLevel, float stepFactor, float* out)
+{
+    const vgi_vct_params& p = tp.p;
+    float result[4] = { 0.f, 0.f, 0.f, 0.f };
+    float voxelSize = p.voxel_size * exp2f(startLevel);
+    float startPos[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize * p.trace_start_offset * 0.5f;
+    float step = 0.0f;
+    float diameter = fmaxf(step * coneCoefficient, p.voxel_size);
+    float occlusion = 0.0f;
+    float curSegmentLength = voxelSize;
+    const float invVoxel = 1.0f / p.voxel_size;
+    while (step < MAX_TRACE_DISTANCE && occlusion < 1.0f) {
+        float position[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            position[k] = startPos[k] + dir[k] * step;
+            d[k] = p.volume_center[k] - position[k];
+        }
+        // level selection as in the clipmap tracer: exact threshold count for the distance term, fast log2 for
+        // the (continuously blended) diameter term
+        const float minLevel = min_level_from_dd(tp, dot3(d, d));
+        const float curLevel = fminf(fmaxf(fmaxf(startLevel, __log2f(diameter * invVoxel)), minLevel), tp.svo_max_level);
+        float lo[4], smp[4];
+        const float fl = floorf(curLevel);
+        const float fr = curLevel - fl;
+        sample_svo(tp, position, (uint32_t)fl, lo);
+        if (fr > 0.0f) {
+            float up[4];
+            sample_svo(tp, position, (uint32_t)fl + 1u, up);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) smp[c] = lo[c] * (1.0f - fr) + up[c] * fr;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) smp[c] = lo[c];
+        }
+        voxelSize = p.voxel_size * exp2f(curLevel);
+        if (smp[0] != 0.0f || smp[1] != 0.0f || smp[2] != 0.0f || smp[3] != 0.0f) { // empty nodes add exact zeros
+            const float correction = __fdividef(curSegmentLength, voxelSize);
+            float opacity = 0.0f;
+            if (smp[3] > 0.0f) opacity = f_clamp(1.0f - exp2f(correction * __log2f(1.0f - smp[3])), 0.0f, 1.0f);
+            const float k1 = f_clamp(1.0f - result[3], 0.0f, 1.0f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) result[c] += k1 * (smp[c] * correction);
+            result[3] += k1 * opacity;
+            occlusion += __fdividef((1.0f - occlusion) * opacity, 1.0f + (step + voxelSize) * p.occlusion_decay);
+        }
+        const float prevStep = step;
+        step += fmaxf(diameter, p.voxel_size) * stepFactor;
+        curSegmentLength = step - prevStep;
+        diameter = step * coneCoefficient;
+    }
+    out[0] = f_clamp(result[0], 0.0f, 1.0f);
+    out[1] = f_clamp(result[1], 0.0f, 1.0f);
+    out[2] = f_clamp(result[2], 0.0f, 1.0f);
+    out[3] = f_clamp(1.0f - occlusion, 0.0f, 1.0f);
+}
+
+// per-pixel combine of the octree tracer (voxelConeTracing_Octree.frag:196-311)
+template <int NCONES>
+DEVFN void svo_finish_pixel(const TraceParams& tp, const PixelSetup& s, size_t pi, const float (*cones)[3],
+                            const float4 (*s_res)[64], int tid, bool needCones, bool needDirect, bool needSpec)
+{
+    const uint32_t mode = tp.p.rendering_mode;
+    float indirect[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+    if (needCones) {
+        float validConeCount = 0.0f;
+        for (int i = 0; i < NCONES; ++i) {
+            const float cosTheta = s.normal[0] * cones[i][0] + s.normal[1] * cones[i][1] + s.normal[2] * cones[i][2];
+            if (cosTheta < 0.0f) continue;
+            const float4 r = s_res[i][tid];
+            indirect[0] += r.x; indirect[1] += r.y; indirect[2] += r.z; indirect[3] += r.w;
+            validConeCount += cosTheta;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) indirect[k] /= validConeCount; // Q11: normalised by the sum of cosines
+        indirect[3] *= tp.p.ambient_occlusion_factor;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) indirect[k] *= s.diffuseColor[k] * tp.p.indirect_diffuse_intensity;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) indirect[k] = f_clamp(indirect[k], 0.0f, 1.0f);
+    }
+
+    float spec[3] = { 0.f, 0.f, 0.f };
+    if (needSpec && (s.specularColor[0] > 1e-6f || s.specularColor[1] > 1e-6f || s.specularColor[2] > 1e-6f) && s.metallic > 1e-6f) {
+        const float I[3] = { -s.view[0], -s.view[1], -s.view[2] };
+        const float dn = dot3(s.normal, I);
+        const float r[3] = { I[0] - 2.0f * dn * s.normal[0], I[1] - 2.0f * dn * s.normal[1], I[2] - 2.0f * dn * s.normal[2] };
+        float sdir[3];
+        normalize3(r, sdir);
+        const float aperture = fmaxf(s.perceptualRoughness, MIN_SPECULAR_APERTURE);
+        float c[4];
+        // ref: voxelConeTracing_Octree.frag:215-219 — stepFactor = max(0.2, uVoxelSize) (Q12)
+        svo_trace_cone(tp, s.startPos, sdir, 2.0f * tanf(aperture * 0.5f), s.minLevel, fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.voxel_size), c);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) spec[k] = (c[k] * s.specularColor[k]) * tp.p.indirect_specular_intensity;
+    }
+
+    float direct[3] = { 0.f, 0.f, 0.f };
+    if (needDirect) {
+        if (s.emission[0] > 0.0f || s.emission[1] > 0.0f || s.emission[2] > 0.0f) {
+            direct[0] = s.emission[0]; direct[1] = s.emission[1]; direct[2] = s.emission[2];
+        } else {
+            const float alphaRoughness = s.perceptualRoughness * s.perceptualRoughness;
+            const float reflectance = fmaxf(fmaxf(s.specularColor[0], s.specularColor[1]), s.specularColor[2]);
+            const float r90 = f_clamp(reflectance * 50.0f, 0.0f, 1.0f);
+            const float* L = tp.light.dir_to_light;
+            float h[3];
+            {
+                const float t[3] = { L[0] + s.view[0], L[1] + s.view[1], L[2] + s.view[2] };
+                normalize3(t, h);
+            }
+            const float NdotL = f_clamp(dot3(s.normal, L), 0.001f, 1.0f);
+            const float NdotV = f_clamp(fabsf(dot3(s.normal, s.view)), 0.001f, 1.0f);
+            const float NdotH = f_clamp(dot3(s.normal, h), 0.0f, 1.0f);
+            const float VdotH = f_clamp(dot3(s.view, h), 0.0f, 1.0f);
+            float brdf[3];
+            microfacet_brdf(NdotL, NdotV, NdotH, VdotH, alphaRoughness, s.specularColor, r90, s.diffuseColor, brdf);
+            const float vis = calc_visibility(tp, s.worldPos);
+            direct[0] = brdf[0] * vis; direct[1] = brdf[1] * vis; direct[2] = brdf[2] * vis;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) direct[k] = f_clamp(direct[k], 0.0f, 1.0f);
+    }
+
+    float4 dc = make_float4(0.f, 0.f, 0.f, 1.f), sc = make_float4(0.f, 0.f, 0.f, 1.f);
+    switch (mode) {
+    case 0: dc = make_float4(s.diffuseColor[0], s.diffuseColor[1], s.diffuseColor[2], 1.f); break;
+    case 1: dc = make_float4(s.specularColor[0], s.specularColor[1], s.specularColor[2], 1.f); break;
+    case 2: dc = make_float4(s.normal[0] * 0.5f + 0.5f, s.normal[1] * 0.5f + 0.5f, s.normal[2] * 0.5f + 0.5f, 1.f); break;
+    case 3: { // minLevelToColor, voxelConeTracing_Octree.frag:433-458
+        float col[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (s.minLevel < 6.0f) {
+            int lower = (int)floorf(s.minLevel);
+            lower = lower < 0 ? 0 : lower;
+            const float fr = f_fract(s.minLevel);
+            for (int k = 0; k < 4; ++k) col[k] = c_level_colors[lower][k] * (1.0f - fr) + c_level_colors[lower + 1][k] * fr;
+        }
+        dc = make_float4(col[0] * 0.5f, col[1] * 0.5f, col[2] * 0.5f, col[3] * 0.5f);
+        break;
+    }
+    case 4: dc = make_float4(direct[0] * indirect[3], direct[1] * indirect[3], direct[2] * indirect[3], 1.f); break;
+    case 5: dc = make_float4(indirect[0], indirect[1], indirect[2], 1.f); break; // direct not added (_Octree.frag:283-287)
+    case 6: sc = make_float4(spec[0], spec[1], spec[2], 1.f); break;
+    case 7: dc = make_float4(indirect[3], indirect[3], indirect[3], 1.f); break;
+    case 8:
+        dc = make_float4(direct[0] * indirect[3] + indirect[0], direct[1] * indirect[3] + indirect[1],
+                         direct[2] * indirect[3] + indirect[2], 1.f);
+        sc = make_float4(spec[0], spec[1], spec[2], 1.f);
+        break;
+    default: break;
+    }
+    tp.out_diffuse[pi] = dc;
+    tp.out_specular[pi] = sc;
+}
+
 // main pass: diffuse cones + direct term + mode switch; pixels that need a specular cone are
 // appended to a compact list and finished by k_trace_specular (the specular march is up to two
 // orders of magnitude longer than a diffuse cone, Q12, and would stall whole warps).
@@ -466,7 +655,9 @@ DEVFN bool pixel_setup(const TraceParams& tp, int px, int py, PixelSetup& s)
 #ifndef VGI_TRACE_SPEC_MINBLOCKS
 #define VGI_TRACE_SPEC_MINBLOCKS 1
 #endif
-template <int NCONES>
+// SVO = true: the same tile / compaction machinery marching the octree (voxelConeTracing_Octree.frag); the
+// per-pixel combine follows that shader (normalisation by the sum of cosines, clamps, specular cone inline).
+template <int NCONES, bool SVO>
 __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(const __grid_constant__ TraceParams tp)
 {
     __shared__ float s_pix[8][TILE_PIX];            // startPos xyz, normal xyz, minLevel, valid
@@ -481,7 +672,7 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     const int tx0 = (blockIdx.x % tilesX) * TILE_W, ty0 = tp.y0 + (tp.tile_phase + (int)(blockIdx.x / tilesX) * tp.tile_stride) * TILE_H;
     const uint32_t mode = tp.p.rendering_mode;
     const bool needCones = mode == 4 || mode == 5 || mode == 7 || mode == 8;
-    const bool needDirect = mode == 4 || mode == 5 || mode == 8;
+    const bool needDirect = SVO ? (mode == 4 || mode == 8) : (mode == 4 || mode == 5 || mode == 8);
     const bool needSpec = mode == 6 || mode == 8;
     const float (*cones)[3] = NCONES == 32 ? c_cones32 : c_cones16;
 
@@ -495,7 +686,7 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
         s_pix[3][tid] = s.normal[0]; s_pix[4][tid] = s.normal[1]; s_pix[5][tid] = s.normal[2];
         s_pix[6][tid] = s.minLevel;
         s_pix[7][tid] = valid ? 1.0f : 0.0f;
-    } else if (tid == 127 && needCones) {
+    } else if (tid == 127 && needCones && !SVO) {
         build_step_table(tp, s_table, tp.cone_coeff_diffuse, fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor));
     }
     __syncthreads();
@@ -541,7 +732,8 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
             const float sp[3] = { s_pix[0][pix], s_pix[1][pix], s_pix[2][pix] };
             const float cosTheta = s_pix[3][pix] * dir[0] + s_pix[4][pix] * dir[1] + s_pix[5][pix] * dir[2];
             float c[4];
-            if (s_table.n >= 0) trace_cone_table(tp, s_table, sp, dir, s_pix[6][pix], c);
+            if (SVO) svo_trace_cone(tp, sp, dir, tp.cone_coeff_diffuse, s_pix[6][pix], fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor), c);
+            else if (s_table.n >= 0) trace_cone_table(tp, s_table, sp, dir, s_pix[6][pix], c);
             else trace_cone(tp, sp, dir, tp.cone_coeff_diffuse, MAX_TRACE_DISTANCE, s_pix[6][pix],
                             fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor), c);
             s_res[cone][pix] = make_float4(c[0] * cosTheta, c[1] * cosTheta, c[2] * cosTheta, c[3] * cosTheta);
@@ -555,6 +747,10 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     pixel_setup(tp, px, py, s);
     const size_t pi = (size_t)py * tp.width + px;
     float indirect[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+    if (SVO) {
+        svo_finish_pixel<NCONES>(tp, s, pi, cones, s_res, tid, needCones, needDirect, needSpec);
+        return;
+    }
     if (needCones) {
 #pragma unroll 4
         for (int i = 0; i < NCONES; ++i) {
@@ -702,212 +898,14 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// SVO cone tracing. ref: voxelConeTracing_Octree.frag:148-409 (bbox parameterised, Q14; same >>1 as the
-// build, Q13). Samples are point descents through the node pool (no filtering), two per step.
-// ---------------------------------------------------------------------------------------------------
-DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t level, float* o)
-{
-    uint32_t resolution = (uint32_t)tp.p.volume_dimension;
-    uint32_t fp[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float scaled = (position[k] - tp.svo_center[k]) / tp.svo_extent;
-        float g = ((scaled + 1.0f) * 0.5f) * (float)resolution;
-        g = f_clamp(g, 0.0f, (float)resolution);
-        fp[k] = ((uint32_t)g) >> 1;
-    }
-    const uint32_t targetResolution = 1u << level;
-    uint32_t idx = 0, cur = 0;
-    do {
-        resolution >>= 1;
-        const uint32_t cx = fp[0] >= resolution, cy = fp[1] >= resolution, cz = fp[2] >= resolution;
-        idx = cur + (cz | (cx << 1) | (cy << 2));
-        cur = __ldg(&tp.svo_nodes[idx].x) & 0x7fffffffu;
-        fp[0] -= cx * resolution; fp[1] -= cy * resolution; fp[2] -= cz * resolution;
-    } while (cur != 0u && resolution > targetResolution);
-    const uint32_t y = __ldg(&tp.svo_nodes[idx].y);
-    o[0] = (float)(y & 0xffu) * (1.0f / 255.0f);
-    o[1] = (float)((y >> 8) & 0xffu) * (1.0f / 255.0f);
-    o[2] = (float)((y >> 16) & 0xffu) * (1.0f / 255.0f);
-    o[3] = (float)(y >> 24) * (1.0f / 255.0f);
-}
-
-DEVFN void svo_trace_cone(const TraceParams& tp, const float* startPos_, const float* dir, float coneCoefficient,
-                          float startLevel, float stepFactor, float* out)
-{
-    const vgi_vct_params& p = tp.p;
-    float result[4] = { 0.f, 0.f, 0.f, 0.f };
-    float voxelSize = p.voxel_size * exp2f(startLevel);
-    float startPos[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize * p.trace_start_offset * 0.5f;
-    float step = 0.0f;
-    float diameter = fmaxf(step * coneCoefficient, p.voxel_size);
-    float occlusion = 0.0f;
-    float curSegmentLength = voxelSize;
-    const float minRadius = p.voxel_size * p.volume_dimension * 0.5f;
-    while (step < MAX_TRACE_DISTANCE && occlusion < 1.0f) {
-        float position[3], d[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            position[k] = startPos[k] + dir[k] * step;
-            d[k] = p.volume_center[k] - position[k];
-        }
-        const float dist = sqrtf(dot3(d, d));
-        const float minLevel = ceilf(log2f(dist / minRadius));
-        float curLevel = log2f(diameter / p.voxel_size);
-        curLevel = fminf(fmaxf(fmaxf(startLevel, curLevel), minLevel), tp.svo_max_level);
-        float lo[4], up[4], smp[4];
-        sample_svo(tp, position, (uint32_t)floorf(curLevel), lo);
-        const float fr = f_fract(curLevel);
-        if (fr > 0.0f) {
-            sample_svo(tp, position, (uint32_t)ceilf(curLevel), up);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) smp[c] = lo[c] * (1.0f - fr) + up[c] * fr;
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) smp[c] = lo[c];
-        }
-        voxelSize = p.voxel_size * exp2f(curLevel);
-        const float correction = curSegmentLength / voxelSize;
-        float opacity = 0.0f;
-        if (smp[3] > 0.0f) opacity = f_clamp(1.0f - exp2f(correction * log2f(1.0f - smp[3])), 0.0f, 1.0f);
-        const float k1 = f_clamp(1.0f - result[3], 0.0f, 1.0f);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) result[c] += k1 * (smp[c] * correction);
-        result[3] += k1 * opacity;
-        occlusion += ((1.0f - occlusion) * opacity) / (1.0f + (step + voxelSize) * p.occlusion_decay);
-        const float prevStep = step;
-        step += fmaxf(diameter, p.voxel_size) * stepFactor;
-        curSegmentLength = step - prevStep;
-        diameter = step * coneCoefficient;
-    }
-    out[0] = f_clamp(result[0], 0.0f, 1.0f);
-    out[1] = f_clamp(result[1], 0.0f, 1.0f);
-    out[2] = f_clamp(result[2], 0.0f, 1.0f);
-    out[3] = f_clamp(1.0f - occlusion, 0.0f, 1.0f);
-}
-
-__global__ void __launch_bounds__(128) k_trace_svo(const __grid_constant__ TraceParams tp)
-{
-    const int px = blockIdx.x * 16 + (threadIdx.x & 15);
-    const int py = tp.y0 + blockIdx.y * 8 + (threadIdx.x >> 4);
-    if (px >= tp.width || py >= tp.y1) return;
-    PixelSetup s;
-    if (!pixel_setup(tp, px, py, s)) return;
-    const size_t pi = (size_t)py * tp.width + px;
-    const uint32_t mode = tp.p.rendering_mode;
-    const bool needCones = mode == 4 || mode == 5 || mode == 7 || mode == 8;
-    const bool needDirect = mode == 4 || mode == 8;
-    const bool needSpec = mode == 6 || mode == 8;
-
-    float indirect[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
-    if (needCones) {
-        const int ncones = tp.p.enable_32_cones ? 32 : 16;
-        const float stepFactor = fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor);
-        float validConeCount = 0.0f;
-        for (int i = 0; i < ncones; ++i) {
-            float dir[3];
-            if (tp.p.enable_32_cones) { dir[0] = c_cones32[i][0]; dir[1] = c_cones32[i][1]; dir[2] = c_cones32[i][2]; }
-            else { dir[0] = c_cones16[i][0]; dir[1] = c_cones16[i][1]; dir[2] = c_cones16[i][2]; }
-            const float cosTheta = dot3(s.normal, dir);
-            if (cosTheta < 0.0f) continue;
-            float c[4];
-            svo_trace_cone(tp, s.startPos, dir, tp.cone_coeff_diffuse, s.minLevel, stepFactor, c);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) indirect[k] += c[k] * cosTheta;
-            validConeCount += cosTheta;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) indirect[k] /= validConeCount; // Q11: normalised by the sum of cosines
-        indirect[3] *= tp.p.ambient_occlusion_factor;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) indirect[k] *= s.diffuseColor[k] * tp.p.indirect_diffuse_intensity;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) indirect[k] = f_clamp(indirect[k], 0.0f, 1.0f);
-    }
-
-    float spec[3] = { 0.f, 0.f, 0.f };
-    if (needSpec && (s.specularColor[0] > 1e-6f || s.specularColor[1] > 1e-6f || s.specularColor[2] > 1e-6f) && s.metallic > 1e-6f) {
-        const float I[3] = { -s.view[0], -s.view[1], -s.view[2] };
-        const float dn = dot3(s.normal, I);
-        const float r[3] = { I[0] - 2.0f * dn * s.normal[0], I[1] - 2.0f * dn * s.normal[1], I[2] - 2.0f * dn * s.normal[2] };
-        float sdir[3];
-        normalize3(r, sdir);
-        const float aperture = fmaxf(s.perceptualRoughness, MIN_SPECULAR_APERTURE);
-        float c[4];
-        // ref: voxelConeTracing_Octree.frag:215-219 — stepFactor = max(0.2, uVoxelSize) (Q12)
-        svo_trace_cone(tp, s.startPos, sdir, 2.0f * tanf(aperture * 0.5f), s.minLevel, fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.voxel_size), c);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) spec[k] = (c[k] * s.specularColor[k]) * tp.p.indirect_specular_intensity;
-    }
-
-    float direct[3] = { 0.f, 0.f, 0.f };
-    if (needDirect) {
-        if (s.emission[0] > 0.0f || s.emission[1] > 0.0f || s.emission[2] > 0.0f) {
-            direct[0] = s.emission[0]; direct[1] = s.emission[1]; direct[2] = s.emission[2];
-        } else {
-            const float alphaRoughness = s.perceptualRoughness * s.perceptualRoughness;
-            const float reflectance = fmaxf(fmaxf(s.specularColor[0], s.specularColor[1]), s.specularColor[2]);
-            const float r90 = f_clamp(reflectance * 50.0f, 0.0f, 1.0f);
-            const float* L = tp.light.dir_to_light;
-            float h[3];
-            {
-                const float t[3] = { L[0] + s.view[0], L[1] + s.view[1], L[2] + s.view[2] };
-                normalize3(t, h);
-            }
-            const float NdotL = f_clamp(dot3(s.normal, L), 0.001f, 1.0f);
-            const float NdotV = f_clamp(fabsf(dot3(s.normal, s.view)), 0.001f, 1.0f);
-            const float NdotH = f_clamp(dot3(s.normal, h), 0.0f, 1.0f);
-            const float VdotH = f_clamp(dot3(s.view, h), 0.0f, 1.0f);
-            float brdf[3];
-            microfacet_brdf(NdotL, NdotV, NdotH, VdotH, alphaRoughness, s.specularColor, r90, s.diffuseColor, brdf);
-            const float vis = calc_visibility(tp, s.worldPos);
-            direct[0] = brdf[0] * vis; direct[1] = brdf[1] * vis; direct[2] = brdf[2] * vis;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) direct[k] = f_clamp(direct[k], 0.0f, 1.0f);
-    }
-
-    float4 dc = make_float4(0.f, 0.f, 0.f, 1.f), sc = make_float4(0.f, 0.f, 0.f, 1.f);
-    switch (mode) {
-    case 0: dc = make_float4(s.diffuseColor[0], s.diffuseColor[1], s.diffuseColor[2], 1.f); break;
-    case 1: dc = make_float4(s.specularColor[0], s.specularColor[1], s.specularColor[2], 1.f); break;
-    case 2: dc = make_float4(s.normal[0] * 0.5f + 0.5f, s.normal[1] * 0.5f + 0.5f, s.normal[2] * 0.5f + 0.5f, 1.f); break;
-    case 3: { // minLevelToColor, voxelConeTracing_Octree.frag:433-458
-        float col[4] = { 0.f, 0.f, 0.f, 0.f };
-        if (s.minLevel < 6.0f) {
-            int lower = (int)floorf(s.minLevel);
-            lower = lower < 0 ? 0 : lower;
-            const float fr = f_fract(s.minLevel);
-            for (int k = 0; k < 4; ++k) col[k] = c_level_colors[lower][k] * (1.0f - fr) + c_level_colors[lower + 1][k] * fr;
-        }
-        dc = make_float4(col[0] * 0.5f, col[1] * 0.5f, col[2] * 0.5f, col[3] * 0.5f);
-        break;
-    }
-    case 4: dc = make_float4(direct[0] * indirect[3], direct[1] * indirect[3], direct[2] * indirect[3], 1.f); break;
-    case 5: dc = make_float4(indirect[0], indirect[1], indirect[2], 1.f); break; // direct not added (_Octree.frag:283-287)
-    case 6: sc = make_float4(spec[0], spec[1], spec[2], 1.f); break;
-    case 7: dc = make_float4(indirect[3], indirect[3], indirect[3], 1.f); break;
-    case 8:
-        dc = make_float4(direct[0] * indirect[3] + indirect[0], direct[1] * indirect[3] + indirect[1],
-                         direct[2] * indirect[3] + indirect[2], 1.f);
-        sc = make_float4(spec[0], spec[1], spec[2], 1.f);
-        break;
-    default: break;
-    }
-    tp.out_diffuse[pi] = dc;
-    tp.out_specular[pi] = sc;
-}
-
 int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
 {
     const int rows = tp.y1 - tp.y0;
     if (rows <= 0 || tp.width <= 0) return 0;
-    dim3 grid((tp.width + 15) / 16, (rows + 7) / 8);
+    const unsigned grid = (unsigned)(((tp.width + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H));
     c->timer.begin("k_trace_svo", s);
-    k_trace_svo<<<grid, 128, 0, s>>>(tp);
+    if (tp.p.enable_32_cones) k_trace_main<32, true><<<grid, 128, 0, s>>>(tp);
+    else k_trace_main<16, true><<<grid, 128, 0, s>>>(tp);
     c->timer.end(s);
     return 1;
 }
@@ -923,8 +921,8 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     if (myTileRows <= 0) return 0;
     const unsigned grid = (unsigned)(((tp.width + TILE_W - 1) / TILE_W) * myTileRows);
     c->timer.begin("k_trace_main", s);
-    if (tp.p.enable_32_cones) k_trace_main<32><<<grid, 128, 0, s>>>(tp);
-    else k_trace_main<16><<<grid, 128, 0, s>>>(tp);
+    if (tp.p.enable_32_cones) k_trace_main<32, false><<<grid, 128, 0, s>>>(tp);
+    else k_trace_main<16, false><<<grid, 128, 0, s>>>(tp);
     ++n;
     c->timer.end(s);
     if (c->mark_main_done) cudaEventRecord(c->mark_main_done, s); // the diffuse image is complete here
