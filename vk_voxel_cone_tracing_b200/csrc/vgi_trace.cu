@@ -451,7 +451,18 @@ DEVFN bool pixel_setup(const TraceParams& tp, int px, int py, PixelSetup& s)
 // SVO cone tracing. ref: voxelConeTracing_Octree.frag:148-409 (bbox parameterised, Q14; same >>1 as the
 // build, Q13). Samples are point descents through the node pool (no filtering), two per step.
 // ---------------------------------------------------------------------------------------------------
-DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t level, float* o)
+DEVFN void svo_unpack(uint32_t y, float* o)
+{
+    o[0] = (float)(y & 0xffu) * (1.0f / 255.0f);
+    o[1] = (float)((y >> 8) & 0xffu) * (1.0f / 255.0f);
+    o[2] = (float)((y >> 16) & 0xffu) * (1.0f / 255.0f);
+    o[3] = (float)(y >> 24) * (1.0f / 255.0f);
+}
+
+// Point samples at `level` (lo) and, when two = true, also at level + 1 (up) with ONE descent: the coarser
+// sample is the node where the descent of sampleSVO (voxelConeTracing_Octree.frag:319-346) would stop for the
+// coarser target resolution, the finer one is at most one step further down the same path.
+DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t level, bool two, float* lo, float* up)
 {
     uint32_t resolution = (uint32_t)tp.p.volume_dimension;
     uint32_t fp[3];
@@ -462,7 +473,8 @@ DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t lev
         g = f_clamp(g, 0.0f, (float)resolution);
         fp[k] = ((uint32_t)g) >> 1;
     }
-    const uint32_t targetResolution = 1u << level;
+    const uint32_t targetLo = 1u << level;
+    const uint32_t targetFirst = two ? targetLo << 1 : targetLo;
     uint32_t idx = 0, cur = 0;
     do {
         resolution >>= 1;
@@ -470,12 +482,24 @@ DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t lev
         idx = cur + (cz | (cx << 1) | (cy << 2));
         cur = __ldg(&tp.svo_nodes[idx].x) & 0x7fffffffu;
         fp[0] -= cx * resolution; fp[1] -= cy * resolution; fp[2] -= cz * resolution;
-    } while (cur != 0u && resolution > targetResolution);
-    const uint32_t y = __ldg(&tp.svo_nodes[idx].y);
-    o[0] = (float)(y & 0xffu) * (1.0f / 255.0f);
-    o[1] = (float)((y >> 8) & 0xffu) * (1.0f / 255.0f);
-    o[2] = (float)((y >> 16) & 0xffu) * (1.0f / 255.0f);
-    o[3] = (float)(y >> 24) * (1.0f / 255.0f);
+    } while (cur != 0u && resolution > targetFirst);
+    const uint32_t yFirst = __ldg(&tp.svo_nodes[idx].y);
+    if (!two) {
+        svo_unpack(yFirst, lo);
+        return;
+    }
+    svo_unpack(yFirst, up);
+    uint32_t yLo = yFirst;
+    // the finer descent continues while a child block exists and the resolution is above its target
+    while (cur != 0u && resolution > targetLo) {
+        resolution >>= 1;
+        const uint32_t cx = fp[0] >= resolution, cy = fp[1] >= resolution, cz = fp[2] >= resolution;
+        idx = cur + (cz | (cx << 1) | (cy << 2));
+        cur = __ldg(&tp.svo_nodes[idx].x) & 0x7fffffffu;
+        fp[0] -= cx * resolution; fp[1] -= cy * resolution; fp[2] -= cz * resolution;
+        yLo = __ldg(&tp.svo_nodes[idx].y);
+    }
+    svo_unpack(yLo, lo);
 }
 
 DEVFN void svo_trace_cone(const TraceParams& tp, const float* startPos_, const float* dir, float coneCoefficient,
@@ -506,10 +530,9 @@ DEVFN void svo_trace_cone(const TraceParams& tp, const float* startPos_, const f
         float lo[4], smp[4];
         const float fl = floorf(curLevel);
         const float fr = curLevel - fl;
-        sample_svo(tp, position, (uint32_t)fl, lo);
+        float up[4];
+        sample_svo(tp, position, (uint32_t)fl, fr > 0.0f, lo, up);
         if (fr > 0.0f) {
-            float up[4];
-            sample_svo(tp, position, (uint32_t)fl + 1u, up);
 #pragma unroll
             for (int c = 0; c < 4; ++c) smp[c] = lo[c] * (1.0f - fr) + up[c] * fr;
         } else {
