@@ -89,6 +89,7 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
         CK(c, cudaMalloc(&c->brick_mask, nb));
         CK(c, cudaMemset(c->brick_mask, 0, nb));
         CK(c, cudaMalloc(&c->footprint, nvox * L));
+        CK(c, cudaMemset(c->footprint, 0, nvox * L)); // read speculatively next to the brick bit: keep it defined
     }
     CK(c, cudaMalloc(&c->block_sums, ((nwords + 4095) / 4096 + 1) * sizeof(uint32_t)));
     CK(c, cudaMalloc(&c->counters, sizeof(Counters)));
