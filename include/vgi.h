@@ -167,6 +167,14 @@ typedef struct vgi_vct_params {
     int32_t  enable_32_cones;
 } vgi_vct_params;
 
+/* ref: VFS/RenderPass/SpecularFilterPass.h:31-37 (16-byte push constant block of specularFilter.frag) */
+typedef struct vgi_filter_params {
+    float   tonemap_gamma;          /* SpecularFilterPass.h:48 (2.2) */
+    float   tonemap_exposure;       /* :49 (0.1) */
+    int32_t tonemap_enable;         /* :50 (0) */
+    int32_t filter_method;          /* :51 (1): 0 = bilateral 15x15, 1 = gaussian 32 x 8 taps, other = bilateral */
+} vgi_filter_params;
+
 /* Counters from the last build, for roofline accounting and overflow diagnosis. */
 typedef struct vgi_stats {
     uint64_t triangles;             /* triangles in the scene */
@@ -267,6 +275,16 @@ int vgi_cone_trace_interleaved(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gb
 /* Fill params with the reference defaults (VoxelConeTracingPass.h:75-82) and the volume fields
  * derived from the ctx's level-0 region (VoxelConeTracingPass.cpp:88-93). */
 int vgi_default_vct_params(vgi_ctx* ctx, vgi_vct_params* out);
+
+/* ---- the pass after cone tracing ------------------------------------------ */
+/* replaces: SpecularFilterPass::onUpdate (SpecularFilterPass.cpp:73-91) + specularFilter.frag:25-53,
+ * filter.glsl:9-24,44-63, tonemapping.glsl:4-26: final = diffuse + filtered specular, optional Uncharted-2
+ * tonemap. diffuse / specular: the two width*height float4 images of vgi_cone_trace, sampled LINEAR +
+ * CLAMP_TO_EDGE as by "VCTSampler" (VoxelConeTracingPass.cpp:147); out: width*height float4
+ * ("FinalOutputImageView", R32G32B32A32_SFLOAT, SpecularFilterPass.cpp:111). params NULL = defaults. */
+void vgi_default_filter_params(vgi_filter_params* out);
+int  vgi_specular_filter(vgi_ctx* ctx, const void* diffuse, const void* specular, uint32_t width,
+                         uint32_t height, const vgi_filter_params* params, void* out, void* stream);
 
 /* ---- whole frame with HOST buffers ---------------------------------------------------------- */
 /* replaces: one iteration of Application::run's pass sequence for this path (Application.cpp:178,192,221:

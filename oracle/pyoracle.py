@@ -160,6 +160,16 @@ def cone_trace(cfg, cam, gbuf, prm, light, shadow, shadow_depth, radiance, rows=
 
 # ---- SVO ------------------------------------------------------------------------------------------
 
+def specular_filter(diffuse, specular, prm):
+    """diffuse / specular: (H, W, 4) float32 numpy; returns the final (H, W, 4) image (vgo_specular_filter)."""
+    h, w = diffuse.shape[:2]
+    d = np.ascontiguousarray(diffuse, dtype=np.float32)
+    s_ = np.ascontiguousarray(specular, dtype=np.float32)
+    out = np.empty((h, w, 4), dtype=np.float32)
+    lib().vgo_specular_filter(_p(d), _p(s_), C.c_uint32(w), C.c_uint32(h), C.byref(prm), _p(out))
+    return out
+
+
 def svo_fragments(level, bb_min, bb_max, osc, light, shadow, shadow_depth, mode_flags=0):
     sh, sw = shadow_depth.shape
     args = (C.c_uint32(level), (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)),

@@ -1049,6 +1049,104 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
     if (taps) *taps = total_taps;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Specular filter + tonemap. ref: specularFilter.frag:25-53, filter.glsl, tonemapping.glsl.
+ * texture() on the RGBA32F attachments: bilinear, CLAMP_TO_EDGE, texel centres at +0.5 (Vulkan spec
+ * 16.8 "texel filtering", full float weights); texCoord of the fullscreen quad = (pixel + 0.5) / size.
+ * Float loop counters are kept literal (32 directions x 8 radii with binary32 accumulation).
+ * ---------------------------------------------------------------------------------------------- */
+static void tex2d_linear_clamp(const float* img, uint32_t w, uint32_t h, float u, float v, float* o)
+{
+    const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float a = x - fx, b = y - fy;
+    int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    x0 = x0 < 0 ? 0 : (x0 > (int)w - 1 ? (int)w - 1 : x0);
+    x1 = x1 < 0 ? 0 : (x1 > (int)w - 1 ? (int)w - 1 : x1);
+    y0 = y0 < 0 ? 0 : (y0 > (int)h - 1 ? (int)h - 1 : y0);
+    y1 = y1 < 0 ? 0 : (y1 > (int)h - 1 ? (int)h - 1 : y1);
+    const float* t00 = img + ((size_t)y0 * w + x0) * 4;
+    const float* t10 = img + ((size_t)y0 * w + x1) * 4;
+    const float* t01 = img + ((size_t)y1 * w + x0) * 4;
+    const float* t11 = img + ((size_t)y1 * w + x1) * 4;
+    for (int k = 0; k < 4; ++k)
+        o[k] = (t00[k] * (1.0f - a) + t10[k] * a) * (1.0f - b) + (t01[k] * (1.0f - a) + t11[k] * a) * b;
+}
+
+/* filter.glsl:9-24 */
+static void gaussian_blur(const float* img, uint32_t w, uint32_t h, float u, float v, float blurSize, float* o)
+{
+    const float DOUBLE_PI = 6.28318530718f, DIRECTIONS = 32.0f, QUALITY = 8.0f;
+    const float rx = blurSize / (float)w, ry = blurSize / (float)h;
+    float color[4];
+    tex2d_linear_clamp(img, w, h, u, v, color);
+    for (float d = 0.0f; d < DOUBLE_PI; d += DOUBLE_PI / DIRECTIONS)
+        for (float i = 1.0f / QUALITY; i <= 1.0f; i += 1.0f / QUALITY) {
+            float t[4];
+            tex2d_linear_clamp(img, w, h, u + (cosf(d) * rx) * i, v + (sinf(d) * ry) * i, t);
+            for (int k = 0; k < 4; ++k) color[k] += t[k];
+        }
+    for (int k = 0; k < 4; ++k) o[k] = color[k] / (QUALITY * DIRECTIONS - 15.0f);
+}
+
+/* filter.glsl:27-63 */
+static float normpdf(float x, float sigma) { return 0.39894f * expf(-0.5f * x * x / (sigma * sigma)) / sigma; }
+static void bilateral_filter(const float* img, uint32_t w, uint32_t h, float u, float v, float* o)
+{
+    static const float KERNEL[15] = { 0.031225216f, 0.033322271f, 0.035206333f, 0.036826804f, 0.038138565f,
+        0.039104044f, 0.039695028f, 0.039894000f, 0.039695028f, 0.039104044f, 0.038138565f, 0.036826804f,
+        0.035206333f, 0.033322271f, 0.031225216f };
+    const float BSIGMA = 10.0f;
+    float fin[3] = { 0.f, 0.f, 0.f }, center[4];
+    tex2d_linear_clamp(img, w, h, u, v, center);
+    float Z = 0.0f;
+    const float bZ = 1.0f / normpdf(0.0f, BSIGMA);
+    const float irx = 1.0f / (float)w, iry = 1.0f / (float)h;
+    for (int i = -7; i <= 7; ++i)
+        for (int j = -7; j <= 7; ++j) {
+            float s[4];
+            tex2d_linear_clamp(img, w, h, u + (float)i * irx, v + (float)j * iry, s);
+            const float dv[3] = { s[0] - center[0], s[1] - center[1], s[2] - center[2] };
+            const float pdf3 = 0.39894f * expf(-0.5f * dot3(dv, dv) / (BSIGMA * BSIGMA)) / BSIGMA;
+            const float factor = pdf3 * bZ * KERNEL[7 + j] * KERNEL[7 + i];
+            Z += factor;
+            for (int k = 0; k < 3; ++k) fin[k] += factor * s[k];
+        }
+    for (int k = 0; k < 3; ++k) o[k] = fin[k] / Z;
+}
+
+/* tonemapping.glsl:9-26 */
+static float uncharted2(float c)
+{
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
+}
+
+void vgo_specular_filter(const float* diffuse, const float* specular, uint32_t w, uint32_t h,
+                         const vgi_filter_params* prm, float* out)
+{
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t py = 0; py < (int64_t)h; ++py)
+        for (uint32_t px = 0; px < w; ++px) {
+            const float u = ((float)px + 0.5f) / (float)w, v = ((float)py + 0.5f) / (float)h;
+            float fc[4];
+            tex2d_linear_clamp(diffuse, w, h, u, v, fc);
+            float sc[4] = { 0.f, 0.f, 0.f, 1.f };
+            if (prm->filter_method == 1) gaussian_blur(specular, w, h, u, v, 0.01f, sc);
+            else bilateral_filter(specular, w, h, u, v, sc);
+            for (int k = 0; k < 3; ++k) fc[k] += sc[k];
+            float* o = out + ((size_t)py * w + px) * 4;
+            if (prm->tonemap_enable == 1) {
+                const float white = 1.0f / uncharted2(11.2f);
+                for (int k = 0; k < 3; ++k)
+                    o[k] = powf(uncharted2(fc[k] * prm->tonemap_exposure) * white, 1.0f / prm->tonemap_gamma);
+                o[3] = fc[3];
+            } else {
+                memcpy(o, fc, sizeof fc);
+            }
+        }
+}
+
 /* SVO path: shares the helpers above (single translation unit). */
 /* thread count of the OpenMP loops (torchrun exports OMP_NUM_THREADS=1; the CPU baseline uses every core) */
 int vgo_set_threads(int n)

@@ -89,6 +89,11 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
                     float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1,
                     uint64_t* taps);
 
+/* ref: specularFilter.frag:25-53, filter.glsl:9-24 (gaussian), :27-63 (bilateral), tonemapping.glsl:4-26;
+ * sampler LINEAR / CLAMP_TO_EDGE (VoxelConeTracingPass.cpp:147). HOST float4 images. */
+void vgo_specular_filter(const float* diffuse, const float* specular, uint32_t w, uint32_t h,
+                         const vgi_filter_params* prm, float* out);
+
 /* ---- SVO (vgi_oracle_svo.inc, compiled as part of vgi_oracle.c) ---- */
 /* ref: voxelizer.vert:37-48, voxelizer.geom:39-56, voxelizer.frag:48-103. Fragments are emitted
  * in (triangle, z, y, x) order. frags may be NULL to count only. returns count. */

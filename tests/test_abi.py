@@ -69,14 +69,15 @@ def test_struct_sizes_match_header(tmp_path):
     from vk_voxel_cone_tracing_b200 import structs as S
     prog = tmp_path / "sizes.c"
     names = ["vgi_config", "vgi_clip_region", "vgi_camera", "vgi_dir_light", "vgi_dir_light_shadow", "vgi_material",
-             "vgi_primitive", "vgi_node_matrix", "vgi_scene_desc", "vgi_gbuffer", "vgi_vct_params", "vgi_stats"]
+             "vgi_primitive", "vgi_node_matrix", "vgi_scene_desc", "vgi_gbuffer", "vgi_vct_params", "vgi_stats",
+             "vgi_filter_params"]
     body = "".join(f'printf("%zu\\n", sizeof({n}));' for n in names)
     prog.write_text(f'#include <stdio.h>\n#include "{HEADER}"\nint main(void){{{body}return 0;}}\n')
     exe = tmp_path / "sizes"
     subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-o", str(exe), str(prog)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     mirrors = [S.Config, S.ClipRegion, S.Camera, S.DirLight, S.DirLightShadow, S.Material, S.Primitive, S.NodeMatrix,
-               S.SceneDesc, S.GBuffer, S.VctParams, S.Stats]
+               S.SceneDesc, S.GBuffer, S.VctParams, S.Stats, S.FilterParams]
     assert sizes == [C.sizeof(m) for m in mirrors]
     assert C.sizeof(S.Material) == 80 and C.sizeof(S.VctParams) == 52   # gltf.glsl:8-26, VoxelConeTracingPass.h:46-59
 

@@ -198,3 +198,25 @@ def test_injection_single_lit_quad(oracle):
     t0 = _atlas_voxel(cfg, rad, 0, 0, 1, 0, 1)
     assert tuple(int(c) for c in t0)[:3] == (0, 0, 0)
     assert tuple(int(c) for c in _atlas_voxel(cfg, op, 0, 0, 1, 0, 1)) == (255, 255, 255, 255)
+
+
+def test_specular_filter_known_answers(oracle):
+    """Closed forms of specularFilter.frag on constant images: the gaussian sums 257 taps and divides by
+    8 * 32 - 15 = 241 (filter.glsl:11-23), the bilateral filter of a constant is the constant, and the
+    Uncharted-2 curve maps its white point 11.2 / exposure to 1 (tonemapping.glsl:21-26)."""
+    from vk_voxel_cone_tracing_b200 import structs as S
+    h, w = 9, 12
+    dif = np.zeros((h, w, 4), np.float32); dif[..., 3] = 1.0
+    spc = np.full((h, w, 4), 0.5, np.float32)
+    out = oracle.specular_filter(dif, spc, S.default_filter_params(1, 0))
+    np.testing.assert_allclose(out[..., :3], 0.5 * 257.0 / 241.0, rtol=2e-6)
+    np.testing.assert_allclose(out[..., 3], 1.0)
+    out = oracle.specular_filter(dif, spc, S.default_filter_params(0, 0))
+    np.testing.assert_allclose(out[..., :3], 0.5, rtol=2e-6)
+    dif[..., :3] = 11.2 / 0.1
+    out = oracle.specular_filter(dif, np.zeros_like(spc), S.default_filter_params(0, 1))
+    np.testing.assert_allclose(out[..., :3], 1.0, rtol=1e-5)
+    # a single bright texel: the gaussian spreads < 1 % of it to each neighbour (blurSize 0.01 is in texels / size)
+    spc[:] = 0.0; spc[4, 6, :3] = 1.0; dif[..., :3] = 0.0
+    out = oracle.specular_filter(dif, spc, S.default_filter_params(1, 0))
+    assert abs(out[4, 6, 0] - 257.0 / 241.0) < 0.02 and 0.0 < out[4, 7, 0] < 0.01 and out[4, 9, 0] == 0.0

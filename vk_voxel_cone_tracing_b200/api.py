@@ -237,6 +237,17 @@ class VoxelGI:
                                          C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), _stream(stream)))
         return out
 
+    def specular_filter(self, diffuse, specular, params=None, out=None, stream=None):
+        """final = diffuse + filtered specular (+ tonemap): the pass after cone tracing (vgi_specular_filter)."""
+        torch = self._torch
+        h, w = diffuse.shape[0], diffuse.shape[1]
+        if out is None:
+            out = torch.empty((h, w, 4), dtype=torch.float32, device=self.device)
+        self._ck(lib().vgi_specular_filter(self._h, C.c_void_p(diffuse.data_ptr()), C.c_void_p(specular.data_ptr()),
+                                          C.c_uint32(w), C.c_uint32(h), C.byref(params) if params is not None else None,
+                                          C.c_void_p(out.data_ptr()), _stream(stream)))
+        return out
+
     # -- helper passes on caller-owned reference-layout atlases (uint8 CUDA tensors of atlas_shape)
     def atlas_clear_region(self, atlas, min_corner, extent, level, stream=None):
         self._ck(lib().vgi_atlas_clear_region(self._h, C.c_void_p(atlas.data_ptr()), (C.c_int32 * 3)(*min_corner),

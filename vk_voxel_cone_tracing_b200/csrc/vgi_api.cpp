@@ -826,6 +826,34 @@ int vgi_atlas_wrap_border(vgi_ctx* c, void* atlas, void* stream)
     return check_launch(c, "vgi_atlas_wrap_border");
 }
 
+// ---- specular filter + tonemap (the pass after cone tracing) --------------------------------------
+
+void vgi_default_filter_params(vgi_filter_params* p)
+{
+    if (!p) return;
+    p->tonemap_gamma = 2.2f;     // ref: SpecularFilterPass.h:48-51
+    p->tonemap_exposure = 0.1f;
+    p->tonemap_enable = 0;
+    p->filter_method = 1;
+}
+
+int vgi_specular_filter(vgi_ctx* c, const void* diffuse, const void* specular, uint32_t width, uint32_t height,
+                        const vgi_filter_params* params, void* out, void* stream)
+{
+    if (!c || !diffuse || !specular || !out) return fail(c, VGI_E_INVALID, "vgi_specular_filter: null argument");
+    if (!width || !height) return fail(c, VGI_E_INVALID, "vgi_specular_filter: empty image");
+    if (out == diffuse || out == specular) return fail(c, VGI_E_INVALID, "vgi_specular_filter: out must not alias an input");
+    vgi_filter_params prm;
+    if (params) prm = *params;
+    else vgi_default_filter_params(&prm);
+    if (prm.tonemap_enable == 1 && !(prm.tonemap_gamma > 0.0f))
+        return fail(c, VGI_E_INVALID, "vgi_specular_filter: tonemap_gamma must be positive");
+    CK(c, cudaSetDevice(c->device));
+    c->launches += vgi_launch_specular_filter(c, diffuse, specular, width, height, &prm, out, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_specular_filter");
+}
+
 // ---- whole frame with host buffers ----------------------------------------------------------------
 
 int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,

@@ -211,5 +211,7 @@ int vgi_launch_atlas_clear(uint8_t* atlas, int R, int L, const int32_t* mc, cons
 int vgi_launch_atlas_copy_alpha(uint8_t* dst, const uint8_t* src, int R, int L, int level, cudaStream_t s);
 int vgi_launch_atlas_downsample(uint8_t* atlas, int R, int L, int band, const int32_t* prev_min, int level, int which, cudaStream_t s);
 int vgi_launch_atlas_wrap(uint8_t* atlas, int R, int L, int literal, cudaStream_t s);
+int vgi_launch_specular_filter(vgi_ctx* c, const void* diffuse, const void* specular, uint32_t width, uint32_t height,
+                               const vgi_filter_params* prm, void* out, cudaStream_t s);
 
 void build_params_from_ctx(const vgi_ctx* c, uint32_t frame_index, BuildParams* bp);

@@ -157,6 +157,20 @@ class VctParams(C.Structure):
 assert C.sizeof(VctParams) == 52
 
 
+class FilterParams(C.Structure):
+    """vgi_filter_params — ref: VFS/RenderPass/SpecularFilterPass.h:31-37 (16 bytes)"""
+    _fields_ = [("tonemap_gamma", C.c_float), ("tonemap_exposure", C.c_float),
+                ("tonemap_enable", C.c_int32), ("filter_method", C.c_int32)]
+
+
+assert C.sizeof(FilterParams) == 16
+
+
+def default_filter_params(filter_method=1, tonemap_enable=0):
+    """Reference defaults (SpecularFilterPass.h:48-51)."""
+    return FilterParams(2.2, 0.1, tonemap_enable, filter_method)
+
+
 class Stats(C.Structure):
     _fields_ = [("triangles", C.c_uint64), ("clip_pairs", C.c_uint64), ("occupied_voxels", C.c_uint64),
                 ("svo_fragments", C.c_uint64), ("svo_nodes", C.c_uint64), ("kernel_launches", C.c_uint64)]
