@@ -47,7 +47,8 @@ def main():
     gi.build_clipmap(0)
     gb = gi.upload_gbuffer(inp["gbuffer"])
     out = (C.c_ulonglong * 8)()
-    names = ["steps", "level_samples", "brick_skipped", "loaded_all_zero", "corners_loaded", "corners_nonzero"]
+    names = ["steps", "level_samples", "brick_skipped", "loaded_all_zero", "corners_loaded", "corners_nonzero",
+             "lane_filtered", "coop_filtered"]
     for mode, label in ((7, "diffuse only (mode 7)"), (6, "specular only (mode 6)")):
         api.lib().vgi_debug_trace_stats(out, 1)
         gi.cone_trace(inp["cam"], gb, gi.default_vct_params(mode))

@@ -640,11 +640,9 @@ static int fill_trace_params(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffe
     tp.store = c->store;
     tp.brick_mask = c->brick_mask;
     tp.footprint = c->footprint;
-    for (int l = 0; l < VGI_MAX_LEVELS; ++l) {
-        // ref: voxelConeTracing.frag:315 — extent = voxelSize * volumeDimension * 2^level
-        const float extent = (prm->voxel_size * prm->volume_dimension) * exp2f((float)l);
-        tp.inv_extent[l] = 1.0f / extent;
-    }
+    // ref: voxelConeTracing.frag:315-317 — extent_l = voxelSize * volumeDimension * 2^level, texel = fract(pos / extent_l) * R
+    tp.vox_scale0 = (float)c->cfg.resolution / (prm->voxel_size * prm->volume_dimension);
+    for (int l = 0; l < VGI_MAX_LEVELS; ++l) tp.level_scale[l] = exp2f(-(float)l);
     {
         // ref: voxelConeTracing.frag:366-368 — minLevel = ceil(log2(dist / minRadius)), clamped to L-1 by the
         // tracer: ceil(log2 x) > k  <=>  x > 2^k. x(dd) = sqrtf(dd) / minRadius is monotone in the squared

@@ -79,7 +79,8 @@ struct TraceParams {
     const VoxelRecord* store;
     const uint8_t* brick_mask;    // 1 bit per 4^3 brick (dilated by one voxel on the high side), see k_brick_mask
     const uint8_t* footprint;     // per voxel of a non-empty brick: which of the 8 footprint records may be non-zero
-    float    inv_extent[VGI_MAX_LEVELS]; // 1 / (voxel_size * R * 2^level)
+    float    vox_scale0;          // R / (voxel_size * volume_dimension): world units -> level-0 voxels
+    float    level_scale[VGI_MAX_LEVELS]; // 2^-level
     float    min_level_dd[VGI_MAX_LEVELS]; // [k]: largest dist^2 with sqrtf(dd) / minRadius <= 2^k (+inf for k >= L-1)
     const void* diffuse; const void* normal; const void* specular; const void* emission;
     const float* depth;
