@@ -276,6 +276,17 @@ int vgi_cone_trace_interleaved(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gb
  * derived from the ctx's level-0 region (VoxelConeTracingPass.cpp:88-93). */
 int vgi_default_vct_params(vgi_ctx* ctx, vgi_vct_params* out);
 
+/* ---- the passes before the path: image inputs without Vulkan ------------------ */
+/* replaces: the depth attachment of ShadowMapPass / ReflectiveShadowMapPass (shadowPass.vert:33: proj * view *
+ * model, clear 1.0) for the ctx's scene. depth: width*height f32 DEVICE buffer (D32), usable as the
+ * shadow_depth of vgi_set_light. Pixel-centre sampling, depth test LESS. */
+int vgi_render_shadow_map(vgi_ctx* ctx, const vgi_dir_light_shadow* shadow, uint32_t width, uint32_t height,
+                          float* depth, void* stream);
+/* replaces: GBufferPass::onUpdate (gBufferPass.vert:45, gBufferPass.frag:62-116, factor-only materials; formats
+ * GBufferPass.cpp:177-194). target: a vgi_gbuffer whose five DEVICE buffers are WRITTEN (width*height texels
+ * each); uncovered pixels get depth 1 and zero attributes. */
+int vgi_render_gbuffer(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gbuffer* target, void* stream);
+
 /* ---- the pass after cone tracing ------------------------------------------ */
 /* replaces: SpecularFilterPass::onUpdate (SpecularFilterPass.cpp:73-91) + specularFilter.frag:25-53,
  * filter.glsl:9-24,44-63, tonemapping.glsl:4-26: final = diffuse + filtered specular, optional Uncharted-2

@@ -19,6 +19,6 @@ for l in out.stderr.splitlines():
     if "k_trace_mainILi16" in l or "k_trace_specular" in l or "registers" in l and "trace" in l:
         print(l)
 print("\n".join(l for l in out.stderr.splitlines() if "Used" in l or "spill" in l))
-objs = [obj] + [os.path.join(B.CSRC, f) for f in ("vgi_build.o", "vgi_svo.o", "vgi_atlas.o", "vgi_post.o", "vgi_api.o")]
+objs = [obj] + [os.path.join(B.CSRC, f) for f in ("vgi_build.o", "vgi_svo.o", "vgi_atlas.o", "vgi_raster.o", "vgi_post.o", "vgi_api.o")]
 subprocess.check_call([B.NVCC] + B.ARCH + ["-shared", "-o", os.path.join(dev, f"libvgi_{name}.so")] + objs + ["-ccbin", B.GXX, "-lcudart"])
 print("built", name)

@@ -18,7 +18,7 @@ def build():
     os.makedirs(DEV, exist_ok=True)
     obj = os.path.join(DEV, "vgi_trace_stats.o")
     subprocess.check_call([B.NVCC] + B.ARCH + B.COMMON + ["-DVGI_TRACE_STATS_BUILD", "-c", os.path.join(B.CSRC, "vgi_trace.cu"), "-o", obj])
-    objs = [obj] + [os.path.join(B.CSRC, f) for f in ("vgi_build.o", "vgi_svo.o", "vgi_atlas.o", "vgi_post.o", "vgi_api.o")]
+    objs = [obj] + [os.path.join(B.CSRC, f) for f in ("vgi_build.o", "vgi_svo.o", "vgi_atlas.o", "vgi_raster.o", "vgi_post.o", "vgi_api.o")]
     subprocess.check_call([B.NVCC] + B.ARCH + ["-shared", "-o", LIB] + objs + ["-ccbin", B.GXX, "-lcudart"])
     return LIB
 

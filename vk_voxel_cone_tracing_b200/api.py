@@ -237,6 +237,29 @@ class VoxelGI:
                                          C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), _stream(stream)))
         return out
 
+    def render_shadow_map(self, shadow, size=4096, out=None, stream=None):
+        """D32 shadow depth of the ctx's scene (vgi_render_shadow_map); returns a (size, size) float32 CUDA tensor."""
+        torch = self._torch
+        if out is None:
+            out = torch.empty((size, size), dtype=torch.float32, device=self.device)
+        self._ck(lib().vgi_render_shadow_map(self._h, C.byref(shadow), C.c_uint32(out.shape[1]), C.c_uint32(out.shape[0]),
+                                            C.c_void_p(out.data_ptr()), _stream(stream)))
+        return out
+
+    def render_gbuffer(self, camera, width, height, out=None, stream=None):
+        """G-buffer of the ctx's scene in the reference formats (vgi_render_gbuffer); returns a dict of CUDA tensors
+        that cone_trace accepts."""
+        torch = self._torch
+        if out is None:
+            out = dict(diffuse=torch.empty((height, width, 4), dtype=torch.uint8, device=self.device),
+                       normal=torch.empty((height, width, 4), dtype=torch.int16, device=self.device),
+                       specular=torch.empty((height, width, 4), dtype=torch.uint8, device=self.device),
+                       emission=torch.empty((height, width, 4), dtype=torch.int16, device=self.device),
+                       depth=torch.empty((height, width), dtype=torch.float32, device=self.device))
+        g = self.gbuffer_struct(out)
+        self._ck(lib().vgi_render_gbuffer(self._h, C.byref(camera), C.byref(g), _stream(stream)))
+        return out
+
     def specular_filter(self, diffuse, specular, params=None, out=None, stream=None):
         """final = diffuse + filtered specular (+ tonemap): the pass after cone tracing (vgi_specular_filter)."""
         torch = self._torch

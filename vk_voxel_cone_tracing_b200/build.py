@@ -18,7 +18,7 @@ GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 # Kernels whose results are quantised (occupancy bits, RGBA8 texels) are compiled without FMA
 # contraction so they follow the same IEEE binary32 contract as the oracle (DESIGN.md "numerics").
-CU_STRICT = ["vgi_build.cu", "vgi_svo.cu", "vgi_atlas.cu"]
+CU_STRICT = ["vgi_build.cu", "vgi_svo.cu", "vgi_atlas.cu", "vgi_raster.cu"]
 CU_FAST = ["vgi_trace.cu", "vgi_post.cu"]
 CPP = ["vgi_api.cpp"]
 HEADERS = ["vgi_internal.h", "vgi_device.cuh", os.path.join("..", "..", "include", "vgi.h")]

@@ -49,6 +49,8 @@ static void free_scene(vgi_ctx* c)
 {
     cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials);
     cudaFree(c->pairs); cudaFree(c->large); cudaFree(c->acc);
+    cudaFree(c->raster_proj); cudaFree(c->raster_large);
+    c->raster_proj = nullptr; c->raster_large = nullptr; c->raster_tri_cap = 0;
     c->tri_pos = c->tri_nrm = nullptr; c->materials = nullptr; c->pairs = nullptr; c->large = nullptr; c->acc = nullptr;
     c->ntri = 0;
 }
@@ -114,7 +116,7 @@ int vgi_destroy(vgi_ctx* c)
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
     cudaFree(c->brick_mask); cudaFree(c->slab_ids); cudaFree(c->slab_recs); cudaFree(c->slab_count); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_inputs); cudaEventDestroy(c->ev_main_done); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_copy_done); }
-    cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch);
+    cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch); cudaFree(c->raster_keys);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
     for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
@@ -822,6 +824,63 @@ int vgi_atlas_wrap_border(vgi_ctx* c, void* atlas, void* stream)
                                          (c->cfg.mode_flags & VGI_MODE_BORDER_LITERAL) ? 1 : 0, (cudaStream_t)stream);
     c->last_stream = (cudaStream_t)stream;
     return check_launch(c, "vgi_atlas_wrap_border");
+}
+
+// ---- producers of the image inputs (the passes before the path) -----------------------------------
+
+static int raster_scratch(vgi_ctx* c, size_t npx)
+{
+    if (c->raster_tri_cap < c->ntri + 1u) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->raster_proj); cudaFree(c->raster_large);
+        c->raster_proj = nullptr; c->raster_large = nullptr;
+        CK(c, cudaMalloc(&c->raster_proj, vgi_raster_proj_bytes(c->ntri)));
+        CK(c, cudaMalloc(&c->raster_large, ((size_t)c->ntri + 1) * sizeof(uint32_t)));
+        c->raster_tri_cap = c->ntri + 1u;
+    }
+    if (c->raster_px_cap < npx) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->raster_keys);
+        c->raster_keys = nullptr; c->raster_px_cap = 0;
+        CK(c, cudaMalloc(&c->raster_keys, npx * sizeof(unsigned long long)));
+        c->raster_px_cap = npx;
+    }
+    return VGI_OK;
+}
+
+int vgi_render_shadow_map(vgi_ctx* c, const vgi_dir_light_shadow* sh, uint32_t width, uint32_t height, float* depth, void* stream)
+{
+    if (!c || !sh || !depth || !width || !height) return fail(c, VGI_E_INVALID, "vgi_render_shadow_map: bad argument");
+    if (!c->tri_pos && c->ntri) return fail(c, VGI_E_STATE, "vgi_render_shadow_map: call vgi_set_scene first");
+    if (!c->materials) return fail(c, VGI_E_STATE, "vgi_render_shadow_map: call vgi_set_scene first");
+    CK(c, cudaSetDevice(c->device));
+    int r = raster_scratch(c, (size_t)width * height);
+    if (r != VGI_OK) return r;
+    float M[16]; // proj * view, column-major (shadowPass.vert:33)
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 4; ++row) {
+            double a = 0;
+            for (int k = 0; k < 4; ++k) a += (double)sh->proj[k * 4 + row] * sh->view[col * 4 + k];
+            M[col * 4 + row] = (float)a;
+        }
+    c->launches += vgi_launch_render_shadow(c, M, width, height, depth, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_render_shadow_map");
+}
+
+int vgi_render_gbuffer(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* target, void* stream)
+{
+    if (!c || !cam || !target) return fail(c, VGI_E_INVALID, "vgi_render_gbuffer: null argument");
+    if (!target->diffuse_rgba8 || !target->normal_rgba16f || !target->specular_rgba8 || !target->emission_rgba16f ||
+        !target->depth_f32 || !target->width || !target->height)
+        return fail(c, VGI_E_INVALID, "vgi_render_gbuffer: incomplete target");
+    if (!c->materials) return fail(c, VGI_E_STATE, "vgi_render_gbuffer: call vgi_set_scene first");
+    CK(c, cudaSetDevice(c->device));
+    int r = raster_scratch(c, (size_t)target->width * target->height);
+    if (r != VGI_OK) return r;
+    c->launches += vgi_launch_render_gbuffer(c, cam->view_proj, target, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return check_launch(c, "vgi_render_gbuffer");
 }
 
 // ---- specular filter + tonemap (the pass after cone tracing) --------------------------------------

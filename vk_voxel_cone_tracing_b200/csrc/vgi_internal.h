@@ -172,6 +172,13 @@ struct vgi_ctx {
     cudaStream_t last_stream = 0;
     uint64_t launches = 0;
 
+    // software rasteriser scratch (vgi_render_shadow_map / vgi_render_gbuffer)
+    void* raster_proj = nullptr;               // projected triangles
+    unsigned long long* raster_keys = nullptr; // per pixel: depth bits << 32 | triangle
+    uint32_t* raster_large = nullptr;          // ntri queue entries + 1 counter
+    size_t raster_px_cap = 0;
+    uint32_t raster_tri_cap = 0;
+
     // cone trace scratch
     uint32_t* spec_list = nullptr;
     size_t spec_capacity = 0;
@@ -212,6 +219,9 @@ int vgi_launch_atlas_clear(uint8_t* atlas, int R, int L, const int32_t* mc, cons
 int vgi_launch_atlas_copy_alpha(uint8_t* dst, const uint8_t* src, int R, int L, int level, cudaStream_t s);
 int vgi_launch_atlas_downsample(uint8_t* atlas, int R, int L, int band, const int32_t* prev_min, int level, int which, cudaStream_t s);
 int vgi_launch_atlas_wrap(uint8_t* atlas, int R, int L, int literal, cudaStream_t s);
+int vgi_launch_render_shadow(vgi_ctx* c, const float* M, uint32_t w, uint32_t h, float* depth, cudaStream_t s);
+int vgi_launch_render_gbuffer(vgi_ctx* c, const float* M, const vgi_gbuffer* target, cudaStream_t s);
+size_t vgi_raster_proj_bytes(uint32_t ntri);
 int vgi_launch_specular_filter(vgi_ctx* c, const void* diffuse, const void* specular, uint32_t width, uint32_t height,
                                const vgi_filter_params* prm, void* out, cudaStream_t s);
 

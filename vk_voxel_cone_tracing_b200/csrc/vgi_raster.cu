@@ -1,0 +1,266 @@
+// vgi_raster.cu — producers of the hot path's image inputs: the directional light's shadow
+// depth map and the camera G-buffer, rendered from the ctx's scene without Vulkan so that batched-view runs
+// (BASELINE configs[4]: 64 cameras at 4K) need no host rasteriser.
+// ref: VFS/Shaders/shadowPass.vert:33 (depth-only, proj * view * model), gBufferPass.vert:45, gBufferPass.frag:62-116
+// (factor-only materials), formats VFS/RenderPass/GBufferPass.cpp:177-194.
+//
+// Rasterisation rule (the software definition the test producers pin: pixel-centre sampling, depth test LESS with ties
+// to the lower triangle index, z clipped to [0,1], triangles with a vertex at w <= 1e-4 skipped): visibility is one
+// 64-bit atomicMin per fragment on (depth bits << 32 | triangle), then a resolve pass shades the winning triangle.
+// Edge functions and interpolation are evaluated in binary64 without FMA contraction (this file is compiled with
+// -fmad=false), so depth and every quantised attribute equal the host producer bit for bit.
+#include <cuda_fp16.h>
+
+#include "vgi_internal.h"
+
+#define DEVFN static __device__ __forceinline__
+
+struct ProjTri {
+    double x[3], y[3], z[3], iw[3]; // pixel coordinates, NDC depth, 1 / w
+    int ok;
+    int pad;
+};
+
+#define RASTER_SMALL_MAX 256   // bounding boxes up to this many pixels are walked by one thread
+
+DEVFN void project_tri(const float* M, const float4* tri_pos, uint32_t t, int w, int h, ProjTri& o)
+{
+    o.ok = 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 p = tri_pos[(size_t)t * 3 + k];
+        double c[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            c[r] = (double)M[r] * p.x + (double)M[4 + r] * p.y + (double)M[8 + r] * p.z + (double)M[12 + r];
+        if (c[3] <= 1e-4) { o.ok = 0; return; }
+        o.iw[k] = 1.0 / c[3];
+        o.x[k] = (c[0] * o.iw[k] * 0.5 + 0.5) * (double)w;
+        o.y[k] = (c[1] * o.iw[k] * 0.5 + 0.5) * (double)h;
+        o.z[k] = c[2] * o.iw[k];
+    }
+}
+
+struct RasterParams {
+    float M[16];
+    const float4* tri_pos;
+    const float4* tri_nrm;
+    const vgi_material* materials;
+    uint32_t ntri;
+    int w, h;
+    ProjTri* proj;
+    unsigned long long* keys;   // per pixel: depth bits << 32 | triangle
+    uint32_t* large;            // triangles whose bounding box one thread should not walk
+    uint32_t* large_count;
+};
+
+struct Box { int x0, x1, y0, y1; double area; bool any; };
+
+DEVFN Box tri_box(const ProjTri& q, int w, int h)
+{
+    Box b;
+    b.any = false;
+    if (!q.ok) return b;
+    const double ymin = fmin(q.y[0], fmin(q.y[1], q.y[2])), ymax = fmax(q.y[0], fmax(q.y[1], q.y[2]));
+    const double xmin = fmin(q.x[0], fmin(q.x[1], q.x[2])), xmax = fmax(q.x[0], fmax(q.x[1], q.x[2]));
+    if (ymax < 0 || ymin > h || xmax < 0 || xmin > w) return b;
+    b.area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
+    if (b.area == 0.0) return b;
+    b.x0 = max((int)floor(xmin - 0.5), 0);
+    b.x1 = min((int)ceil(xmax - 0.5), w - 1);
+    b.y0 = max((int)floor(ymin - 0.5), 0);
+    b.y1 = min((int)ceil(ymax - 0.5), h - 1);
+    b.any = b.x0 <= b.x1 && b.y0 <= b.y1;
+    return b;
+}
+
+DEVFN void raster_pixel(const RasterParams& rp, const ProjTri& q, double area, uint32_t t, int x, int y)
+{
+    const double px = x + 0.5, py = y + 0.5;
+    const double e0 = (q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py);
+    const double e1 = (q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py);
+    // e / area < 0 <=> the signs differ (e != 0): most pixels of a bounding box leave before the two divisions
+    if ((e0 != 0.0 && (e0 < 0.0) != (area < 0.0)) || (e1 != 0.0 && (e1 < 0.0) != (area < 0.0))) return;
+    const double w0 = e0 / area;
+    const double w1 = e1 / area;
+    const double w2 = 1.0 - w0 - w1;
+    if (w0 < 0 || w1 < 0 || w2 < 0) return;
+    const double z = w0 * q.z[0] + w1 * q.z[1] + w2 * q.z[2];
+    if (z < 0.0 || z > 1.0) return;
+    const float zf = (float)z;
+    if (!(zf < 1.0f)) return; // the cleared depth is 1 and the test is LESS
+    const unsigned long long key = ((unsigned long long)__float_as_uint(zf) << 32) | t;
+    atomicMin(rp.keys + (size_t)y * rp.w + x, key);
+}
+
+__global__ void __launch_bounds__(256) k_raster_clear(unsigned long long* keys, size_t n, uint32_t* large_count)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ~0ull;
+    if (i == 0) *large_count = 0u;
+}
+
+__global__ void __launch_bounds__(128) k_raster_small(const __grid_constant__ RasterParams rp)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rp.ntri) return;
+    ProjTri q;
+    project_tri(rp.M, rp.tri_pos, t, rp.w, rp.h, q);
+    rp.proj[t] = q;
+    const Box b = tri_box(q, rp.w, rp.h);
+    if (!b.any) return;
+    if ((long long)(b.x1 - b.x0 + 1) * (b.y1 - b.y0 + 1) > RASTER_SMALL_MAX) {
+        rp.large[atomicAdd(rp.large_count, 1u)] = t;
+        return;
+    }
+    for (int y = b.y0; y <= b.y1; ++y)
+        for (int x = b.x0; x <= b.x1; ++x) raster_pixel(rp, q, b.area, t, x, y);
+}
+
+// one block per 64 x 64-pixel piece of a large triangle's bounding box (grid.y walks the queue)
+__global__ void __launch_bounds__(256) k_raster_large(const __grid_constant__ RasterParams rp)
+{
+    const uint32_t n = *rp.large_count;
+    for (uint32_t i = blockIdx.y; i < n; i += gridDim.y) {
+        const uint32_t t = rp.large[i];
+        const ProjTri& q = rp.proj[t];
+        const Box b = tri_box(q, rp.w, rp.h);
+        const int tilesX = (b.x1 - b.x0 + 64) / 64, tilesY = (b.y1 - b.y0 + 64) / 64;
+        for (int tile = blockIdx.x; tile < tilesX * tilesY; tile += gridDim.x) {
+            const int tx = b.x0 + (tile % tilesX) * 64, ty = b.y0 + (tile / tilesX) * 64;
+            for (int p = threadIdx.x; p < 64 * 64; p += 256) {
+                const int x = tx + (p & 63), y = ty + (p >> 6);
+                if (x <= b.x1 && y <= b.y1) raster_pixel(rp, q, b.area, t, x, y);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_raster_resolve_depth(const unsigned long long* keys, size_t n, float* depth)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    depth[i] = (k == ~0ull) ? 1.0f : __uint_as_float((uint32_t)(k >> 32));
+}
+
+DEVFN uint8_t to_unorm8(float x)
+{
+    if (!(x > 0.0f)) return 0;
+    if (x > 1.0f) x = 1.0f;
+    return (uint8_t)(x * 255.0f + 0.5f);
+}
+
+struct GBufferTarget {
+    uchar4* diffuse; uint2* normal; uchar4* specular; uint2* emission; float* depth;
+};
+
+DEVFN uint2 pack_half4(float a, float b, float c, float d)
+{
+    const __half2 lo = __halves2half2(__float2half_rn(a), __float2half_rn(b));
+    const __half2 hi = __halves2half2(__float2half_rn(c), __float2half_rn(d));
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+// ref: gBufferPass.frag:62-116 for factor-only materials
+__global__ void __launch_bounds__(256) k_raster_resolve_gbuffer(const __grid_constant__ RasterParams rp, const GBufferTarget g)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= rp.w || y >= rp.h) return;
+    const size_t pi = (size_t)y * rp.w + x;
+    const unsigned long long k = rp.keys[pi];
+    if (k == ~0ull) {
+        g.diffuse[pi] = make_uchar4(0, 0, 0, 0);
+        g.specular[pi] = make_uchar4(0, 0, 0, 0);
+        g.normal[pi] = make_uint2(0u, 0u);
+        g.emission[pi] = make_uint2(0u, 0u);
+        g.depth[pi] = 1.0f;
+        return;
+    }
+    g.depth[pi] = __uint_as_float((uint32_t)(k >> 32));
+    const uint32_t t = (uint32_t)k;
+    const ProjTri q = rp.proj[t];
+    const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
+    const double px = x + 0.5, py = y + 0.5;
+    double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
+    double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
+    double b2 = 1.0 - b0 - b1;
+    b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2]; // perspective-correct attribute interpolation
+    const double bs = b0 + b1 + b2;
+    b0 /= bs; b1 /= bs; b2 /= bs;
+    const float4 n0 = rp.tri_nrm[(size_t)t * 3], n1 = rp.tri_nrm[(size_t)t * 3 + 1], n2 = rp.tri_nrm[(size_t)t * 3 + 2];
+    const double n[3] = { b0 * n0.x + b1 * n1.x + b2 * n2.x, b0 * n0.y + b1 * n1.y + b2 * n2.y, b0 * n0.z + b1 * n1.z + b2 * n2.z };
+    const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const int mi = __float_as_int(rp.tri_pos[(size_t)t * 3].w);
+    const vgi_material& m = rp.materials[mi];
+    float rough = m.roughness_factor, metal = m.metallic_factor;
+    rough = rough < 0.04f ? 0.04f : (rough > 1.0f ? 1.0f : rough); // MIN_ROUGHNESS clamp, untextured
+    metal = metal < 0.0f ? 0.0f : (metal > 1.0f ? 1.0f : metal);
+    uint8_t dif[3], spc[3];
+    float nn[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float base = m.base_color_factor[c];
+        dif[c] = to_unorm8(base * (1.0f - 0.04f) * (1.0f - metal));
+        spc[c] = to_unorm8(0.04f * (1.0f - metal) + base * metal);
+        nn[c] = (float)((ln > 0 ? n[c] / ln : 0.0) * 0.5 + 0.5);
+    }
+    g.diffuse[pi] = make_uchar4(dif[0], dif[1], dif[2], to_unorm8(rough));
+    g.specular[pi] = make_uchar4(spc[0], spc[1], spc[2], to_unorm8(metal));
+    g.normal[pi] = pack_half4(nn[0], nn[1], nn[2], 1.0f);
+    g.emission[pi] = pack_half4(m.emissive_factor[0], m.emissive_factor[1], m.emissive_factor[2], 1.0f);
+}
+
+static int launch_visibility(vgi_ctx* c, const RasterParams& rp, cudaStream_t s)
+{
+    const size_t npx = (size_t)rp.w * rp.h;
+    c->timer.begin("k_raster_clear", s);
+    k_raster_clear<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(rp.keys, npx, rp.large_count);
+    c->timer.end(s);
+    int n = 1;
+    if (rp.ntri) {
+        c->timer.begin("k_raster_small", s);
+        k_raster_small<<<(rp.ntri + 127) / 128, 128, 0, s>>>(rp);
+        c->timer.end(s);
+        c->timer.begin("k_raster_large", s);
+        k_raster_large<<<dim3(16, 1184), 256, 0, s>>>(rp); // 8 x 148 queue walkers, 16 blocks per triangle
+        c->timer.end(s);
+        n += 2;
+    }
+    return n;
+}
+
+int vgi_launch_render_shadow(vgi_ctx* c, const float* M, uint32_t w, uint32_t h, float* depth, cudaStream_t s)
+{
+    RasterParams rp;
+    memcpy(rp.M, M, sizeof rp.M);
+    rp.tri_pos = c->tri_pos; rp.tri_nrm = c->tri_nrm; rp.materials = c->materials; rp.ntri = c->ntri;
+    rp.w = (int)w; rp.h = (int)h;
+    rp.proj = (ProjTri*)c->raster_proj; rp.keys = c->raster_keys; rp.large = c->raster_large; rp.large_count = c->raster_large + c->ntri;
+    int n = launch_visibility(c, rp, s);
+    const size_t npx = (size_t)w * h;
+    c->timer.begin("k_raster_resolve_depth", s);
+    k_raster_resolve_depth<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(rp.keys, npx, depth);
+    c->timer.end(s);
+    return n + 1;
+}
+
+int vgi_launch_render_gbuffer(vgi_ctx* c, const float* M, const vgi_gbuffer* target, cudaStream_t s)
+{
+    RasterParams rp;
+    memcpy(rp.M, M, sizeof rp.M);
+    rp.tri_pos = c->tri_pos; rp.tri_nrm = c->tri_nrm; rp.materials = c->materials; rp.ntri = c->ntri;
+    rp.w = (int)target->width; rp.h = (int)target->height;
+    rp.proj = (ProjTri*)c->raster_proj; rp.keys = c->raster_keys; rp.large = c->raster_large; rp.large_count = c->raster_large + c->ntri;
+    int n = launch_visibility(c, rp, s);
+    GBufferTarget g;
+    g.diffuse = (uchar4*)target->diffuse_rgba8; g.normal = (uint2*)target->normal_rgba16f;
+    g.specular = (uchar4*)target->specular_rgba8; g.emission = (uint2*)target->emission_rgba16f;
+    g.depth = (float*)target->depth_f32;
+    c->timer.begin("k_raster_resolve_gbuffer", s);
+    k_raster_resolve_gbuffer<<<dim3((rp.w + 31) / 32, (rp.h + 7) / 8), 256, 0, s>>>(rp, g);
+    c->timer.end(s);
+    return n + 1;
+}
+
+size_t vgi_raster_proj_bytes(uint32_t ntri) { return (size_t)(ntri ? ntri : 1) * sizeof(ProjTri); }
