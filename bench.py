@@ -160,6 +160,7 @@ class CpuFrameSampler:
         self.level_s = {l: [] for l in range(self.cfg.level_count)}
         self.trace_s = []
         self.taps = []          # tri-linear taps of the sampled rows, scaled to the frame (SURVEY 8d A_cone)
+        self.taps_diffuse = []  # ... of the diffuse cones alone (what k_trace_main marches)
         self.i = 0
 
     def build_level(self, l):
@@ -185,8 +186,10 @@ class CpuFrameSampler:
         t = time.perf_counter()
         _, _, taps = O.cone_trace(self.cfg, inp["cam"], self.hg, self.prm, inp["light"], inp["shadow"], inp["shadow_depth"],
                                   self.rad, rows=(y0, y0 + rows))
+        dt = time.perf_counter() - t
         self.taps.append(taps * (HEIGHT / rows))
-        return (time.perf_counter() - t) * (HEIGHT / rows)
+        self.taps_diffuse.append((taps - O.last_specular_taps()) * (HEIGHT / rows))
+        return dt * (HEIGHT / rows)
 
     def prime(self):
         """Fill the atlases once (untimed) so the trace samples march through real radiance."""
@@ -375,7 +378,7 @@ def run_vgi(args):
     step_ms, build_ms, trace_ms, e2e_ms, t_wall = t.tolist()
 
     # ---- per-kernel CUDA-event timing (separate pass: the events would perturb the headline number)
-    roof, roof_trace, roof_stage, kernels = None, None, None, {}
+    roof, roof_trace, roof_stage, roof_dominant, kernels = None, None, None, None, {}
     if rank == 0:
         gi.set_timing(True)
         gi.reset_timings()
@@ -403,7 +406,9 @@ def run_vgi(args):
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (ach / hbm_peak) if ach else None, "traffic": ncu_traffic(name), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms_launch,
-                    "share_of_build": build_k[name][0] / sum(v[0] for v in build_k.values())}
+                    "share_of_build": build_k[name][0] / sum(v[0] for v in build_k.values()),
+                    "note": "dominant kernel of the HBM-bound half of the metric (voxelize+inject+mip); the dominant kernel of the "
+                            "whole step, k_trace_main, is L1 / issue bound: see roofline_dominant_kernel"}
         trace_k = {k: v for k, v in tm.items() if k.startswith("k_trace")}
         if trace_k:
             tms = sum(v[0] for v in trace_k.values()) / args.steps
@@ -448,6 +453,34 @@ def run_vgi(args):
         frame()
         torch.cuda.synchronize()
 
+    # ---- the passes either side of the path, reported beside the metric, not part of it
+    adjacent = None
+    if rank == 0:
+        from vk_voxel_cone_tracing_b200 import structs as S2
+        fprm = S2.default_filter_params(1, 1)
+        rg = gi.render_gbuffer(inp["cam"], WIDTH, HEIGHT)
+        rs = gi.render_shadow_map(inp["shadow"], SHADOW)
+        fo = gi.specular_filter(out[0], out[1], fprm)
+        same_inputs = bool(torch.equal(rs.cpu(), torch.from_numpy(inp["shadow_depth"]))
+                           and torch.equal(rg["depth"].cpu(), torch.from_numpy(inp["gbuffer"]["depth"])))
+        aev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc3 = np.zeros(3)
+        for i in range(7):
+            flush.zero_()
+            aev[0].record()
+            gi.render_shadow_map(inp["shadow"], SHADOW, out=rs)
+            aev[1].record()
+            gi.render_gbuffer(inp["cam"], WIDTH, HEIGHT, out=rg)
+            aev[2].record()
+            gi.specular_filter(out[0], out[1], fprm, out=fo)
+            aev[3].record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                acc3 += [aev[0].elapsed_time(aev[1]), aev[1].elapsed_time(aev[2]), aev[2].elapsed_time(aev[3])]
+        adjacent = {"shadow_map_4096_ms": acc3[0] / 5, "gbuffer_1080p_ms": acc3[1] / 5,
+                    "specular_filter_gaussian_tonemap_1080p_ms": acc3[2] / 5,
+                    "device_rendered_inputs_equal_host_rendered": same_inputs}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -465,6 +498,18 @@ def run_vgi(args):
             roof_trace.update({"taps_per_frame": taps, "algorithmic_bytes": a_cone,
                                "achieved": a_cone / (trace_ms * 1e-3) / 1e9,
                                "frac": a_cone / (trace_ms * 1e-3) / 1e9 / roof_trace["peak"]})
+            if smp.taps_diffuse and "k_trace_main" in kernels:
+                # the dominant kernel of the step on its own: diffuse cones' taps + the compulsory G-buffer / output bytes
+                td = float(np.mean(smp.taps_diffuse))
+                a_main = 32.0 * td + 60.0 * WIDTH * HEIGHT
+                ms_main = kernels["k_trace_main"]["ms_per_step"]
+                roof_dominant = {"kernel": "k_trace_main", "bound": "l1", "share_of_step": ms_main / step_ms,
+                                 "taps_per_launch": td, "algorithmic_bytes_per_launch": a_main, "ms_per_launch": ms_main,
+                                 "achieved": a_main / (ms_main * 1e-3) / 1e9, "peak": roof_trace["peak"], "unit": "GB/s",
+                                 "frac": a_main / (ms_main * 1e-3) / 1e9 / roof_trace["peak"],
+                                 "peak_source": roof_trace["peak_source"], "traffic": ncu_traffic("k_trace_main"),
+                                 "note": "SURVEY 8(d): cone tracing is bounded by L1 bandwidth / issue rate, not HBM (DRAM traffic "
+                                         "per launch in `traffic`); the `roofline` object carries the dominant HBM-bound kernel"}
 
     if rank == 0:
         line = {
@@ -481,7 +526,8 @@ def run_vgi(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "wall_ms_per_step": t_wall},
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
-            "clocks": clk, "roofline": roof, "roofline_stage": roof_stage, "roofline_cone_trace": roof_trace,
+            "clocks": clk, "roofline": roof, "roofline_dominant_kernel": roof_dominant, "roofline_stage": roof_stage,
+            "roofline_cone_trace": roof_trace, "adjacent_passes": adjacent,
             "svo": svo, "kernels": kernels,
             "cpu_baseline": cpu,
         }

@@ -39,6 +39,7 @@ def lib():
         _lib.vgo_scene_triangle_count.restype = C.c_uint32
         _lib.vgo_voxelize_level.restype = C.c_uint64
         _lib.vgo_voxelization_pass.restype = C.c_uint64
+        _lib.vgo_last_specular_taps.restype = C.c_uint64
         _lib.vgo_svo_fragments.restype = C.c_uint32
         _lib.vgo_svo_build.restype = C.c_uint32
         _lib.vgo_svo_canonicalize.restype = C.c_uint32
@@ -159,6 +160,11 @@ def cone_trace(cfg, cam, gbuf, prm, light, shadow, shadow_depth, radiance, rows=
 
 
 # ---- SVO ------------------------------------------------------------------------------------------
+
+def last_specular_taps():
+    """Tri-linear taps of the specular cones alone in the last cone_trace call."""
+    return int(lib().vgo_last_specular_taps())
+
 
 def specular_filter(diffuse, specular, prm):
     """diffuse / specular: (H, W, 4) float32 numpy; returns the final (H, W, 4) image (vgo_specular_filter)."""

@@ -908,6 +908,8 @@ static void normalize3(const float* v, float* o)
 /* ref: voxelConeTracing.frag:143-294. The G-buffer is fetched at the pixel (texCoord is the pixel
  * centre, so the reference's LINEAR fetch degenerates to the texel). texCoord = ((x+0.5)/w, (y+0.5)/h)
  * from voxelConeTracing.vert; no y flip (Q18). */
+static uint64_t g_last_specular_taps = 0;
+
 void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuffer* g,
                     const vgi_vct_params* prm, const vgi_dir_light* light,
                     const vgi_dir_light_shadow* shadow, const float* shadow_depth,
@@ -923,7 +925,8 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
     float lightV[3];
     light_dir(light, lightV);
 
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_taps)
+    uint64_t spec_taps = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_taps, spec_taps)
     for (int64_t py = (int64_t)y0; py < (int64_t)y1; ++py) {
         trace_ctx tc = { cfg, prm, radiance, atlas_W(cfg), atlas_H(cfg), atlas_D(cfg), 0 };
         for (uint32_t px = 0; px < g->width; ++px) {
@@ -987,8 +990,10 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
                 float sdir[3];
                 for (int k = 0; k < 3; ++k) sdir[k] = I[k] - (2.0f * dn) * normal[k];
                 float c[4];
+                const uint64_t taps_before = tc.taps;
                 trace_cone(&tc, startPos, sdir, f_max(perceptualRoughness, MIN_SPECULAR_APERTURE),
                            MAX_TRACE_DISTANCE, minLevel, prm->voxel_size /* Q12 */, c);
+                spec_taps += tc.taps - taps_before;
                 for (int k = 0; k < 3; ++k) indirectSpecular[k] += (c[k] * specularColor[k]) * prm->indirect_specular_intensity;
             }
 
@@ -1047,7 +1052,11 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
         total_taps += tc.taps;
     }
     if (taps) *taps = total_taps;
+    g_last_specular_taps = spec_taps;
 }
+
+/* taps of the specular cones alone in the last vgo_cone_trace call (per-kernel roofline accounting in bench.py) */
+uint64_t vgo_last_specular_taps(void) { return g_last_specular_taps; }
 
 /* ------------------------------------------------------------------------------------------------
  * Specular filter + tonemap. ref: specularFilter.frag:25-53, filter.glsl, tonemapping.glsl.

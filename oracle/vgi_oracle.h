@@ -89,6 +89,9 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
                     float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1,
                     uint64_t* taps);
 
+/* taps of the specular cones alone in the last vgo_cone_trace call */
+uint64_t vgo_last_specular_taps(void);
+
 /* ref: specularFilter.frag:25-53, filter.glsl:9-24 (gaussian), :27-63 (bilateral), tonemapping.glsl:4-26;
  * sampler LINEAR / CLAMP_TO_EDGE (VoxelConeTracingPass.cpp:147). HOST float4 images. */
 void vgo_specular_filter(const float* diffuse, const float* specular, uint32_t w, uint32_t h,
