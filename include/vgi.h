@@ -257,6 +257,25 @@ int vgi_get_slab_pack(vgi_ctx* ctx, void** ids, void** recs, uint32_t* count);
 int vgi_slab_unpack(vgi_ctx* ctx, const void* ids, const void* recs, uint32_t count, void* stream);
 int vgi_slab_build_end(vgi_ctx* ctx, uint32_t frame_index, void* stream);
 
+/* ---- peer build: the slab-sharded build with the exchange done by the kernels over NVLink peer memory ----
+ * One ctx per GPU of one node (one process per GPU). Every GPU maps the voxel store, the occupancy words and a
+ * row of arrival flags of every other GPU through CUDA IPC; a build then voxelizes + injects the own slab of texel
+ * planes, stores its occupancy words and finalized records straight into ALL stores and meets the other GPUs at
+ * three flag barriers inside the stream: no collective library call, no host round trip, no staging buffers.
+ *   vgi_peer_export   handles: 3 x VGI_IPC_HANDLE_BYTES (store, occupancy, flags) of this ctx — exchange them
+ *                     between the processes (e.g. torch.distributed.all_gather_object)
+ *   vgi_peer_attach   all_handles: nranks x 3 x VGI_IPC_HANDLE_BYTES in rank order; resolution % nranks == 0;
+ *                     sets the slab to planes [rank * R / nranks, (rank + 1) * R / nranks)
+ *   vgi_peer_build_clipmap   = vgi_build_clipmap, bit for bit, on every GPU; all ranks must call it for the same
+ *                     frame with the same regions / scene / light (a barrier waits ~3 s for a missing peer, then
+ *                     gives up and the next vgi_get_stats fails with VGI_E_OVERFLOW, mask bit 0x20)
+ * The stream order of each rank must keep its readers of the store (cone traces) before its next build. */
+#define VGI_IPC_HANDLE_BYTES 64
+int vgi_peer_export(vgi_ctx* ctx, void* handles);
+int vgi_peer_attach(vgi_ctx* ctx, uint32_t rank, uint32_t nranks, const void* all_handles);
+int vgi_peer_build_clipmap(vgi_ctx* ctx, uint32_t frame_index, void* stream);
+int vgi_peer_detach(vgi_ctx* ctx);
+
 /* ---- cone tracing --------------------------------------------------------------------------- */
 /* replaces: VoxelConeTracingPass::onUpdate (VoxelConeTracingPass.cpp:75-106) + voxelConeTracing.frag.
  * out_diffuse / out_specular: width*height float4 (R32G32B32A32_SFLOAT, VoxelConeTracingPass.cpp:141-144).

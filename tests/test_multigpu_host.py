@@ -67,6 +67,10 @@ def _worker(rank, world, port, q):
         # 3. an empty contribution from one rank
         counts0, _, _ = M.all_gather_varlen(ids, recs, 0 if rank == 0 else 3)
         ok3 = counts0 == [0] + [3] * (world - 1)
+        # 4. IPC handle blobs of the peer build come back concatenated in rank order on every rank
+        blob = bytes([rank * 16 + k for k in range(16)]) * 12          # 192 bytes, distinct per rank
+        everyone = M.exchange_handles(blob)
+        ok3 = ok3 and everyone == b"".join(bytes([r * 16 + k for k in range(16)]) * 12 for r in range(world))
         q.put((rank, ok1, ok2, ok3))
     finally:
         dist.destroy_process_group()

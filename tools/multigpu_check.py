@@ -42,18 +42,24 @@ def main():
         gi.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
         return gi
 
-    ref, shard = make(), make()
+    ref, shard, peer = make(), make(), make()
     sb = M.SlabBuild(shard)
-    ok_build = True
+    pb = M.PeerBuild(peer)
+    ok_build, ok_peer = True, True
     for frame in range(a.frames):
         cam = tuple(np.array(inp["cam_pos"]) + np.array([0.37, -0.11, 0.29]) * frame)
         ref.update_regions(cam)
         shard.update_regions(cam)
+        peer.update_regions(cam)
         ref.build_clipmap(frame)
         sb.build(frame)
+        pb.build(frame)
         for which in (0, 1):
-            same = torch.equal(ref.export_atlas(which), shard.export_atlas(which))
-            ok_build = ok_build and bool(same)
+            want = ref.export_atlas(which)
+            ok_build = ok_build and bool(torch.equal(want, shard.export_atlas(which)))
+            ok_peer = ok_peer and bool(torch.equal(want, peer.export_atlas(which)))
+        if peer.stats().occupied_voxels == 0:
+            ok_peer = False
     # row-sharded trace on the sharded store vs full trace on the reference store
     gb = ref.upload_gbuffer(inp["gbuffer"])
     prm = ref.default_vct_params(8)
@@ -69,13 +75,17 @@ def main():
     mine = (tile_rows % world) == rank
     for k in range(2):
         ok_trace = ok_trace and torch.equal(inter[k][mine], full[k][mine])
-    flags = torch.tensor([int(ok_build), int(ok_trace)], device="cuda")
+    # the peer-built store traces to the same image
+    ptrace = peer.cone_trace(inp["cam"], gb, prm)
+    ok_peer = ok_peer and all(torch.equal(ptrace[k], full[k]) for k in range(2))
+    flags = torch.tensor([int(ok_build), int(ok_trace), int(ok_peer)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 
     timing = {}
     if a.time_iters:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for name, fn in (("replicated_build_ms", lambda: ref.build_clipmap(0)), ("slab_build_ms", lambda: sb.build(0)),
+                         ("peer_build_ms", lambda: pb.build(0)),
                          ("full_trace_ms", lambda: ref.cone_trace(inp["cam"], gb, prm, out=full)),
                          ("row_sharded_trace_ms", lambda: shard.cone_trace(inp["cam"], gb, prm, out=part, rows=(y0, y1))),
                          ("tile_interleaved_trace_ms", lambda: shard.cone_trace(inp["cam"], gb, prm, out=inter, part=(rank, world)))):
@@ -93,9 +103,11 @@ def main():
             timing[name] = float(t)
     if rank == 0:
         print(json.dumps({"world": world, "scene": a.scene, "res": a.res, "slab_build_bit_exact": bool(flags[0]),
-                          "row_sharded_trace_bit_exact": bool(flags[1]), **timing}), flush=True)
+                          "row_sharded_trace_bit_exact": bool(flags[1]), "peer_build_bit_exact": bool(flags[2]),
+                          **timing}), flush=True)
+    pb.close()
     dist.destroy_process_group()
-    if not (flags[0] and flags[1]):
+    if not (flags[0] and flags[1] and flags[2]):
         sys.exit(1)
 
 

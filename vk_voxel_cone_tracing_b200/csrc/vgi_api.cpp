@@ -45,6 +45,8 @@ void vgi_default_config(vgi_config* cfg)
 
 const char* vgi_last_error(const vgi_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
+static void peer_close(vgi_ctx* c);
+
 static void free_scene(vgi_ctx* c)
 {
     cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials);
@@ -117,6 +119,8 @@ int vgi_destroy(vgi_ctx* c)
     cudaFree(c->brick_mask); cudaFree(c->slab_ids); cudaFree(c->slab_recs); cudaFree(c->slab_count); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_inputs); cudaEventDestroy(c->ev_main_done); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_copy_done); }
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch); cudaFree(c->raster_keys);
+    peer_close(c);
+    cudaFree(c->sync_flags);
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
     for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
@@ -824,6 +828,96 @@ int vgi_atlas_wrap_border(vgi_ctx* c, void* atlas, void* stream)
                                          (c->cfg.mode_flags & VGI_MODE_BORDER_LITERAL) ? 1 : 0, (cudaStream_t)stream);
     c->last_stream = (cudaStream_t)stream;
     return check_launch(c, "vgi_atlas_wrap_border");
+}
+
+// ---- peer build: slab-sharded build with kernel-side exchange over NVLink peer memory -----------------
+
+static void peer_close(vgi_ctx* c)
+{
+    for (int r = 0; r < VGI_MAX_PEERS; ++r)
+        for (int k = 0; k < 3; ++k)
+            if (c->peer_opened[r][k]) { cudaIpcCloseMemHandle(c->peer_opened[r][k]); c->peer_opened[r][k] = nullptr; }
+    c->peers = PeerSet{};
+    c->peers_attached = false;
+}
+
+int vgi_peer_export(vgi_ctx* c, void* handles)
+{
+    if (!c || !handles) return fail(c, VGI_E_INVALID, "vgi_peer_export: null argument");
+    if (!c->store_owned || !c->store) return fail(c, VGI_E_STATE, "vgi_peer_export: the voxel store must be the ctx's own allocation");
+    CK(c, cudaSetDevice(c->device));
+    if (!c->sync_flags) {
+        CK(c, cudaMalloc(&c->sync_flags, VGI_MAX_PEERS * sizeof(uint32_t)));
+        CK(c, cudaMemset(c->sync_flags, 0, VGI_MAX_PEERS * sizeof(uint32_t)));
+        c->peer_epoch = 0;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == VGI_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles;
+    CK(c, cudaIpcGetMemHandle(&h[0], c->store));
+    CK(c, cudaIpcGetMemHandle(&h[1], c->occ));
+    CK(c, cudaIpcGetMemHandle(&h[2], c->sync_flags));
+    return VGI_OK;
+}
+
+int vgi_peer_attach(vgi_ctx* c, uint32_t rank, uint32_t nranks, const void* all_handles)
+{
+    if (!c || !all_handles) return fail(c, VGI_E_INVALID, "vgi_peer_attach: null argument");
+    if (nranks < 1 || nranks > VGI_MAX_PEERS || rank >= nranks) return fail(c, VGI_E_INVALID, "vgi_peer_attach: bad rank / nranks");
+    if (c->cfg.resolution % nranks) return fail(c, VGI_E_INVALID, "vgi_peer_attach: resolution must be a multiple of nranks");
+    if (!c->sync_flags) return fail(c, VGI_E_STATE, "vgi_peer_attach: call vgi_peer_export first");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    peer_close(c);
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+    for (uint32_t r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            c->peers.store[r] = c->store; c->peers.occ[r] = c->occ; c->peers.flags[r] = c->sync_flags;
+            continue;
+        }
+        void* p[3] = { nullptr, nullptr, nullptr };
+        for (int k = 0; k < 3; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&p[k], h[r * 3 + k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                peer_close(c);
+                cudaGetLastError();
+                return fail(c, VGI_E_CUDA, std::string("vgi_peer_attach: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+            c->peer_opened[r][k] = p[k];
+        }
+        c->peers.store[r] = (VoxelRecord*)p[0]; c->peers.occ[r] = (uint32_t*)p[1]; c->peers.flags[r] = (uint32_t*)p[2];
+    }
+    c->peers.n = (int)nranks;
+    c->peers.rank = (int)rank;
+    c->peers_attached = true;
+    const uint32_t planes = c->cfg.resolution / nranks;
+    return vgi_set_slab(c, rank * planes, (rank + 1) * planes);
+}
+
+int vgi_peer_detach(vgi_ctx* c)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_peer_detach: null ctx");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    peer_close(c);
+    return vgi_set_slab(c, 0, c->cfg.resolution);
+}
+
+int vgi_peer_build_clipmap(vgi_ctx* c, uint32_t frame_index, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_peer_build_clipmap: null ctx");
+    if (!c->peers_attached) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: call vgi_peer_attach first");
+    if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: call vgi_set_scene first");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: call vgi_set_light first");
+    CK(c, cudaSetDevice(c->device));
+    BuildParams bp;
+    build_params_from_ctx(c, frame_index, &bp);
+    cudaStream_t s = (cudaStream_t)stream;
+    c->svo_counters_fresh = false;
+    c->launches += vgi_launch_peer_build(c, bp, c->peers, &c->peer_epoch, s);
+    c->last_stream = s;
+    c->voxelized = false;
+    c->built = true;
+    return check_launch(c, "vgi_peer_build_clipmap");
 }
 
 // ---- producers of the image inputs (the passes before the path) -----------------------------------

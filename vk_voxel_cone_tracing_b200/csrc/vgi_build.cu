@@ -421,6 +421,9 @@ struct SlabPack {
     uint4*    recs;     // 2 x uint4 per record
     uint32_t* count;
     uint32_t  cap;
+    // MODE 3 (peer build): the voxel stores of every GPU, this one included, mapped into this address space
+    VoxelRecord* peer_store[VGI_MAX_PEERS];
+    int       npeers;
 };
 
 template <int MODE>
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
         const int vx = (int)(vid & (uint32_t)Rm), vy = (int)((vid >> logR) & (uint32_t)Rm), vz = (int)(vid >> (2 * logR));
         const uint32_t wis = vid >> 5;
         const uint32_t lane = vid & 31u;
-        if (MODE == 1 && (vz < bp.z0 || vz >= bp.z1)) continue;
+        if ((MODE == 1 || MODE == 3) && (vz < bp.z0 || vz >= bp.z1)) continue;
         const uint32_t oword = __ldg(occL + wis);
         VoxelRecord* dstp = storeL + ((((size_t)vz << logR) + vy) << logR) + vx;
         uint4* dst = reinterpret_cast<uint4*>(dstp);
@@ -505,6 +508,16 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
         if (MODE != 2) {
             own.hi.z = raw ? 0xffffffffu : 0u;          // opacity alpha faces 0..3
             own.hi.w = raw ? 0x0001ffffu : 0u;          // opacity alpha faces 4,5 ; raw flag ; pad
+        }
+        if (MODE == 3) {
+            // the record goes straight into every GPU's store over NVLink (two 16-byte stores per peer)
+            const size_t off = (size_t)level * nvox + ((((size_t)vz << logR) + vy) << logR) + vx;
+            for (int r = 0; r < pack.npeers; ++r) {
+                uint4* pd = reinterpret_cast<uint4*>(pack.peer_store[r] + off);
+                pd[0] = own.lo;
+                pd[1] = own.hi;
+            }
+            continue;
         }
         if (MODE == 1) {
             dst[0] = own.lo;
@@ -828,6 +841,92 @@ int vgi_launch_slab_end(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
         LAUNCH("k_level_records_mip", k_level_records<2><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
     launch_brick(c, bp, cur, s, n);
     c->nz_cur = cur;
+    return n;
+}
+
+// ---- peer build: the slab-sharded build with the exchange done by the kernels themselves ------------
+// Every GPU maps the voxel store, the occupancy words and a row of sync flags of every other GPU (CUDA IPC over
+// NVLink / NVSwitch). A GPU voxelizes and injects its own slab of texel planes, stores its occupancy words and its
+// finalized records directly into all stores, and the GPUs meet at flag barriers: no NCCL call, no host round trip,
+// no staging buffers. The result equals vgi_build_clipmap on one GPU bit for bit.
+
+// All GPUs arrive: slot [rank] of every GPU's flag row receives this barrier's epoch (release, system scope), then
+// every GPU waits for all slots of its own row. Preceded in stream order by the kernels whose stores it publishes.
+__global__ void k_peer_barrier(PeerSet ps, uint32_t epoch, Counters* cnt)
+{
+    __threadfence_system();
+    const int r = threadIdx.x;
+    if (r < ps.n) {
+        uint32_t* remote = ps.flags[r] + ps.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(remote), "r"(epoch) : "memory");
+        const uint32_t* mine = ps.flags[ps.rank] + r;
+        const long long t0 = clock64();
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > 6000000000ll) { atomicOr(&cnt->overflow, 32u); break; } // ~3 s: a peer never arrived
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// this GPU's slab of the occupancy words -> every other GPU's occupancy array (whole words, zeros included)
+__global__ void __launch_bounds__(256) k_peer_push_occ(PeerSet ps, const uint32_t* __restrict__ occ, int L, uint32_t wordsPerLevel,
+                                                        uint32_t w0, uint32_t w1)
+{
+    const uint32_t span = w1 - w0;
+    const size_t total = (size_t)span * L;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t idx = (i / span) * wordsPerLevel + w0 + (i % span);
+        const uint32_t v = occ[idx];
+        for (int r = 0; r < ps.n; ++r)
+            if (r != ps.rank) ps.occ[r][idx] = v;
+    }
+}
+
+int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, uint32_t* epoch, cudaStream_t s)
+{
+    int n = 0;
+    const uint32_t wordsPerLevel = (uint32_t)(((size_t)bp.R * bp.R * bp.R) >> 5);
+    const uint32_t planeWords = (uint32_t)(((size_t)bp.R * bp.R) >> 5);
+    const uint32_t w0 = (uint32_t)bp.z0 * planeWords, w1 = (uint32_t)bp.z1 * planeWords;
+    const size_t nwords = (size_t)wordsPerLevel * bp.L;
+    // own slab: voxelize, scan, inject. Only the own planes are cleared: the other planes of the occupancy array are
+    // overwritten word by word by their owners every frame.
+    cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
+    for (int l = 0; l < bp.L; ++l)
+        cudaMemsetAsync(c->occ + (size_t)l * wordsPerLevel + w0, 0, (size_t)(w1 - w0) * sizeof(uint32_t), s);
+    if (bp.ntri) {
+        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
+        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
+    }
+    const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
+    LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));
+    LAUNCH("k_scan_sums", k_scan_sums<<<1, 1024, 0, s>>>(c->block_sums, nblk, &c->counters->occ_total));
+    LAUNCH("k_scan_final", k_scan_final<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums, c->occ_prefix));
+    n += launch_inject(c, bp, s);
+    // barrier A: every GPU is done with last frame's volume and with its own scan -> occupancy words may travel
+    LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
+    LAUNCH("k_peer_push_occ", k_peer_push_occ<<<148 * 2, 256, 0, s>>>(ps, c->occ, bp.L, wordsPerLevel, w0, w1));
+    // barrier B: the occupancy of the whole volume is in place on every GPU
+    LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
+    const int cur = c->nz_cur ^ 1;
+    launch_masks(c, bp, cur, s, n);
+    SlabPack pack = { nullptr, nullptr, nullptr, 0u };
+    for (int r = 0; r < ps.n; ++r) pack.peer_store[r] = ps.store[r];
+    pack.npeers = ps.n;
+    for (int l = 0; l < bp.L; ++l)
+        LAUNCH("k_level_records_peer", k_level_records<3><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, pack));
+    // barrier C: every record of every slab has reached every store
+    LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
+    const SlabPack none = { nullptr, nullptr, nullptr, 0u };
+    for (int l = 1; l < bp.L; ++l)
+        LAUNCH("k_level_records_mip", k_level_records<2><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
+    launch_brick(c, bp, cur, s, n);
+    c->nz_cur = cur;
+    cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
     return n;
 }
 

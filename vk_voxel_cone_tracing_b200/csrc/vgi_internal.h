@@ -71,6 +71,15 @@ struct Counters {
     uint32_t pad[7];
 };
 
+// peer build (vgi_peer_*): device pointers of every GPU's buffers, mapped through CUDA IPC; [rank] = this GPU's own
+#define VGI_MAX_PEERS 8
+struct PeerSet {
+    VoxelRecord* store[VGI_MAX_PEERS];
+    uint32_t*    occ[VGI_MAX_PEERS];
+    uint32_t*    flags[VGI_MAX_PEERS];  // one row of VGI_MAX_PEERS arrival epochs per GPU
+    int n, rank;
+};
+
 struct TraceParams {
     vgi_vct_params p;
     float    view_proj_inv[16];
@@ -172,6 +181,13 @@ struct vgi_ctx {
     cudaStream_t last_stream = 0;
     uint64_t launches = 0;
 
+    // peer build
+    PeerSet peers = {};
+    bool peers_attached = false;
+    uint32_t* sync_flags = nullptr;      // this GPU's flag row (exported)
+    uint32_t peer_epoch = 0;
+    void* peer_opened[VGI_MAX_PEERS][3] = {};
+
     // software rasteriser scratch (vgi_render_shadow_map / vgi_render_gbuffer)
     void* raster_proj = nullptr;               // projected triangles
     unsigned long long* raster_keys = nullptr; // per pixel: depth bits << 32 | triangle
@@ -212,6 +228,7 @@ int vgi_launch_slab_begin(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_slab_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_slab_unpack(vgi_ctx* c, const uint32_t* ids, const uint4* recs, uint32_t count, cudaStream_t s);
 int vgi_launch_slab_end(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
+int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, uint32_t* epoch, cudaStream_t s);
 int vgi_launch_export(vgi_ctx* c, int which, uint8_t* dst, int literal_border, cudaStream_t s);
 int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);
 int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s);

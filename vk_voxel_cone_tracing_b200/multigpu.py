@@ -115,3 +115,42 @@ class SlabBuild:
         gi._ck(lib.vgi_slab_build_end(gi._h, C.c_uint32(frame_index), st))
         self._keep = (ids_all, recs_all)   # alive until the unpack kernels ran
         return sum(counts)
+
+
+def exchange_handles(blob, group=None):
+    """All ranks contribute one bytes blob (their IPC handles); returns the concatenation in rank order."""
+    world = dist.get_world_size(group)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, bytes(blob), group=group)
+    assert all(len(b) == len(blob) for b in blobs)
+    return b"".join(blobs)
+
+
+class PeerBuild:
+    """Slab-sharded clipmap build whose exchange is done by the kernels themselves over NVLink peer memory
+    (vgi_peer_*): every GPU maps every other GPU's voxel store / occupancy words / arrival flags through CUDA IPC, writes
+    its slab's results into all stores and meets the others at flag barriers inside the stream. One process per GPU of
+    one node; torch.distributed only carries the 192-byte handle blobs at set-up."""
+
+    HANDLE_BYTES = 3 * 64
+
+    def __init__(self, gi, group=None):
+        from . import api
+        self.gi, self.group, self._api = gi, group, api
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        lib = api.lib()
+        mine = (C.c_byte * self.HANDLE_BYTES)()
+        gi._ck(lib.vgi_peer_export(gi._h, mine))
+        everyone = exchange_handles(bytes(mine), group)
+        buf = (C.c_byte * len(everyone)).from_buffer_copy(everyone)
+        gi._ck(lib.vgi_peer_attach(gi._h, C.c_uint32(self.rank), C.c_uint32(self.world), buf))
+        dist.barrier(group)            # every rank has mapped every buffer before the first build
+
+    def build(self, frame_index=0, stream=None):
+        gi, api = self.gi, self._api
+        gi._ck(api.lib().vgi_peer_build_clipmap(gi._h, C.c_uint32(frame_index), api._stream(stream)))
+
+    def close(self):
+        gi, api = self.gi, self._api
+        dist.barrier(self.group)       # nobody unmaps while a peer may still write
+        gi._ck(api.lib().vgi_peer_detach(gi._h))
