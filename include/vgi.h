@@ -264,8 +264,8 @@ int vgi_slab_build_end(vgi_ctx* ctx, uint32_t frame_index, void* stream);
  * three flag barriers inside the stream: no collective library call, no host round trip, no staging buffers.
  *   vgi_peer_export   handles: 3 x VGI_IPC_HANDLE_BYTES (store, occupancy, flags) of this ctx — exchange them
  *                     between the processes (e.g. torch.distributed.all_gather_object)
- *   vgi_peer_attach   all_handles: nranks x 3 x VGI_IPC_HANDLE_BYTES in rank order; resolution % nranks == 0;
- *                     sets the slab to planes [rank * R / nranks, (rank + 1) * R / nranks)
+ *   vgi_peer_attach   all_handles: nranks x 3 x VGI_IPC_HANDLE_BYTES in rank order; nranks a power of two <= 8;
+ *                     this GPU then owns the texel planes z with z mod nranks == rank (round-robin: balanced)
  *   vgi_peer_build_clipmap   = vgi_build_clipmap, bit for bit, on every GPU; all ranks must call it for the same
  *                     frame with the same regions / scene / light (a barrier waits ~3 s for a missing peer, then
  *                     gives up and the next vgi_get_stats fails with VGI_E_OVERFLOW, mask bit 0x20)

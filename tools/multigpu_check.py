@@ -101,6 +101,16 @@ def main():
             t = torch.tensor([ev[0].elapsed_time(ev[1]) / a.time_iters], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             timing[name] = float(t)
+    if a.time_iters:
+        # per-kernel times of the peer build (CUDA events on this rank's stream; barriers include the wait for the slowest GPU)
+        peer.set_timing(True)
+        peer.reset_timings()
+        dist.barrier()
+        for _ in range(a.time_iters):
+            pb.build(0)
+        torch.cuda.synchronize()
+        timing["peer_build_kernels_us_rank0"] = {k: round(v[0] / a.time_iters * 1e3, 1) for k, v in peer.timings().items()}
+        peer.set_timing(False)
     if rank == 0:
         print(json.dumps({"world": world, "scene": a.scene, "res": a.res, "slab_build_bit_exact": bool(flags[0]),
                           "row_sharded_trace_bit_exact": bool(flags[1]), "peer_build_bit_exact": bool(flags[2]),

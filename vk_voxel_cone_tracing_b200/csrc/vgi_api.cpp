@@ -417,6 +417,8 @@ void build_params_from_ctx(const vgi_ctx* c, uint32_t frame_index, BuildParams* 
     bp->max_large = c->max_large;
     bp->z0 = c->z0;
     bp->z1 = c->z1;
+    bp->z_mask = c->z_mask;
+    bp->z_rem = c->z_rem;
     bp->shadow_compare = (c->cfg.mode_flags & VGI_MODE_SHADOW_COMPARE) ? 1 : 0;
     uint32_t mask = 0;
     for (int l = 0; l < bp->L; ++l) {
@@ -521,6 +523,7 @@ int vgi_set_slab(vgi_ctx* c, uint32_t z0, uint32_t z1)
     if (!c || z0 >= z1 || z1 > c->cfg.resolution) return fail(c, VGI_E_INVALID, "vgi_set_slab: bad range");
     c->z0 = (int)z0;
     c->z1 = (int)z1;
+    c->z_mask = c->z_rem = 0;
     return VGI_OK;
 }
 
@@ -863,7 +866,7 @@ int vgi_peer_attach(vgi_ctx* c, uint32_t rank, uint32_t nranks, const void* all_
 {
     if (!c || !all_handles) return fail(c, VGI_E_INVALID, "vgi_peer_attach: null argument");
     if (nranks < 1 || nranks > VGI_MAX_PEERS || rank >= nranks) return fail(c, VGI_E_INVALID, "vgi_peer_attach: bad rank / nranks");
-    if (c->cfg.resolution % nranks) return fail(c, VGI_E_INVALID, "vgi_peer_attach: resolution must be a multiple of nranks");
+    if (nranks & (nranks - 1)) return fail(c, VGI_E_INVALID, "vgi_peer_attach: nranks must be a power of two");
     if (!c->sync_flags) return fail(c, VGI_E_STATE, "vgi_peer_attach: call vgi_peer_export first");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->last_stream));
@@ -889,8 +892,13 @@ int vgi_peer_attach(vgi_ctx* c, uint32_t rank, uint32_t nranks, const void* all_
     c->peers.n = (int)nranks;
     c->peers.rank = (int)rank;
     c->peers_attached = true;
-    const uint32_t planes = c->cfg.resolution / nranks;
-    return vgi_set_slab(c, rank * planes, (rank + 1) * planes);
+    // texel planes are dealt round-robin (z mod nranks == rank): neighbouring planes carry similar geometry, so every
+    // GPU gets an equal share of the pairs whatever the scene's extent along z
+    c->z0 = 0;
+    c->z1 = (int)c->cfg.resolution;
+    c->z_mask = (int)nranks - 1;
+    c->z_rem = (int)rank;
+    return VGI_OK;
 }
 
 int vgi_peer_detach(vgi_ctx* c)

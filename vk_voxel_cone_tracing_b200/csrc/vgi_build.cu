@@ -17,7 +17,7 @@ DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair
 {
     const int Rm = bp.R - 1;
     const uint32_t x = vx & Rm, y = vy & Rm, z = vz & Rm;
-    if ((int)z < bp.z0 || (int)z >= bp.z1) return;   // slab-sharded build: this GPU owns texel planes [z0, z1)
+    if (!owns_plane(bp, (int)z)) return;   // slab-sharded build: the texel planes this GPU owns
     const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
     const size_t w = (size_t)level * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
     const uint32_t bit = 1u << (x & 31u);
@@ -61,29 +61,31 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
             ny = ts.hi[1] - ts.lo[1] + 1;
             const int nz = ts.hi[2] - ts.lo[2] + 1;
             const long long vol = (long long)nx * ny * nz;
+            // slab-sharded build: this GPU owns the texel planes [z0, z1); planes of other GPUs are skipped before
+            // any overlap test (and a big triangle is queued only where it can touch the slab)
+            const int Rm = bp.R - 1;
+            const bool slab = bp.z0 > 0 || bp.z1 < bp.R || bp.z_mask != 0;
             if (vol > SMALL_BOX_MAX) {
-                const uint32_t slot = atomicAdd(&cnt->large, 1u);
-                if (slot < bp.max_large) large[slot] = make_uint2(t, (uint32_t)l);
-                else atomicOr(&cnt->overflow, 2u);
+                bool mine = !slab;
+                for (int z = ts.lo[2]; z <= ts.hi[2] && !mine; ++z) mine = owns_plane(bp, z & Rm);
+                if (mine) {
+                    const uint32_t slot = atomicAdd(&cnt->large, 1u);
+                    if (slot < bp.max_large) large[slot] = make_uint2(t, (uint32_t)l);
+                    else atomicOr(&cnt->overflow, 2u);
+                }
             } else {
                 lo0 = ts.lo[0]; lo1 = ts.lo[1]; lo2 = ts.lo[2];
                 int i = 0;
-                for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
+                for (int z = ts.lo[2]; z <= ts.hi[2]; ++z) {
+                    if (slab && !owns_plane(bp, z & Rm)) { i += nx * ny; continue; }
                     for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
                         for (int x = ts.lo[0]; x <= ts.hi[0]; ++x, ++i)
                             if (tri_overlaps_voxel(ts, x, y, z)) hits |= 1ull << i;
+                }
             }
         }
     }
-    // drop the hits outside this GPU's slab (slab-sharded build) before reserving space
     const int Rm = bp.R - 1;
-    if (bp.z0 > 0 || bp.z1 < bp.R) {
-        for (unsigned long long h = hits; h; h &= h - 1) {
-            const int i = __ffsll((long long)h) - 1;
-            const int z = (lo2 + i / (nx * ny)) & Rm;
-            if (z < bp.z0 || z >= bp.z1) hits &= ~(1ull << i);
-        }
-    }
     const uint32_t n = (uint32_t)__popcll(hits);
     uint32_t incl = n;
 #pragma unroll
@@ -427,7 +429,7 @@ struct SlabPack {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level, const uint32_t* __restrict__ occ,
+__global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level_arg, const uint32_t* __restrict__ occ,
                                                         const uint32_t* __restrict__ occ_prefix,
                                                         const uint32_t* __restrict__ acc, const uint32_t* __restrict__ nzCur,
                                                         const uint32_t* __restrict__ visitList, uint32_t listCap,
@@ -437,6 +439,8 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = (float)i / 255.0f;
     __syncthreads();
 
+    // peer build: the levels are independent before the mip pass, one launch covers them all (blockIdx.y = level)
+    const int level = MODE == 3 ? (int)blockIdx.y : level_arg;
     const int R = bp.R, Rm = R - 1, half = R >> 1, logR = bp.logR;
     const int wpr = R >> 5;
     const size_t nvox = (size_t)R * R * R;
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
         const int vx = (int)(vid & (uint32_t)Rm), vy = (int)((vid >> logR) & (uint32_t)Rm), vz = (int)(vid >> (2 * logR));
         const uint32_t wis = vid >> 5;
         const uint32_t lane = vid & 31u;
-        if ((MODE == 1 || MODE == 3) && (vz < bp.z0 || vz >= bp.z1)) continue;
+        if ((MODE == 1 || MODE == 3) && !owns_plane(bp, vz)) continue;
         const uint32_t oword = __ldg(occL + wis);
         VoxelRecord* dstp = storeL + ((((size_t)vz << logR) + vy) << logR) + vx;
         uint4* dst = reinterpret_cast<uint4*>(dstp);
@@ -872,17 +876,27 @@ __global__ void k_peer_barrier(PeerSet ps, uint32_t epoch, Counters* cnt)
     __threadfence_system();
 }
 
-// this GPU's slab of the occupancy words -> every other GPU's occupancy array (whole words, zeros included)
-__global__ void __launch_bounds__(256) k_peer_push_occ(PeerSet ps, const uint32_t* __restrict__ occ, int L, uint32_t wordsPerLevel,
-                                                        uint32_t w0, uint32_t w1)
+// The occupancy words of the texel planes this GPU owns (a plane of R x R bits = R * R / 32 consecutive words, a
+// multiple of four for every supported R): cleared before the voxelizer, then stored into every other GPU's occupancy
+// array after it (whole words, zeros included) with 16-byte stores.
+template <bool PUSH>
+__global__ void __launch_bounds__(256) k_peer_own_planes(PeerSet ps, BuildParams bp, uint32_t* __restrict__ occ)
 {
-    const uint32_t span = w1 - w0;
-    const size_t total = (size_t)span * L;
+    const uint32_t plane4 = (uint32_t)(((size_t)bp.R * bp.R) >> 7);         // uint4 per plane
+    const uint32_t wordsPerLevel = (uint32_t)(((size_t)bp.R * bp.R * bp.R) >> 5);
+    const size_t total = (size_t)plane4 * bp.R * bp.L;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t idx = (i / span) * wordsPerLevel + w0 + (i % span);
-        const uint32_t v = occ[idx];
-        for (int r = 0; r < ps.n; ++r)
-            if (r != ps.rank) ps.occ[r][idx] = v;
+        const uint32_t q = (uint32_t)(i % plane4);
+        const int z = (int)((i / plane4) % bp.R), l = (int)(i / ((size_t)plane4 * bp.R));
+        if (!owns_plane(bp, z)) continue;
+        const size_t idx = (size_t)l * wordsPerLevel + (((size_t)z * plane4 + q) << 2);
+        if (PUSH) {
+            const uint4 v = *reinterpret_cast<const uint4*>(occ + idx);
+            for (int r = 0; r < ps.n; ++r)
+                if (r != ps.rank) *reinterpret_cast<uint4*>(ps.occ[r] + idx) = v;
+        } else {
+            *reinterpret_cast<uint4*>(occ + idx) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 }
 
@@ -890,14 +904,11 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
 {
     int n = 0;
     const uint32_t wordsPerLevel = (uint32_t)(((size_t)bp.R * bp.R * bp.R) >> 5);
-    const uint32_t planeWords = (uint32_t)(((size_t)bp.R * bp.R) >> 5);
-    const uint32_t w0 = (uint32_t)bp.z0 * planeWords, w1 = (uint32_t)bp.z1 * planeWords;
     const size_t nwords = (size_t)wordsPerLevel * bp.L;
     // own slab: voxelize, scan, inject. Only the own planes are cleared: the other planes of the occupancy array are
     // overwritten word by word by their owners every frame.
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
-    for (int l = 0; l < bp.L; ++l)
-        cudaMemsetAsync(c->occ + (size_t)l * wordsPerLevel + w0, 0, (size_t)(w1 - w0) * sizeof(uint32_t), s);
+    LAUNCH("k_peer_clear_occ", k_peer_own_planes<false><<<148 * 4, 256, 0, s>>>(ps, bp, c->occ));
     if (bp.ntri) {
         LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
         LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
@@ -909,7 +920,7 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
     n += launch_inject(c, bp, s);
     // barrier A: every GPU is done with last frame's volume and with its own scan -> occupancy words may travel
     LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
-    LAUNCH("k_peer_push_occ", k_peer_push_occ<<<148 * 2, 256, 0, s>>>(ps, c->occ, bp.L, wordsPerLevel, w0, w1));
+    LAUNCH("k_peer_push_occ", k_peer_own_planes<true><<<148 * 4, 256, 0, s>>>(ps, bp, c->occ));
     // barrier B: the occupancy of the whole volume is in place on every GPU
     LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
     const int cur = c->nz_cur ^ 1;
@@ -917,8 +928,7 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
     SlabPack pack = { nullptr, nullptr, nullptr, 0u };
     for (int r = 0; r < ps.n; ++r) pack.peer_store[r] = ps.store[r];
     pack.npeers = ps.n;
-    for (int l = 0; l < bp.L; ++l)
-        LAUNCH("k_level_records_peer", k_level_records<3><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, pack));
+    LAUNCH("k_level_records_peer", k_level_records<3><<<dim3(148 * 2, bp.L), 128, 0, s>>>(bp, 0, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, pack));
     // barrier C: every record of every slab has reached every store
     LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
     const SlabPack none = { nullptr, nullptr, nullptr, 0u };

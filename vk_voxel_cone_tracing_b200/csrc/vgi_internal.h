@@ -42,7 +42,8 @@ struct BuildParams {
     uint32_t max_occ;       // capacity of the accumulator table (occupied voxels)
     uint32_t max_large;
     uint32_t level_mask;    // levels whose radiance is (re)injected this frame (cadence)
-    int      z0, z1;        // slab of records this GPU writes
+    int      z0, z1;        // slab of records this GPU writes: texel planes z in [z0, z1) ...
+    int      z_mask, z_rem; // ... with (z & z_mask) == z_rem (peer build: planes dealt round-robin; 0, 0 = every plane)
     int      shadow_compare;
 };
 
@@ -79,6 +80,12 @@ struct PeerSet {
     uint32_t*    flags[VGI_MAX_PEERS];  // one row of VGI_MAX_PEERS arrival epochs per GPU
     int n, rank;
 };
+
+// does this GPU own texel plane z (slab-sharded builds)?
+static __host__ __device__ __forceinline__ bool owns_plane(const BuildParams& bp, int z)
+{
+    return z >= bp.z0 && z < bp.z1 && (z & bp.z_mask) == bp.z_rem;
+}
 
 struct TraceParams {
     vgi_vct_params p;
@@ -175,7 +182,7 @@ struct vgi_ctx {
     Counters* counters = nullptr;
     Counters* h_counters = nullptr; // pinned
     uint32_t max_pairs = 0, max_occ = 0, max_large = 0;
-    int z0 = 0, z1 = 0;
+    int z0 = 0, z1 = 0, z_mask = 0, z_rem = 0;
     bool voxelized = false, built = false;
     uint32_t frame_of_voxelize = 0;
     cudaStream_t last_stream = 0;

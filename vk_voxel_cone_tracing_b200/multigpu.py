@@ -11,10 +11,13 @@ SURVEY.md section 8(e):
     and runs the mips replicated. The result equals the single-GPU build bit for bit
     (tools/multigpu_check.py verifies that on the GPU box).
 
-Measured trade-off (B200, configs[1]): the replicated build costs 0.86 ms per GPU; the slab build saves at
-most (N-1)/N of the voxelize + inject part (~0.6 ms) and pays two NCCL all-gathers and one host read of the
-record counts, so replication wins for N <= 8 at this scene size — bench.py therefore replicates the build
-and shards the views; the slab path is here for volumes whose build does not fit the frame budget."""
+  * `PeerBuild` is the same sharding with the exchange done by the kernels themselves over NVLink peer memory
+    (CUDA IPC mapped stores, direct stores into every GPU, flag barriers in the stream; vgi_peer_*).
+
+Measured (B200, configs[1], profiles/r1_peer_build.json): replicated build 0.74 ms per GPU; NCCL slab build
+0.80-0.86 ms (two all-gathers + one host read of the record counts cost what the sharded voxelize + inject
+saves); peer build 0.58 / 0.47 / 0.44 ms on 2 / 4 / 8 GPUs. bench.py renders N different views (different clip
+regions), so it replicates the build and shards the views."""
 import ctypes as C
 
 import torch
