@@ -253,3 +253,48 @@ def test_error_paths():
     with pytest.raises(VgiError) as e:
         VoxelGI(S.default_config(100, 2))
     assert e.value.code == S.VGI_E_INVALID
+
+
+def test_peer_build_single_rank_equals_build_clipmap(oracle):
+    """The peer build (vgi_peer_*: kernel-side exchange over mapped peer memory) with a world of one GPU: the same
+    kernels, flag barriers and plane-ownership logic as on 8 GPUs (tools/multigpu_check.py checks 2 / 4 / 8), compared
+    bit for bit with vgi_build_clipmap over frames with cadence and a moving camera."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from vk_voxel_cone_tracing_b200 import multigpu as M
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    inp = common.cornell_inputs(64, 1024, 128, 128)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        gis = []
+        for _ in range(2):
+            gi = VoxelGI(inp["cfg"])
+            gi.set_scene(inp["scene"])
+            gi.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
+            gis.append(gi)
+        ref, peer = gis
+        pb = M.PeerBuild(peer)
+        for frame in range(4):
+            cam = tuple(np.array(inp["cam_pos"]) + np.array([0.41, -0.13, 0.27]) * frame)
+            ref.update_regions(cam)
+            peer.update_regions(cam)
+            ref.build_clipmap(frame)
+            pb.build(frame)
+            for which in (0, 1):
+                assert torch.equal(ref.export_atlas(which), peer.export_atlas(which)), (frame, which)
+        assert peer.stats().occupied_voxels == ref.stats().occupied_voxels > 0
+        pb.close()
+        # after detaching, the ctx builds alone again
+        peer.build_clipmap(4)
+        ref.build_clipmap(4)
+        assert torch.equal(ref.export_atlas(1), peer.export_atlas(1))
+    finally:
+        if own_group:
+            dist.destroy_process_group()

@@ -937,7 +937,7 @@ static int raster_scratch(vgi_ctx* c, size_t npx)
         cudaFree(c->raster_proj); cudaFree(c->raster_large);
         c->raster_proj = nullptr; c->raster_large = nullptr;
         CK(c, cudaMalloc(&c->raster_proj, vgi_raster_proj_bytes(c->ntri)));
-        CK(c, cudaMalloc(&c->raster_large, ((size_t)c->ntri + 1) * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&c->raster_large, ((size_t)c->ntri + 2) * sizeof(uint32_t)));
         c->raster_tri_cap = c->ntri + 1u;
     }
     if (c->raster_px_cap < npx) {

@@ -22,6 +22,7 @@ struct ProjTri {
 };
 
 #define RASTER_SMALL_MAX 256   // bounding boxes up to this many pixels are walked by one thread
+#define RASTER_HUGE_MIN (128 * 128)    // boxes above this many pixels are spread over the whole grid
 
 DEVFN void project_tri(const float* M, const float4* tri_pos, uint32_t t, int w, int h, ProjTri& o)
 {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) k_raster_clear(unsigned long long* keys, 
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = ~0ull;
-    if (i == 0) *large_count = 0u;
+    if (i == 0) { large_count[0] = 0u; large_count[1] = 0u; }
 }
 
 __global__ void __launch_bounds__(128) k_raster_small(const __grid_constant__ RasterParams rp)
@@ -109,7 +110,12 @@ __global__ void __launch_bounds__(128) k_raster_small(const __grid_constant__ Ra
     rp.proj[t] = q;
     const Box b = tri_box(q, rp.w, rp.h);
     if (!b.any) return;
-    if ((long long)(b.x1 - b.x0 + 1) * (b.y1 - b.y0 + 1) > RASTER_SMALL_MAX) {
+    const long long boxPx = (long long)(b.x1 - b.x0 + 1) * (b.y1 - b.y0 + 1);
+    if (boxPx > RASTER_HUGE_MIN) {          // huge boxes queue up from the end of the same array
+        rp.large[rp.ntri - 1u - atomicAdd(rp.large_count + 1, 1u)] = t;
+        return;
+    }
+    if (boxPx > RASTER_SMALL_MAX) {
         rp.large[atomicAdd(rp.large_count, 1u)] = t;
         return;
     }
@@ -117,21 +123,35 @@ __global__ void __launch_bounds__(128) k_raster_small(const __grid_constant__ Ra
         for (int x = b.x0; x <= b.x1; ++x) raster_pixel(rp, q, b.area, t, x, y);
 }
 
-// one block per 64 x 64-pixel piece of a large triangle's bounding box (grid.y walks the queue)
+// medium boxes (257 .. RASTER_HUGE_MIN pixels): one warp per triangle, lanes stride over the box row-major
 __global__ void __launch_bounds__(256) k_raster_large(const __grid_constant__ RasterParams rp)
 {
     const uint32_t n = *rp.large_count;
-    for (uint32_t i = blockIdx.y; i < n; i += gridDim.y) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warpsPerGrid) {
         const uint32_t t = rp.large[i];
         const ProjTri& q = rp.proj[t];
         const Box b = tri_box(q, rp.w, rp.h);
-        const int tilesX = (b.x1 - b.x0 + 64) / 64, tilesY = (b.y1 - b.y0 + 64) / 64;
+        const int bw = b.x1 - b.x0 + 1, bh = b.y1 - b.y0 + 1;
+        for (int p = (int)lane; p < bw * bh; p += 32) raster_pixel(rp, q, b.area, t, b.x0 + p % bw, b.y0 + p / bw);
+    }
+}
+
+// the few triangles that cover a large part of the image (floors, walls): every block of the grid takes pieces
+__global__ void __launch_bounds__(256) k_raster_huge(const __grid_constant__ RasterParams rp)
+{
+    const uint32_t n = rp.large_count[1];
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t t = rp.large[rp.ntri - 1u - i];
+        const ProjTri& q = rp.proj[t];
+        const Box b = tri_box(q, rp.w, rp.h);
+        const int tilesX = (b.x1 - b.x0 + 32) / 32, tilesY = (b.y1 - b.y0 + 32) / 32;
         for (int tile = blockIdx.x; tile < tilesX * tilesY; tile += gridDim.x) {
-            const int tx = b.x0 + (tile % tilesX) * 64, ty = b.y0 + (tile / tilesX) * 64;
-            for (int p = threadIdx.x; p < 64 * 64; p += 256) {
-                const int x = tx + (p & 63), y = ty + (p >> 6);
-                if (x <= b.x1 && y <= b.y1) raster_pixel(rp, q, b.area, t, x, y);
-            }
+            const int tx = b.x0 + (tile % tilesX) * 32, ty = b.y0 + (tile / tilesX) * 32;
+            const int tw = min(32, b.x1 - tx + 1), th = min(32, b.y1 - ty + 1);
+            for (int p = threadIdx.x; p < tw * th; p += 256)
+                raster_pixel(rp, q, b.area, t, tx + p % tw, ty + p / tw);
         }
     }
 }
@@ -223,9 +243,12 @@ static int launch_visibility(vgi_ctx* c, const RasterParams& rp, cudaStream_t s)
         k_raster_small<<<(rp.ntri + 127) / 128, 128, 0, s>>>(rp);
         c->timer.end(s);
         c->timer.begin("k_raster_large", s);
-        k_raster_large<<<dim3(16, 1184), 256, 0, s>>>(rp); // 8 x 148 queue walkers, 16 blocks per triangle
+        k_raster_large<<<148 * 8, 256, 0, s>>>(rp);
         c->timer.end(s);
-        n += 2;
+        c->timer.begin("k_raster_huge", s);
+        k_raster_huge<<<148 * 8, 256, 0, s>>>(rp);
+        c->timer.end(s);
+        n += 3;
     }
     return n;
 }
