@@ -1033,7 +1033,6 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     if (c->stage_bytes < need) {
         CK(c, cudaStreamSynchronize(c->last_stream));
         cudaFree(c->stage);
-    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_inputs); cudaEventDestroy(c->ev_main_done); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_copy_done); }
         c->stage = nullptr;
         c->stage_bytes = 0;
         CK(c, cudaMalloc(&c->stage, need));
@@ -1058,7 +1057,10 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     CK(c, cudaEventRecord(c->ev_fork, s));
     CK(c, cudaStreamWaitEvent(cs, c->ev_fork, 0));
     // main stream: shadow map (needed by the injection) then the build; copy stream: the G-buffer, which only the
-    // tracer needs, travels while the clipmap is built
+    // tracer needs, travels while the clipmap is built.
+    // (Measured and rejected: tracing the image in four row bands so that band k uploads while band k-1 marches and
+    // finished rows go home early — the specular kernel's tail, its longest march, is then paid once per band:
+    // 8.4 ms instead of 7.5 ms per 1080p frame.)
     if (host_shadow_depth) {
         const size_t sb = (size_t)c->light.sw * c->light.sh * sizeof(float);
         if (!c->shadow_owned || c->shadow_owned_bytes < sb) {
