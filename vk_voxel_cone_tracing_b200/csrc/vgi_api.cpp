@@ -121,6 +121,7 @@ int vgi_destroy(vgi_ctx* c)
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch); cudaFree(c->raster_keys);
     peer_close(c);
     cudaFree(c->sync_flags);
+    if (c->side_stream) { cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->ev_side_fork); cudaEventDestroy(c->ev_side_masks); cudaEventDestroy(c->ev_side_done); }
     cudaFreeHost(c->h_counters);
     c->timer.resolve();
     for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
@@ -853,6 +854,11 @@ int vgi_peer_export(vgi_ctx* c, void* handles)
         CK(c, cudaMalloc(&c->sync_flags, VGI_MAX_PEERS * sizeof(uint32_t)));
         CK(c, cudaMemset(c->sync_flags, 0, VGI_MAX_PEERS * sizeof(uint32_t)));
         c->peer_epoch = 0;
+    }
+    {   // the planes other GPUs own are only ever written by them: start from a defined state
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        const size_t nwords = (((size_t)c->cfg.resolution * c->cfg.resolution * c->cfg.resolution) >> 5) * c->cfg.level_count;
+        CK(c, cudaMemset(c->occ, 0, nwords * sizeof(uint32_t)));
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == VGI_IPC_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles;

@@ -779,16 +779,37 @@ static int launch_inject(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
     return n;
 }
 
+// side stream for the mask kernels (fork: after the occupancy is final; join: before the records need the visit lists)
+static cudaStream_t side_fork(vgi_ctx* c, cudaStream_t s)
+{
+    if (!c->side_stream) {
+        if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { c->side_stream = nullptr; return s; }
+        cudaEventCreateWithFlags(&c->ev_side_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_side_masks, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming);
+    }
+    cudaEventRecord(c->ev_side_fork, s);
+    cudaStreamWaitEvent(c->side_stream, c->ev_side_fork, 0);
+    return c->side_stream;
+}
+
 int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
-    int n = launch_inject(c, bp, s);
+    int n = 0;
     // nz masks ping-pong between frames: nz[cur] is written by this build, nz[cur ^ 1] is last frame's
     const int cur = c->nz_cur ^ 1;
-    launch_masks(c, bp, cur, s, n);
+    // k_level_masks and k_brick_mask need the occupancy bits only: they run beside k_inject / k_level_records
+    const cudaStream_t side = side_fork(c, s);
+    launch_masks(c, bp, cur, side, n);
+    if (side != s) cudaEventRecord(c->ev_side_masks, side);
+    launch_brick(c, bp, cur, side, n);
+    if (side != s) cudaEventRecord(c->ev_side_done, side);
+    n += launch_inject(c, bp, s);
+    if (side != s) cudaStreamWaitEvent(s, c->ev_side_masks, 0);
     const SlabPack none = { nullptr, nullptr, nullptr, 0u };
     for (int l = 0; l < bp.L; ++l)
         LAUNCH("k_level_records", k_level_records<0><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
-    launch_brick(c, bp, cur, s, n);
+    if (side != s) cudaStreamWaitEvent(s, c->ev_side_done, 0);
     c->nz_cur = cur;
     cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
     return n;
@@ -917,14 +938,20 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
     LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));
     LAUNCH("k_scan_sums", k_scan_sums<<<1, 1024, 0, s>>>(c->block_sums, nblk, &c->counters->occ_total));
     LAUNCH("k_scan_final", k_scan_final<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums, c->occ_prefix));
-    n += launch_inject(c, bp, s);
     // barrier A: every GPU is done with last frame's volume and with its own scan -> occupancy words may travel
     LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
     LAUNCH("k_peer_push_occ", k_peer_own_planes<true><<<148 * 4, 256, 0, s>>>(ps, bp, c->occ));
     // barrier B: the occupancy of the whole volume is in place on every GPU
     LAUNCH("k_peer_barrier", k_peer_barrier<<<1, 32, 0, s>>>(ps, ++*epoch, c->counters));
+    // the masks of the whole volume (replicated bit arithmetic) run on the side stream beside the own slab's injection
     const int cur = c->nz_cur ^ 1;
-    launch_masks(c, bp, cur, s, n);
+    const cudaStream_t side = side_fork(c, s);
+    launch_masks(c, bp, cur, side, n);
+    if (side != s) cudaEventRecord(c->ev_side_masks, side);
+    launch_brick(c, bp, cur, side, n);
+    if (side != s) cudaEventRecord(c->ev_side_done, side);
+    n += launch_inject(c, bp, s);
+    if (side != s) cudaStreamWaitEvent(s, c->ev_side_masks, 0);
     SlabPack pack = { nullptr, nullptr, nullptr, 0u };
     for (int r = 0; r < ps.n; ++r) pack.peer_store[r] = ps.store[r];
     pack.npeers = ps.n;
@@ -934,7 +961,7 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
     const SlabPack none = { nullptr, nullptr, nullptr, 0u };
     for (int l = 1; l < bp.L; ++l)
         LAUNCH("k_level_records_mip", k_level_records<2><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
-    launch_brick(c, bp, cur, s, n);
+    if (side != s) cudaStreamWaitEvent(s, c->ev_side_done, 0);
     c->nz_cur = cur;
     cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s);
     return n;

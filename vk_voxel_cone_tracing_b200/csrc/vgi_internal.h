@@ -206,6 +206,11 @@ struct vgi_ctx {
     uint32_t* spec_list = nullptr;
     size_t spec_capacity = 0;
 
+    // build: the empty-space / visit-list masks depend on the occupancy alone, so they run on a side stream next to
+    // the injection and the record pass (created on first use)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_side_fork = nullptr, ev_side_masks = nullptr, ev_side_done = nullptr;
+
     // vgi_frame_host: second stream + events so that PCIe copies overlap the kernels
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_inputs = nullptr, ev_main_done = nullptr, ev_fork = nullptr, ev_copy_done = nullptr;
