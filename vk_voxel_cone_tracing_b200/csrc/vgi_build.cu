@@ -782,6 +782,7 @@ static int launch_inject(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 // side stream for the mask kernels (fork: after the occupancy is final; join: before the records need the visit lists)
 static cudaStream_t side_fork(vgi_ctx* c, cudaStream_t s)
 {
+    if (c->timer.enabled) return s;   // per-kernel timing (vgi_set_timing): one stream, so that no kernel's time includes a neighbour's
     if (!c->side_stream) {
         if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { c->side_stream = nullptr; return s; }
         cudaEventCreateWithFlags(&c->ev_side_fork, cudaEventDisableTiming);
