@@ -158,3 +158,90 @@ def test_max_resolution_512_single_level_vs_oracle(oracle):
     assert (ed <= tol_d).all(), (float(ed.max()), float(np.abs(ref_d[covered]).max()))
     assert (es <= tol_s).all(), (float(es.max()), float(np.abs(ref_s[covered]).max()))
     assert np.abs(ed[np.abs(ref_d[covered]) <= 1.0]).max() <= 1e-3
+
+
+def test_config4_default_clipmap_128_6_and_4k_rows_vs_oracle(oracle):
+    """BASELINE configs[3]: the reference's shipped default clipmap (R = 128, L = 6) on the Sponza-scale mesh —
+    both atlases bit-exact against the oracle — and a 3840 x 2160 cone trace whose G-buffer is rendered on the device;
+    the oracle traces three 8-row bands of it (a whole 4K frame would take the CPU a minute)."""
+    import torch
+    from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    scene = synth.atrium()
+    cfg = S.default_config(128, 6)
+    light, shadow = synth.make_light()
+    cam_pos = (-8.0, 3.0, 0.0)
+    W, H = 3840, 2160
+    cam = synth.make_camera(cam_pos, (1.0, 0.0, 0.0), aspect=W / H)
+    gi = VoxelGI(cfg)
+    gi.set_scene(scene)
+    depth = gi.render_shadow_map(shadow, 2048)
+    gi.set_light(light, shadow, depth)
+    gi.update_regions(cam_pos)
+    gi.build_clipmap(0)
+    depth_h = depth.cpu().numpy()
+    regs = oracle.regions(cfg, cam_pos)
+    op, rad, pairs = oracle.build_clipmap(cfg, regs, oracle.OracleScene(scene), light, shadow, depth_h, 0)
+    assert gi.stats().clip_pairs == pairs
+    assert np.array_equal(gi.export_atlas(0).cpu().numpy(), op)
+    assert np.array_equal(gi.export_atlas(1).cpu().numpy(), rad)
+    gb = gi.render_gbuffer(cam, W, H)
+    prm = gi.default_vct_params(8)
+    d, s = gi.cone_trace(cam, gb, prm)
+    hgb = {k: (v.cpu().numpy().view(np.uint16) if v.dtype == torch.int16 else v.cpu().numpy()) for k, v in gb.items()}
+    hg = oracle.HostGBuffer(hgb["diffuse"], hgb["normal"], hgb["specular"], hgb["emission"], hgb["depth"])
+    dn, sn = d.cpu().numpy(), s.cpu().numpy()
+    covered = 0
+    for y0 in (400, 1080, 1900):
+        rd, rs, _ = oracle.cone_trace(cfg, cam, hg, prm, light, shadow, depth_h, rad, rows=(y0, y0 + 8))
+        cov = hgb["depth"][y0:y0 + 8] < 1.0
+        covered += int(cov.sum())
+        assert np.abs(dn[y0:y0 + 8] - rd[y0:y0 + 8])[cov].max() <= 1e-3
+        assert np.abs(sn[y0:y0 + 8] - rs[y0:y0 + 8])[cov].max() <= 1e-3
+    assert covered > 20000
+
+
+def test_config5_orbit_views_sharded_by_view():
+    """BASELINE configs[4], single-GPU part: the seeded camera orbit is dealt to ranks view by view
+    (multigpu.views_for_rank); every view's G-buffer is rendered on the device and traced against one shared volume;
+    a view traced alone equals the same view traced in the batch (no state leaks between views)."""
+    import torch
+    from vk_voxel_cone_tracing_b200 import multigpu as M, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    scene = synth.atrium()
+    cfg = S.default_config(128, 6)
+    light, shadow = synth.make_light()
+    gi = VoxelGI(cfg)
+    gi.set_scene(scene)
+    gi.set_light(light, shadow, gi.render_shadow_map(shadow, 2048))
+    lo, hi = scene.world_bbox()
+    centre = (np.asarray(lo) + np.asarray(hi)) * 0.5
+    gi.update_regions(tuple(float(x) for x in centre))
+    gi.build_clipmap(0)
+    rng = np.random.RandomState(5)
+    n_views, world = 16, 8
+    cams = []
+    for v in range(n_views):
+        ang = 2.0 * np.pi * v / n_views
+        pos = centre + np.array([rng.uniform(6, 12) * np.cos(ang), rng.uniform(2, 8) - centre[1], rng.uniform(6, 12) * np.sin(ang)])
+        dirv = centre - pos
+        cams.append(synth.make_camera(tuple(pos), tuple(dirv / np.linalg.norm(dirv)), aspect=16 / 9))
+    owned = [list(M.views_for_rank(n_views, r, world)) for r in range(world)]
+    assert sorted(v for o in owned for v in o) == list(range(n_views)) and all(len(o) == 2 for o in owned)
+    prm = gi.default_vct_params(8)
+    W, H = 640, 360
+    batch = {}
+    for v in owned[3] + owned[5]:
+        gb = gi.render_gbuffer(cams[v], W, H)
+        d, s = gi.cone_trace(cams[v], gb, prm)
+        assert float((gb["depth"] < 1.0).float().mean()) > 0.2      # the orbit looks at the scene
+        assert torch.isfinite(d).all() and torch.isfinite(s).all()
+        batch[v] = (d.clone(), s.clone())
+    v = owned[5][0]
+    alone = VoxelGI(cfg)
+    alone.set_scene(scene)
+    alone.set_light(light, shadow, alone.render_shadow_map(shadow, 2048))
+    alone.update_regions(tuple(float(x) for x in centre))
+    alone.build_clipmap(0)
+    d, s = alone.cone_trace(cams[v], alone.render_gbuffer(cams[v], W, H), prm)
+    assert torch.equal(d, batch[v][0]) and torch.equal(s, batch[v][1])
