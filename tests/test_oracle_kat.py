@@ -220,3 +220,114 @@ def test_specular_filter_known_answers(oracle):
     spc[:] = 0.0; spc[4, 6, :3] = 1.0; dif[..., :3] = 0.0
     out = oracle.specular_filter(dif, spc, S.default_filter_params(1, 0))
     assert abs(out[4, 6, 0] - 257.0 / 241.0) < 0.02 and 0.0 < out[4, 7, 0] < 0.01 and out[4, 9, 0] == 0.0
+
+
+def _trace_cone_uniform(c, start_pos, direction, aperture, start_level, step_factor, prm, levels):
+    """voxelConeTracing.frag:341-392 written out for a volume whose every texel is `c`: the three face taps
+    return c each, so the sample is c * (d.x^2 + d.y^2 + d.z^2) at every position and level. Plain float64
+    arithmetic, transcribed from the shader text independently of the C oracle."""
+    vs0, dim = prm.voxel_size, prm.volume_dimension
+    centre = np.array(prm.volume_center[:], dtype=np.float64)
+    w = direction * direction
+    sample = c * w[0] + c * w[1] + c * w[2]
+    cone_coeff = 2.0 * np.tan(aperture * 0.5)
+    voxel = vs0 * 2.0 ** start_level
+    pos0 = start_pos + direction * voxel * prm.trace_start_offset * 0.5
+    step, diameter, occlusion = 0.0, max(0.0, vs0), 0.0
+    result = np.zeros(4)
+    seg = voxel
+    min_radius = vs0 * dim * 0.5
+    while step < 30.0 and occlusion < 1.0:
+        p = pos0 + direction * step
+        dist = np.linalg.norm(centre - p)
+        min_level = np.ceil(np.log2(dist / min_radius))
+        cur = np.log2(diameter / vs0)
+        cur = min(max(max(start_level, cur), min_level), levels - 1)
+        voxel = vs0 * 2.0 ** cur
+        corr = seg / voxel
+        rad = sample[:3] * corr
+        op = min(max(1.0 - (1.0 - sample[3]) ** corr, 0.0), 1.0)
+        result += min(max(1.0 - result[3], 0.0), 1.0) * np.array([rad[0], rad[1], rad[2], op])
+        occlusion += (1.0 - occlusion) * op / (1.0 + (step + voxel) * prm.occlusion_decay)
+        prev = step
+        step += max(diameter, vs0) * step_factor
+        seg = step - prev
+        diameter = step * cone_coeff
+    return np.array([result[0], result[1], result[2], 1.0 - occlusion])
+
+
+def test_uniform_volume_cone_accumulation_closed_form(oracle):
+    """A radiance atlas filled with one RGBA value: position and level drop out of every texture fetch, which
+    leaves the marching schedule (step sequence, level selection, segment correction, front-to-back blend, occlusion
+    decay), the 16-cone gather and the mode switch. Those are transcribed here from the shader text in float64 and
+    compared with the oracle's image for modes 7 (VXAO), 5 (emissive pixel: emission * AO + indirect) and 6 (specular
+    cone with stepFactor = uVoxelSize, Q12)."""
+    cfg = S.default_config(32, 3)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    rad = oracle.new_atlas(cfg)
+    texel = np.array([51, 102, 153, 26], dtype=np.uint8)
+    rad[...] = texel
+    c = texel.astype(np.float64) / 255.0
+    light, shadow = synth.make_light(origin=(0.0, 20.0, -3.5))
+    sdepth = np.ones((64, 64), dtype=np.float32)
+    cam = synth.make_camera((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), aspect=1.0)
+    n = np.array([0.0, 0.6, 0.8])
+    W = H = 2
+    e = 0.25
+    gb = dict(diffuse=np.tile(np.array([255, 255, 255, 51], np.uint8), (H, W, 1)),       # roughness 0.2
+              specular=np.tile(np.array([255, 128, 64, 255], np.uint8), (H, W, 1)),      # F0 colour, metallic 1
+              normal=np.tile((np.append(n * 0.5 + 0.5, 1.0)).astype(np.float16).view(np.uint16), (H, W, 1)),
+              emission=np.tile(np.array([e, e, e, 1.0], np.float16).view(np.uint16), (H, W, 1)),
+              depth=np.full((H, W), 0.995, np.float32))
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    cones = np.array([
+        [0.57735, 0.57735, 0.57735], [0.57735, -0.57735, -0.57735], [-0.57735, 0.57735, -0.57735],
+        [-0.57735, -0.57735, 0.57735], [-0.903007, -0.182696, -0.388844], [-0.903007, 0.182696, 0.388844],
+        [0.903007, -0.182696, 0.388844], [0.903007, 0.182696, -0.388844], [-0.388844, -0.903007, -0.182696],
+        [0.388844, -0.903007, 0.182696], [0.388844, 0.903007, -0.182696], [-0.388844, 0.903007, 0.182696],
+        [-0.182696, -0.388844, -0.903007], [0.182696, 0.388844, -0.903007], [-0.182696, 0.388844, 0.903007],
+        [0.182696, -0.388844, 0.903007]])
+    vpi = np.array(cam.view_proj_inv[:], dtype=np.float64).reshape(4, 4).T       # column-major float[16]
+    eye = np.array(cam.eye_pos[:], dtype=np.float64)
+    for mode in (7, 5, 6):
+        prm = S.default_vct_params(regs[0], 32, mode)
+        d, s, _ = oracle.cone_trace(cfg, cam, hg, prm, light, shadow, sdepth, rad)
+        for (py, px) in ((0, 0), (1, 1)):
+            tc = np.array([(px + 0.5) / W, (py + 0.5) / H])
+            clip = vpi @ np.array([tc[0] * 2 - 1, tc[1] * 2 - 1, 0.995, 1.0])       # no y flip (Q18)
+            world = clip[:3] / clip[3]
+            nn = np.array([np.float16(v * 0.5 + 0.5) for v in n], dtype=np.float64) * 2.0 - 1.0
+            nn /= np.linalg.norm(nn)
+            # calcMinLevel, voxelConeTracing.frag:394-414
+            centre = np.array(prm.volume_center[:], dtype=np.float64)
+            dist = np.linalg.norm(centre - world)
+            min_radius = prm.voxel_size * prm.volume_dimension * 0.5
+            ml = max(np.log2(dist / min_radius), 0.0)
+            f = dist / (min_radius * 2.0 ** np.ceil(ml))
+            min_level = np.ceil(ml) + ((f - 0.5) * 2.0 if f > 0.5 else 0.0)
+            start = world + nn * (prm.voxel_size * 2.0 ** min_level) * prm.trace_start_offset
+            ind = np.array([0.0, 0.0, 0.0, 1.0])                                   # Q15
+            for cd in cones:
+                cos = float(nn @ cd)
+                if cos < 0.0:
+                    continue
+                ind += _trace_cone_uniform(c, start, cd, 0.872665, min_level, max(0.2, prm.min_trace_step_factor), prm, 3) * cos
+            ind /= 16.0                                                            # Q11
+            ind[3] *= prm.ambient_occlusion_factor
+            ind[:3] *= (255.0 / 255.0) * prm.indirect_diffuse_intensity
+            if mode == 7:
+                want = np.array([ind[3]] * 3 + [1.0])
+                got = d[py, px]
+            elif mode == 5:
+                emis = float(np.float16(e))
+                want = np.append(emis * ind[3] + ind[:3], 1.0)
+                got = d[py, px]
+            else:
+                view = eye - world
+                view /= np.linalg.norm(view)
+                I = -view
+                refl = I - 2.0 * (nn @ I) * nn
+                spec = _trace_cone_uniform(c, start, refl, max(51.0 / 255.0, 0.05), min_level, prm.voxel_size, prm, 3)
+                want = np.append(spec[:3] * (np.array([255, 128, 64]) / 255.0) * prm.indirect_specular_intensity, 1.0)
+                got = s[py, px]
+            assert np.allclose(got, want, rtol=2e-4, atol=2e-5), (mode, py, px, got, want)
