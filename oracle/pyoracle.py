@@ -204,15 +204,16 @@ def svo_canonicalize(nodes):
 
 
 def svo_cone_trace(cam, gbuf, prm, light, shadow, shadow_depth, nodes, bb_min, bb_max, clip_level_count=6,
-                   rows=None):
+                   rows=None, mode_flags=0):
     h, w = gbuf.height, gbuf.width
     out_d = np.zeros((h, w, 4), dtype=np.float32)
     out_s = np.zeros((h, w, 4), dtype=np.float32)
     y0, y1 = rows if rows is not None else (0, h)
     sh, sw = shadow_depth.shape
     g = gbuf.struct()
-    lib().vgo_svo_cone_trace(C.byref(cam), C.byref(g), C.byref(prm), C.byref(light), C.byref(shadow),
-                             _p(shadow_depth), C.c_uint32(sw), C.c_uint32(sh), _p(nodes),
-                             (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)),
-                             C.c_uint32(clip_level_count), _p(out_d), _p(out_s), C.c_uint32(y0), C.c_uint32(y1))
+    lib().vgo_svo_cone_trace_mode(C.byref(cam), C.byref(g), C.byref(prm), C.byref(light), C.byref(shadow),
+                                  _p(shadow_depth), C.c_uint32(sw), C.c_uint32(sh), _p(nodes),
+                                  (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)),
+                                  C.c_uint32(clip_level_count), C.c_uint32(mode_flags), _p(out_d), _p(out_s),
+                                  C.c_uint32(y0), C.c_uint32(y1))
     return out_d, out_s

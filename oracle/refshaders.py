@@ -1,0 +1,200 @@
+"""ctypes wrapper around oracle/_ref/libvgi_refshaders.so — the reference's own GLSL compiled for the CPU by
+oracle/glsl_shim/build_ref.py. TEST INFRASTRUCTURE ONLY: it pins the oracle (tests/test_ref_shaders.py,
+oracle/glsl_shim/gen_golden.py) and may serve bench.py's --impl reference leg; the product package never imports it.
+
+Atlases are numpy uint8 arrays of shape (D, H, W, 4) in the reference image layout (structs.atlas_shape)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(_HERE, "glsl_shim"))
+import build_ref  # noqa: E402
+
+sys.path.pop(0)
+
+from vk_voxel_cone_tracing_b200 import structs as S  # noqa: E402
+
+_lib = None
+
+
+def available():
+    """True when the library exists or can be built (the reference tree is present)."""
+    return os.path.exists(build_ref.OUT_SO) or build_ref.reference_available()
+
+
+def build(force=False):
+    return build_ref.build(force=force)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build()
+        if path is None:
+            raise RuntimeError("libvgi_refshaders.so is not built and the reference tree is not present")
+        _lib = C.CDLL(path)
+        _lib.ref_octree_build.restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _dims(atlas):
+    d, h, w, c = atlas.shape
+    assert c == 4 and atlas.dtype == np.uint8 and atlas.flags["C_CONTIGUOUS"]
+    return C.c_int(w), C.c_int(h), C.c_int(d)
+
+
+# ---- clipmap compute passes --------------------------------------------------------------------
+
+def downsample(cfg, regs, level, atlas, which):
+    """opacityDownSample.comp (which = 0) / radianceDownSample.comp (which = 1) as DownSampler::cmdDownSample runs them."""
+    fn = lib().ref_opacity_downsample if which == 0 else lib().ref_radiance_downsample
+    prev = (C.c_int * 3)(*regs[level - 1].min_corner)
+    fn(_p(atlas), *_dims(atlas), prev, C.c_int(level), C.c_int(cfg.resolution), C.c_int(cfg.downsample_band))
+
+
+def wrap_border(cfg, atlas, literal=True):
+    """borderWrapping.comp. literal: the host's dispatch of (R + 2) >> 3 groups (BorderWrapper.cpp:139, Q4);
+    otherwise enough groups to reach the high border too."""
+    r = cfg.resolution
+    groups = (r + 2) >> 3 if literal else (r + 2 + 7) >> 3
+    lib().ref_border_wrap(_p(atlas), *_dims(atlas), C.c_uint(r), C.c_uint(2), C.c_uint(S.VGI_FACES),
+                          C.c_uint(cfg.level_count), C.c_uint(groups))
+
+
+def clear_region(cfg, atlas, min_corner, extent, level):
+    """clipmapCleaning.comp as ClipmapCleaner::cmdClearImageClipmapRegion runs it."""
+    lib().ref_clipmap_clean(_p(atlas), *_dims(atlas), (C.c_int * 3)(*min_corner), C.c_int(level),
+                            (C.c_uint * 3)(*extent), C.c_int(cfg.resolution), C.c_uint(S.VGI_FACES))
+
+
+def copy_alpha(cfg, level, dst, src):
+    """copyAlphaImage.comp as CopyAlpha::cmdImageCopyAlpha runs it."""
+    assert dst.shape == src.shape
+    lib().ref_copy_alpha(_p(dst), _p(src), *_dims(dst), C.c_int(level), C.c_int(cfg.resolution), C.c_int(S.VGI_FACES))
+
+
+# ---- octree ---------------------------------------------------------------------------------------
+
+def svo_build(level, frags, capacity=None, subdivision_only=False):
+    """The six octreeNode*.comp programs in OctreeBuilder::cmdBuild's order, invocations executed sequentially."""
+    frags = np.ascontiguousarray(frags, dtype=np.uint32)
+    n = frags.shape[0]
+    if capacity is None:
+        capacity = min(max(1000000, n << 3), 500000000)     # OctreeBuilder.cpp:109-112
+    nodes = np.zeros((capacity, 2), dtype=np.uint32)
+    cnt = lib().ref_octree_build(C.c_uint(level), _p(frags), C.c_uint(n), _p(nodes), C.c_uint(capacity),
+                                 C.c_int(1 if subdivision_only else 0))
+    assert cnt != 0xffffffff, "node pool too small"
+    return nodes[:cnt].copy()
+
+
+# ---- cone tracing ---------------------------------------------------------------------------------
+
+class _TraceArgs(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int), ("y0", C.c_int), ("y1", C.c_int),
+        ("view_proj", C.c_void_p), ("view_proj_inv", C.c_void_p), ("eye", C.c_void_p),
+        ("diffuse", C.c_void_p), ("normal", C.c_void_p), ("specular", C.c_void_p), ("emission", C.c_void_p),
+        ("depth", C.c_void_p),
+        ("radiance", C.c_void_p), ("W", C.c_int), ("H", C.c_int), ("D", C.c_int),
+        ("shadow_depth", C.c_void_p), ("sw", C.c_int), ("sh", C.c_int),
+        ("light_direction", C.c_void_p), ("light_intensity", C.c_float), ("light_color", C.c_void_p),
+        ("shadow_view", C.c_void_p), ("shadow_proj", C.c_void_p), ("z_near", C.c_float), ("z_far", C.c_float),
+        ("volume_center", C.c_void_p), ("rendering_mode", C.c_uint), ("voxel_size", C.c_float),
+        ("volume_dimension", C.c_float), ("trace_start_offset", C.c_float), ("indirect_diffuse_intensity", C.c_float),
+        ("ambient_occlusion_factor", C.c_float), ("min_trace_step_factor", C.c_float),
+        ("indirect_specular_intensity", C.c_float), ("occlusion_decay", C.c_float), ("enable_32_cones", C.c_int),
+        ("clip_level_count", C.c_int),
+        ("out_diffuse", C.c_void_p), ("out_specular", C.c_void_p), ("out_discarded", C.c_void_p),
+    ]
+
+
+class _SvoTraceArgs(C.Structure):
+    _fields_ = [f for f in _TraceArgs._fields_ if f[0] not in ("radiance", "W", "H", "D")]
+    _fields_.insert([f[0] for f in _fields_].index("shadow_depth"), ("nodes", C.c_void_p))
+
+
+def _decode_gbuffer(gbuf):
+    """What the texture unit does to the G-buffer formats (GBufferPass.cpp:177-194): UNORM8 -> c / 255 in binary32,
+    binary16 widened exactly."""
+    to_f = lambda u8: (u8.astype(np.float32) / np.float32(255.0)).astype(np.float32)  # noqa: E731
+    nrm = gbuf.normal.view(np.float16) if gbuf.normal.dtype != np.float16 else gbuf.normal
+    emi = gbuf.emission.view(np.float16) if gbuf.emission.dtype != np.float16 else gbuf.emission
+    h, w = gbuf.height, gbuf.width
+    return (np.ascontiguousarray(to_f(gbuf.diffuse.reshape(h, w, 4))), np.ascontiguousarray(nrm.reshape(h, w, 4).astype(np.float32)),
+            np.ascontiguousarray(to_f(gbuf.specular.reshape(h, w, 4))), np.ascontiguousarray(emi.reshape(h, w, 4).astype(np.float32)),
+            np.ascontiguousarray(gbuf.depth.reshape(h, w).astype(np.float32)))
+
+
+def _fill_common(a, keep, cam, gbuf, prm, light, shadow, shadow_depth, clip_level_count, rows):
+    h, w = gbuf.height, gbuf.width
+    dif, nrm, spc, emi, dep = _decode_gbuffer(gbuf)
+    out_d = np.zeros((h, w, 4), dtype=np.float32)
+    out_s = np.zeros((h, w, 4), dtype=np.float32)
+    disc = np.zeros((h, w), dtype=np.uint8)
+    sd = np.ascontiguousarray(shadow_depth, dtype=np.float32)
+    arrs = dict(
+        view_proj=np.array(list(cam.view_proj), dtype=np.float32), view_proj_inv=np.array(list(cam.view_proj_inv), dtype=np.float32),
+        eye=np.array(list(cam.eye_pos), dtype=np.float32), diffuse=dif, normal=nrm, specular=spc, emission=emi, depth=dep,
+        shadow_depth=sd, light_direction=np.array(list(light.direction), dtype=np.float32),
+        light_color=np.array(list(light.color), dtype=np.float32), shadow_view=np.array(list(shadow.view), dtype=np.float32),
+        shadow_proj=np.array(list(shadow.proj), dtype=np.float32), volume_center=np.array(list(prm.volume_center), dtype=np.float32),
+        out_diffuse=out_d, out_specular=out_s, out_discarded=disc)
+    keep.append(arrs)
+    for k, v in arrs.items():
+        setattr(a, k, v.ctypes.data)
+    a.width, a.height = w, h
+    a.y0, a.y1 = rows if rows is not None else (0, h)
+    a.sh, a.sw = sd.shape
+    a.light_intensity = light.intensity
+    a.z_near, a.z_far = shadow.z_near, shadow.z_far
+    for f in ("rendering_mode", "voxel_size", "volume_dimension", "trace_start_offset", "indirect_diffuse_intensity",
+              "ambient_occlusion_factor", "min_trace_step_factor", "indirect_specular_intensity", "occlusion_decay",
+              "enable_32_cones"):
+        setattr(a, f, getattr(prm, f))
+    a.clip_level_count = clip_level_count
+    return out_d, out_s, disc
+
+
+def cone_trace(cfg, cam, gbuf, prm, light, shadow, shadow_depth, radiance, rows=None):
+    """voxelConeTracing.frag, one invocation per pixel. gbuf: pyoracle.HostGBuffer. Returns (diffuse, specular, discarded)."""
+    a, keep = _TraceArgs(), []
+    out = _fill_common(a, keep, cam, gbuf, prm, light, shadow, shadow_depth, cfg.level_count, rows)
+    rad = np.ascontiguousarray(radiance)
+    a.radiance = rad.ctypes.data
+    a.D, a.H, a.W = rad.shape[:3]
+    lib().ref_cone_trace(C.byref(a))
+    return out
+
+
+def svo_cone_trace(cam, gbuf, prm, light, shadow, shadow_depth, nodes, clip_level_count=6, rows=None):
+    """voxelConeTracing_Octree.frag (the scene bounding box is the constant pair inside the shader, Q14)."""
+    a, keep = _SvoTraceArgs(), []
+    out = _fill_common(a, keep, cam, gbuf, prm, light, shadow, shadow_depth, clip_level_count, rows)
+    nd = np.ascontiguousarray(nodes, dtype=np.uint32)
+    a.nodes = nd.ctypes.data
+    lib().ref_svo_cone_trace(C.byref(a))
+    return out
+
+
+SPONZA_BB_MIN = (-15.367, -1.011, -9.462)   # voxelConeTracing_Octree.frag:321
+SPONZA_BB_MAX = (14.399, 11.43, 8.84)       # voxelConeTracing_Octree.frag:322
+
+
+def specular_filter(diffuse, specular, prm):
+    """specularFilter.frag, one invocation per pixel; prm: structs.FilterParams."""
+    h, w = diffuse.shape[:2]
+    d = np.ascontiguousarray(diffuse, dtype=np.float32)
+    s = np.ascontiguousarray(specular, dtype=np.float32)
+    out = np.empty((h, w, 4), dtype=np.float32)
+    lib().ref_specular_filter(_p(d), _p(s), C.c_int(w), C.c_int(h), C.c_float(prm.tonemap_gamma),
+                              C.c_float(prm.tonemap_exposure), C.c_int(prm.tonemap_enable), C.c_int(prm.filter_method),
+                              _p(out))
+    return out

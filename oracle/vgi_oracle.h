@@ -120,6 +120,13 @@ void vgo_svo_cone_trace(const vgi_camera* cam, const vgi_gbuffer* gbuf, const vg
                         const uint32_t* nodes, const float bb_min[3], const float bb_max[3],
                         uint32_t clip_level_count,
                         float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1);
+/* same with mode_flags: VGI_MODE_SVO_LITERAL keeps the shipped sampling (no >>1, Q13) */
+void vgo_svo_cone_trace_mode(const vgi_camera* cam, const vgi_gbuffer* gbuf, const vgi_vct_params* prm,
+                             const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                             const float* shadow_depth, uint32_t sw, uint32_t sh,
+                             const uint32_t* nodes, const float bb_min[3], const float bb_max[3],
+                             uint32_t clip_level_count, uint32_t mode_flags,
+                             float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1);
 
 #ifdef __cplusplus
 }
