@@ -1,0 +1,133 @@
+"""Golden vectors produced by the REFERENCE'S OWN SHADERS (oracle/_ref/libvgi_refshaders.so, built by build_ref.py from
+/root/reference/VFS/Shaders) -> tests/golden/ref_shader_golden.npz.
+
+Run here (the reference tree is not on the GPU box): python oracle/glsl_shim/gen_golden.py
+tests/test_ref_shaders.py::test_oracle_matches_reference_shader_golden_* then checks the oracle against these files on
+any machine, and (when the library is present) re-checks that the stored outputs are what the shaders produce today.
+
+Every input a test needs is stored next to the outputs, so the fixtures do not depend on the synthetic-scene code or on
+the oracle's own clipmap build staying the same."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as O, refshaders as Rf  # noqa: E402
+from vk_voxel_cone_tracing_b200 import structs as S  # noqa: E402
+from tests.common import cornell_inputs  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "ref_shader_golden.npz")
+
+DS_R, DS_L, DS_CAM = 16, 3, (3.3, -1.2, 7.9)
+TRACE_R, TRACE_W, TRACE_H, TRACE_SHADOW = 16, 24, 24, 128
+SVO_LEVEL = 6
+
+
+def struct_bytes(s):
+    return np.frombuffer(bytes(s), dtype=np.uint8).copy()
+
+
+def sparse_atlas(cfg, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, size=S.atlas_shape(cfg), dtype=np.uint8)
+    a[rng.random(a.shape[:3]) < 0.7] = 0
+    return a
+
+
+def random_fragments(level, n, seed):
+    """Fragment words in the packing of voxelizer.frag:99-100 (12-bit x, y, split z; RGB + a count nibble of 1)."""
+    rng = np.random.default_rng(seed)
+    res = 1 << level
+    p = np.clip(rng.normal(res / 2, res / 5, size=(n, 3)).astype(np.int64), 0, res).astype(np.uint32)
+    col = rng.integers(0, 256, size=(n, 3), dtype=np.uint32)
+    x = p[:, 0] | (p[:, 1] << 12) | ((p[:, 2] & 0xff) << 24)
+    y = ((p[:, 2] >> 8) << 28) | col[:, 0] | (col[:, 1] << 8) | (col[:, 2] << 16) | (1 << 24)
+    return np.stack([x, y], axis=1).astype(np.uint32)
+
+
+def main():
+    O.build()
+    Rf.build()
+    g = {}
+
+    # ---- A-C: atlas compute passes (opacityDownSample / radianceDownSample / borderWrapping / clipmapCleaning / copyAlphaImage)
+    cfg = S.default_config(DS_R, DS_L)
+    regs = O.regions(cfg, DS_CAM)
+    a = sparse_atlas(cfg, 11)
+    g["ds_cfg"] = np.array([DS_R, DS_L, cfg.downsample_band], dtype=np.int32)
+    g["ds_min_corners"] = np.array([list(r.min_corner) for r in regs], dtype=np.int32)
+    g["ds_in"] = a
+    for which, name in ((0, "opacity"), (1, "radiance")):
+        x = a.copy()
+        for level in range(1, DS_L):
+            Rf.downsample(cfg, regs, level, x, which)
+        g[f"ds_out_{name}"] = x
+    for lit, name in ((True, "literal"), (False, "full")):
+        x = a.copy()
+        Rf.wrap_border(cfg, x, literal=lit)
+        g[f"border_out_{name}"] = x
+    x = a.copy()
+    g["clear_min_corner"] = np.array([5, 0, 11], dtype=np.int32)     # the reference only passes non-negative corners
+    g["clear_extent"] = np.array([DS_R, 7, DS_R], dtype=np.uint32)
+    Rf.clear_region(cfg, x, g["clear_min_corner"].tolist(), g["clear_extent"].tolist(), 1)
+    g["clear_out"] = x
+    x = a.copy()
+    Rf.copy_alpha(cfg, 2, x, np.ascontiguousarray(a[::-1]))          # source atlas = the input flipped in z
+    g["copy_alpha_out"] = x
+
+    # ---- D: the six octreeNode*.comp programs in OctreeBuilder::cmdBuild's order
+    frags = random_fragments(SVO_LEVEL, 2000, 12)
+    g["svo_level"] = np.array([SVO_LEVEL], dtype=np.int32)
+    g["svo_frags"] = frags
+    g["svo_nodes"] = Rf.svo_build(SVO_LEVEL, frags)
+
+    # ---- E: voxelConeTracing.frag on the Cornell box (R = 16, L = 6)
+    inp = cornell_inputs(resolution=TRACE_R, shadow_size=TRACE_SHADOW, width=TRACE_W, height=TRACE_H)
+    cfg = inp["cfg"]
+    regs = O.regions(cfg, inp["cam_pos"])
+    osc = O.OracleScene(inp["scene"])
+    _, rad, _ = O.build_clipmap(cfg, regs, osc, inp["light"], inp["shadow"], inp["shadow_depth"], 0)
+    gb = inp["gbuffer"]
+    hg = O.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    g["trace_cfg"] = np.array([TRACE_R, cfg.level_count, TRACE_W, TRACE_H], dtype=np.int32)
+    g["trace_radiance"] = rad
+    for k in ("diffuse", "normal", "specular", "emission", "depth"):
+        g[f"trace_gb_{k}"] = np.ascontiguousarray(gb[k])
+    g["trace_shadow_depth"] = np.ascontiguousarray(inp["shadow_depth"])
+    g["trace_cam"] = struct_bytes(inp["cam"])
+    g["trace_light"] = struct_bytes(inp["light"])
+    g["trace_shadow"] = struct_bytes(inp["shadow"])
+    prm = S.default_vct_params(regs[0], cfg.resolution, 8)
+    g["trace_prm"] = struct_bytes(prm)
+    for mode, c32 in ((8, 0), (7, 0), (8, 1), (3, 0)):
+        prm.rendering_mode, prm.enable_32_cones = mode, c32
+        d, s, disc = Rf.cone_trace(cfg, inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+        g[f"trace_out_m{mode}_c{c32}_diffuse"], g[f"trace_out_m{mode}_c{c32}_specular"] = d, s
+    g["trace_discarded"] = disc
+
+    # ---- F: voxelConeTracing_Octree.frag on an octree of the same scene (bbox = the shader's constants, Q14)
+    cfrags = O.svo_fragments(SVO_LEVEL, Rf.SPONZA_BB_MIN, Rf.SPONZA_BB_MAX, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    nodes = Rf.svo_build(SVO_LEVEL, cfrags)
+    g["svotrace_nodes"] = nodes
+    prm = S.default_vct_params(regs[0], cfg.resolution, 8)
+    prm.volume_dimension = float(1 << SVO_LEVEL)
+    g["svotrace_prm"] = struct_bytes(prm)
+    for mode in (8, 7):
+        prm.rendering_mode = mode
+        d, s, _ = Rf.svo_cone_trace(inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], nodes, 6)
+        g[f"svotrace_out_m{mode}_diffuse"], g[f"svotrace_out_m{mode}_specular"] = d, s
+
+    # ---- G: specularFilter.frag on the images of E
+    d, s = g["trace_out_m8_c0_diffuse"], g["trace_out_m8_c0_specular"]
+    for method in (0, 1):
+        for tm in (0, 1):
+            g[f"filter_out_f{method}_t{tm}"] = Rf.specular_filter(d, s, S.default_filter_params(method, tm))
+
+    np.savez_compressed(OUT, **g)
+    print(OUT, os.path.getsize(OUT), "bytes;", len(g), "arrays")
+
+
+if __name__ == "__main__":
+    main()

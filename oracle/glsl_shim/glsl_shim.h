@@ -111,8 +111,12 @@ inline float ceil(float x) { return ::ceilf(x); }
 inline float round(float x) { return ::roundf(x); }
 inline float fract(float x) { return x - ::floorf(x); }
 inline float mod(float x, float y) { return x - y * ::floorf(x / y); }
-inline float min(float a, float b) { return b < a ? b : a; }
-inline float max(float a, float b) { return a < b ? b : a; }
+// NaN operands: GLSL leaves min / max / clamp undefined. IEEE 754 minNum / maxNum (the non-NaN operand wins) is what
+// NVIDIA hardware (FMNMX), CUDA's fminf / fmaxf and the oracle's f_min / f_max composition in f_clamp do; it matters in
+// traceCone when the filtered alpha exceeds 1 by an ulp (32-cone weights) and pow(1 - a, c) of a negative base is NaN:
+// clamp(1 - NaN, 0, 1) is then 0, not NaN.
+inline float min(float a, float b) { return ::fminf(a, b); }
+inline float max(float a, float b) { return ::fmaxf(a, b); }
 inline int   min(int a, int b) { return b < a ? b : a; }
 inline int   max(int a, int b) { return a < b ? b : a; }
 inline uint  min(uint a, uint b) { return b < a ? b : a; }

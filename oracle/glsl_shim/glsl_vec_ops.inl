@@ -59,8 +59,9 @@
 #undef GLSL_F1
     friend V abs(const V& a) { V r; for (int i = 0; i < dim; ++i) r.d[i] = a.d[i] < (T)0 ? (T)(-a.d[i]) : a.d[i]; return r; }
     friend V pow(const V& a, const V& b) requires std::is_floating_point_v<T> { V r; for (int i = 0; i < dim; ++i) r.d[i] = ::powf(a.d[i], b.d[i]); return r; }
-    friend V min(const V& a, const V& b) { V r; for (int i = 0; i < dim; ++i) r.d[i] = b.d[i] < a.d[i] ? b.d[i] : a.d[i]; return r; }
-    friend V max(const V& a, const V& b) { V r; for (int i = 0; i < dim; ++i) r.d[i] = a.d[i] < b.d[i] ? b.d[i] : a.d[i]; return r; }
+    // floats: IEEE minNum / maxNum like the scalar versions in glsl_shim.h (x != x only for NaN)
+    friend V min(const V& a, const V& b) { V r; for (int i = 0; i < dim; ++i) r.d[i] = (b.d[i] < a.d[i] || a.d[i] != a.d[i]) ? b.d[i] : a.d[i]; return r; }
+    friend V max(const V& a, const V& b) { V r; for (int i = 0; i < dim; ++i) r.d[i] = (a.d[i] < b.d[i] || a.d[i] != a.d[i]) ? b.d[i] : a.d[i]; return r; }
     friend V min(const V& a, T b) { return min(a, V(b)); }
     friend V max(const V& a, T b) { return max(a, V(b)); }
     friend V clamp(const V& x, const V& lo, const V& hi) { return min(max(x, lo), hi); }

@@ -1,0 +1,268 @@
+"""The oracle against the REFERENCE'S OWN SHADER TEXT.
+
+oracle/glsl_shim compiles the reference's GLSL for the CPU (oracle/_ref/libvgi_refshaders.so; only possible where
+/root/reference exists). Two layers:
+  * golden: tests/golden/ref_shader_golden.npz holds inputs + the outputs those shaders produced
+    (oracle/glsl_shim/gen_golden.py); the oracle must reproduce them — runs anywhere;
+  * live: with the library present, the oracle and the shaders run side by side on fresh random inputs, and the
+    stored golden outputs are re-derived.
+Integer / byte results are compared bit for bit. Float images were bit-identical when generated (both sides evaluate the
+same binary32 expressions without contraction); the golden layer allows 2e-6 for a different libm.
+
+What this pins: opacity + radiance down-sampling (incl. the blend band), border wrapping (literal and full), region
+clearing, copy-alpha, the octree build (topology word of every node; colours where one fragment lands in a leaf), the
+clipmap and octree cone-tracing fragment shaders in their rendering modes, the specular filter + tonemap.
+What it cannot pin (fixed-function rasterisation): which voxels a triangle covers."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from vk_voxel_cone_tracing_b200 import structs as S
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_shader_golden.npz")
+FLOAT_TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.fixture(scope="module")
+def refshaders():
+    from oracle import refshaders as Rf
+    if not Rf.available():
+        pytest.skip("reference tree not present and oracle/_ref/libvgi_refshaders.so not prebuilt")
+    Rf.build()
+    return Rf
+
+
+def _struct(cls, raw):
+    return cls.from_buffer_copy(bytes(raw))
+
+
+def _ds_setup(g):
+    r, l, band = (int(v) for v in g["ds_cfg"])
+    cfg = S.default_config(r, l, downsample_band=band)
+    regs = (S.ClipRegion * l)()
+    for i in range(l):
+        for k in range(3):
+            regs[i].min_corner[k] = int(g["ds_min_corners"][i, k])
+            regs[i].extent[k] = r
+    return cfg, regs
+
+
+def _trace_setup(g, oracle):
+    r, l, w, h = (int(v) for v in g["trace_cfg"])
+    cfg = S.default_config(r, l)
+    hg = oracle.HostGBuffer(*(np.ascontiguousarray(g[f"trace_gb_{k}"]) for k in ("diffuse", "normal", "specular", "emission", "depth")))
+    cam, light, shadow = _struct(S.Camera, g["trace_cam"]), _struct(S.DirLight, g["trace_light"]), _struct(S.DirLightShadow, g["trace_shadow"])
+    return cfg, hg, cam, light, shadow, np.ascontiguousarray(g["trace_shadow_depth"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden layer (no reference needed)
+# ---------------------------------------------------------------------------------------------------
+
+def test_golden_downsample_border_clear_copyalpha(oracle, golden):
+    g = golden
+    cfg, regs = _ds_setup(g)
+    for which, name in ((0, "opacity"), (1, "radiance")):
+        x = g["ds_in"].copy()
+        for level in range(1, cfg.level_count):
+            oracle.downsample(cfg, regs, level, x, which)
+        assert np.array_equal(x, g[f"ds_out_{name}"]), f"{name} down-sample differs from the reference shader"
+        assert not np.array_equal(x, g["ds_in"])
+    for lit, name in ((True, "literal"), (False, "full")):
+        x = g["ds_in"].copy()
+        oracle.wrap_border(cfg, x, literal=lit)
+        assert np.array_equal(x, g[f"border_out_{name}"]), f"border wrap ({name}) differs from the reference shader"
+    x = g["ds_in"].copy()
+    oracle.clear_region(cfg, x, g["clear_min_corner"].tolist(), g["clear_extent"].tolist(), 1)
+    assert np.array_equal(x, g["clear_out"])
+    x = g["ds_in"].copy()
+    oracle.copy_alpha(cfg, 2, x, np.ascontiguousarray(g["ds_in"][::-1]))
+    assert np.array_equal(x, g["copy_alpha_out"])
+
+
+def test_golden_octree_build(oracle, golden):
+    g = golden
+    level, frags, want = int(g["svo_level"][0]), np.ascontiguousarray(g["svo_frags"]), g["svo_nodes"]
+    for flags in (S.VGI_MODE_SVO_LITERAL, 0):   # the topology is the same in both modes
+        got = oracle.svo_build(level, frags, mode_flags=flags)
+        assert got.shape == want.shape
+        assert np.array_equal(got[:, 0], want[:, 0]), "node pool topology differs from the reference's octreeNode*.comp"
+    # colours: leaves that received exactly one fragment hold that fragment's RGB in both (Q10 only changes how several
+    # fragments are averaged; the oracle's alpha is 255, the reference keeps its count nibble)
+    got = oracle.svo_build(level, frags, mode_flags=S.VGI_MODE_SVO_LITERAL)
+    leaf = (want[:, 0] == 0x80000000) & ((want[:, 1] >> 24) == 1)   # flagged, no children, count nibble 1
+    assert leaf.sum() > 100
+    assert np.array_equal(got[leaf, 1] & 0xffffff, want[leaf, 1] & 0xffffff)
+
+
+@pytest.mark.parametrize("mode,c32", [(8, 0), (7, 0), (8, 1), (3, 0)])
+def test_golden_clipmap_cone_trace(oracle, golden, mode, c32):
+    g = golden
+    cfg, hg, cam, light, shadow, sd = _trace_setup(g, oracle)
+    prm = _struct(S.VctParams, g["trace_prm"])
+    prm.rendering_mode, prm.enable_32_cones = mode, c32
+    d, s, _ = oracle.cone_trace(cfg, cam, hg, prm, light, shadow, sd, np.ascontiguousarray(g["trace_radiance"]))
+    cov = g["trace_discarded"] == 0
+    assert cov.sum() > 100
+    assert float(np.abs(d - g[f"trace_out_m{mode}_c{c32}_diffuse"])[cov].max()) <= FLOAT_TOL
+    assert float(np.abs(s - g[f"trace_out_m{mode}_c{c32}_specular"])[cov].max()) <= FLOAT_TOL
+    if mode == 8:   # a real image: direct + indirect + specular all present
+        assert float(g[f"trace_out_m8_c{c32}_diffuse"][..., :3].max()) > 0.05
+        assert float(g[f"trace_out_m8_c{c32}_specular"][..., :3].max()) > 0.05
+
+
+@pytest.mark.parametrize("mode", [8, 7])
+def test_golden_octree_cone_trace(oracle, golden, mode):
+    from oracle import refshaders as Rf     # constants only
+    g = golden
+    _, hg, cam, light, shadow, sd = _trace_setup(g, oracle)
+    prm = _struct(S.VctParams, g["svotrace_prm"])
+    prm.rendering_mode = mode
+    d, s = oracle.svo_cone_trace(cam, hg, prm, light, shadow, sd, np.ascontiguousarray(g["svotrace_nodes"]),
+                                 Rf.SPONZA_BB_MIN, Rf.SPONZA_BB_MAX, 6, mode_flags=S.VGI_MODE_SVO_LITERAL)
+    cov = g["trace_discarded"] == 0
+    assert float(np.abs(d - g[f"svotrace_out_m{mode}_diffuse"])[cov].max()) <= FLOAT_TOL
+    assert float(np.abs(s - g[f"svotrace_out_m{mode}_specular"])[cov].max()) <= FLOAT_TOL
+
+
+@pytest.mark.parametrize("method,tonemap", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_golden_specular_filter(oracle, golden, method, tonemap):
+    g = golden
+    out = oracle.specular_filter(g["trace_out_m8_c0_diffuse"], g["trace_out_m8_c0_specular"], S.default_filter_params(method, tonemap))
+    assert float(np.abs(out - g[f"filter_out_f{method}_t{tonemap}"]).max()) <= FLOAT_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# live layer (needs oracle/_ref/libvgi_refshaders.so, i.e. the reference tree or a prebuilt library)
+# ---------------------------------------------------------------------------------------------------
+
+def test_live_golden_outputs_are_what_the_shaders_produce(refshaders, golden):
+    g = golden
+    cfg, regs = _ds_setup(g)
+    x = g["ds_in"].copy()
+    for level in range(1, cfg.level_count):
+        refshaders.downsample(cfg, regs, level, x, 0)
+    assert np.array_equal(x, g["ds_out_opacity"])
+    assert np.array_equal(refshaders.svo_build(int(g["svo_level"][0]), g["svo_frags"]), g["svo_nodes"])
+
+
+@pytest.mark.parametrize("resolution,cam", [(16, (0.0, 0.0, 0.0)), (32, (3.3, -1.2, 7.9)), (32, (-40.0, 2.5, 13.0))])
+def test_live_atlas_passes_random(oracle, refshaders, resolution, cam):
+    rng = np.random.default_rng(resolution + int(abs(cam[0]) * 10))
+    cfg = S.default_config(resolution, 4)
+    regs = oracle.regions(cfg, cam)
+    for which in (0, 1):
+        a = rng.integers(0, 256, size=S.atlas_shape(cfg), dtype=np.uint8)
+        a[rng.random(a.shape[:3]) < 0.5] = 0
+        for level in range(1, cfg.level_count):
+            x, y = a.copy(), a.copy()
+            oracle.downsample(cfg, regs, level, x, which)
+            refshaders.downsample(cfg, regs, level, y, which)
+            assert np.array_equal(x, y), (which, level)
+            assert not np.array_equal(x, a)
+    a = rng.integers(0, 256, size=S.atlas_shape(cfg), dtype=np.uint8)
+    b = rng.integers(0, 256, size=S.atlas_shape(cfg), dtype=np.uint8)
+    for lit in (True, False):
+        x, y = a.copy(), a.copy()
+        oracle.wrap_border(cfg, x, literal=lit)
+        refshaders.wrap_border(cfg, y, literal=lit)
+        assert np.array_equal(x, y)
+    for level in range(cfg.level_count):
+        x, y = a.copy(), a.copy()
+        oracle.copy_alpha(cfg, level, x, b)
+        refshaders.copy_alpha(cfg, level, y, b)
+        assert np.array_equal(x, y)
+        x, y = a.copy(), a.copy()
+        mc, ext = [3, 9, 0], [resolution, resolution // 2, resolution]
+        oracle.clear_region(cfg, x, mc, ext, level)
+        refshaders.clear_region(cfg, y, mc, ext, level)
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("level", [3, 5, 8])
+def test_live_octree_build_random(oracle, refshaders, level):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(GOLDEN), "..", "..", "oracle", "glsl_shim", "gen_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    frags = gen.random_fragments(level, 3000, 100 + level)
+    want = refshaders.svo_build(level, frags)
+    got = oracle.svo_build(level, frags, mode_flags=S.VGI_MODE_SVO_LITERAL)
+    assert got.shape == want.shape and np.array_equal(got[:, 0], want[:, 0])
+    # one fragment per (halved) voxel: every colour word's RGB agrees, leaves and interior means alike
+    p = np.stack([frags[:, 0] & 0xfff, (frags[:, 0] >> 12) & 0xfff, ((frags[:, 0] >> 24) & 0xff) | ((frags[:, 1] >> 20) & 0xf00)], axis=1) >> 1
+    _, idx = np.unique(p[:, 0].astype(np.uint64) | (p[:, 1].astype(np.uint64) << 16) | (p[:, 2].astype(np.uint64) << 32), return_index=True)
+    uniq = np.ascontiguousarray(frags[np.sort(idx)])
+    want = refshaders.svo_build(level, uniq)
+    got = oracle.svo_build(level, uniq, mode_flags=S.VGI_MODE_SVO_LITERAL)
+    assert np.array_equal(got[:, 0], want[:, 0])
+    assert np.array_equal(got[:, 1] & 0xffffff, want[:, 1] & 0xffffff)
+
+
+def test_live_cone_trace_and_filter_cornell(oracle, refshaders):
+    from tests.common import cornell_inputs
+    inp = cornell_inputs(resolution=32, shadow_size=512, width=40, height=40)
+    cfg = inp["cfg"]
+    regs = oracle.regions(cfg, inp["cam_pos"])
+    osc = oracle.OracleScene(inp["scene"])
+    _, rad, _ = oracle.build_clipmap(cfg, regs, osc, inp["light"], inp["shadow"], inp["shadow_depth"], 0)
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    cov = gb["depth"] < 1.0
+    d8 = s8 = None
+    for mode in range(9):
+        for c32 in (0, 1):
+            prm = S.default_vct_params(regs[0], cfg.resolution, mode)
+            prm.enable_32_cones = c32
+            d0, s0, _ = oracle.cone_trace(cfg, inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+            d1, s1, disc = refshaders.cone_trace(cfg, inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+            assert np.array_equal(disc.astype(bool), ~cov)
+            assert np.array_equal(d0[cov], d1[cov]) and np.array_equal(s0[cov], s1[cov]), (mode, c32)
+            if mode == 8 and c32 == 0:
+                d8, s8 = d1, s1
+    assert float(d8[..., :3].max()) > 0.05 and float(s8[..., :3].max()) > 0.05
+    for method in (0, 1):
+        for tm in (0, 1):
+            fp = S.default_filter_params(method, tm)
+            assert np.array_equal(oracle.specular_filter(d8, s8, fp), refshaders.specular_filter(d8, s8, fp))
+    # octree tracer on the same G-buffer (tree built by the reference's programs from the oracle's canonical fragments)
+    frags = oracle.svo_fragments(6, refshaders.SPONZA_BB_MIN, refshaders.SPONZA_BB_MAX, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    nodes = refshaders.svo_build(6, frags)
+    for mode in (8, 7, 5, 4, 3):
+        prm = S.default_vct_params(regs[0], cfg.resolution, mode)
+        prm.volume_dimension = 64.0
+        a_d, a_s = oracle.svo_cone_trace(inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], nodes,
+                                         refshaders.SPONZA_BB_MIN, refshaders.SPONZA_BB_MAX, 6, mode_flags=S.VGI_MODE_SVO_LITERAL)
+        b_d, b_s, _ = refshaders.svo_cone_trace(inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], nodes, 6)
+        assert np.array_equal(a_d[cov], b_d[cov]) and np.array_equal(a_s[cov], b_s[cov]), mode
+
+
+def test_live_q6_radiance_downsample_does_not_compile_as_shipped(refshaders):
+    """`lerpFactor` is declared inside the `if` and used after it. The repaired text (build_ref.py R10) builds;
+    the shipped text must fail on exactly that identifier."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "..", "oracle", "glsl_shim"))
+    import build_ref as B
+    sys.path.pop(0)
+    if not B.reference_available():
+        pytest.skip("needs the reference tree")
+    r = B.compile_unit(B.unit_source("radianceDownSample.comp", repair_q6=False), os.devnull)
+    assert r.returncode != 0 and "lerpFactor" in r.stderr
+
+
+def test_refshader_library_is_test_infrastructure_only():
+    """Nothing in the product package may reach into oracle/ (the reference-shader library included)."""
+    pkg = os.path.join(os.path.dirname(os.path.dirname(__file__)), "vk_voxel_cone_tracing_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".c")):
+                with open(os.path.join(root, f), errors="replace") as fh:
+                    text = fh.read()
+                assert "refshaders" not in text and "glsl_shim" not in text and "oracle/_ref" not in text, f
