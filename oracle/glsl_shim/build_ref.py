@@ -10,7 +10,8 @@ source, rewritten or not, is written anywhere: only the shared library lands in 
 Rewrite rules (none of them touches an expression's operators, operands or order):
   R1  comments, `#version`, `#extension` removed; `#include "x.glsl"` inlined (the include guards stay).
   R2  `layout ( ... )` qualifiers removed; the bare `in;` left over from `layout(local_size...) in;` removed;
-      `layout(constant_id = n) const T X = v;` -> `T X = v;` (a specialisation constant: the driver may override it).
+      `layout(constant_id = n) const T X = v;` -> `T X = v;` (a specialisation constant: the driver may override it;
+      it stays `const` when it sizes an array); memory qualifiers (readonly, writeonly, coherent, volatile, restrict) removed.
   R3  interface blocks: `uniform|buffer|in|out Name { members } inst;` -> `struct Name { members } inst;`,
       without an instance name -> the members become globals; unsized arrays `T a[];` -> `T* a;`.
   R4  global `in T x;` / `out T x;` -> `thread_local T x;`; global `uniform T x;` -> `T x;`.
@@ -46,7 +47,7 @@ UNITS = [
     "opacityDownSample.comp", "radianceDownSample.comp", "borderWrapping.comp", "clipmapCleaning.comp",
     "copyAlphaImage.comp", "octreeNodeInit.comp", "octreeNodeFlag.comp", "octreeNodeAlloc.comp",
     "octreeNodeModifyArg.comp", "octreeNodeLeafWrite.comp", "octreeNodeMipmapWrite.comp",
-    "voxelConeTracing.frag", "voxelConeTracing_Octree.frag", "specularFilter.frag",
+    "voxelConeTracing.frag", "voxelConeTracing_Octree.frag", "specularFilter.frag", "msaaInjectRadiance.frag",
 ]
 
 
@@ -103,11 +104,14 @@ def translate(shader, repair_q6=True):
         assert n == 1
         s, n = re.subn(r"float(\s+lerpFactor\s*=\s*max\()", r"\1", s)
         assert n == 1
-    s = re.sub(r"\blayout\s*\(\s*constant_id[^)]*\)\s*const\b", "", s)   # R2: specialisation constants -> globals the driver may set
+    def _spec(m):      # R2: specialisation constants -> globals the driver may set, unless they size an array
+        name = re.match(r"\s*\w+\s+(\w+)", m.group(1)).group(1)
+        return ("const" if re.search(r"\[\s*" + name + r"\s*\]", s) else "") + m.group(1)
+    s = re.sub(r"\blayout\s*\(\s*constant_id[^)]*\)\s*const\b([^;]*)", _spec, s)
+    s = re.sub(r"\b(?:readonly|writeonly|coherent|restrict|volatile)\b", "", s)   # memory qualifiers mean nothing here
     s = re.sub(r"\blayout\s*\([^)]*\)", "", s)
     s = re.sub(r"^\s*in\s*;", "", s, flags=re.M)
-    s = re.sub(r"((?:\b(?:readonly|writeonly|coherent|volatile|restrict)\s+)*)\b(uniform|buffer|in|out)\s+(\w+)\s*"
-               r"\{([^}]*)\}\s*(\w*)\s*;", _block, s, flags=re.S)                           # R3
+    s = re.sub(r"()\b(uniform|buffer|in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w*)\s*;", _block, s, flags=re.S)    # R3
     s = re.sub(r"^[ \t]*(?:flat\s+)?(?:in|out)\s+(\w+)\s+(\w+)\s*;", r"thread_local \1 \2;", s, flags=re.M)   # R4
     s = re.sub(r"^[ \t]*uniform\s+", "", s, flags=re.M)
     s = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)(\s*\[)", r"\1 \2\3", s)                    # R5

@@ -125,6 +125,14 @@ def main():
         for tm in (0, 1):
             g[f"filter_out_f{method}_t{tm}"] = Rf.specular_filter(d, s, S.default_filter_params(method, tm))
 
+    # ---- H: msaaInjectRadiance.frag on every 12th sample the oracle shades at level 1 of the same scene
+    fr = O.inject_fragments(cfg, regs, 1, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    sel = np.arange(0, fr["pos"].shape[0], 12)
+    cnt, coords, vals = Rf.inject_fragments(cfg, regs, 1, fr["pos"][sel], fr["nrm"][sel], fr["mat"][sel], osc.materials,
+                                            inp["light"], inp["shadow"], inp["shadow_depth"])
+    g["inject_sel"], g["inject_pos"], g["inject_nrm"], g["inject_mat"] = sel, fr["pos"][sel], fr["nrm"][sel], fr["mat"][sel]
+    g["inject_out_count"], g["inject_out_coords"], g["inject_out_values"] = cnt, coords, vals
+
     np.savez_compressed(OUT, **g)
     print(OUT, os.path.getsize(OUT), "bytes;", len(g), "arrays")
 

@@ -185,11 +185,21 @@ inline void imageStore(const image3D& img, const ivec3& p, const vec4& v)
 }
 // r32ui view of the same memory (VoxelRadianceR32View)
 struct uimage3D { uint32_t* data; int W, H, D; };
+// optional per-thread log of the texels an invocation's atomics touched (drivers that inspect single fragments)
+struct atomic_log { int n; int xyz[16][3]; };
+inline thread_local atomic_log* g_atomic_log = nullptr;
 inline uint imageAtomicCompSwap(const uimage3D& img, const ivec3& p, uint compare, uint value)
 {
+    if (p.x < 0 || p.y < 0 || p.z < 0 || p.x >= img.W || p.y >= img.H || p.z >= img.D) return compare;   // discarded
     uint32_t* t = img.data + ((size_t)p.z * (size_t)img.H + (size_t)p.y) * (size_t)img.W + (size_t)p.x;
     const uint old = *t;
-    if (old == compare) *t = value;
+    if (old == compare) {
+        *t = value;
+        if (g_atomic_log && g_atomic_log->n < 16) {
+            int* e = g_atomic_log->xyz[g_atomic_log->n++];
+            e[0] = p.x; e[1] = p.y; e[2] = p.z;
+        }
+    }
     return old;
 }
 inline uint atomicCompSwap(uint& mem, uint compare, uint value) { const uint old = mem; if (old == compare) mem = value; return old; }

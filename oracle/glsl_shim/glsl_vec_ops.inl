@@ -4,6 +4,7 @@
 // arguments the way they do in a GLSL compiler's closed overload set.
     typedef tvec V;
     typedef tvec<bool, dim> BV;
+    explicit operator T() const { return d[0]; }   // GLSL: float(vec3) takes the first component (SURVEY Q2 relies on it)
     T& operator[](int i) { return d[i]; }
     const T& operator[](int i) const { return d[i]; }
     friend V operator-(const V& a) { V r; for (int i = 0; i < dim; ++i) r.d[i] = (T)(-a.d[i]); return r; }

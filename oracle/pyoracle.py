@@ -103,6 +103,22 @@ def inject_level(cfg, regs, level, osc, light, shadow, shadow_depth, radiance):
                            _p(radiance))
 
 
+def inject_fragments(cfg, regs, level, osc, light, shadow, shadow_depth):
+    """The samples inject_level shades + their shading results (vgo_inject_fragments); dict of numpy arrays."""
+    h, w = shadow_depth.shape
+    fn = lib().vgo_inject_fragments
+    fn.restype = C.c_uint64
+    head = (C.byref(cfg), regs, C.c_uint32(level), C.byref(osc.tris), _p(osc.materials), C.byref(light), C.byref(shadow),
+            _p(shadow_depth), C.c_uint32(w), C.c_uint32(h))
+    nul = C.c_void_p(0)
+    n = int(fn(*head, C.c_uint64(0), nul, nul, nul, nul, nul, nul, nul))
+    out = dict(pos=np.zeros((n, 3), np.float32), nrm=np.zeros((n, 3), np.float32), mat=np.zeros(n, np.int32),
+               voxel=np.zeros((n, 3), np.int32), nfaces=np.zeros(n, np.int32), faces=np.zeros((n, 6), np.int32),
+               q=np.zeros((n, 6, 3), np.uint32))
+    fn(*head, C.c_uint64(n), *(_p(out[k]) for k in ("pos", "nrm", "mat", "voxel", "nfaces", "faces", "q")))
+    return out
+
+
 def clear_region(cfg, atlas, min_corner, extent, level):
     lib().vgo_clear_region(C.byref(cfg), _p(atlas), (C.c_int32 * 3)(*min_corner), (C.c_uint32 * 3)(*extent),
                            C.c_uint32(level))

@@ -198,3 +198,51 @@ def specular_filter(diffuse, specular, prm):
                               C.c_float(prm.tonemap_exposure), C.c_int(prm.tonemap_enable), C.c_int(prm.filter_method),
                               _p(out))
     return out
+
+
+# ---- radiance injection, per fragment -------------------------------------------------------------
+
+class _InjectArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("position", C.c_void_p), ("normal", C.c_void_p), ("material_index", C.c_void_p),
+        ("materials", C.c_void_p),
+        ("region_min_corner", C.c_void_p), ("clip_level", C.c_uint), ("region_max_corner", C.c_void_p),
+        ("clip_max_extent", C.c_float), ("voxel_size", C.c_float), ("resolution", C.c_int),
+        ("shadow_depth", C.c_void_p), ("sw", C.c_int), ("sh", C.c_int),
+        ("light_direction", C.c_void_p), ("light_intensity", C.c_float), ("light_color", C.c_void_p),
+        ("shadow_view", C.c_void_p), ("shadow_proj", C.c_void_p), ("z_near", C.c_float), ("z_far", C.c_float),
+        ("W", C.c_int), ("H", C.c_int), ("D", C.c_int),
+        ("out_count", C.c_void_p), ("out_coords", C.c_void_p), ("out_values", C.c_void_p),
+    ]
+
+
+def voxelization_desc(region):
+    """VoxelizationDesc as Voxelizer::cmdVoxelize fills it (Voxelizer.cpp:235-256), in binary32."""
+    f = np.float32
+    vs = f(region.voxel_size)
+    mn = np.array([f(c) * vs - f(1e-6) for c in region.min_corner], dtype=np.float32)
+    mx = np.array([f(int(c) + int(e)) * vs + f(1e-6) for c, e in zip(region.min_corner, region.extent)], dtype=np.float32)
+    return mn, mx, float(f(region.extent[0]) * vs), float(vs)
+
+
+def inject_fragments(cfg, regs, level, position, normal, material_index, materials, light, shadow, shadow_depth):
+    """msaaInjectRadiance.frag, one invocation per given fragment on a cleared r32ui image.
+    Returns (count[n], coords[n, 6, 3] atlas texel, values[n, 6] packed RGBA8 word)."""
+    n = position.shape[0]
+    a = _InjectArgs()
+    mn, mx, ext, vs = voxelization_desc(regs[level])
+    sd = np.ascontiguousarray(shadow_depth, dtype=np.float32)
+    keep = dict(position=np.ascontiguousarray(position, np.float32), normal=np.ascontiguousarray(normal, np.float32),
+                material_index=np.ascontiguousarray(material_index, np.int32), materials=np.ascontiguousarray(materials),
+                region_min_corner=mn, region_max_corner=mx, shadow_depth=sd,
+                light_direction=np.array(list(light.direction), np.float32), light_color=np.array(list(light.color), np.float32),
+                shadow_view=np.array(list(shadow.view), np.float32), shadow_proj=np.array(list(shadow.proj), np.float32),
+                out_count=np.zeros(n, np.int32), out_coords=np.zeros((n, 6, 3), np.int32), out_values=np.zeros((n, 6), np.uint32))
+    for k, v in keep.items():
+        setattr(a, k, v.ctypes.data)
+    a.n, a.clip_level, a.clip_max_extent, a.voxel_size, a.resolution = n, level, ext, vs, cfg.resolution
+    a.sh, a.sw = sd.shape
+    a.light_intensity, a.z_near, a.z_far = light.intensity, shadow.z_near, shadow.z_far
+    a.D, a.H, a.W = S.atlas_shape(cfg)[:3]
+    lib().ref_inject_fragments(C.byref(a))
+    return keep["out_count"], keep["out_coords"], keep["out_values"]

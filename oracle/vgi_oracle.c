@@ -515,6 +515,54 @@ void vgo_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uin
     free(occ);
 }
 
+/* Test aid: the samples vgo_inject_level shades, in (triangle, z, y, x) order, with their shading results
+ * (faces[f], q[f][rgb] = the 16-bit fixed-point contributions). tests/test_ref_shaders.py feeds pos / nrm / mat
+ * to the reference's msaaInjectRadiance.frag and compares. Arrays may be NULL when capacity == 0 (count only). */
+uint64_t vgo_inject_fragments(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,
+                              const vgo_tris* tris, const vgi_material* materials,
+                              const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                              const float* shadow_depth, uint32_t sw, uint32_t sh_, uint64_t capacity,
+                              float* pos, float* nrm, int32_t* mat, int32_t* voxel, int32_t* nfaces,
+                              int32_t* faces, uint32_t* q)
+{
+    const uint32_t R = cfg_R(cfg);
+    const vgi_clip_region* rg = &regions[level];
+    shadow_ctx sc = { shadow, shadow_depth, sw, sh_, (cfg->mode_flags & VGI_MODE_SHADOW_COMPARE) != 0 };
+    float lightDir[3];
+    light_dir(light, lightDir);
+    uint64_t n = 0;
+    for (uint32_t t = 0; t < tris->count; ++t) {
+        tri_setup ts;
+        const float* p = tris->pos + (size_t)t * 9;
+        tri_setup_init(&ts, p, rg->voxel_size, rg->min_corner, R);
+        if (!ts.valid) continue;
+        const vgi_material* m = &materials[tris->mat[t]];
+        for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
+            for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
+                for (int x = ts.lo[0]; x <= ts.hi[0]; ++x) {
+                    if (!tri_overlaps_voxel(&ts, x, y, z)) continue;
+                    inject_sample s;
+                    if (!inject_sample_point(&ts, p, tris->nrm + (size_t)t * 9, rg->voxel_size, x, y, z, &s)) continue;
+                    if (n < capacity) {
+                        int fc[6];
+                        uint32_t qq[6][3];
+                        const int nf = shade_fragment(m, light, lightDir, &sc, &s, fc, qq);
+                        memcpy(pos + n * 3, s.pos, sizeof s.pos);
+                        memcpy(nrm + n * 3, s.nrm, sizeof s.nrm);
+                        mat[n] = tris->mat[t];
+                        voxel[n * 3] = x; voxel[n * 3 + 1] = y; voxel[n * 3 + 2] = z;
+                        nfaces[n] = nf;
+                        for (int f = 0; f < 6; ++f) {
+                            faces[n * 6 + f] = f < nf ? fc[f] : -1;
+                            for (int k = 0; k < 3; ++k) q[(n * 6 + f) * 3 + k] = f < nf ? qq[f][k] : 0u;
+                        }
+                    }
+                    ++n;
+                }
+    }
+    return n;
+}
+
 /* A9. ref: copyAlphaImage.comp:16-29 — dispatched over R^3 (CopyAlpha.cpp:126-127) */
 void vgo_copy_alpha(const vgi_config* cfg, uint32_t level, uint8_t* dst, const uint8_t* src)
 {

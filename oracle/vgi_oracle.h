@@ -61,6 +61,14 @@ void vgo_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uin
                       const vgo_tris* tris, const vgi_material* materials,
                       const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
                       const float* shadow_depth, uint32_t sw, uint32_t sh, uint8_t* radiance);
+/* test aid: the samples vgo_inject_level shades (position, un-normalised normal, material, unwrapped voxel) and their
+ * shading results (faces, 16-bit fixed-point rgb); capacity == 0 counts only. Returns the number of samples. */
+uint64_t vgo_inject_fragments(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,
+                              const vgo_tris* tris, const vgi_material* materials,
+                              const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                              const float* shadow_depth, uint32_t sw, uint32_t sh, uint64_t capacity,
+                              float* pos, float* nrm, int32_t* mat, int32_t* voxel, int32_t* nfaces,
+                              int32_t* faces, uint32_t* q);
 /* ref: copyAlphaImage.comp:16-29 */
 void vgo_copy_alpha(const vgi_config* cfg, uint32_t level, uint8_t* dst, const uint8_t* src);
 /* ref: opacityDownSample.comp:28-138 (which=0), radianceDownSample.comp:28-139 with Q6 repaired (which=1) */

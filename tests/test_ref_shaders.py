@@ -139,6 +139,55 @@ def test_golden_specular_filter(oracle, golden, method, tonemap):
     assert float(np.abs(out - g[f"filter_out_f{method}_t{tonemap}"]).max()) <= FLOAT_TOL
 
 
+def _check_injection(cfg, level, fr, sel, cnt, coords, vals):
+    """Oracle samples fr[sel] against what msaaInjectRadiance.frag wrote for them (one invocation each, cleared image).
+    * the same number of face texels (3, or 6 for emissive materials; 0 = discarded);
+    * the same faces, in the same order;
+    * every colour byte is the truncation of a value inside the oracle's 16-bit fixed-point cell: with q the oracle's
+      round(v * 65536), the shader's uint(v * 255) must lie in [floor((q - 0.5) * 255 / 65536), floor((q + 0.5) * 255 / 65536)]
+      - i.e. the shaded radiance agrees to 2^-17 and the quantisation rule (truncate once) is the same;
+    * the texel: the shader addresses the voxel that CONTAINS the sample point; the oracle attributes the sample to the
+      voxel whose overlap with the triangle produced it (canonical conservative coverage). They coincide when
+      the point lies inside that voxel, which is required here; elsewhere the difference is the documented deviation."""
+    r, rb = cfg.resolution, cfg.resolution + 2
+    assert np.array_equal(cnt, fr["nfaces"][sel])
+    assert set(np.unique(cnt).tolist()) <= {0, 3, 6} and (cnt == 3).sum() > 100
+    k = np.arange(6)[None, :] < cnt[:, None]
+    faces = fr["faces"][sel]
+    assert np.array_equal((coords[..., 0] // rb)[k], faces[k])
+    q = fr["q"][sel].astype(np.float64)
+    lo = np.minimum(np.floor((q - 0.5) * 255.0 / 65536.0), 255)
+    hi = np.minimum(np.floor((q + 0.5) * 255.0 / 65536.0), 255)
+    for ch in range(3):
+        b = ((vals >> (8 * ch)) & 0xff).astype(np.float64)
+        assert np.all((b >= lo[..., ch])[k]) and np.all((b <= hi[..., ch])[k]), ch
+    assert np.all(((vals >> 24) == 1)[k])     # the CAS average's count
+    vox = fr["voxel"][sel]
+    want = np.stack([1 + (vox[:, 0] & (r - 1)), 1 + (vox[:, 1] & (r - 1)) + level * rb, 1 + (vox[:, 2] & (r - 1))], axis=1)
+    got = np.stack([coords[:, 0, 0] % rb, coords[:, 0, 1], coords[:, 0, 2]], axis=1)
+    same = np.all(want == got, axis=1) | (cnt == 0)
+    vs = 16.0 * (1 << level) / r
+    rel = fr["pos"][sel].astype(np.float64) / vs - vox            # position inside its voxel <=> every component in [0, 1)
+    inside = np.all((rel > 1e-4) & (rel < 1.0 - 1e-4), axis=1)
+    assert np.all(same[inside]), "a sample inside the oracle's voxel was addressed elsewhere by the shader"
+    assert inside.sum() >= 100      # (walls of the Cornell box lie exactly on voxel faces at the coarse levels)
+
+
+def test_golden_injection_fragments(oracle, golden):
+    """Depends on the Cornell generator: if this fails on the position check, re-run oracle/glsl_shim/gen_golden.py."""
+    from tests.common import cornell_inputs
+    g = golden
+    r, l, w, h = (int(v) for v in g["trace_cfg"])
+    inp = cornell_inputs(resolution=r, shadow_size=g["trace_shadow_depth"].shape[0], width=w, height=h)
+    cfg = inp["cfg"]
+    regs = oracle.regions(cfg, inp["cam_pos"])
+    osc = oracle.OracleScene(inp["scene"])
+    fr = oracle.inject_fragments(cfg, regs, 1, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    sel = g["inject_sel"]
+    assert np.array_equal(fr["pos"][sel], g["inject_pos"]) and np.array_equal(fr["nrm"][sel], g["inject_nrm"])
+    _check_injection(cfg, 1, fr, sel, g["inject_out_count"], g["inject_out_coords"], g["inject_out_values"])
+
+
 # ---------------------------------------------------------------------------------------------------
 # live layer (needs oracle/_ref/libvgi_refshaders.so, i.e. the reference tree or a prebuilt library)
 # ---------------------------------------------------------------------------------------------------
@@ -242,6 +291,20 @@ def test_live_cone_trace_and_filter_cornell(oracle, refshaders):
                                          refshaders.SPONZA_BB_MIN, refshaders.SPONZA_BB_MAX, 6, mode_flags=S.VGI_MODE_SVO_LITERAL)
         b_d, b_s, _ = refshaders.svo_cone_trace(inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], nodes, 6)
         assert np.array_equal(a_d[cov], b_d[cov]) and np.array_equal(a_s[cov], b_s[cov]), mode
+
+
+@pytest.mark.parametrize("level", [0, 2, 4])
+def test_live_injection_fragments(oracle, refshaders, level):
+    from tests.common import cornell_inputs
+    inp = cornell_inputs(resolution=32, shadow_size=512, width=16, height=16)
+    cfg = inp["cfg"]
+    regs = oracle.regions(cfg, inp["cam_pos"])
+    osc = oracle.OracleScene(inp["scene"])
+    fr = oracle.inject_fragments(cfg, regs, level, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    sel = np.arange(fr["pos"].shape[0])
+    cnt, coords, vals = refshaders.inject_fragments(cfg, regs, level, fr["pos"], fr["nrm"], fr["mat"], osc.materials,
+                                                    inp["light"], inp["shadow"], inp["shadow_depth"])
+    _check_injection(cfg, level, fr, sel, cnt, coords, vals)
 
 
 def test_live_q6_radiance_downsample_does_not_compile_as_shipped(refshaders):
