@@ -9,17 +9,19 @@ source, rewritten or not, is written anywhere: only the shared library lands in 
 
 Rewrite rules (none of them touches an expression's operators, operands or order):
   R1  comments, `#version`, `#extension` removed; `#include "x.glsl"` inlined (the include guards stay).
-  R2  `layout ( ... )` qualifiers removed; the bare `in;` left over from `layout(local_size...) in;` removed;
+  R2  `layout ( ... )` qualifiers removed; the bare `in;` / `out;` left over from `layout(local_size...) in;` etc. removed;
       `layout(constant_id = n) const T X = v;` -> `T X = v;` (a specialisation constant: the driver may override it;
       it stays `const` when it sizes an array); memory qualifiers (readonly, writeonly, coherent, volatile, restrict) removed.
   R3  interface blocks: `uniform|buffer|in|out Name { members } inst;` -> `struct Name { members } inst;`,
-      without an instance name -> the members become globals; unsized arrays `T a[];` -> `T* a;`.
+      without an instance name -> the members become globals; unsized arrays `T a[];` -> `T* a;`;
+      a geometry shader's per-vertex input block `} gs_in[];` -> `gs_in[3]` (triangles).
   R4  global `in T x;` / `out T x;` -> `thread_local T x;`; global `uniform T x;` -> `T x;`.
   R5  parameter qualifiers: `out|inout T x` -> `T& x` (arrays: qualifier dropped, C++ arrays decay), `in T x` -> `T x`.
   R6  float literals get an `f` suffix (GLSL literals are binary32).
   R7  multi-component swizzles `.xyz` -> `.xyz()` (glsl_vec_ops.inl).
   R8  array constructors `T[n]( ... )` -> `{ ... }`.
-  R9  `main` -> `shader_main` (macro), `discard` -> flag + return (macro), built-in variables (macros).
+  R9  `main` -> `shader_main` (macro), `discard` -> flag + return (macro), built-in variables (macros;
+      `gl_in[i].gl_Position` -> the member the macro cannot name).
   R10 Q6: radianceDownSample.comp declares `lerpFactor` inside the `if` and uses it after it, so
       the shader does not compile as shipped (tests/test_ref_shaders.py checks that it really fails); the repaired
       build hoists the declaration in front of the `if`, initialised to 0.0 as opacityDownSample.comp:59 does.
@@ -48,6 +50,7 @@ UNITS = [
     "copyAlphaImage.comp", "octreeNodeInit.comp", "octreeNodeFlag.comp", "octreeNodeAlloc.comp",
     "octreeNodeModifyArg.comp", "octreeNodeLeafWrite.comp", "octreeNodeMipmapWrite.comp",
     "voxelConeTracing.frag", "voxelConeTracing_Octree.frag", "specularFilter.frag", "msaaInjectRadiance.frag",
+    "msaaVoxelizer.geom", "msaaVoxelizer.frag",
 ]
 
 
@@ -73,7 +76,8 @@ def _block(m):
     body = re.sub(r"(\w+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2;", body)     # unsized array -> pointer
     if inst:
         tl = "thread_local " if kind in ("in", "out") else ""
-        return f"struct {name} {{{body}}}; {tl}{name} {inst};"
+        arr = "[3]" if m.group(6) else ""      # per-vertex input array of a geometry shader fed with triangles
+        return f"struct {name} {{{body}}}; {tl}{name} {inst}{arr};"
     return body
 
 
@@ -110,14 +114,15 @@ def translate(shader, repair_q6=True):
     s = re.sub(r"\blayout\s*\(\s*constant_id[^)]*\)\s*const\b([^;]*)", _spec, s)
     s = re.sub(r"\b(?:readonly|writeonly|coherent|restrict|volatile)\b", "", s)   # memory qualifiers mean nothing here
     s = re.sub(r"\blayout\s*\([^)]*\)", "", s)
-    s = re.sub(r"^\s*in\s*;", "", s, flags=re.M)
-    s = re.sub(r"()\b(uniform|buffer|in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w*)\s*;", _block, s, flags=re.S)    # R3
+    s = re.sub(r"^\s*(?:in|out)\s*;", "", s, flags=re.M)
+    s = re.sub(r"()\b(uniform|buffer|in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w*)\s*(\[\s*\d*\s*\])?\s*;", _block, s, flags=re.S)    # R3
     s = re.sub(r"^[ \t]*(?:flat\s+)?(?:in|out)\s+(\w+)\s+(\w+)\s*;", r"thread_local \1 \2;", s, flags=re.M)   # R4
     s = re.sub(r"^[ \t]*uniform\s+", "", s, flags=re.M)
     s = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)(\s*\[)", r"\1 \2\3", s)                    # R5
     s = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)", r"\1& \2", s)
     s = re.sub(r"([(,]\s*)in\s+(\w+\s+\w+)", r"\1\2", s)
     s = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])", r"\1f", s)        # R6
+    s = re.sub(r"(\bgl_in\s*\[[^\]]*\]\s*\.)gl_Position\b", r"\1cur_position", s)             # R9: gl_Position is a macro
     s = _array_ctor(s)                                                                      # R8
     s = re.sub(r"\.([xyzw]{2,4}|[rgba]{2,4})\b(?!\s*\()", r".\1()", s)                      # R7
     return s

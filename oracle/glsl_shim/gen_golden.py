@@ -47,6 +47,30 @@ def random_fragments(level, n, seed):
     return np.stack([x, y], axis=1).astype(np.uint32)
 
 
+def voxelizer_test_triangles(seed):
+    """Random world-space triangles + the tie cases of msaaVoxelizer.geom:27-32 (axis-aligned planes, |nx| == |ny|)."""
+    rng = np.random.default_rng(seed)
+    tri = rng.normal(0, 3, size=(1200, 3, 3)).astype(np.float32)
+    tri[:100, :, 2] = 1.0
+    tri[100:200, :, 0] = -2.0
+    tri[200:300, :, 1] = 0.5
+    d = rng.normal(0, 1, size=(100, 3, 2)).astype(np.float32)
+    tri[300:400, :, 0], tri[300:400, :, 1], tri[300:400, :, 2] = d[..., 0], d[..., 0], d[..., 1]
+    return tri
+
+
+def voxel_centres(region, resolution, n, seed):
+    rng = np.random.default_rng(seed)
+    v = np.array(list(region.min_corner)) + rng.integers(0, resolution, size=(n, 3))
+    return ((v + 0.5) * np.float32(region.voxel_size)).astype(np.float32)
+
+
+def centre_triangles(ctr, voxel_size):
+    """One small triangle strictly inside the voxel around each centre."""
+    off = np.float32([[0.1, 0, 0.05], [-0.1, 0.1, 0], [0, -0.1, -0.05]]) * np.float32(voxel_size)
+    return ctr[:, None, :] + off[None]
+
+
 def main():
     O.build()
     Rf.build()
@@ -132,6 +156,22 @@ def main():
                                             inp["light"], inp["shadow"], inp["shadow_depth"])
     g["inject_sel"], g["inject_pos"], g["inject_nrm"], g["inject_mat"] = sel, fr["pos"][sel], fr["nrm"][sel], fr["mat"][sel]
     g["inject_out_count"], g["inject_out_coords"], g["inject_out_values"] = cnt, coords, vals
+
+    # ---- I: msaaVoxelizer.geom (dominant axis) and msaaVoxelizer.frag (region test, toroidal texel addressing, 6 stores)
+    tri = voxelizer_test_triangles(21)
+    g["geom_tris"] = tri
+    g["geom_axis"], _ = Rf.voxelizer_geometry(tri)
+    cfgv = S.default_config(16, 4)
+    regsv = O.regions(cfgv, (-21.7, -21.7, -21.7))      # camera on the diagonal: Q2's scalar clamp is harmless
+    g["vox_cfg"] = np.array([16, 4, 2], dtype=np.int32)
+    g["vox_min_corner"] = np.array(list(regsv[2].min_corner), dtype=np.int32)
+    g["vox_voxel_size"] = np.array([regsv[2].voxel_size], dtype=np.float32)
+    ctr = voxel_centres(regsv[2], 16, 300, 22)
+    g["vox_positions"] = ctr
+    y = O.new_atlas(cfgv)
+    Rf.voxelizer_fragments(cfgv, regsv, 2, ctr, y)
+    g["vox_out_texels"] = np.argwhere(y[..., 0] > 0).astype(np.int16)
+    assert np.all(y[y[..., 0] > 0] == 255)
 
     np.savez_compressed(OUT, **g)
     print(OUT, os.path.getsize(OUT), "bytes;", len(g), "arrays")

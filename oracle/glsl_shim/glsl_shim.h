@@ -280,10 +280,15 @@ inline vec4 textureLod(const sampler2D& s, const vec2& c, float /*lod: samplers 
 inline vec4 textureProj(const sampler2D& s, const vec4& c) { return texture(s, vec2(c.x / c.w, c.y / c.w)); }
 
 // ---- per-invocation built-in variables ----
+struct per_vertex { vec4 cur_position; };   // `gl_in[i].gl_Position` (gl_Position is a macro below)
 struct invocation {
     uvec3 gl_GlobalInvocationID;
     vec4  gl_FragCoord;
     bool  discarded;
+    // geometry stage: inputs, the current output vertex, and what EmitVertex() recorded
+    per_vertex in_vertices[3];
+    vec4 cur_position; int cur_viewport;
+    int emitted; vec4 out_position[8]; int out_viewport[8];
 };
 inline thread_local invocation g_inv;
 
@@ -325,6 +330,17 @@ struct ref_octree_state {
     using glsl::atomicAdd; using glsl::atomicOr; using glsl::barrier; using glsl::memoryBarrier; \
     using glsl::texture; using glsl::textureLod; using glsl::textureProj; using glsl::texelFetch; using glsl::textureSize;
 
+inline void EmitVertex();
+inline void EndPrimitive() {}
+inline void EmitVertex()
+{
+    glsl::invocation& v = glsl::g_inv;
+    if (v.emitted < 8) { v.out_position[v.emitted] = v.cur_position; v.out_viewport[v.emitted] = v.cur_viewport; }
+    ++v.emitted;
+}
+#define gl_in (glsl::g_inv.in_vertices)
+#define gl_Position (glsl::g_inv.cur_position)
+#define gl_ViewportIndex (glsl::g_inv.cur_viewport)
 #define gl_GlobalInvocationID (glsl::g_inv.gl_GlobalInvocationID)
 #define gl_FragCoord (glsl::g_inv.gl_FragCoord)
 #define discard do { glsl::g_inv.discarded = true; return; } while (0)

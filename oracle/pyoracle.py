@@ -119,6 +119,23 @@ def inject_fragments(cfg, regs, level, osc, light, shadow, shadow_depth):
     return out
 
 
+def dominant_axis(tri_pos):
+    """tri_pos: (n, 3, 3) float32 world-space triangles -> (n,) axis (vgo_dominant_axis)."""
+    t = np.ascontiguousarray(tri_pos, dtype=np.float32)
+    return np.array([lib().vgo_dominant_axis(C.c_void_p(t[i].ctypes.data)) for i in range(t.shape[0])], dtype=np.int32)
+
+
+class TriangleSoup:
+    """A bare world-space triangle list for the voxelization entry points (what OracleScene provides from a scene)."""
+
+    def __init__(self, pos, nrm=None, mat=None):
+        self.pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3, 3)
+        n = self.pos.shape[0]
+        self.nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3, 3) if nrm is not None else np.tile(np.float32([0, 0, 1]), (n, 3, 1))
+        self.mat = np.ascontiguousarray(mat, dtype=np.int32) if mat is not None else np.zeros(n, dtype=np.int32)
+        self.tris = Tris(n, self.pos.ctypes.data, self.nrm.ctypes.data, self.mat.ctypes.data)
+
+
 def clear_region(cfg, atlas, min_corner, extent, level):
     lib().vgo_clear_region(C.byref(cfg), _p(atlas), (C.c_int32 * 3)(*min_corner), (C.c_uint32 * 3)(*extent),
                            C.c_uint32(level))

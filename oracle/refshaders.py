@@ -246,3 +246,27 @@ def inject_fragments(cfg, regs, level, position, normal, material_index, materia
     a.D, a.H, a.W = S.atlas_shape(cfg)[:3]
     lib().ref_inject_fragments(C.byref(a))
     return keep["out_count"], keep["out_coords"], keep["out_values"]
+
+
+# ---- opacity voxelization stages ------------------------------------------------------------------
+
+def voxelizer_geometry(tri_pos, view_proj=None):
+    """msaaVoxelizer.geom per triangle: (axis[n] = gl_ViewportIndex, clip[n, 3, 4] = uViewProj[axis] * position)."""
+    t = np.ascontiguousarray(tri_pos, dtype=np.float32).reshape(-1, 3, 3)
+    n = t.shape[0]
+    vp = np.ascontiguousarray(view_proj, dtype=np.float32) if view_proj is not None else np.tile(np.eye(4, dtype=np.float32).reshape(16), (3, 1))
+    axis = np.zeros(n, dtype=np.int32)
+    clip = np.zeros((n, 3, 4), dtype=np.float32)
+    lib().ref_voxelizer_geometry(C.c_int(n), _p(t), _p(vp), _p(axis), _p(clip))
+    return axis, clip
+
+
+def voxelizer_fragments(cfg, regs, level, position, atlas):
+    """msaaVoxelizer.frag, one invocation per given world position, storing into `atlas`. Returns discarded[n]."""
+    pos = np.ascontiguousarray(position, dtype=np.float32)
+    n = pos.shape[0]
+    mn, mx, ext, vs = voxelization_desc(regs[level])
+    disc = np.zeros(n, dtype=np.uint8)
+    lib().ref_voxelizer_fragments(C.c_int(n), _p(pos), _p(atlas), *_dims(atlas), _p(mn), C.c_uint(level), _p(mx),
+                                  C.c_float(ext), C.c_float(vs), C.c_int(cfg.resolution), _p(disc))
+    return disc

@@ -149,6 +149,13 @@ static int cross_and_axis(const float* p /*9*/, float* N)
     return (ax > ay && ax > az) ? 0 : ((ay > az) ? 1 : 2);
 }
 
+/* test aid: the dominant axis of a world-space triangle (msaaVoxelizer.geom:27-32) */
+int vgo_dominant_axis(const float* p /*9*/)
+{
+    float N[3];
+    return cross_and_axis(p, N);
+}
+
 /* q: triangle in grid units (unit voxels at integer coordinates); candidate voxels are clipped to
  * [clipLo, clipHi] (inclusive). ts->N / ts->axis must already be set by the caller. */
 static void tri_setup_grid(tri_setup* ts, float q[3][3], const int* clipLo, const int* clipHi);

@@ -47,6 +47,8 @@ void vgo_regions(const vgi_config* cfg, const float cam[3], vgi_clip_region* out
 uint32_t vgo_scene_triangle_count(const vgi_scene_desc* s);
 void     vgo_scene_triangles(const vgi_scene_desc* s, float* pos, float* nrm, int32_t* mat);
 
+/* test aid: dominant axis of a world-space triangle, ref: msaaVoxelizer.geom:27-32 (ties -> z, then y) */
+int vgo_dominant_axis(const float* p /*9*/);
 /* ref: VoxelizationPass.cpp:104-126 (vkCmdClearColorImage) */
 void vgo_clear_atlas(const vgi_config* cfg, uint8_t* atlas);
 /* ref: msaaVoxelizer.geom:27-49, msaaVoxelizer.frag:43-73 with canonical conservative coverage (Q3).

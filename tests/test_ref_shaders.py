@@ -188,6 +188,31 @@ def test_golden_injection_fragments(oracle, golden):
     _check_injection(cfg, 1, fr, sel, g["inject_out_count"], g["inject_out_coords"], g["inject_out_values"])
 
 
+def _gen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(GOLDEN), "..", "..", "oracle", "glsl_shim", "gen_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    return gen
+
+
+def test_golden_voxelizer_axis_and_addressing(oracle, golden):
+    g = golden
+    assert np.array_equal(oracle.dominant_axis(g["geom_tris"]), g["geom_axis"])
+    assert len(np.unique(g["geom_axis"])) == 3
+    r, l, level = (int(v) for v in g["vox_cfg"])
+    cfg = S.default_config(r, l)
+    regs = (S.ClipRegion * l)()
+    for k in range(3):
+        regs[level].min_corner[k] = int(g["vox_min_corner"][k])
+        regs[level].extent[k] = r
+    regs[level].voxel_size = float(g["vox_voxel_size"][0])
+    x = oracle.new_atlas(cfg)
+    oracle.voxelize_level(cfg, regs, level, oracle.TriangleSoup(_gen().centre_triangles(g["vox_positions"], regs[level].voxel_size)), x)
+    assert np.array_equal(np.argwhere(x[..., 0] > 0).astype(np.int16), g["vox_out_texels"])
+    assert np.all(x[x[..., 0] > 0] == 255)
+
+
 # ---------------------------------------------------------------------------------------------------
 # live layer (needs oracle/_ref/libvgi_refshaders.so, i.e. the reference tree or a prebuilt library)
 # ---------------------------------------------------------------------------------------------------
@@ -237,11 +262,7 @@ def test_live_atlas_passes_random(oracle, refshaders, resolution, cam):
 
 @pytest.mark.parametrize("level", [3, 5, 8])
 def test_live_octree_build_random(oracle, refshaders, level):
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(GOLDEN), "..", "..", "oracle", "glsl_shim", "gen_golden.py"))
-    gen = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(gen)
-    frags = gen.random_fragments(level, 3000, 100 + level)
+    frags = _gen().random_fragments(level, 3000, 100 + level)
     want = refshaders.svo_build(level, frags)
     got = oracle.svo_build(level, frags, mode_flags=S.VGI_MODE_SVO_LITERAL)
     assert got.shape == want.shape and np.array_equal(got[:, 0], want[:, 0])
@@ -305,6 +326,52 @@ def test_live_injection_fragments(oracle, refshaders, level):
     cnt, coords, vals = refshaders.inject_fragments(cfg, regs, level, fr["pos"], fr["nrm"], fr["mat"], osc.materials,
                                                     inp["light"], inp["shadow"], inp["shadow_depth"])
     _check_injection(cfg, level, fr, sel, cnt, coords, vals)
+
+
+def test_live_voxelizer_geometry_axis(oracle, refshaders):
+    gen = _gen()
+    for seed in (1, 2):
+        tri = gen.voxelizer_test_triangles(seed)
+        axis, clip = refshaders.voxelizer_geometry(tri)
+        assert np.array_equal(oracle.dominant_axis(tri), axis)
+        assert np.array_equal(clip[..., :3], tri) and np.all(clip[..., 3] == 1.0)     # identity uViewProj
+
+
+@pytest.mark.parametrize("cam", [(0.0, 0.0, 0.0), (5.3, 5.3, 5.3), (-21.7, -21.7, -21.7)])
+def test_live_voxelizer_fragment_addressing(oracle, refshaders, cam):
+    """Opacity stores: region test, fract-wrapped toroidal texel, six faces. Cameras on the x = y = z diagonal keep the
+    scalar clamp of msaaVoxelizer.frag:46 (Q2) harmless, so shader and oracle must agree texel for texel."""
+    gen = _gen()
+    cfg = S.default_config(32, 4)
+    regs = oracle.regions(cfg, cam)
+    for level in range(4):
+        ctr = gen.voxel_centres(regs[level], 32, 300, 7 + level)
+        x, y = oracle.new_atlas(cfg), oracle.new_atlas(cfg)
+        oracle.voxelize_level(cfg, regs, level, oracle.TriangleSoup(gen.centre_triangles(ctr, regs[level].voxel_size)), x)
+        disc = refshaders.voxelizer_fragments(cfg, regs, level, ctr, y)
+        assert not disc.any() and np.array_equal(x, y)
+        assert int((x[..., 0] > 0).sum()) > 1500
+
+
+def test_live_q2_scalar_clamp_quantified(oracle, refshaders):
+    """SURVEY Q2, measured: with the camera off the diagonal the shader clamps y and z to the X bounds of the region
+    (float(vec3) takes .x). It addresses the oracle's (per-axis, canonical) texel exactly when every coordinate of the
+    fragment lies inside the x bounds, and a different one otherwise."""
+    gen = _gen()
+    cfg = S.default_config(32, 3)
+    regs = oracle.regions(cfg, (5.3, -1.2, 7.9))
+    level = 0
+    mc, vs = np.array(list(regs[level].min_corner)), np.float32(regs[level].voxel_size)
+    assert len(set(mc.tolist())) == 3
+    ctr = gen.voxel_centres(regs[level], 32, 250, 3)
+    tris = gen.centre_triangles(ctr, vs)
+    inside = np.all((ctr > mc[0] * vs) & (ctr < (mc[0] + 32) * vs), axis=1)
+    assert 20 < inside.sum() < 230
+    for i in range(ctr.shape[0]):
+        x, y = oracle.new_atlas(cfg), oracle.new_atlas(cfg)
+        oracle.voxelize_level(cfg, regs, level, oracle.TriangleSoup(tris[i:i + 1]), x)
+        refshaders.voxelizer_fragments(cfg, regs, level, ctr[i:i + 1], y)
+        assert np.array_equal(x, y) == bool(inside[i]), i
 
 
 def test_live_q6_radiance_downsample_does_not_compile_as_shipped(refshaders):
