@@ -14,8 +14,9 @@ cadence) + 1080p 16-cone CombinedGI cone trace (rendering mode 8, diffuse + spec
 N > 1 (torchrun, one rank per GPU): every rank renders its own camera view of the same scene
 (batched views, sharded by view, no data-path collective) — weak scaling.
 
---impl reference: the CPU oracle (a port of the reference's shaders: the reference itself is GLSL on
-a Windows/Vulkan host and cannot run here) on the host cores, on a bounded sample of the same frame.
+--impl reference: the reference's own shaders compiled for the CPU (oracle/_ref/libvgi_refshaders.so, see
+oracle/glsl_shim/) on the host cores, on a bounded sample of the same frame; the fixed-function triangle coverage
+and the injection loop come from the CPU oracle (cpu_baseline.port_share). Without the library: the oracle port alone.
 """
 import argparse
 import json
@@ -157,6 +158,18 @@ class CpuFrameSampler:
         gb = inp["gbuffer"]
         self.hg = O.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
         self.prm = S.default_vct_params(self.regs[0], self.cfg.resolution, 8)
+        # the reference's own shaders compiled for the CPU (oracle/_ref/libvgi_refshaders.so, built where
+        # /root/reference exists and shipped with the snapshot): used for every stage they cover
+        self.Rf = None
+        try:
+            from oracle import refshaders as Rf
+            if Rf.available():
+                Rf.lib()
+                self.Rf = Rf
+        except Exception as e:  # the port below still gives a CPU number
+            print(f"bench.py: reference-shader library unavailable ({e}); CPU arm falls back to the oracle port", file=sys.stderr)
+        self.kind = "reference" if self.Rf is not None else "port"
+        self.port_s = 0.0       # seconds of recorded samples spent in oracle-port code (scaled to the frame like the rest)
         self.level_s = {l: [] for l in range(self.cfg.level_count)}
         self.trace_s = []
         self.taps = []          # tri-linear taps of the sampled rows, scaled to the frame (SURVEY 8d A_cone)
@@ -164,29 +177,42 @@ class CpuFrameSampler:
         self.i = 0
 
     def build_level(self, l):
+        """Returns (seconds, seconds of it spent in oracle-port code)."""
         O, cfg, inp = self.O, self.cfg, self.inp
+        P = self.Rf if self.Rf is not None else O     # the programmable stages the reference's shaders cover
         R = cfg.resolution
         t = time.perf_counter()
-        mc = list(self.regs[l].min_corner)
-        O.clear_region(cfg, self.op, mc, (R, R, R), l)          # this level's share of the full clear
+        # this level's share of the clears (the reference clears whole levels: RadianceInjectionPass.cpp:77 passes corner 0)
+        P.clear_region(cfg, self.op, (0, 0, 0), (R, R, R), l)
+        P.clear_region(cfg, self.rad, (0, 0, 0), (R, R, R), l)
+        tp = time.perf_counter()
+        # triangle coverage is fixed-function in the reference, and its injection average depends on the order the
+        # hardware retires fragments: both come from the oracle (canonical coverage, exact mean)
         O.voxelize_level(cfg, self.regs, l, self.osc, self.op)
-        if l > 0:
-            O.downsample(cfg, self.regs, l, self.op, 0)
-        O.clear_region(cfg, self.rad, mc, (R, R, R), l)
         O.inject_level(cfg, self.regs, l, self.osc, inp["light"], inp["shadow"], inp["shadow_depth"], self.rad)
-        O.copy_alpha(cfg, l, self.rad, self.op)
+        port = time.perf_counter() - tp
         if l > 0:
-            O.downsample(cfg, self.regs, l, self.rad, 1)
-        return time.perf_counter() - t
+            P.downsample(cfg, self.regs, l, self.op, 0)
+        P.copy_alpha(cfg, l, self.rad, self.op)
+        if l > 0:
+            P.downsample(cfg, self.regs, l, self.rad, 1)
+        dt = time.perf_counter() - t
+        return dt, (port if self.Rf is not None else dt)
 
     def trace_rows(self, k):
         O, inp = self.O, self.inp
         rows = HEIGHT // TRACE_ROW_STRIDE
         y0 = (k % TRACE_ROW_STRIDE) * rows
-        t = time.perf_counter()
-        _, _, taps = O.cone_trace(self.cfg, inp["cam"], self.hg, self.prm, inp["light"], inp["shadow"], inp["shadow_depth"],
-                                  self.rad, rows=(y0, y0 + rows))
-        dt = time.perf_counter() - t
+        args = (self.cfg, inp["cam"], self.hg, self.prm, inp["light"], inp["shadow"], inp["shadow_depth"], self.rad)
+        if self.Rf is not None:     # timed: voxelConeTracing.frag itself; the oracle run after it only counts the taps
+            t = time.perf_counter()
+            self.Rf.cone_trace(*args, rows=(y0, y0 + rows))
+            dt = time.perf_counter() - t
+            _, _, taps = O.cone_trace(*args, rows=(y0, y0 + rows))
+        else:
+            t = time.perf_counter()
+            _, _, taps = O.cone_trace(*args, rows=(y0, y0 + rows))
+            dt = time.perf_counter() - t
         self.taps.append(taps * (HEIGHT / rows))
         self.taps_diffuse.append((taps - O.last_specular_taps()) * (HEIGHT / rows))
         return dt * (HEIGHT / rows)
@@ -198,12 +224,22 @@ class CpuFrameSampler:
 
     def step(self, record=True):
         l = self.i % self.cfg.level_count
-        tb = self.build_level(l)
+        tb, tport = self.build_level(l)
         tt = self.trace_rows(self.i * 7 + 3)
         self.i += 1
         if record:
             self.level_s[l].append(tb)
             self.trace_s.append(tt)
+            self.port_s += tport if self.Rf is not None else tport + tt
+
+    def port_share(self):
+        """Fraction of the reported frame time that ran oracle-port code rather than the reference's shaders."""
+        total = sum(sum(v) for v in self.level_s.values()) + sum(self.trace_s)
+        return float(self.port_s / total) if total > 0 else float("nan")
+
+    def describe(self):
+        return dict(kind=self.kind, cores=self.threads, sample=self.SAMPLE if self.Rf is None else self.SAMPLE_REF,
+                    port_share=self.port_share())
 
     def frame_seconds(self):
         means = [np.mean(v) for v in self.level_s.values() if v]
@@ -211,6 +247,11 @@ class CpuFrameSampler:
         trace = float(np.mean(self.trace_s)) if self.trace_s else float("nan")
         return build, trace
 
+    SAMPLE_REF = ("per step: clipmap build of ONE level (cycling 0..5) + cone trace of 1/32 of the 1080 rows, running the "
+                  "reference's own GLSL compiled for the CPU (oracle/_ref/libvgi_refshaders.so: clipmapCleaning, copyAlphaImage, "
+                  "opacity/radianceDownSample .comp and voxelConeTracing.frag); triangle coverage (fixed-function in the reference) "
+                  "and the injection loop come from the oracle port (port_share = their share of the time); frame time = sum of "
+                  "per-level means + 32 x mean row-sample time")
     SAMPLE = ("per step: oracle clipmap build of ONE level (cycling 0..5: clear, voxelize, inject, copy-alpha, "
               "opacity+radiance down-sample) + cone trace of 1/32 of the 1080 rows; frame time = sum of per-level "
               "means + 32 x mean row-sample time")
@@ -245,8 +286,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 texels)",
         "data": "synthetic", "config": {"workload": WORKLOAD},
         "stages": {"build_ms": 1e3 * build_s, "trace_ms": 1e3 * trace_s, "sample_wall_s": wall},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": smp.threads, "kind": "port",
-                         "sample": CpuFrameSampler.SAMPLE},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", **smp.describe()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -490,8 +530,7 @@ def run_vgi(args):
         for _ in range(LEVELS):
             smp.step()
         b_s, t_s = smp.frame_seconds()
-        cpu = {"value": 1.0 / (b_s + t_s), "unit": "frames/s", "cores": smp.threads, "kind": "port",
-               "sample": CpuFrameSampler.SAMPLE, "build_ms": 1e3 * b_s, "trace_ms": 1e3 * t_s}
+        cpu = {"value": 1.0 / (b_s + t_s), "unit": "frames/s", **smp.describe(), "build_ms": 1e3 * b_s, "trace_ms": 1e3 * t_s}
         if roof_trace and smp.taps:
             taps = float(np.mean(smp.taps))
             a_cone = 32.0 * taps + 60.0 * WIDTH * HEIGHT

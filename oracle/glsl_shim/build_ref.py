@@ -41,7 +41,7 @@ OUT_DIR = os.path.join(ROOT, "oracle", "_ref")
 OUT_SO = os.path.join(OUT_DIR, "libvgi_refshaders.so")
 # the image exports CXX=/opt/gcc/bin/g++, a wrapper without libgomp (same remark as oracle/Makefile): use the system g++
 GXX = os.environ.get("VGI_ORACLE_CXX", "/usr/bin/g++")
-CXXFLAGS = ["-std=c++20", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
+CXXFLAGS = ["-std=c++20", "-O3", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp",
             "-Werror=float-conversion", "-Wno-attributes", "-I", HERE]
 
 # shader file -> driver (oracle/glsl_shim/drivers/*.inc)

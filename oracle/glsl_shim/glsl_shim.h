@@ -213,6 +213,7 @@ enum filter_mode { NEAREST = 0, LINEAR = 1 };
 
 inline int wrap_index(long i, int n, int mode, bool& border)
 {
+    if (i >= 0 && i < n) return (int)i;      // in range: every mode agrees (and no integer division)
     if (mode == REPEAT) { long m = i % n; return (int)(m < 0 ? m + n : m); }
     if (mode == CLAMP_TO_EDGE) return (int)(i < 0 ? 0 : (i >= n ? n - 1 : i));
     if (i < 0 || i >= n) { border = true; return 0; }
@@ -294,8 +295,20 @@ inline thread_local invocation g_inv;
 
 // vkCmdDispatch(gx, gy, gz) of a shader with local size (lx, ly, lz): every invocation, sequentially, in
 // gl_GlobalInvocationID order (x fastest). Sequential execution is one legal schedule of the dispatch.
-template <class F> inline void dispatch(uint gx, uint gy, uint gz, uint lx, uint ly, uint lz, F&& shader_main)
+template <class F> inline void dispatch(uint gx, uint gy, uint gz, uint lx, uint ly, uint lz, F&& shader_main, bool independent = false)
 {
+    if (independent) {
+        // invocations that neither read what another one writes nor use atomics (the atlas passes): z planes across the
+        // host threads - any schedule gives the same image, and the CPU baseline may use every core
+#pragma omp parallel for schedule(static)
+        for (long z = 0; z < (long)(gz * lz); ++z)
+            for (uint y = 0; y < gy * ly; ++y)
+                for (uint x = 0; x < gx * lx; ++x) {
+                    g_inv.gl_GlobalInvocationID = uvec3(x, y, (uint)z);
+                    shader_main();
+                }
+        return;
+    }
     for (uint z = 0; z < gz * lz; ++z)
         for (uint y = 0; y < gy * ly; ++y)
             for (uint x = 0; x < gx * lx; ++x) {

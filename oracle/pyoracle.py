@@ -1,7 +1,7 @@
 """ctypes wrapper around oracle/_build/libvgi_oracle.so — TEST INFRASTRUCTURE ONLY.
 
 May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs, never by the product package. PARITY UNPINNED (see vgi_oracle.h)."""
+legs, never by the product package. Pinned against the reference's shader text (see vgi_oracle.h)."""
 import ctypes as C
 import os
 import subprocess

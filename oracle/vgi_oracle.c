@@ -1,6 +1,6 @@
 /*
  * vgi_oracle.c — CPU oracle for the clipmap voxel-GI path. See vgi_oracle.h for the contract
- * (TEST INFRASTRUCTURE ONLY, PARITY UNPINNED, IEEE binary32 without FMA contraction).
+ * (TEST INFRASTRUCTURE ONLY, parity status in vgi_oracle.h, IEEE binary32 without FMA contraction).
  *
  * Every function cites the reference file:line it restates. Where the reference leaves behaviour
  * to the Vulkan implementation (raster coverage, UNORM conversion, texture filtering) the software

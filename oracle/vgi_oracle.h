@@ -5,11 +5,15 @@
  * may include, link or call this. Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- *  and its GLSL cannot be executed here (no Vulkan ICD / GLSL compiler).
- * The oracle follows the shader text line by line (citations on every function) and is pinned
- * by analytic known-answer tests in tests/test_oracle_kat.py plus glm golden matrices generated
- * from the reference's vendored glm (oracle/ref_glm/).
+ * PARITY: the reference ships no tests, golden vectors or fixtures for this path and its
+ * GLSL cannot run as GLSL here (no Vulkan ICD / GLSL compiler). The oracle is pinned instead against the reference's
+ * own SHADER TEXT compiled for the CPU (oracle/glsl_shim -> oracle/_ref/libvgi_refshaders.so): tests/test_ref_shaders.py
+ * compares them live and through tests/golden/ref_shader_golden.npz - down-sampling, border wrap, clear, copy-alpha,
+ * octree build, both cone tracers and the specular filter are bit-identical, the injection shading agrees to 2^-17.
+ * STILL UNPINNED: triangle coverage (fixed-function rasteriser + MSAA in the reference, quirk Q3) - the canonical
+ * conservative coverage below is a stated deviation checked by closed-form known answers (tests/test_oracle_kat.py).
+ * Camera / light / voxelizer matrices are pinned by golden vectors generated from the reference's vendored glm
+ * (oracle/ref_glm/).
  *
  * Arithmetic contract: IEEE-754 binary32, round-to-nearest-even, NO fused multiply-add
  * (build with -ffp-contract=off), expressions evaluated left to right as written in the GLSL.
