@@ -35,3 +35,29 @@ def atrium_inputs(resolution=256, shadow_size=4096, width=1920, height=1080, lev
 def psnr(a, b, peak=1.0):
     mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
     return 200.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+# ---- inputs shared by the GPU parity tests and their CPU twins (tests/test_ref_shaders.py checks on the CPU that the
+# oracle and the reference's shaders agree on exactly these inputs; the GPU tests then compare libvgi with both) ----
+HELPER_CAM = (1.3, -0.7, 2.9)
+HELPER_CLEAR_CASES = (((0, 0, 0), (32, 32, 32), 1), ((5, 30, 17), (9, 4, 20), 2))     # non-negative corners (the reference's only use)
+
+
+def helper_config(mode_flags=0, levels=3):
+    return S.default_config(32, levels, downsample_band=3, mode_flags=mode_flags)
+
+
+def random_atlas(cfg, seed):
+    rng = np.random.RandomState(seed)
+    a = rng.randint(0, 256, size=S.atlas_shape(cfg)).astype(np.uint8)
+    a[rng.rand(*a.shape[:3]) < 0.5] = 0       # realistic sparsity
+    return a
+
+
+def filter_images(h, w, seed):
+    rng = np.random.RandomState(seed)
+    dif = rng.rand(h, w, 4).astype(np.float32)
+    spc = (rng.rand(h, w, 4) * 3.0).astype(np.float32)    # indirect_specular_intensity = 3
+    spc[rng.rand(h, w) < 0.6] = (0.0, 0.0, 0.0, 1.0)      # most pixels have no specular cone
+    dif[..., 3] = 1.0
+    return dif, spc

@@ -18,11 +18,8 @@ def ctx():
 
 
 def _random_atlas(cfg, seed):
-    from vk_voxel_cone_tracing_b200 import structs as S
-    rng = np.random.RandomState(seed)
-    a = rng.randint(0, 256, size=S.atlas_shape(cfg)).astype(np.uint8)
-    a[rng.rand(*a.shape[:3]) < 0.5] = 0       # realistic sparsity
-    return a
+    from tests import common
+    return common.random_atlas(cfg, seed)
 
 
 def test_clear_region(ctx, oracle):

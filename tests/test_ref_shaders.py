@@ -374,6 +374,63 @@ def test_live_q2_scalar_clamp_quantified(oracle, refshaders):
         assert np.array_equal(x, y) == bool(inside[i]), i
 
 
+def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
+    """CPU twin of tests/test_gpu_ref_shaders.py: on exactly the inputs those tests feed libvgi, the oracle and the
+    reference's shaders agree (bit for bit), so "libvgi == oracle" and "libvgi == reference shader" are one statement."""
+    from tests import common
+    cfg = common.helper_config()
+    regs = oracle.regions(cfg, common.HELPER_CAM)
+    for which in (0, 1):
+        a = common.random_atlas(cfg, 4 + which)
+        x, y = a.copy(), a.copy()
+        for level in (1, 2):
+            oracle.downsample(cfg, regs, level, x, which)
+            refshaders.downsample(cfg, regs, level, y, which)
+        assert np.array_equal(x, y) and (x != a).any()
+    dst, src = common.random_atlas(cfg, 2), common.random_atlas(cfg, 3)
+    for level in range(3):
+        x, y = dst.copy(), dst.copy()
+        oracle.copy_alpha(cfg, level, x, src)
+        refshaders.copy_alpha(cfg, level, y, src)
+        assert np.array_equal(x, y)
+    a = common.random_atlas(cfg, 1)
+    for mc, ext, level in common.HELPER_CLEAR_CASES:
+        x, y = a.copy(), a.copy()
+        oracle.clear_region(cfg, x, mc, ext, level)
+        refshaders.clear_region(cfg, y, mc, ext, level)
+        assert np.array_equal(x, y) and (x != a).any()
+    for literal in (False, True):
+        bcfg = S.default_config(32, 2, mode_flags=S.VGI_MODE_BORDER_LITERAL if literal else 0)
+        a = common.random_atlas(bcfg, 9)
+        x, y = a.copy(), a.copy()
+        oracle.wrap_border(bcfg, x, literal)
+        refshaders.wrap_border(bcfg, y, literal)
+        assert np.array_equal(x, y)
+    for method in (0, 1):
+        for tonemap in (0, 1):
+            dif, spc = common.filter_images(45, 71, 7 + method)
+            prm = S.default_filter_params(method, tonemap)
+            assert np.array_equal(oracle.specular_filter(dif, spc, prm), refshaders.specular_filter(dif, spc, prm))
+    inp = common.cornell_inputs()
+    osc = oracle.OracleScene(inp["scene"])
+    cregs = oracle.regions(inp["cfg"], inp["cam_pos"])
+    _, rad, _ = oracle.build_clipmap(inp["cfg"], cregs, osc, inp["light"], inp["shadow"], inp["shadow_depth"], 0)
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    cov = gb["depth"] < 1.0
+    for mode in (7, 8):
+        prm = S.default_vct_params(cregs[0], inp["cfg"].resolution, mode)
+        d0, s0, _ = oracle.cone_trace(inp["cfg"], inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+        d1, s1, disc = refshaders.cone_trace(inp["cfg"], inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+        assert np.array_equal(disc.astype(bool), ~cov)
+        assert np.array_equal(d0[cov], d1[cov]) and np.array_equal(s0[cov], s1[cov])
+    lo, hi = inp["scene"].world_bbox()
+    for level in (5, 7):
+        frags = oracle.svo_fragments(level, lo, hi, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+        a, b = oracle.svo_build(level, frags), refshaders.svo_build(level, frags)
+        assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+
+
 def test_live_q6_radiance_downsample_does_not_compile_as_shipped(refshaders):
     """SURVEY Q6: `lerpFactor` is declared inside the `if` and used after it. The repaired text (build_ref.py R10) builds;
     the shipped text must fail on exactly that identifier."""
