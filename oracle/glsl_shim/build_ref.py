@@ -50,7 +50,7 @@ UNITS = [
     "copyAlphaImage.comp", "octreeNodeInit.comp", "octreeNodeFlag.comp", "octreeNodeAlloc.comp",
     "octreeNodeModifyArg.comp", "octreeNodeLeafWrite.comp", "octreeNodeMipmapWrite.comp",
     "voxelConeTracing.frag", "voxelConeTracing_Octree.frag", "specularFilter.frag", "msaaInjectRadiance.frag",
-    "msaaVoxelizer.geom", "msaaVoxelizer.frag",
+    "msaaVoxelizer.geom", "msaaVoxelizer.frag", "voxelizer.frag",
 ]
 
 

@@ -173,6 +173,18 @@ def main():
     g["vox_out_texels"] = np.argwhere(y[..., 0] > 0).astype(np.int16)
     assert np.all(y[y[..., 0] > 0] == 255)
 
+    # ---- J: voxelizer.frag (SVO fragment shader) on every 40th sample of the same scene at level 5: as shipped (biased
+    #         position in; literal colour, Q21/Q22) and with a 1 x 1 white base-colour texture + world position in
+    #         (= the oracle's canonical colour)
+    lo, hi = inp["scene"].world_bbox()
+    smp = O.svo_fragment_samples(5, lo, hi, osc)
+    sel = np.arange(0, smp["world"].shape[0], 40)
+    g["svofrag_sel"], g["svofrag_world"], g["svofrag_biased"] = sel, smp["world"][sel], smp["biased"][sel]
+    for name, pos, white in (("literal", smp["biased"][sel], False), ("canonical", smp["world"][sel], True)):
+        disc, words = Rf.svo_fragments(5, pos, smp["nrm"][sel], smp["mat"][sel], osc.materials, inp["light"], inp["shadow"],
+                                       inp["shadow_depth"], white_base_color_texture=white)
+        g[f"svofrag_out_{name}_discarded"], g[f"svofrag_out_{name}_words"] = disc, words
+
     np.savez_compressed(OUT, **g)
     print(OUT, os.path.getsize(OUT), "bytes;", len(g), "arrays")
 

@@ -220,6 +220,19 @@ def svo_fragments(level, bb_min, bb_max, osc, light, shadow, shadow_depth, mode_
     return frags
 
 
+def svo_fragment_samples(level, bb_min, bb_max, osc):
+    """The sample behind every covered (triangle, voxel) of svo_fragments, before the shading's discard; dict of arrays."""
+    fn = lib().vgo_svo_fragment_samples
+    fn.restype = C.c_uint32
+    head = (C.c_uint32(level), (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)), C.byref(osc.tris))
+    nul = C.c_void_p(0)
+    n = int(fn(*head, C.c_uint32(0), nul, nul, nul, nul, nul))
+    out = dict(world=np.zeros((n, 3), np.float32), biased=np.zeros((n, 3), np.float32), nrm=np.zeros((n, 3), np.float32),
+               mat=np.zeros(n, np.int32), voxel=np.zeros((n, 3), np.int32))
+    fn(*head, C.c_uint32(n), *(_p(out[k]) for k in ("world", "biased", "nrm", "mat", "voxel")))
+    return out
+
+
 def svo_build(level, frags, capacity=None, mode_flags=0):
     n = frags.shape[0]
     if capacity is None:

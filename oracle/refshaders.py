@@ -270,3 +270,41 @@ def voxelizer_fragments(cfg, regs, level, position, atlas):
     lib().ref_voxelizer_fragments(C.c_int(n), _p(pos), _p(atlas), *_dims(atlas), _p(mn), C.c_uint(level), _p(mx),
                                   C.c_float(ext), C.c_float(vs), C.c_int(cfg.resolution), _p(disc))
     return disc
+
+
+# ---- SVO fragment shader, per fragment ------------------------------------------------------------
+
+class _SvoFragArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("position", C.c_void_p), ("normal", C.c_void_p), ("material_index", C.c_void_p),
+        ("materials", C.c_void_p), ("material_count", C.c_int), ("white_base_color_texture", C.c_int),
+        ("voxel_resolution", C.c_uint),
+        ("shadow_depth", C.c_void_p), ("sw", C.c_int), ("sh", C.c_int),
+        ("light_direction", C.c_void_p), ("light_intensity", C.c_float), ("light_color", C.c_void_p),
+        ("shadow_view", C.c_void_p), ("shadow_proj", C.c_void_p), ("z_near", C.c_float), ("z_far", C.c_float),
+        ("out_discarded", C.c_void_p), ("out_words", C.c_void_p),
+    ]
+
+
+def svo_fragments(level, position, normal, material_index, materials, light, shadow, shadow_depth, white_base_color_texture=False):
+    """voxelizer.frag (uIsCountMode = 0), one invocation per given fragment: position = the biased [0,1] position the
+    geometry shader emits. white_base_color_texture binds a 1 x 1 white texture as every material's base-colour texture,
+    which turns `color = texture * pbrBaseColorFactor` into the factor (the oracle's canonical colour, Q21).
+    Returns (discarded[n], words[n, 2])."""
+    n = position.shape[0]
+    a = _SvoFragArgs()
+    sd = np.ascontiguousarray(shadow_depth, dtype=np.float32)
+    keep = dict(position=np.ascontiguousarray(position, np.float32), normal=np.ascontiguousarray(normal, np.float32),
+                material_index=np.ascontiguousarray(material_index, np.int32), materials=np.ascontiguousarray(materials),
+                shadow_depth=sd, light_direction=np.array(list(light.direction), np.float32),
+                light_color=np.array(list(light.color), np.float32), shadow_view=np.array(list(shadow.view), np.float32),
+                shadow_proj=np.array(list(shadow.proj), np.float32),
+                out_discarded=np.zeros(n, np.uint8), out_words=np.zeros((n, 2), np.uint32))
+    for k, v in keep.items():
+        setattr(a, k, v.ctypes.data)
+    a.n, a.material_count, a.white_base_color_texture = n, keep["materials"].shape[0], 1 if white_base_color_texture else 0
+    a.voxel_resolution = 1 << level
+    a.sh, a.sw = sd.shape
+    a.light_intensity, a.z_near, a.z_far = light.intensity, shadow.z_near, shadow.z_far
+    lib().ref_svo_fragments(C.byref(a))
+    return keep["out_discarded"], keep["out_words"]

@@ -213,6 +213,45 @@ def test_golden_voxelizer_axis_and_addressing(oracle, golden):
     assert np.all(x[x[..., 0] > 0] == 255)
 
 
+def _check_svo_fragments(level, smp, sel, lit, can, out_lit, out_can):
+    """voxelizer.frag per oracle sample. out_* = (discarded, words) of the shader; lit / can = the oracle's fragment
+    lists in literal / canonical mode (one fragment per sample, same order, when nothing is discarded).
+    * as shipped (biased position in): nothing the oracle keeps is discarded, the colour word (28 bits incl. the alpha
+      nibble) is bit-identical, and the packed voxel is the oracle's whenever the sample lies inside that voxel;
+    * with a 1 x 1 white base-colour texture bound and the world position in, the shader's `texture * factor` colour is
+      the oracle's canonical colour (Q21 / Q22): bit-identical colour words."""
+    n = smp["world"].shape[0]
+    assert lit.shape[0] == n and can.shape[0] == n, "a sample was discarded: the fragment lists no longer line up"
+    res = 1 << level
+    (dl, wl), (dc, wc) = out_lit, out_can
+    assert not dl.any() and not dc.any()
+    assert np.array_equal(wl[:, 1] & 0x0fffffff, lit[sel, 1] & 0x0fffffff)
+    assert np.array_equal(wc[:, 1] & 0x0fffffff, can[sel, 1] & 0x0fffffff)
+    assert len(np.unique(can[sel, 1] & 0xffffff)) > 20            # real shading, not a constant
+    unpack = lambda w: np.stack([w[:, 0] & 0xfff, (w[:, 0] >> 12) & 0xfff, ((w[:, 0] >> 24) & 0xff) | ((w[:, 1] >> 28) << 8)], axis=1)  # noqa: E731
+    same = np.all(unpack(wl) == unpack(lit[sel]), axis=1)
+    rel = smp["biased"][sel].astype(np.float64) * res - smp["voxel"][sel]
+    inside = np.all((rel > 1e-3) & (rel < 1.0 - 1e-3), axis=1)
+    assert inside.sum() >= 100 and np.all(same[inside])
+
+
+def test_golden_svo_fragment_shader(oracle, golden):
+    """Depends on the Cornell generator like test_golden_injection_fragments."""
+    from tests.common import cornell_inputs
+    g = golden
+    r, l, w, h = (int(v) for v in g["trace_cfg"])
+    inp = cornell_inputs(resolution=r, shadow_size=g["trace_shadow_depth"].shape[0], width=w, height=h)
+    osc = oracle.OracleScene(inp["scene"])
+    lo, hi = inp["scene"].world_bbox()
+    smp = oracle.svo_fragment_samples(5, lo, hi, osc)
+    sel = g["svofrag_sel"]
+    assert np.array_equal(smp["world"][sel], g["svofrag_world"]) and np.array_equal(smp["biased"][sel], g["svofrag_biased"])
+    args = (5, lo, hi, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    _check_svo_fragments(5, smp, sel, oracle.svo_fragments(*args, S.VGI_MODE_SVO_LITERAL), oracle.svo_fragments(*args, 0),
+                         (g["svofrag_out_literal_discarded"], g["svofrag_out_literal_words"]),
+                         (g["svofrag_out_canonical_discarded"], g["svofrag_out_canonical_words"]))
+
+
 # ---------------------------------------------------------------------------------------------------
 # live layer (needs oracle/_ref/libvgi_refshaders.so, i.e. the reference tree or a prebuilt library)
 # ---------------------------------------------------------------------------------------------------
@@ -372,6 +411,21 @@ def test_live_q2_scalar_clamp_quantified(oracle, refshaders):
         oracle.voxelize_level(cfg, regs, level, oracle.TriangleSoup(tris[i:i + 1]), x)
         refshaders.voxelizer_fragments(cfg, regs, level, ctr[i:i + 1], y)
         assert np.array_equal(x, y) == bool(inside[i]), i
+
+
+@pytest.mark.parametrize("level", [5, 7])
+def test_live_svo_fragment_shader(oracle, refshaders, level):
+    from tests.common import cornell_inputs
+    inp = cornell_inputs(resolution=32, shadow_size=512, width=16, height=16)
+    osc = oracle.OracleScene(inp["scene"])
+    lo, hi = inp["scene"].world_bbox()
+    smp = oracle.svo_fragment_samples(level, lo, hi, osc)
+    sel = np.arange(smp["world"].shape[0])
+    args = (level, lo, hi, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    common = (smp["nrm"], smp["mat"], osc.materials, inp["light"], inp["shadow"], inp["shadow_depth"])
+    _check_svo_fragments(level, smp, sel, oracle.svo_fragments(*args, S.VGI_MODE_SVO_LITERAL), oracle.svo_fragments(*args, 0),
+                         refshaders.svo_fragments(level, smp["biased"], *common),
+                         refshaders.svo_fragments(level, smp["world"], *common, white_base_color_texture=True))
 
 
 def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
