@@ -9,7 +9,7 @@ cadence) + 1080p 16-cone CombinedGI cone trace (rendering mode 8, diffuse + spec
   e2e    frames/s through the C-ABI host-buffer call vgi_frame_host(): per step the G-buffer and the
          shadow map are copied from pinned host memory, both output images are copied back
   stages build_ms (the "voxelize+inject+mip ms @256^3" half of the metric) and trace_ms / trace_fps
-  roofline / roofline_cone_trace / cpu_baseline: see DESIGN.md "measurement"
+  roofline (dominant kernel) / roofline_hbm_kernel / roofline_stage / roofline_cone_trace / cpu_baseline: see DESIGN.md "measurement"
 
 N > 1 (torchrun, one rank per GPU): every rank renders its own camera view of the same scene
 (batched views, sharded by view, no data-path collective) — weak scaling.
@@ -448,7 +448,7 @@ def run_vgi(args):
                     "algorithmic_bytes_per_launch": ab, "ms_per_launch": ms_launch,
                     "share_of_build": build_k[name][0] / sum(v[0] for v in build_k.values()),
                     "note": "dominant kernel of the HBM-bound half of the metric (voxelize+inject+mip); the dominant kernel of the "
-                            "whole step, k_trace_main, is L1 / issue bound: see roofline_dominant_kernel"}
+                            "whole step, k_trace_main, is L1 / issue bound: see roofline"}
         trace_k = {k: v for k, v in tm.items() if k.startswith("k_trace")}
         if trace_k:
             tms = sum(v[0] for v in trace_k.values()) / args.steps
@@ -548,7 +548,7 @@ def run_vgi(args):
                                  "frac": a_main / (ms_main * 1e-3) / 1e9 / roof_trace["peak"],
                                  "peak_source": roof_trace["peak_source"], "traffic": ncu_traffic("k_trace_main"),
                                  "note": "SURVEY 8(d): cone tracing is bounded by L1 bandwidth / issue rate, not HBM (DRAM traffic "
-                                         "per launch in `traffic`); the `roofline` object carries the dominant HBM-bound kernel"}
+                                         "per launch in `traffic`); `roofline_hbm_kernel` carries the dominant HBM-bound kernel"}
 
     if rank == 0:
         line = {
@@ -565,7 +565,9 @@ def run_vgi(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "wall_ms_per_step": t_wall},
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
-            "clocks": clk, "roofline": roof, "roofline_dominant_kernel": roof_dominant, "roofline_stage": roof_stage,
+            # `roofline` = the dominant kernel of the step (k_trace_main, bounded by L1 / issue rate per SURVEY 8d); without
+            # the oracle's tap count (N > 1 or --no-cpu-baseline) it falls back to the dominant HBM-bound kernel
+            "clocks": clk, "roofline": roof_dominant or roof, "roofline_hbm_kernel": roof, "roofline_stage": roof_stage,
             "roofline_cone_trace": roof_trace, "adjacent_passes": adjacent,
             "svo": svo, "kernels": kernels,
             "cpu_baseline": cpu,
