@@ -73,6 +73,9 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
     vgi_ctx* c = new (std::nothrow) vgi_ctx();
     if (!c) return fail(nullptr, VGI_E_NOMEM, "vgi_create: out of host memory");
     c->cfg = *cfg;
+    // every allocation below may fail (the store alone is 3.2 GB at 6 x 256^3): on any error the partly built ctx is torn
+    // down again (all pointers start out null) and the message survives in vgi_last_error(NULL)
+    const int rc = [&]() -> int {
     if (cfg->device >= 0) { CK(c, cudaSetDevice(cfg->device)); }
     CK(c, cudaGetDevice(&c->device));
     memset(&c->light, 0, sizeof(c->light));
@@ -100,6 +103,16 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
     CK(c, cudaMemset(c->counters, 0, sizeof(Counters)));
     CK(c, cudaMallocHost(&c->h_counters, sizeof(Counters)));
     memset(c->h_counters, 0, sizeof(Counters));
+    return VGI_OK;
+    }();
+    if (rc != VGI_OK) {
+        const std::string msg = g_err;
+        cudaGetLastError();     // clear the sticky allocation error before tearing down
+        vgi_destroy(c);
+        g_err = msg;
+        *out = nullptr;
+        return rc;
+    }
     c->z0 = 0;
     c->z1 = (int)R;
     // default regions: camera at the origin
