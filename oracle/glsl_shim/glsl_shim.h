@@ -95,7 +95,9 @@ inline float radians(float d) { return d * 0.017453292519943295f; }
 inline float sin(float x) { return ::sinf(x); }
 inline float cos(float x) { return ::cosf(x); }
 inline float tan(float x) { return ::tanf(x); }
-inline float pow(float x, float y) { return ::powf(x, y); }
+// pow(x, y) is undefined for x < 0 in GLSL; GPUs evaluate exp2(y * log2(x)) = NaN for every negative base, whereas powf(negative,
+// integer) is finite. Follow the hardware (the oracle's glsl_pow does the same; see the note on min / max below).
+inline float pow(float x, float y) { return x < 0.0f ? NAN : ::powf(x, y); }
 inline float exp(float x) { return ::expf(x); }
 inline float log(float x) { return ::logf(x); }
 inline float exp2(float x) { return ::exp2f(x); }

@@ -59,7 +59,7 @@
     GLSL_F1(sin, ::sinf(x)) GLSL_F1(cos, ::cosf(x)) GLSL_F1(round, ::roundf(x))
 #undef GLSL_F1
     friend V abs(const V& a) { V r; for (int i = 0; i < dim; ++i) r.d[i] = a.d[i] < (T)0 ? (T)(-a.d[i]) : a.d[i]; return r; }
-    friend V pow(const V& a, const V& b) requires std::is_floating_point_v<T> { V r; for (int i = 0; i < dim; ++i) r.d[i] = ::powf(a.d[i], b.d[i]); return r; }
+    friend V pow(const V& a, const V& b) requires std::is_floating_point_v<T> { V r; for (int i = 0; i < dim; ++i) r.d[i] = a.d[i] < (T)0 ? (T)NAN : (T)::powf(a.d[i], b.d[i]); return r; }
     // floats: IEEE minNum / maxNum like the scalar versions in glsl_shim.h (x != x only for NaN)
     friend V min(const V& a, const V& b) { V r; for (int i = 0; i < dim; ++i) r.d[i] = (b.d[i] < a.d[i] || a.d[i] != a.d[i]) ? b.d[i] : a.d[i]; return r; }
     friend V max(const V& a, const V& b) { V r; for (int i = 0; i < dim; ++i) r.d[i] = (a.d[i] < b.d[i] || a.d[i] != a.d[i]) ? b.d[i] : a.d[i]; return r; }

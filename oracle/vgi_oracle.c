@@ -24,6 +24,11 @@ static inline float f_clamp(float x, float lo, float hi) { return f_min(f_max(x,
 static inline float f_fract(float x) { return x - floorf(x); }
 /* GLSL mix(x,y,a) = x*(1-a) + y*a */
 static inline float f_mix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+/* GLSL pow(x, y): "results are undefined if x < 0". GPUs evaluate exp2(y * log2(x)), i.e. NaN for every negative base,
+ * while the C library's powf(negative, integer) is finite. traceCone reaches this when the filtered alpha exceeds 1 by an
+ * ulp: with NaN, clamp(1 - NaN, 0, 1) is 0 on the hardware (minNum / maxNum), with powf(-e, 1.0) it would be 1. The oracle
+ * follows the hardware (so do the CUDA kernels: exp2f(c * log2f(x))) and the shim (glsl_shim.h). */
+static inline float glsl_pow(float x, float y) { return x < 0.0f ? NAN : powf(x, y); }
 static inline float dot3(const float* a, const float* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
 
 /* Vulkan UNORM8 decode: c / 255 (exact IEEE division). */
@@ -902,7 +907,7 @@ static void trace_cone(trace_ctx* t, const float* startPos_, const float* dir, f
         voxelSize = p->voxel_size * exp2f(curLevel);
         const float correction = curSegmentLength / voxelSize;
         for (int k = 0; k < 3; ++k) radiance[k] = radiance[k] * correction;
-        opacity = f_clamp(1.0f - powf(1.0f - opacity, correction), 0.0f, 1.0f);
+        opacity = f_clamp(1.0f - glsl_pow(1.0f - opacity, correction), 0.0f, 1.0f);
         const float k1 = f_clamp(1.0f - result[3], 0.0f, 1.0f);
         result[0] += k1 * radiance[0];
         result[1] += k1 * radiance[1];
@@ -938,7 +943,7 @@ static void microfacet_brdf(float NdotL, float NdotV, float NdotH, float VdotH, 
                             const float* r0, const float* r90, const float* diffuseColor, float* o)
 {
     const float M_PI_REF = 3.141592f;
-    const float fw = powf(f_clamp(1.0f - VdotH, 0.0f, 1.0f), 5.0f);
+    const float fw = glsl_pow(f_clamp(1.0f - VdotH, 0.0f, 1.0f), 5.0f);
     const float r = alphaRoughness;
     const float attL = 2.0f * NdotL / (NdotL + sqrtf(r * r + (1.0f - r * r) * (NdotL * NdotL)));
     const float attV = 2.0f * NdotV / (NdotV + sqrtf(r * r + (1.0f - r * r) * (NdotV * NdotV)));
@@ -1203,7 +1208,7 @@ void vgo_specular_filter(const float* diffuse, const float* specular, uint32_t w
             if (prm->tonemap_enable == 1) {
                 const float white = 1.0f / uncharted2(11.2f);
                 for (int k = 0; k < 3; ++k)
-                    o[k] = powf(uncharted2(fc[k] * prm->tonemap_exposure) * white, 1.0f / prm->tonemap_gamma);
+                    o[k] = glsl_pow(uncharted2(fc[k] * prm->tonemap_exposure) * white, 1.0f / prm->tonemap_gamma);
                 o[3] = fc[3];
             } else {
                 memcpy(o, fc, sizeof fc);
