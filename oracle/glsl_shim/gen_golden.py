@@ -185,6 +185,17 @@ def main():
                                        inp["shadow_depth"], white_base_color_texture=white)
         g[f"svofrag_out_{name}_discarded"], g[f"svofrag_out_{name}_words"] = disc, words
 
+    # ---- K: gBufferPass.frag on the fragments of a small view of the atrium (23 materials, smooth normals)
+    from tests.common import atrium_inputs
+    from vk_voxel_cone_tracing_b200 import raster
+    ainp = atrium_inputs(resolution=32, shadow_size=64, width=80, height=45, levels=3)
+    mat, nrm = raster.gbuffer_attributes(ainp["scene"], ainp["cam"], 80, 45)
+    cov = mat >= 0
+    g["gbuf_material"], g["gbuf_normal_in"] = mat, nrm
+    d, n, s, e, disc = Rf.gbuffer_fragments(nrm[cov], mat[cov], np.ascontiguousarray(ainp["scene"].materials))
+    assert not disc.any()
+    g["gbuf_out_diffuse"], g["gbuf_out_normal"], g["gbuf_out_specular"], g["gbuf_out_emission"] = d, n, s, e
+
     np.savez_compressed(OUT, **g)
     print(OUT, os.path.getsize(OUT), "bytes;", len(g), "arrays")
 

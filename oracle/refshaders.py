@@ -308,3 +308,19 @@ def svo_fragments(level, position, normal, material_index, materials, light, sha
     a.light_intensity, a.z_near, a.z_far = light.intensity, shadow.z_near, shadow.z_far
     lib().ref_svo_fragments(C.byref(a))
     return keep["out_discarded"], keep["out_words"]
+
+
+# ---- G-buffer fragment shader, per fragment -------------------------------------------------------
+
+def gbuffer_fragments(normal, material_index, materials):
+    """gBufferPass.frag, one invocation per given fragment (interpolated un-normalised normal, material).
+    Returns float32 (n, 4) arrays diffuse, normal, specular, emission (the four colour attachments before format
+    conversion) and discarded[n]."""
+    nrm = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    n = nrm.shape[0]
+    mi = np.ascontiguousarray(material_index, np.int32)
+    mats = np.ascontiguousarray(materials)
+    outs = [np.zeros((n, 4), np.float32) for _ in range(4)]
+    disc = np.zeros(n, np.uint8)
+    lib().ref_gbuffer_fragments(C.c_int(n), _p(nrm), _p(mi), _p(mats), *(_p(o) for o in outs), _p(disc))
+    return (*outs, disc)

@@ -252,6 +252,33 @@ def test_golden_svo_fragment_shader(oracle, golden):
                          (g["svofrag_out_canonical_discarded"], g["svofrag_out_canonical_words"]))
 
 
+def _check_gbuffer(gb, cov, d, n, s, e):
+    """The host rasteriser's G-buffer (which vgi_render_gbuffer reproduces bit for bit, tests/test_gpu_raster.py) against
+    gBufferPass.frag's four colour outputs after the fixed-function format conversion: RGBA8 UNORM round-to-nearest for
+    diffuse (+ roughness) and specular (+ metallic), binary16 round-to-nearest-even for emission and the encoded normal.
+    Colours bit-identical; the normal within one binary16 ulp (the rasteriser interpolates and normalises in binary64)."""
+    to8 = lambda x: np.floor(np.clip(x, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)  # noqa: E731
+    assert cov.sum() > 1000
+    assert np.array_equal(to8(d), gb["diffuse"][cov]) and np.array_equal(to8(s), gb["specular"][cov])
+    assert np.array_equal(e.astype(np.float16).view(np.uint16), gb["emission"][cov])
+    dn = np.abs(n.astype(np.float16).view(np.uint16).astype(np.int32) - gb["normal"][cov].astype(np.int32))
+    assert dn.max() <= 1 and (dn == 0).mean() > 0.99
+    assert len(np.unique(gb["diffuse"][cov].reshape(-1, 4), axis=0)) > 10       # many materials in view
+
+
+def test_golden_gbuffer_fragment_shader(golden):
+    """Depends on the atrium generator: if the attribute check fails, re-run oracle/glsl_shim/gen_golden.py."""
+    from tests.common import atrium_inputs
+    from vk_voxel_cone_tracing_b200 import raster
+    g = golden
+    inp = atrium_inputs(resolution=32, shadow_size=64, width=80, height=45, levels=3)
+    mat, nrm = raster.gbuffer_attributes(inp["scene"], inp["cam"], 80, 45)
+    assert np.array_equal(mat, g["gbuf_material"]) and np.array_equal(nrm, g["gbuf_normal_in"])
+    cov = mat >= 0
+    assert np.array_equal(cov, inp["gbuffer"]["depth"] < 1.0)
+    _check_gbuffer(inp["gbuffer"], cov, g["gbuf_out_diffuse"], g["gbuf_out_normal"], g["gbuf_out_specular"], g["gbuf_out_emission"])
+
+
 # ---------------------------------------------------------------------------------------------------
 # live layer (needs oracle/_ref/libvgi_refshaders.so, i.e. the reference tree or a prebuilt library)
 # ---------------------------------------------------------------------------------------------------
@@ -426,6 +453,22 @@ def test_live_svo_fragment_shader(oracle, refshaders, level):
     _check_svo_fragments(level, smp, sel, oracle.svo_fragments(*args, S.VGI_MODE_SVO_LITERAL), oracle.svo_fragments(*args, 0),
                          refshaders.svo_fragments(level, smp["biased"], *common),
                          refshaders.svo_fragments(level, smp["world"], *common, white_base_color_texture=True))
+
+
+def test_live_gbuffer_fragment_shader(refshaders):
+    from tests.common import atrium_inputs, cornell_inputs
+    from vk_voxel_cone_tracing_b200 import raster
+    for inp, w, h in ((atrium_inputs(resolution=32, shadow_size=64, width=160, height=90, levels=3), 160, 90),
+                      (cornell_inputs(resolution=32, shadow_size=128, width=96, height=96), 96, 96)):
+        mat, nrm = raster.gbuffer_attributes(inp["scene"], inp["cam"], w, h)
+        cov = mat >= 0
+        d, n, s, e, disc = refshaders.gbuffer_fragments(nrm[cov], mat[cov], np.ascontiguousarray(inp["scene"].materials))
+        assert not disc.any() and np.array_equal(cov, inp["gbuffer"]["depth"] < 1.0)
+        if w == 160:
+            _check_gbuffer(inp["gbuffer"], cov, d, n, s, e)
+        else:   # few materials in this view: colours only
+            to8 = lambda x: np.floor(np.clip(x, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)  # noqa: E731
+            assert np.array_equal(to8(d), inp["gbuffer"]["diffuse"][cov]) and np.array_equal(to8(s), inp["gbuffer"]["specular"][cov])
 
 
 def test_live_inputs_of_the_gpu_tests(oracle, refshaders):

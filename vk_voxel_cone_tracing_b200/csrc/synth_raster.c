@@ -223,3 +223,41 @@ int vgs_gbuffer(const vgi_scene_desc* scene, const vgi_camera* cam, uint32_t w, 
     free(tris);
     return 0;
 }
+
+/* Test aid: what the rasteriser hands the G-buffer fragment stage at every pixel - the material index (-1 = not covered)
+ * and the perspective-correctly interpolated, un-normalised world normal (the `fs_in.normal` of gBufferPass.frag), same
+ * visibility and interpolation as vgs_gbuffer. tests/test_ref_shaders.py feeds them to the reference's gBufferPass.frag. */
+int vgs_gbuffer_attributes(const vgi_scene_desc* scene, const vgi_camera* cam, uint32_t w, uint32_t h,
+                           int32_t* material, float* normal)
+{
+    uint32_t ntri;
+    tri_world* tris = world_tris(scene, &ntri);
+    int32_t* ids = (int32_t*)malloc((size_t)w * h * sizeof(int32_t));
+    float* depth = (float*)malloc((size_t)w * h * sizeof(float));
+    raster_ids(cam->view_proj, tris, ntri, w, h, depth, ids);
+#pragma omp parallel for schedule(static)
+    for (int64_t y = 0; y < (int64_t)h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const size_t pi = (size_t)y * w + x;
+            material[pi] = -1;
+            normal[pi * 3] = normal[pi * 3 + 1] = normal[pi * 3 + 2] = 0.0f;
+            if (ids[pi] < 0) continue;
+            const tri_world* t = &tris[ids[pi]];
+            proj_tri q;
+            project(cam->view_proj, t, w, h, &q);
+            const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
+            const double px = x + 0.5, py = y + 0.5;
+            double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
+            double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
+            double b2 = 1.0 - b0 - b1;
+            b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2];
+            const double bs = b0 + b1 + b2;
+            b0 /= bs; b1 /= bs; b2 /= bs;
+            for (int k = 0; k < 3; ++k) normal[pi * 3 + k] = (float)(b0 * t->n[0][k] + b1 * t->n[1][k] + b2 * t->n[2][k]);
+            material[pi] = t->mat;
+        }
+    free(depth);
+    free(ids);
+    free(tris);
+    return 0;
+}

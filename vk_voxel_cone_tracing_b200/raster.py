@@ -43,3 +43,14 @@ def gbuffer(scene, camera, width, height):
                       C.c_void_p(specular.ctypes.data), C.c_void_p(emission.ctypes.data),
                       C.c_void_p(depth.ctypes.data))
     return dict(diffuse=diffuse, normal=normal, specular=specular, emission=emission, depth=depth)
+
+
+def gbuffer_attributes(scene, camera, width, height):
+    """Test aid: per pixel the material index (-1 = not covered) and the interpolated, un-normalised world normal the
+    G-buffer fragment stage receives (vgs_gbuffer_attributes)."""
+    material = np.empty((height, width), dtype=np.int32)
+    normal = np.empty((height, width, 3), dtype=np.float32)
+    d = scene.desc()
+    lib().vgs_gbuffer_attributes(C.byref(d), C.byref(camera), C.c_uint32(width), C.c_uint32(height),
+                                 C.c_void_p(material.ctypes.data), C.c_void_p(normal.ctypes.data))
+    return material, normal
