@@ -324,3 +324,21 @@ def gbuffer_fragments(normal, material_index, materials):
     disc = np.zeros(n, np.uint8)
     lib().ref_gbuffer_fragments(C.c_int(n), _p(nrm), _p(mi), _p(mats), *(_p(o) for o in outs), _p(disc))
     return (*outs, disc)
+
+
+# ---- vertex stage of the voxelization passes -------------------------------------------------------
+
+def voxelizer_vertices(scene):
+    """msaaVoxelizer.vert over every triangle vertex of a synth.Scene in draw order: (pos[n, 3, 3], nrm[n, 3, 3])."""
+    pos = np.ascontiguousarray(scene.positions, np.float32)
+    nrm = np.ascontiguousarray(scene.normals, np.float32)
+    idx = np.ascontiguousarray(scene.indices, np.uint32)
+    prims = np.ascontiguousarray(scene.primitives)
+    nodes = np.ascontiguousarray(scene.nodes)
+    assert prims.dtype.itemsize == 20 and nodes.dtype.itemsize == 128
+    fn = lib().ref_voxelizer_vertices
+    fn.restype = C.c_uint
+    n = int(fn(_p(pos), _p(nrm), _p(idx), _p(prims), C.c_uint(prims.shape[0]), _p(nodes), C.c_void_p(0), C.c_void_p(0)))
+    out_p, out_n = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+    fn(_p(pos), _p(nrm), _p(idx), _p(prims), C.c_uint(prims.shape[0]), _p(nodes), _p(out_p), _p(out_n))
+    return out_p, out_n

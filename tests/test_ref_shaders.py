@@ -471,6 +471,16 @@ def test_live_gbuffer_fragment_shader(refshaders):
             assert np.array_equal(to8(d), inp["gbuffer"]["diffuse"][cov]) and np.array_equal(to8(s), inp["gbuffer"]["specular"][cov])
 
 
+def test_live_vertex_stage_world_transform(oracle, refshaders):
+    """msaaVoxelizer.vert over every triangle vertex in draw order (the atrium has rotated / scaled node matrices) against
+    the oracle's world-space triangle soup (vgo_scene_triangles): positions and itModel-transformed normals, bit for bit."""
+    from vk_voxel_cone_tracing_b200 import synth
+    for scene in (synth.cornell_box(), synth.atrium()):
+        osc = oracle.OracleScene(scene)
+        pos, nrm = refshaders.voxelizer_vertices(scene)
+        assert pos.shape == osc.pos.shape and np.array_equal(pos, osc.pos) and np.array_equal(nrm, osc.nrm)
+
+
 def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
     """CPU twin of tests/test_gpu_ref_shaders.py: on exactly the inputs those tests feed libvgi, the oracle and the
     reference's shaders agree (bit for bit), so "libvgi == oracle" and "libvgi == reference shader" are one statement."""
