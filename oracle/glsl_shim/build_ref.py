@@ -51,7 +51,7 @@ UNITS = [
     "octreeNodeModifyArg.comp", "octreeNodeLeafWrite.comp", "octreeNodeMipmapWrite.comp",
     "voxelConeTracing.frag", "voxelConeTracing_Octree.frag", "specularFilter.frag", "msaaInjectRadiance.frag",
     "msaaVoxelizer.geom", "msaaVoxelizer.frag", "voxelizer.frag",
-    "gBufferPass.frag", "msaaVoxelizer.vert",
+    "gBufferPass.frag", "msaaVoxelizer.vert", "voxelizer.vert", "voxelizer.geom",
 ]
 
 

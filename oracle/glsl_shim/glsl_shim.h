@@ -292,6 +292,7 @@ struct invocation {
     per_vertex in_vertices[3];
     vec4 cur_position; int cur_viewport;
     int emitted; vec4 out_position[8]; int out_viewport[8];
+    void (*emit_hook)(int vertex);      // driver callback: capture the shader's own per-vertex outputs at EmitVertex()
 };
 inline thread_local invocation g_inv;
 
@@ -351,6 +352,7 @@ inline void EmitVertex()
 {
     glsl::invocation& v = glsl::g_inv;
     if (v.emitted < 8) { v.out_position[v.emitted] = v.cur_position; v.out_viewport[v.emitted] = v.cur_viewport; }
+    if (v.emit_hook) v.emit_hook(v.emitted);
     ++v.emitted;
 }
 #define gl_in (glsl::g_inv.in_vertices)

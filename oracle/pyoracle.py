@@ -220,6 +220,15 @@ def svo_fragments(level, bb_min, bb_max, osc, light, shadow, shadow_depth, mode_
     return frags
 
 
+def svo_vertex_stage(level, bb_min, bb_max, osc):
+    """(ndc[n, 3, 3], biased[n, 3, 3], axis[n]) of every triangle (vgo_svo_vertex_stage)."""
+    n = osc.pos.shape[0]
+    ndc, biased, axis = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3, 3), np.float32), np.zeros(n, np.int32)
+    lib().vgo_svo_vertex_stage(C.c_uint32(level), (C.c_float * 3)(*map(float, bb_min)), (C.c_float * 3)(*map(float, bb_max)),
+                               C.byref(osc.tris), _p(ndc), _p(biased), _p(axis))
+    return ndc, biased, axis
+
+
 def svo_fragment_samples(level, bb_min, bb_max, osc):
     """The sample behind every covered (triangle, voxel) of svo_fragments, before the shading's discard; dict of arrays."""
     fn = lib().vgo_svo_fragment_samples

@@ -342,3 +342,24 @@ def voxelizer_vertices(scene):
     out_p, out_n = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3, 3), np.float32)
     fn(_p(pos), _p(nrm), _p(idx), _p(prims), C.c_uint(prims.shape[0]), _p(nodes), _p(out_p), _p(out_n))
     return out_p, out_n
+
+
+def svo_vertex_stage(scene, bb_min, bb_max):
+    """voxelizer.vert then voxelizer.geom over every triangle of a synth.Scene in draw order:
+    (ndc[n, 3, 3] = gl_Position.xyz of the vertex stage, biased[n, 3, 3] = gs_out.position, axis[n] = gl_ViewportIndex,
+    normal[n, 3, 3] = gs_out.normal)."""
+    pos = np.ascontiguousarray(scene.positions, np.float32)
+    nrm = np.ascontiguousarray(scene.normals, np.float32)
+    idx = np.ascontiguousarray(scene.indices, np.uint32)
+    prims = np.ascontiguousarray(scene.primitives)
+    nodes = np.ascontiguousarray(scene.nodes)
+    bb = np.array(list(map(float, bb_min)) + list(map(float, bb_max)), np.float32)
+    fn = lib().ref_svo_vertices
+    fn.restype = C.c_uint
+    n = int(fn(_p(pos), _p(nrm), _p(idx), _p(prims), C.c_uint(prims.shape[0]), _p(nodes), _p(bb), C.c_void_p(0), C.c_void_p(0)))
+    ndc, vnrm = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+    fn(_p(pos), _p(nrm), _p(idx), _p(prims), C.c_uint(prims.shape[0]), _p(nodes), _p(bb), _p(ndc), _p(vnrm))
+    axis = np.zeros(n, np.int32)
+    biased, gnrm = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+    lib().ref_svo_geometry(C.c_int(n), _p(ndc), _p(vnrm), _p(axis), _p(biased), _p(gnrm))
+    return ndc, biased, axis, gnrm

@@ -119,6 +119,10 @@ uint32_t vgo_svo_fragments(uint32_t level, const float bb_min[3], const float bb
                            const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
                            const float* shadow_depth, uint32_t sw, uint32_t sh,
                            uint32_t mode_flags, uint32_t* frags);
+/* test aid: per triangle what voxelizer.vert / voxelizer.geom compute before rasterisation (normalised and biased vertex
+ * positions, dominant axis from the normalised positions) */
+void vgo_svo_vertex_stage(uint32_t level, const float bb_min[3], const float bb_max[3], const vgo_tris* tris,
+                          float* ndc, float* biased, int32_t* axis);
 /* test aid: the sample behind every covered (triangle, voxel) of vgo_svo_fragments (before the shading's discard), same
  * order: world position, biased [0,1] position, un-normalised normal, material, voxel. capacity == 0 counts only. */
 uint32_t vgo_svo_fragment_samples(uint32_t level, const float bb_min[3], const float bb_max[3], const vgo_tris* tris,

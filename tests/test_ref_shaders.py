@@ -481,6 +481,19 @@ def test_live_vertex_stage_world_transform(oracle, refshaders):
         assert pos.shape == osc.pos.shape and np.array_equal(pos, osc.pos) and np.array_equal(nrm, osc.nrm)
 
 
+def test_live_svo_vertex_and_geometry_stages(oracle, refshaders):
+    """voxelizer.vert (normalisation by the scene box) chained into voxelizer.geom (dominant axis from the normalised
+    positions, bias to [0,1], normal pass-through) against the oracle's svo_to_grid / cross_and_axis, bit for bit."""
+    from vk_voxel_cone_tracing_b200 import synth
+    for scene in (synth.cornell_box(), synth.atrium()):
+        osc = oracle.OracleScene(scene)
+        lo, hi = scene.world_bbox()
+        ndc0, biased0, axis0 = oracle.svo_vertex_stage(7, lo, hi, osc)
+        ndc, biased, axis, nrm = refshaders.svo_vertex_stage(scene, lo, hi)
+        assert np.array_equal(ndc, ndc0) and np.array_equal(biased, biased0) and np.array_equal(axis, axis0)
+        assert np.array_equal(nrm, osc.nrm) and len(np.unique(axis)) == 3
+
+
 def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
     """CPU twin of tests/test_gpu_ref_shaders.py: on exactly the inputs those tests feed libvgi, the oracle and the
     reference's shaders agree (bit for bit), so "libvgi == oracle" and "libvgi == reference shader" are one statement."""
