@@ -9,9 +9,12 @@ oracle/glsl_shim compiles the reference's GLSL for the CPU (oracle/_ref/libvgi_r
 Integer / byte results are compared bit for bit. Float images were bit-identical when generated (both sides evaluate the
 same binary32 expressions without contraction); the golden layer allows 2e-6 for a different libm.
 
-What this pins: opacity + radiance down-sampling (incl. the blend band), border wrapping (literal and full), region
-clearing, copy-alpha, the octree build (topology word of every node; colours where one fragment lands in a leaf), the
-clipmap and octree cone-tracing fragment shaders in their rendering modes, the specular filter + tonemap.
+What this pins: the vertex stages (world transform; SVO normalisation, bias and dominant axis), opacity + radiance
+down-sampling (incl. the blend band), border wrapping (literal and full), region clearing, copy-alpha, the opacity
+voxelizer's dominant axis and texel addressing, the injection shading per fragment, the SVO fragment shader (literal and
+canonical colour), the octree build (topology word of every node; colours where one fragment lands in a leaf), the
+clipmap and octree cone-tracing fragment shaders in their rendering modes, the specular filter + tonemap, the G-buffer
+fragment shader.
 What it cannot pin (fixed-function rasterisation): which voxels a triangle covers."""
 import ctypes as C
 import os
