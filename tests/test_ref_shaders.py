@@ -497,6 +497,42 @@ def test_live_svo_vertex_and_geometry_stages(oracle, refshaders):
         assert np.array_equal(nrm, osc.nrm) and len(np.unique(axis)) == 3
 
 
+def test_live_whole_build_with_reference_passes(oracle, refshaders):
+    """The pass sequences of VoxelizationPass::render / RadianceInjectionPass::render on the atrium with an off-diagonal
+    camera (negative, unequal region corners; six levels), every programmable post-raster pass run by the REFERENCE's shader:
+    oracle coverage + injection, then copyAlphaImage / opacity + radiance down-sampling / border wrap from the shader library.
+    Both atlases must equal the oracle's own full passes byte for byte; the traced images likewise."""
+    from tests.common import atrium_inputs
+    inp = atrium_inputs(resolution=32, shadow_size=256, width=96, height=54, levels=6)
+    cfg = inp["cfg"]
+    regs = oracle.regions(cfg, inp["cam_pos"])
+    osc = oracle.OracleScene(inp["scene"])
+    op, rad, _ = oracle.build_clipmap(cfg, regs, osc, inp["light"], inp["shadow"], inp["shadow_depth"], 0)
+    assert len({tuple(r.min_corner) for r in regs}) > 1 and min(regs[0].min_corner) < 0
+    op2, rad2 = oracle.new_atlas(cfg), oracle.new_atlas(cfg)
+    for l in range(cfg.level_count):
+        oracle.voxelize_level(cfg, regs, l, osc, op2)
+    for l in range(1, cfg.level_count):
+        refshaders.downsample(cfg, regs, l, op2, 0)
+    refshaders.wrap_border(cfg, op2, literal=False)
+    assert np.array_equal(op, op2)
+    for l in range(cfg.level_count):
+        oracle.inject_level(cfg, regs, l, osc, inp["light"], inp["shadow"], inp["shadow_depth"], rad2)
+    for l in range(cfg.level_count):
+        refshaders.copy_alpha(cfg, l, rad2, op2)
+    for l in range(1, cfg.level_count):
+        refshaders.downsample(cfg, regs, l, rad2, 1)
+    refshaders.wrap_border(cfg, rad2, literal=False)
+    assert np.array_equal(rad, rad2) and (rad[..., :3] > 0).sum() > 1000
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    cov = gb["depth"] < 1.0
+    prm = S.default_vct_params(regs[0], cfg.resolution, 8)
+    d0, s0, _ = oracle.cone_trace(cfg, inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+    d1, s1, _ = refshaders.cone_trace(cfg, inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad2)
+    assert np.array_equal(d0[cov], d1[cov]) and np.array_equal(s0[cov], s1[cov])
+
+
 def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
     """CPU twin of tests/test_gpu_ref_shaders.py: on exactly the inputs those tests feed libvgi, the oracle and the
     reference's shaders agree (bit for bit), so "libvgi == oracle" and "libvgi == reference shader" are one statement."""
