@@ -124,13 +124,21 @@ class _SvoTraceArgs(C.Structure):
 def _decode_gbuffer(gbuf):
     """What the texture unit does to the G-buffer formats (GBufferPass.cpp:177-194): UNORM8 -> c / 255 in binary32,
     binary16 widened exactly."""
+    cached = getattr(gbuf, "_decoded_for_refshaders", None)     # decode once per G-buffer, not once per traced row block
+    if cached is not None:
+        return cached
     to_f = lambda u8: (u8.astype(np.float32) / np.float32(255.0)).astype(np.float32)  # noqa: E731
     nrm = gbuf.normal.view(np.float16) if gbuf.normal.dtype != np.float16 else gbuf.normal
     emi = gbuf.emission.view(np.float16) if gbuf.emission.dtype != np.float16 else gbuf.emission
     h, w = gbuf.height, gbuf.width
-    return (np.ascontiguousarray(to_f(gbuf.diffuse.reshape(h, w, 4))), np.ascontiguousarray(nrm.reshape(h, w, 4).astype(np.float32)),
-            np.ascontiguousarray(to_f(gbuf.specular.reshape(h, w, 4))), np.ascontiguousarray(emi.reshape(h, w, 4).astype(np.float32)),
-            np.ascontiguousarray(gbuf.depth.reshape(h, w).astype(np.float32)))
+    out = (np.ascontiguousarray(to_f(gbuf.diffuse.reshape(h, w, 4))), np.ascontiguousarray(nrm.reshape(h, w, 4).astype(np.float32)),
+           np.ascontiguousarray(to_f(gbuf.specular.reshape(h, w, 4))), np.ascontiguousarray(emi.reshape(h, w, 4).astype(np.float32)),
+           np.ascontiguousarray(gbuf.depth.reshape(h, w).astype(np.float32)))
+    try:
+        gbuf._decoded_for_refshaders = out
+    except AttributeError:
+        pass
+    return out
 
 
 def _fill_common(a, keep, cam, gbuf, prm, light, shadow, shadow_depth, clip_level_count, rows):
