@@ -86,8 +86,6 @@ template <class V> struct swz {
     swz& operator OP(T s) { V t = (V)*this; t OP s; return *this = t; }
     GLSL_SWZ_ASSIGN(+=) GLSL_SWZ_ASSIGN(-=) GLSL_SWZ_ASSIGN(*=) GLSL_SWZ_ASSIGN(/=)
 #undef GLSL_SWZ_ASSIGN
-    // a swizzle of a swizzle result / member access on it goes through the value
-    T x_() const { return *p[0]; }
 };
 
 // ---- scalar built-ins (GLSL 8.1 - 8.3), binary32 ----
