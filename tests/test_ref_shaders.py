@@ -533,6 +533,44 @@ def test_live_whole_build_with_reference_passes(oracle, refshaders):
     assert np.array_equal(d0[cov], d1[cov]) and np.array_equal(s0[cov], s1[cov])
 
 
+@pytest.mark.parametrize("case", range(6))
+def test_live_cone_trace_random_cameras_and_parameters(oracle, refshaders, case):
+    """Seeded sweep: random camera pose inside either scene, random frame index (cadence), rendering mode, cone set, start
+    offset, step factor, occlusion decay, intensities - oracle and voxelConeTracing.frag bit for bit (NaNs in the same places)."""
+    from tests.common import atrium_inputs, cornell_inputs
+    from vk_voxel_cone_tracing_b200 import raster, synth
+    rng = np.random.default_rng(100 + case)
+    r = int(rng.choice([32, 64]))
+    if case % 2 == 0:
+        inp, (w, h) = cornell_inputs(resolution=r, shadow_size=256, width=40, height=40), (40, 40)
+        cam_pos = tuple(rng.uniform(-3, 3, 3).tolist())
+    else:
+        inp, (w, h) = atrium_inputs(resolution=r, shadow_size=256, width=48, height=27, levels=6), (48, 27)
+        cam_pos = (float(rng.uniform(-12, 12)), float(rng.uniform(0, 9)), float(rng.uniform(-7, 7)))
+    look = rng.normal(size=3)
+    look /= np.linalg.norm(look)
+    cam = synth.make_camera(cam_pos, tuple(look.tolist()), aspect=w / h)
+    gb = raster.gbuffer(inp["scene"], cam, w, h)
+    cfg = inp["cfg"]
+    regs = oracle.regions(cfg, cam_pos)
+    osc = oracle.OracleScene(inp["scene"])
+    _, rad, _ = oracle.build_clipmap(cfg, regs, osc, inp["light"], inp["shadow"], inp["shadow_depth"], int(rng.integers(0, 4)))
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    cov = gb["depth"] < 1.0
+    prm = S.default_vct_params(regs[0], cfg.resolution, int(rng.choice([8, 8, 7, 5, 6, 4])))
+    prm.enable_32_cones = int(rng.integers(0, 2))
+    prm.trace_start_offset = float(rng.choice([0.0, 0.5, 1.0, 2.0]))
+    prm.min_trace_step_factor = float(rng.choice([0.1, 0.2, 0.5, 1.0, 2.0]))
+    prm.occlusion_decay = float(rng.choice([0.0, 1.0, 2.0, 5.0]))
+    prm.indirect_diffuse_intensity = float(rng.choice([1.0, 8.0, 15.0]))
+    prm.ambient_occlusion_factor = float(rng.choice([0.25, 0.5, 1.0]))
+    args = (cfg, cam, hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+    d0, s0, _ = oracle.cone_trace(*args)
+    d1, s1, disc = refshaders.cone_trace(*args)
+    assert np.array_equal(disc.astype(bool), ~cov)
+    assert np.array_equal(d0[cov], d1[cov], equal_nan=True) and np.array_equal(s0[cov], s1[cov], equal_nan=True)
+
+
 def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
     """CPU twin of tests/test_gpu_ref_shaders.py: on exactly the inputs those tests feed libvgi, the oracle and the
     reference's shaders agree (bit for bit), so "libvgi == oracle" and "libvgi == reference shader" are one statement."""
