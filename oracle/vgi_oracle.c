@@ -799,7 +799,14 @@ typedef struct trace_ctx {
     const uint8_t* atlas;
     size_t W, H, D;
     uint64_t taps;
-} trace_ctx;
+    /* work statistics (vgo_debug_cell_stats; off unless enabled): which = 0 diffuse / 1 specular cones */
+    int stats_on, which, slot;
+    int64_t prev_key[2];
+    uint64_t st[2][5];      /* steps, level samples, samples whose (level, base cell) differs from the previous step's, */
+} trace_ctx;                /* samples that are exactly zero, steps whose whole sample is zero */
+
+static int g_cell_stats_on = 0;
+static uint64_t g_cell_stats[2][5];
 
 /* sampler3D, LINEAR, REPEAT (Voxelizer.cpp:183). Software trilinear: unnormalised coordinate
  * c = s*size - 0.5, i0 = floor(c), w = c - i0, texels wrapped modulo size, RGBA8 decoded c/255,
@@ -853,6 +860,18 @@ static void sample_clipmap(trace_ctx* t, const float* worldPos, int level, const
         for (int c = 0; c < 4; ++c) acc[c] = (f == 0) ? tx[c] * weight[0] : acc[c] + tx[c] * weight[f];
     }
     memcpy(o, acc, sizeof acc);
+    if (t->stats_on) {      /* base cell of the tri-linear footprint at this level (face-independent) */
+        int64_t key = level;
+        for (int k = 0; k < 3; ++k) {
+            const float c = f_fract(worldPos[k] / extent) * p->volume_dimension - 0.5f;
+            key = key * 4096 + ((int64_t)floorf(c) + 1);
+        }
+        uint64_t* st = t->st[t->which];
+        st[1]++;
+        if (key != t->prev_key[t->slot]) st[2]++;
+        t->prev_key[t->slot] = key;
+        if (acc[0] == 0.0f && acc[1] == 0.0f && acc[2] == 0.0f && acc[3] == 0.0f) st[3]++;
+    }
 }
 
 /* ref: voxelConeTracing.frag:329-339 */
@@ -863,10 +882,16 @@ static void sample_clipmap_linear(trace_ctx* t, const float* worldPos, float cur
     const float fo[3] = { (float)faceIndex[0] / (float)VGI_FACES, (float)faceIndex[1] / (float)VGI_FACES,
                           (float)faceIndex[2] / (float)VGI_FACES };
     float lo[4], up[4];
+    t->slot = 0;
     sample_clipmap(t, worldPos, lower, fo, weight, lo);
+    t->slot = 1;
     sample_clipmap(t, worldPos, upper, fo, weight, up);
     const float fr = f_fract(curLevel);
     for (int c = 0; c < 4; ++c) o[c] = f_mix(lo[c], up[c], fr);
+    if (t->stats_on) {
+        t->st[t->which][0]++;
+        if (o[0] == 0.0f && o[1] == 0.0f && o[2] == 0.0f && o[3] == 0.0f) t->st[t->which][4]++;
+    }
 }
 
 /* ref: voxelConeTracing.frag:341-392 */
@@ -988,7 +1013,11 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
     uint64_t spec_taps = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_taps, spec_taps)
     for (int64_t py = (int64_t)y0; py < (int64_t)y1; ++py) {
-        trace_ctx tc = { cfg, prm, radiance, atlas_W(cfg), atlas_H(cfg), atlas_D(cfg), 0 };
+        trace_ctx tc;
+        memset(&tc, 0, sizeof tc);
+        tc.cfg = cfg; tc.prm = prm; tc.atlas = radiance;
+        tc.W = atlas_W(cfg); tc.H = atlas_H(cfg); tc.D = atlas_D(cfg);
+        tc.stats_on = g_cell_stats_on;
         for (uint32_t px = 0; px < g->width; ++px) {
             const size_t pi = (size_t)py * g->width + px;
             const float depth = g->depth_f32[pi];
@@ -1034,6 +1063,7 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
                 const float cosTheta = dot3(normal, dirs[i]);
                 if (cosTheta < 0.0f) continue;
                 float c[4];
+                tc.which = 0; tc.prev_key[0] = tc.prev_key[1] = -1;
                 trace_cone(&tc, startPos, dirs[i], aperture, MAX_TRACE_DISTANCE, minLevel,
                            f_max(MIN_TRACE_STEP_FACTOR, prm->min_trace_step_factor), c);
                 for (int k = 0; k < 4; ++k) indirect[k] += c[k] * cosTheta;
@@ -1051,6 +1081,7 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
                 for (int k = 0; k < 3; ++k) sdir[k] = I[k] - (2.0f * dn) * normal[k];
                 float c[4];
                 const uint64_t taps_before = tc.taps;
+                tc.which = 1; tc.prev_key[0] = tc.prev_key[1] = -1;
                 trace_cone(&tc, startPos, sdir, f_max(perceptualRoughness, MIN_SPECULAR_APERTURE),
                            MAX_TRACE_DISTANCE, minLevel, prm->voxel_size /* Q12 */, c);
                 spec_taps += tc.taps - taps_before;
@@ -1110,9 +1141,24 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
             memcpy(out_specular + pi * 4, scn, sizeof scn);
         }
         total_taps += tc.taps;
+        if (tc.stats_on)
+            for (int w = 0; w < 2; ++w)
+                for (int k = 0; k < 5; ++k) __atomic_fetch_add(&g_cell_stats[w][k], tc.st[w][k], __ATOMIC_RELAXED);
     }
     if (taps) *taps = total_taps;
     g_last_specular_taps = spec_taps;
+}
+
+/* Work statistics of the cone marches (development aid for the kernels' design, tools/trace_model.py): enable != 0 switches
+ * the counting on for later vgo_cone_trace calls; out (may be NULL) receives and resets the counters [diffuse|specular][steps,
+ * level samples, samples in a new (level, base cell) compared with the previous step, all-zero samples, all-zero steps]. */
+void vgo_debug_cell_stats(int enable, uint64_t* out)
+{
+    g_cell_stats_on = enable;
+    if (out) {
+        memcpy(out, g_cell_stats, sizeof g_cell_stats);
+        memset(g_cell_stats, 0, sizeof g_cell_stats);
+    }
 }
 
 /* taps of the specular cones alone in the last vgo_cone_trace call (per-kernel roofline accounting in bench.py) */

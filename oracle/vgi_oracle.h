@@ -103,6 +103,11 @@ void vgo_cone_trace(const vgi_config* cfg, const vgi_camera* cam, const vgi_gbuf
                     float* out_diffuse, float* out_specular, uint32_t y0, uint32_t y1,
                     uint64_t* taps);
 
+/* development aid: work statistics of the cone marches. enable != 0 turns counting on for later vgo_cone_trace calls; out
+ * (10 values, may be NULL) receives and resets [diffuse | specular][steps, level samples, samples in a new (level, base cell)
+ * compared with the previous step, all-zero samples, all-zero steps] */
+void vgo_debug_cell_stats(int enable, uint64_t* out);
+
 /* taps of the specular cones alone in the last vgo_cone_trace call */
 uint64_t vgo_last_specular_taps(void);
 
