@@ -233,9 +233,12 @@ def voxelization_desc(region):
     return mn, mx, float(f(region.extent[0]) * vs), float(vs)
 
 
-def inject_fragments(cfg, regs, level, position, normal, material_index, materials, light, shadow, shadow_depth):
+def inject_fragments(cfg, regs, level, position, normal, material_index, materials, light, shadow, shadow_depth,
+                     accumulate=False):
     """msaaInjectRadiance.frag, one invocation per given fragment on a cleared r32ui image.
-    Returns (count[n], coords[n, 6, 3] atlas texel, values[n, 6] packed RGBA8 word)."""
+    Returns (count[n], coords[n, 6, 3] atlas texel, values[n, 6] packed RGBA8 word).
+    accumulate=True: all fragments in the given order on ONE image (the reference's CAS running average for that order, Q10);
+    returns the radiance atlas (D, H, W, 4) uint8 with the running count in the alpha byte."""
     n = position.shape[0]
     a = _InjectArgs()
     mn, mx, ext, vs = voxelization_desc(regs[level])
@@ -252,6 +255,10 @@ def inject_fragments(cfg, regs, level, position, normal, material_index, materia
     a.sh, a.sw = sd.shape
     a.light_intensity, a.z_near, a.z_far = light.intensity, shadow.z_near, shadow.z_far
     a.D, a.H, a.W = S.atlas_shape(cfg)[:3]
+    if accumulate:
+        img = np.zeros(S.atlas_shape(cfg)[:3], dtype=np.uint32)
+        lib().ref_inject_accumulate(C.byref(a), _p(img))
+        return img.view(np.uint8).reshape(S.atlas_shape(cfg))
     lib().ref_inject_fragments(C.byref(a))
     return keep["out_count"], keep["out_coords"], keep["out_values"]
 

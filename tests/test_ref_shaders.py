@@ -628,6 +628,39 @@ def test_live_inputs_of_the_gpu_tests(oracle, refshaders):
         assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
 
 
+def test_live_q10_cas_running_average_quantified(oracle, refshaders):
+    """SURVEY Q10, measured with the reference's own shader: msaaInjectRadiance.frag run over all fragments of a level on ONE
+    image (its CAS running average, sequential order) against the exact mean of the very same per-fragment contributions.
+    Facts: a texel with one contribution holds it unchanged; the count lives in the alpha byte and wraps modulo 256; with
+    several contributions the per-insert truncation (and, past 255, the wrap) moves the result away from the exact mean -
+    which is why the canonical mode (oracle and kernels) accumulates exactly and truncates once."""
+    from tests.common import atrium_inputs
+    inp = atrium_inputs(resolution=64, shadow_size=1024, width=16, height=9, levels=6)
+    cfg = inp["cfg"]
+    regs = oracle.regions(cfg, inp["cam_pos"])
+    osc = oracle.OracleScene(inp["scene"])
+    level = 2
+    fr = oracle.inject_fragments(cfg, regs, level, osc, inp["light"], inp["shadow"], inp["shadow_depth"])
+    args = (cfg, regs, level, fr["pos"], fr["nrm"], fr["mat"], osc.materials, inp["light"], inp["shadow"], inp["shadow_depth"])
+    cnt, coords, vals = refshaders.inject_fragments(*args)
+    cas = refshaders.inject_fragments(*args, accumulate=True)
+    d_, h_, w_ = cas.shape[:3]
+    k = np.arange(6)[None, :] < cnt[:, None]
+    c, v = coords[k], vals[k]
+    lin = (c[:, 2].astype(np.int64) * h_ + c[:, 1]) * w_ + c[:, 0]
+    order = np.argsort(lin, kind="stable")
+    lin, v = lin[order], v[order]
+    uniq, start, n = np.unique(lin, return_index=True, return_counts=True)
+    exact = np.stack([np.floor(np.add.reduceat(((v >> (8 * ch)) & 0xff).astype(np.float64), start) / n) for ch in range(3)], axis=1)
+    got = cas.reshape(-1, 4)[uniq]
+    assert np.array_equal(got[:, 3], (n % 256).astype(np.uint8))                 # the count byte wraps
+    single = n == 1
+    assert single.sum() >= 1 and np.array_equal(got[single, :3].astype(np.float64), exact[single])
+    lit = exact.max(axis=1) > 0
+    dev = np.abs(got[:, :3].astype(np.float64) - exact)[lit]
+    assert n.max() > 255 and 0.5 < dev.mean() < 20.0 and dev.max() >= 8            # round 1: mean 3.4 LSB, max 38 on this input
+
+
 def test_live_q6_radiance_downsample_does_not_compile_as_shipped(refshaders):
     """SURVEY Q6: `lerpFactor` is declared inside the `if` and used after it. The repaired text (build_ref.py R10) builds;
     the shipped text must fail on exactly that identifier."""
