@@ -245,3 +245,50 @@ def test_config5_orbit_views_sharded_by_view():
     alone.build_clipmap(0)
     d, s = alone.cone_trace(cams[v], alone.render_gbuffer(cams[v], W, H), prm)
     assert torch.equal(d, batch[v][0]) and torch.equal(s, batch[v][1])
+
+
+def test_headline_frame_matches_the_oracle(full):
+    """The configuration every quoted number is measured on (bench.py: 262 144 triangles, 6 x 256^3, frame 0, 1920x1080,
+    mode 8), compared directly: both atlases byte for byte with the oracle's build, and 40 image rows spread over the
+    frame with the oracle's trace (and with the reference's voxelConeTracing.frag where oracle/_ref travelled) at the
+    bars of BASELINE.json's north_star: max abs <= 1e-3, PSNR >= 50 dB."""
+    inp, make, store, torch = full
+    from oracle import pyoracle as O
+    O.build()
+    cfg = inp["cfg"]
+    gi = make()
+    gi.build_clipmap(0)
+    regs = O.regions(cfg, inp["cam_pos"])
+    osc = O.OracleScene(inp["scene"])
+    op, rad, pairs = O.build_clipmap(cfg, regs, osc, inp["light"], inp["shadow"], inp["shadow_depth"], 0)
+    assert pairs == gi.stats().clip_pairs
+    got = gi.export_atlas(0).cpu().numpy()
+    assert np.array_equal(got, op), f"opacity atlas: {int(np.count_nonzero(got != op))} bytes differ"
+    got = gi.export_atlas(1).cpu().numpy()
+    assert np.array_equal(got, rad), f"radiance atlas: {int(np.count_nonzero(got != rad))} bytes differ"
+    del got, op
+
+    gbh = inp["gbuffer"]
+    hg = O.HostGBuffer(gbh["diffuse"], gbh["normal"], gbh["specular"], gbh["emission"], gbh["depth"])
+    prm = gi.default_vct_params(8)
+    d, s = gi.cone_trace(inp["cam"], gi.upload_gbuffer(gbh), prm)
+    d, s = d.cpu().numpy(), s.cpu().numpy()
+    try:
+        from oracle import refshaders as Rf
+        shaders = Rf if (Rf.available() and Rf.lib() is not None) else None
+    except Exception:
+        shaders = None
+    rows = [int(y) for y in np.linspace(0, 1079, 40)]
+    refs_d, refs_s, gots_d, gots_s = [], [], [], []
+    args = (cfg, inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], rad)
+    for y in rows:
+        rd, rs, _ = O.cone_trace(*args, rows=(y, y + 1))
+        cov = gbh["depth"][y] < 1.0
+        if shaders is not None:     # the checker against the reference's own shader on the same row
+            sd, ss, _ = shaders.cone_trace(*args, rows=(y, y + 1))
+            assert np.array_equal(sd[y][cov], rd[y][cov]) and np.array_equal(ss[y][cov], rs[y][cov])
+        refs_d.append(rd[y][cov]); refs_s.append(rs[y][cov]); gots_d.append(d[y][cov]); gots_s.append(s[y][cov])
+    rd, rs, gd, gs = (np.concatenate(v) for v in (refs_d, refs_s, gots_d, gots_s))
+    assert rd.shape[0] > 30000
+    assert float(np.abs(gd - rd).max()) <= 1e-3 and float(np.abs(gs - rs).max()) <= 1e-3
+    assert common.psnr(gd, rd) >= 50.0 and common.psnr(gs, rs) >= 50.0

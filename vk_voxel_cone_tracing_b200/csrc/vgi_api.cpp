@@ -16,6 +16,8 @@ static int fail(vgi_ctx* c, int code, const std::string& msg)
     if (c) c->err = msg;
     return code;
 }
+// for the other translation units: their messages must reach vgi_last_error(NULL) too
+void vgi_set_thread_error(const std::string& msg) { g_err = msg; }
 #define CK(ctx, call)                                                                                         \
     do {                                                                                                      \
         cudaError_t e_ = (call);                                                                              \
@@ -66,7 +68,12 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
     if (L < 1 || L > VGI_MAX_LEVELS) return fail(nullptr, VGI_E_INVALID, "vgi_create: level_count out of range");
     if (!(cfg->extent_level0 > 0.0f)) return fail(nullptr, VGI_E_INVALID, "vgi_create: extent_level0 must be positive");
     for (uint32_t i = 0; i < L; ++i)
+    {
         if (cfg->clip_min_change[i] == 0) return fail(nullptr, VGI_E_INVALID, "vgi_create: clip_min_change must be >= 1");
+        // levels with a parent are down-sampled in 2x2x2 blocks addressed by min_corner >> 1 (VoxelizationPass.h:57: 2,2,2,2,2,1)
+        if (i + 1 < L && (cfg->clip_min_change[i] & 1u))
+            return fail(nullptr, VGI_E_INVALID, "vgi_create: clip_min_change must be even on every level that has a parent");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, VGI_E_CUDA, "vgi_create: no CUDA device (libvgi has no CPU fallback)");
@@ -125,6 +132,7 @@ int vgi_create(const vgi_config* cfg, vgi_ctx** out)
 int vgi_destroy(vgi_ctx* c)
 {
     if (!c) return VGI_OK;
+    cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_scene(c);
     if (c->store_owned) cudaFree(c->store);
@@ -142,9 +150,28 @@ int vgi_destroy(vgi_ctx* c)
     return VGI_OK;
 }
 
+// The bounded device lists report overflow through Counters::overflow (h_counters is refreshed by every build). One message
+// per bit, so that a peer-barrier timeout is not reported as a pair-list problem. Call only after the build's stream was synchronised.
+static int report_overflow(vgi_ctx* c, const char* who)
+{
+    const uint32_t m = c->h_counters->overflow;
+    if (!m) return VGI_OK;
+    char buf[320];
+    int n = snprintf(buf, sizeof buf, "%s: device list overflow (mask 0x%x):", who, m);
+    auto add = [&](const char* fmt, unsigned a, unsigned b) { if (n < (int)sizeof buf) n += snprintf(buf + n, sizeof buf - n, fmt, a, b); };
+    if (m & 1u) add(" (triangle, voxel) pair list full, %u capacity %u - raise vgi_config.max_fragments;", c->h_counters->pairs, c->max_pairs);
+    if (m & 2u) add(" large-triangle queue full (capacity %u)%.0u;", c->max_large, 0u);
+    if (m & 4u) add(" accumulator / visit / exchange list full, %u occupied voxels, capacity %u - raise vgi_config.max_fragments;", c->h_counters->occ_total, c->max_occ);
+    if (m & 8u) add(" octree fragment list full, %u capacity %u;", c->h_counters->svo_frags, c->svo_frag_capacity);
+    if (m & 16u) add(" octree node pool full, %u capacity %u;", c->h_counters->svo_counter, c->svo_node_capacity);
+    if (m & 32u) add(" peer build: a barrier timed out waiting for another GPU (epoch %u)%.0u;", c->peer_epoch, 0u);
+    return fail(c, VGI_E_OVERFLOW, buf);
+}
+
 int vgi_get_stats(vgi_ctx* c, vgi_stats* out)
 {
     if (!c || !out) return fail(c, VGI_E_INVALID, "vgi_get_stats: null argument");
+    CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->last_stream));
     CK(c, cudaMemcpy(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
     out->triangles = c->ntri;
@@ -157,13 +184,7 @@ int vgi_get_stats(vgi_ctx* c, vgi_stats* out)
     out->svo_fragments = c->svo_nfrag;
     out->svo_nodes = c->svo_nnodes;
     out->kernel_launches = c->launches;
-    if (c->h_counters->overflow) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "device list overflow (mask 0x%x): pairs=%u/%u occupied=%u/%u — raise vgi_config.max_fragments",
-                 c->h_counters->overflow, c->h_counters->pairs, c->max_pairs, c->h_counters->occ_total, c->max_occ);
-        return fail(c, VGI_E_OVERFLOW, buf);
-    }
-    return VGI_OK;
+    return report_overflow(c, "vgi_get_stats");
 }
 
 // ---- per-kernel timing ---------------------------------------------------------------------------
@@ -274,6 +295,7 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
         ntri += pr.index_count / 3;
     }
     if (ntri > 0x7fffffffull) return fail(c, VGI_E_INVALID, "vgi_set_scene: too many triangles");
+    CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->last_stream));
     free_scene(c);
     std::vector<float4> pos(ntri * 3), nrm(ntri * 3);
@@ -318,7 +340,9 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     const uint32_t R = c->cfg.resolution, L = c->cfg.level_count;
     uint64_t maxPairs = c->cfg.max_fragments;
     if (!maxPairs) {
-        maxPairs = ntri * 48;
+        // pairs scale with the surface area in voxels, not only with the triangle count: a few wall-sized triangles
+        // cover ~R^2 voxels each on every level they span, so the default also carries an R^2 L term
+        maxPairs = ntri * 48 + 24ull * R * R * L;
         if (maxPairs < (1ull << 22)) maxPairs = 1ull << 22;
         if (maxPairs > (1ull << 27)) maxPairs = 1ull << 27;
     }
@@ -358,6 +382,7 @@ int vgi_set_light(vgi_ctx* c, const vgi_dir_light* light, const vgi_dir_light_sh
     lp.sw = (int)w;
     lp.sh = (int)h;
     if (is_host) {
+        CK(c, cudaSetDevice(c->device));
         CK(c, cudaStreamSynchronize(c->last_stream));
         cudaFree(c->shadow_owned);
         c->shadow_owned = nullptr;
@@ -401,10 +426,17 @@ int vgi_set_regions(vgi_ctx* c, const vgi_clip_region* regions, uint32_t count)
 {
     if (!c || !regions || count != c->cfg.level_count) return fail(c, VGI_E_INVALID, "vgi_set_regions: bad argument");
     for (uint32_t i = 0; i < count; ++i) {
-        if (regions[i].extent[0] != c->cfg.resolution || !(regions[i].voxel_size > 0.0f))
-            return fail(c, VGI_E_INVALID, "vgi_set_regions: extent must equal the resolution");
-        c->regions[i] = regions[i];
+        for (int k = 0; k < 3; ++k) {
+            if (regions[i].extent[k] != c->cfg.resolution)
+                return fail(c, VGI_E_INVALID, "vgi_set_regions: every extent must equal the resolution");
+            // a level that has a parent is down-sampled in 2x2x2 blocks addressed by min_corner >> 1: an odd corner would
+            // shift the child blocks by one toroidal plane (the reference snaps these levels in steps of 2, VoxelizationPass.h:57)
+            if (i + 1 < count && (regions[i].min_corner[k] & 1))
+                return fail(c, VGI_E_INVALID, "vgi_set_regions: min_corner must be even on every level that has a parent");
+        }
+        if (!(regions[i].voxel_size > 0.0f)) return fail(c, VGI_E_INVALID, "vgi_set_regions: voxel_size must be positive");
     }
+    for (uint32_t i = 0; i < count; ++i) c->regions[i] = regions[i];
     c->regions_set = true;
     return VGI_OK;
 }
@@ -462,7 +494,12 @@ int vgi_voxelize_opacity(vgi_ctx* c, void* stream)
     cudaStream_t s = (cudaStream_t)stream;
     c->launches += vgi_launch_voxelize(c, bp, s);
     c->last_stream = s;
-    c->svo_counters_fresh = false;
+    if (c->svo_counters_fresh && c->svo_built) {    // keep the octree's node count before its counters are reused
+        cudaStreamSynchronize(c->last_stream);
+        c->svo_nnodes = c->h_counters->svo_counter;
+    }
+    c->svo_counters_fresh = false;  // the counters block and the pair buffer are shared with the octree path:
+    c->svo_voxelized = false;       // its fragment list is gone (vgi_svo_build then fails with VGI_E_STATE instead of building an empty tree)
     c->voxelized = true;
     return check_launch(c, "vgi_voxelize_opacity");
 }
@@ -520,6 +557,7 @@ int vgi_bind_voxel_store(vgi_ctx* c, void* dev_ptr, size_t bytes)
     if (!c || !dev_ptr) return fail(c, VGI_E_INVALID, "vgi_bind_voxel_store: null argument");
     if (bytes < c->store_bytes) return fail(c, VGI_E_INVALID, "vgi_bind_voxel_store: buffer too small");
     if (((uintptr_t)dev_ptr) & 31u) return fail(c, VGI_E_INVALID, "vgi_bind_voxel_store: buffer must be 32-byte aligned");
+    CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->last_stream));
     if (c->store_owned) cudaFree(c->store);
     c->store = (VoxelRecord*)dev_ptr;
@@ -558,7 +596,12 @@ int vgi_slab_build_begin(vgi_ctx* c, uint32_t frame_index, void* stream)
     BuildParams bp;
     build_params_from_ctx(c, frame_index, &bp);
     cudaStream_t s = (cudaStream_t)stream;
-    c->svo_counters_fresh = false;
+    if (c->svo_counters_fresh && c->svo_built) {    // keep the octree's node count before its counters are reused
+        cudaStreamSynchronize(c->last_stream);
+        c->svo_nnodes = c->h_counters->svo_counter;
+    }
+    c->svo_counters_fresh = false;  // the counters block and the pair buffer are shared with the octree path:
+    c->svo_voxelized = false;       // its fragment list is gone (vgi_svo_build then fails with VGI_E_STATE instead of building an empty tree)
     c->launches += vgi_launch_slab_begin(c, bp, s);
     c->last_stream = s;
     c->slab_phase = 1;
@@ -593,9 +636,11 @@ int vgi_get_slab_pack(vgi_ctx* c, void** ids, void** recs, uint32_t* count)
     if (c->slab_phase != 2) return fail(c, VGI_E_STATE, "vgi_get_slab_pack: call vgi_slab_finalize first");
     uint32_t n = 0;
     CK(c, cudaMemcpyAsync(&n, c->slab_count, sizeof n, cudaMemcpyDeviceToHost, c->last_stream));
+    CK(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->last_stream)); // this build's, not a stale copy
     CK(c, cudaStreamSynchronize(c->last_stream));
-    if (n > c->slab_cap || (c->h_counters->overflow & 4u))
+    if (n > c->slab_cap)
         return fail(c, VGI_E_OVERFLOW, "vgi_get_slab_pack: exchange buffer overflow — raise vgi_config.max_fragments");
+    { const int ro = report_overflow(c, "vgi_get_slab_pack"); if (ro != VGI_OK) return ro; }
     if (ids) *ids = c->slab_ids;
     if (recs) *recs = c->slab_recs;
     if (count) *count = n;
@@ -939,7 +984,12 @@ int vgi_peer_build_clipmap(vgi_ctx* c, uint32_t frame_index, void* stream)
     BuildParams bp;
     build_params_from_ctx(c, frame_index, &bp);
     cudaStream_t s = (cudaStream_t)stream;
-    c->svo_counters_fresh = false;
+    if (c->svo_counters_fresh && c->svo_built) {    // keep the octree's node count before its counters are reused
+        cudaStreamSynchronize(c->last_stream);
+        c->svo_nnodes = c->h_counters->svo_counter;
+    }
+    c->svo_counters_fresh = false;  // the counters block and the pair buffer are shared with the octree path:
+    c->svo_voxelized = false;       // its fragment list is gone (vgi_svo_build then fails with VGI_E_STATE instead of building an empty tree)
     c->launches += vgi_launch_peer_build(c, bp, c->peers, &c->peer_epoch, s);
     c->last_stream = s;
     c->voxelized = false;
@@ -1123,7 +1173,8 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     // join: the caller's stream is complete only when the side copies are
     CK(c, cudaStreamWaitEvent(s, c->ev_copy_done, 0));
     CK(c, cudaStreamSynchronize(s));
-    return VGI_OK;
+    // the build's counters came home with it: a dropped pair or record means the image is wrong, say so
+    return report_overflow(c, "vgi_frame_host");
 }
 
 // ---- Vulkan interop (VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd) --------------------

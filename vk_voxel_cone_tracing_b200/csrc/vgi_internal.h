@@ -255,3 +255,4 @@ int vgi_launch_specular_filter(vgi_ctx* c, const void* diffuse, const void* spec
                                const vgi_filter_params* prm, void* out, cudaStream_t s);
 
 void build_params_from_ctx(const vgi_ctx* c, uint32_t frame_index, BuildParams* bp);
+void vgi_set_thread_error(const std::string& msg);   // sets the string vgi_last_error(NULL) returns (vgi_api.cpp)

@@ -447,11 +447,10 @@ __global__ void __launch_bounds__(256) k_svo_emit(SvoLayout lay, const uint32_t*
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static thread_local std::string g_svo_err;
 static int svo_fail(vgi_ctx* c, int code, const std::string& msg)
 {
     if (c) c->err = msg;
-    g_svo_err = msg;
+    vgi_set_thread_error(msg);  // vgi_last_error(NULL) reads the string vgi_api.cpp owns
     return code;
 }
 #define SCK(call)                                                                                             \
@@ -634,9 +633,11 @@ int vgi_svo_get_nodes(vgi_ctx* c, void** dev_ptr, uint32_t* count)
     if (!c) return svo_fail(c, VGI_E_INVALID, "vgi_svo_get_nodes: null ctx");
     if (!c->svo_built) return svo_fail(c, VGI_E_STATE, "vgi_svo_get_nodes: call vgi_svo_build first");
     SCK(cudaStreamSynchronize(c->last_stream));
-    if (c->h_counters->overflow & 16u)
-        return svo_fail(c, VGI_E_OVERFLOW, "vgi_svo_get_nodes: node pool overflow — raise vgi_config.svo_max_nodes");
-    c->svo_nnodes = c->h_counters->svo_counter;
+    if (c->svo_counters_fresh) {    // otherwise a clipmap build has reused the counters since: the count cached by vgi_svo_build stands
+        if (c->h_counters->overflow & 16u)
+            return svo_fail(c, VGI_E_OVERFLOW, "vgi_svo_get_nodes: node pool overflow — raise vgi_config.svo_max_nodes");
+        c->svo_nnodes = c->h_counters->svo_counter;
+    }
     if (dev_ptr) *dev_ptr = c->svo_nodes;
     if (count) *count = c->svo_nnodes;
     return VGI_OK;

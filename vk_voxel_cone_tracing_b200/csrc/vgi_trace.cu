@@ -485,6 +485,227 @@ DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have
     out[3] = 1.0f - cs.occlusion;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// v2 march: no per-lane emptiness probes on the cooperative path. Per step every lane only computes where its
+// one or two level samples lie (cell key + weights); a vote checks that the lanes' cells form at most two groups
+// per level sample (first / last live lane: a warp straddles one cell boundary or one boundary of the cone-major
+// work list), and ONE fetch pass serves both samples: lane j = 8 * group + corner tests the cell's brick bit and
+// footprint byte, fetches its corner record, blends the three face texels with its group's cone weights and parks
+// the float4 in shared memory (double-buffered per step). The ballot of that pass is the emptiness test of the
+// whole step for the whole warp: all-zero steps cost no gather and no accumulation, and every lane then sums only
+// the non-zero corners of its cell. Steps whose lanes are more scattered take the per-lane path of v1.
+// ---------------------------------------------------------------------------------------------------
+#ifndef VGI_TRACE_V2
+#define VGI_TRACE_V2 1
+#endif
+
+// per-cone constants of the fetch lanes, two float4 per cone in shared memory:
+// [0] = word offsets of the three face texels inside a record (as bit patterns) , [1] = kx, ky, kz
+DEVFN void cone_face_table(const float* dir, float4* dst)
+{
+    const ConeFaces f = cone_faces(dir);
+    dst[0] = make_float4(__uint_as_float(f.negX ? 1u : 0u), __uint_as_float(f.negY ? 3u : 2u), __uint_as_float(f.negZ ? 5u : 4u), 0.0f);
+    dst[1] = make_float4(f.kx, f.ky, f.kz, 0.0f);
+}
+
+// cell index + weights of a level sample (probe_level without the two mask loads)
+DEVFN uint32_t level_cell(const TraceParams& tp, const float* posV, int level, float* w)
+{
+    const int Rm = tp.R - 1, logR = tp.logR;
+    const float sc = tp.level_scale[level];
+    const float MAGIC = 12582912.0f;
+    uint32_t i0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float f = fmaf(posV[k], sc, MAGIC - 1.0f);
+        i0[k] = __float_as_uint(f) & (uint32_t)Rm;
+        const float r = f - MAGIC;
+        w[k] = fmaf(posV[k], sc, -r) - 0.5f;
+    }
+    STAT(1, 1);
+    return ((((((uint32_t)level << logR) + i0[2]) << logR) + i0[1]) << logR) + i0[0];
+}
+
+// fetch lane: corner `corner` of the cell `vox` for cone `cone`; false when that record is known to be zero
+DEVFN bool coop_fetch(const TraceParams& tp, uint32_t vox, unsigned corner, const float4* s_face, int cone, float4& out)
+{
+    const int R = tp.R, Rm = R - 1, logR = tp.logR;
+    const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
+    const uint32_t level = vox >> (3 * logR);
+    const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
+    const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
+    const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
+    const uint32_t m = __ldg(tp.footprint + vox);   // meaningful only where the brick bit is set
+    const bool brick = (bbyte >> ((ix >> 2) & 7u)) & 1u;
+    if (!(brick && ((m >> corner) & 1u))) return false;
+    int off = 0;
+    if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
+    if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
+    if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+    const float4 fo = s_face[2 * cone], fk = s_face[2 * cone + 1];
+    const uint32_t tx = __ldg(rec + __float_as_uint(fo.x));
+    const uint32_t ty = __ldg(rec + __float_as_uint(fo.y));
+    const uint32_t tz = __ldg(rec + __float_as_uint(fo.z));
+    STAT(4, 1);
+    const float2 kx2 = make_float2(fk.x, fk.x), ky2 = make_float2(fk.y, fk.y), kz2 = make_float2(fk.z, fk.z);
+    float2 lo = __fmul2_rn(kx2, unpack2(tx, 0x7540u, 0x7541u)), hi = __fmul2_rn(kx2, unpack2(tx, 0x7542u, 0x7543u));
+    lo = __ffma2_rn(ky2, unpack2(ty, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(ky2, unpack2(ty, 0x7542u, 0x7543u), hi);
+    lo = __ffma2_rn(kz2, unpack2(tz, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(kz2, unpack2(tz, 0x7542u, 0x7543u), hi);
+    out = make_float4(lo.x, lo.y, hi.x, hi.y);
+    return true;
+}
+
+// a lane's weighted sum over the parked non-zero corners (bits of m) of its cell
+DEVFN void coop_gather_w(const float* w, uint32_t m, const float4* s_corner, float* out)
+{
+    const float wx0 = 1.0f - w[0], wy0 = 1.0f - w[1], wz0 = 1.0f - w[2];
+    const float wxy[4] = { wx0 * wy0, w[0] * wy0, wx0 * w[1], w[0] * w[1] };
+    float2 lo = make_float2(0.f, 0.f), hi = lo;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (!((m >> c) & 1u)) continue;
+        const float wc = wxy[c & 3] * ((c & 4) ? w[2] : wz0);
+        const float4 v = s_corner[c];
+        const float2 w2 = make_float2(wc, wc);
+        lo = __ffma2_rn(w2, make_float2(v.x, v.y), lo);
+        hi = __ffma2_rn(w2, make_float2(v.z, v.w), hi);
+    }
+    out[0] = lo.x; out[1] = lo.y; out[2] = hi.x; out[3] = hi.y;
+}
+
+// per-lane filter of a level sample from its cell index and weights (the v1 path, for scattered steps)
+DEVFN bool lane_filter(const TraceParams& tp, uint32_t vox, const float* w, const ConeFaces& cf, float* out)
+{
+    const int Rm = tp.R - 1, logR = tp.logR;
+    const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
+    const uint32_t level = vox >> (3 * logR);
+    const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
+    const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
+    const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
+    const uint32_t m = __ldg(tp.footprint + vox);
+    Footprint fp;
+    fp.vox = vox;
+    fp.mask = ((bbyte >> ((ix >> 2) & 7u)) & 1u) ? m : 0u;
+    fp.w[0] = w[0]; fp.w[1] = w[1]; fp.w[2] = w[2];
+    if (!fp.mask) return false;
+    filter_footprint(tp, fp, cf, out);
+    return true;
+}
+
+// The diffuse march of one warp, v2. `sec` = this lane's cone is the second cone of the warp's slice of the work
+// list (c0 = first, c1 = last); `multi` = the slice holds more than two cones (per-lane path throughout).
+DEVFN void march_warp_v2(const TraceParams& tp, const StepTable& t, bool have, int cone, int c0, int c1, bool multi,
+                         const float* startPos_, const float* dir, float startLevel, const float4* s_face, float4* s_coop /* 64 */,
+                         unsigned lane, float* out)
+{
+    const vgi_vct_params& p = tp.p;
+    ConeState cs = { { 0.f, 0.f, 0.f, 0.f }, 0.0f };
+    const float voxelSize0 = p.voxel_size * exp2f(startLevel);
+    float startPos[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) startPos[k] = startPos_[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
+    const uint32_t secBit = (cone != c0) ? 0x80000000u : 0u;
+    float prevStep = 0.0f;
+    bool alive = have;
+    const float topLevel = (float)(tp.L - 1);
+    const unsigned g = lane >> 3, corner = lane & 7u;
+    for (int k = 0; k < t.n; ++k) {
+        const unsigned aliveMask = __ballot_sync(FULL_MASK, alive);
+        if (!aliveMask) break;
+        const float step = t.step[k];
+        const float seg = k == 0 ? voxelSize0 : step - prevStep;
+        prevStep = step;
+        uint32_t keyLo = 0u, keyHi = 0u;
+        float wLo[3] = { 0.f, 0.f, 0.f }, wHi[3] = { 0.f, 0.f, 0.f };
+        float curLevel = 0.0f, fr = 0.0f;
+        if (alive) {
+            STAT(0, 1);
+            float position[3], d[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                position[a] = startPos[a] + dir[a] * step;
+                d[a] = p.volume_center[a] - position[a];
+            }
+            const float lodk = t.lod[k];
+            const float minLevel = lodk >= topLevel ? 0.0f : min_level_from_dd(tp, dot3(d, d));
+            curLevel = fminf(fmaxf(fmaxf(startLevel, lodk), minLevel), topLevel);
+            const float fl = floorf(curLevel);
+            fr = curLevel - fl;
+            const float posV[3] = { position[0] * tp.vox_scale0, position[1] * tp.vox_scale0, position[2] * tp.vox_scale0 };
+            keyLo = level_cell(tp, posV, (int)fl, wLo) | secBit;
+            if (fr > 0.0f) keyHi = level_cell(tp, posV, (int)fl + 1, wHi) | secBit; // Q17
+        }
+        const bool wantHi = alive && fr > 0.0f;
+        const unsigned hiMask = __ballot_sync(FULL_MASK, wantHi);
+        const int la = __ffs(aliveMask) - 1, lb = 31 - __clz(aliveMask);
+        const uint32_t keyA = __shfl_sync(FULL_MASK, keyLo, la), keyB = __shfl_sync(FULL_MASK, keyLo, lb);
+        const bool inA = keyLo == keyA;
+        bool scattered = alive && !(inA || keyLo == keyB);
+        uint32_t keyC = 0u, keyD = 0u;
+        bool inC = false;
+        if (hiMask) {
+            const int ha = __ffs(hiMask) - 1, hb = 31 - __clz(hiMask);
+            keyC = __shfl_sync(FULL_MASK, keyHi, ha);
+            keyD = __shfl_sync(FULL_MASK, keyHi, hb);
+            inC = keyHi == keyC;
+            scattered = scattered || (wantHi && !(inC || keyHi == keyD));
+        }
+        float smp[4] = { 0.f, 0.f, 0.f, 0.f }, up[4] = { 0.f, 0.f, 0.f, 0.f };
+        bool any = false;
+        if (multi || __any_sync(FULL_MASK, scattered)) {
+            STAT(6, 1);
+            if (alive) {
+                const float sdir[3] = { dir[0], dir[1], dir[2] };
+                const ConeFaces cf = cone_faces(sdir);
+                any = lane_filter(tp, keyLo & 0x7fffffffu, wLo, cf, smp);
+                if (wantHi) any = lane_filter(tp, keyHi & 0x7fffffffu, wHi, cf, up) || any;
+            }
+        } else {
+            STAT(7, 1);
+            const uint32_t keyG = g == 0u ? keyA : (g == 1u ? keyB : (g == 2u ? keyC : keyD));
+            const bool validG = g == 0u ? true : (g == 1u ? keyB != keyA : (g == 2u ? hiMask != 0u : (hiMask != 0u && keyD != keyC)));
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool nz = validG && coop_fetch(tp, keyG & 0x7fffffffu, corner, s_face, (keyG >> 31) ? c1 : c0, v);
+            const unsigned nzMask = __ballot_sync(FULL_MASK, nz);
+            if (nzMask) {
+                float4* buf = s_coop + ((k & 1) << 5);
+                if (nz) buf[lane] = v;
+                __syncwarp();
+                if (alive) {
+                    const uint32_t mLo = (nzMask >> (inA ? 0 : 8)) & 0xffu;
+                    if (mLo) { coop_gather_w(wLo, mLo, buf + (inA ? 0 : 8), smp); any = true; }
+                    if (wantHi) {
+                        const uint32_t mHi = (nzMask >> (inC ? 16 : 24)) & 0xffu;
+                        if (mHi) { coop_gather_w(wHi, mHi, buf + (inC ? 16 : 24), up); any = true; }
+                    }
+                }
+            } else {
+                STAT(2, 1);
+            }
+        }
+        if (any) {
+            if (fr > 0.0f) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
+            }
+            const float voxelSize = p.voxel_size * exp2f(curLevel);
+            const float correction = __fdividef(seg, voxelSize);
+            float opacity = 0.0f;
+            if (smp[3] > 0.0f) opacity = f_clamp(1.0f - exp2f(correction * __log2f(1.0f - smp[3])), 0.0f, 1.0f);
+            const float k1 = f_clamp(1.0f - cs.result[3], 0.0f, 1.0f);
+            cs.result[0] += k1 * (smp[0] * correction);
+            cs.result[1] += k1 * (smp[1] * correction);
+            cs.result[2] += k1 * (smp[2] * correction);
+            cs.result[3] += k1 * opacity;
+            cs.occlusion += __fdividef((1.0f - cs.occlusion) * opacity, 1.0f + (step + voxelSize) * p.occlusion_decay);
+            alive = cs.occlusion < 1.0f;
+        }
+    }
+    out[0] = cs.result[0]; out[1] = cs.result[1]; out[2] = cs.result[2];
+    out[3] = 1.0f - cs.occlusion;
+}
+
 // ref: voxelConeTracing.frag:394-414
 DEVFN float calc_min_level(const TraceParams& tp, const float* worldPos)
 {
@@ -859,7 +1080,12 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     __shared__ uint16_t s_list[NCONES * TILE_PIX];
     __shared__ int s_warp_count[4];
     __shared__ StepTable s_table;
+#if VGI_TRACE_V2
+    __shared__ float4 s_coop[4][64];                // per warp, double-buffered: 4 groups x 8 pre-blended corner records
+    __shared__ float4 s_face[2 * NCONES];           // per cone: face-texel word offsets, direction weights (fetch lanes)
+#else
     __shared__ float4 s_coop[4][16];                // per warp: the eight pre-blended corner records of a shared cell
+#endif
 
     const int tid = threadIdx.x;
     const int tilesX = (tp.width + TILE_W - 1) / TILE_W;
@@ -884,21 +1110,28 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     }
     if (tid == 127 && needCones && !SVO)
         build_step_table(tp, s_table, tp.cone_coeff_diffuse, fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor));
+#if VGI_TRACE_V2
+    if (!SVO && needCones && tid >= 64 && tid < 64 + NCONES) {
+        const float fdir[3] = { cones[tid - 64][0], cones[tid - 64][1], cones[tid - 64][2] };
+        cone_face_table(fdir, s_face + 2 * (tid - 64));
+    }
+#endif
     __syncthreads();
 
     if (needCones) {
         // ---- phase 2a: cone-major compaction; warp w owns slots [w * S/4, (w+1) * S/4)
         constexpr int SLOTS = NCONES * TILE_PIX, PER_WARP = SLOTS / 4;
         const int warp = tid >> 5, lane = tid & 31;
-        float cosT[PER_WARP / 32];
+        uint32_t actBits = 0u;
         int cnt = 0;
 #pragma unroll
         for (int k = 0; k < PER_WARP / 32; ++k) {
             const int slot = warp * PER_WARP + k * 32 + lane;
             const int cone = slot / TILE_PIX, pix = slot % TILE_PIX;
             const float c = s_pix[3][pix] * cones[cone][0] + s_pix[4][pix] * cones[cone][1] + s_pix[5][pix] * cones[cone][2];
+            // one predicate for both passes (a NaN cosine - zero-length G-buffer normal - traces like the shader: NaN colours)
             const bool act = s_pix[7][pix] != 0.0f && !(c < 0.0f);
-            cosT[k] = act ? c : -1.0f;
+            actBits |= act ? (1u << k) : 0u;
             cnt += __popc(__ballot_sync(0xffffffffu, act));
         }
         if (lane == 0) s_warp_count[warp] = cnt;
@@ -912,7 +1145,7 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
 #pragma unroll
         for (int k = 0; k < PER_WARP / 32; ++k) {
             const int slot = warp * PER_WARP + k * 32 + lane;
-            const bool act = cosT[k] >= 0.0f;
+            const bool act = (actBits >> k) & 1u;
             const unsigned b = __ballot_sync(0xffffffffu, act);
             if (act) s_list[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)slot;
             else s_res[slot / TILE_PIX][slot % TILE_PIX] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -930,7 +1163,15 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
                 const float sp[3] = { s_pix[0][pix], s_pix[1][pix], s_pix[2][pix] };
                 const float cosTheta = s_pix[3][pix] * dir[0] + s_pix[4][pix] * dir[1] + s_pix[5][pix] * dir[2];
                 float c[4];
+#if VGI_TRACE_V2
+                // the warp's slice of the cone-major list: first and last cone; more than two -> per-lane path
+                const unsigned haveMask = __ballot_sync(FULL_MASK, have);
+                const int c0 = __shfl_sync(FULL_MASK, cone, 0), c1 = __shfl_sync(FULL_MASK, cone, 31 - __clz(haveMask | 1u));
+                const bool multi = __any_sync(FULL_MASK, have && cone != c0 && cone != c1);
+                march_warp_v2(tp, s_table, have, cone, c0, c1, multi, sp, dir, s_pix[6][pix], s_face, s_coop[warp], (unsigned)lane, c);
+#else
                 march_warp_table(tp, s_table, have, cone, cones, sp, dir, s_pix[6][pix], s_coop[warp], (unsigned)lane, c);
+#endif
                 if (have) s_res[cone][pix] = make_float4(c[0] * cosTheta, c[1] * cosTheta, c[2] * cosTheta, c[3] * cosTheta);
             }
         } else
