@@ -329,6 +329,16 @@ int vgi_frame_host(vgi_ctx* ctx, uint32_t frame_index, const float camera_pos[3]
                    const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular,
                    void* stream);
 
+/* Same frame for a headless / batched VIEW: nothing but this call's structs goes up. The G-buffer (width x height) is
+ * rasterised on the device from the ctx's scene (vgi_render_gbuffer = GBufferPass::onUpdate) and, when `shadow` is not
+ * NULL, so is the shadow map at the size given to vgi_set_light (vgi_render_shadow_map = the ShadowMapPass depth
+ * attachment; NULL = keep the current one). Then regions, clipmap build, cone trace; both images are downloaded to the
+ * HOST pointers and `stream` is synchronised. */
+int vgi_frame_view_host(vgi_ctx* ctx, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                        uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
+                        const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular,
+                        void* stream);
+
 /* ---- sparse voxel octree -------------------------------------------------------------------- */
 /* replaces: SparseVoxelizer::preVoxelize + cmdVoxelize (SparseVoxelizer.cpp:248-326) — one pass,
  * no host read-back. bb_min/bb_max: scene world bounding box (voxelizer.vert:42-47). */
@@ -370,6 +380,10 @@ int vgi_import_vk_semaphore(vgi_ctx* ctx, int fd, void** handle);
 int vgi_wait_vk_semaphore(vgi_ctx* ctx, void* handle, void* stream);
 int vgi_signal_vk_semaphore(vgi_ctx* ctx, void* handle, void* stream);
 int vgi_release_vk_semaphore(vgi_ctx* ctx, void* handle);
+/* Block the calling thread until everything queued on `stream` has finished (cudaStreamSynchronize for hosts that do
+ * not link the CUDA runtime themselves): the CPU-side alternative to the semaphore pair above — what the reference does
+ * today with fence.waitForAllFences between its pre-pass batch and the frame (Application.cpp:199-201). */
+int vgi_synchronize(vgi_ctx* ctx, void* stream);
 
 #ifdef __cplusplus
 }

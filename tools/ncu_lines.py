@@ -16,9 +16,10 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    dis = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     lines_of_inst = []
     cur_line, active = None, False
+    fresh, cur_is_cu = True, False
     src_file = None
     for l in dis.splitlines():
         if l.startswith(".text."):
@@ -28,15 +29,30 @@ def main():
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
-            cur_line = int(m.group(2))
-            src_file = m.group(1)
+            # -gi prints the inline chain innermost first: keep the innermost frame that lies in a .cu file (intrinsics
+            # from the toolkit headers are attributed to the line that calls them)
+            if fresh or not cur_is_cu:
+                if fresh or m.group(1).endswith(".cu"):
+                    cur_line = int(m.group(2))
+                    cur_is_cu = m.group(1).endswith(".cu")
+                    if cur_is_cu:
+                        src_file = m.group(1)
+            fresh = False
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             lines_of_inst.append(cur_line)
+            fresh = True
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    h = rows[1]
-    data = [r for r in rows[2:] if len(r) > h.index('Instructions Executed')]
+    # a report may hold several launches: sections start with a "Kernel Name" row followed by the header row
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    want = re.sub(r"^_Z\d*", "", kern)
+    base = re.match(r"[A-Za-z_]+", want).group(0)
+    pick = [i for i in starts if base in rows[i][1] and ((base + "<") in rows[i][1]) == ("IL" in want)]
+    s0 = (pick or starts)[0]
+    s1 = min([i for i in starts if i > s0] + [len(rows)])
+    h = rows[s0 + 1]
+    data = [r for r in rows[s0 + 2:s1] if len(r) > h.index('Instructions Executed')]
     assert abs(len(data) - len(lines_of_inst)) <= 16, (len(data), len(lines_of_inst))  # trailing padding
     iN, iP = h.index('Instructions Executed'), h.index('# Samples')
     inst, samp = Counter(), Counter()

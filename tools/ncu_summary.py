@@ -27,16 +27,22 @@ def ncu(rep, page):
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    which = sys.argv[3] if len(sys.argv) > 3 else None      # substring of the kernel name (reports with several launches)
     raw = ncu(rep, "raw")
     h = raw[0]
-    print("# kernel:", raw[2][h.index("Kernel Name")] if "Kernel Name" in h else "?")
+    iK = h.index("Kernel Name")
+    row = next((r for r in raw[2:] if which is None or which in r[iK]), raw[2])
+    print("# kernel:", row[iK])
     for k in KEYS:
         if k in h:
             i = h.index(k)
-            print(f"{k:72s} {raw[2][i]:>16s} {raw[1][i]}")
+            print(f"{k:72s} {row[i]:>16s} {raw[1][i]}")
     src = ncu(rep, "source")
-    hs = src[1]
-    data = [r for r in src[2:] if len(r) > hs.index('Instructions Executed')]
+    starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
+    s0 = next((i for i in starts if which is None or which in src[i][1]), starts[0])
+    s1 = min([i for i in starts if i > s0] + [len(src)])
+    hs = src[s0 + 1]
+    data = [r for r in src[s0 + 2:s1] if len(r) > hs.index('Instructions Executed')]
     iS, iN, iP = hs.index('Source'), hs.index('Instructions Executed'), hs.index('# Samples')
     byop, samp = Counter(), Counter()
     for r in data:

@@ -307,6 +307,18 @@ class VoxelGI:
                                       sd, prm, C.c_void_p(ptr(out_diffuse)), C.c_void_p(ptr(out_specular)),
                                       _stream(stream)))
 
+    def frame_view_host(self, frame_index, camera_pos, camera, width, height, shadow, params, out_diffuse, out_specular,
+                        stream=None):
+        """Batched / headless view: G-buffer (and, with shadow != None, the shadow map) rasterised on the device, only
+        the camera goes up; out_*: (H, W, 4) float32 (pinned) CPU tensors / numpy arrays. Synchronous."""
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        prm = C.byref(params) if params is not None else None
+        sh = C.byref(shadow) if shadow is not None else None
+        self._ck(lib().vgi_frame_view_host(self._h, C.c_uint32(frame_index), _f3(camera_pos), C.byref(camera),
+                                           C.c_uint32(width), C.c_uint32(height), sh, prm,
+                                           C.c_void_p(ptr(out_diffuse)), C.c_void_p(ptr(out_specular)), _stream(stream)))
+
     # -- per-kernel timing
     def set_timing(self, enable=True):
         self._ck(lib().vgi_set_timing(self._h, C.c_int(1 if enable else 0)))

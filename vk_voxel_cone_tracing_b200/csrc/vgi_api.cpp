@@ -137,7 +137,7 @@ int vgi_destroy(vgi_ctx* c)
     free_scene(c);
     if (c->store_owned) cudaFree(c->store);
     cudaFree(c->occ); cudaFree(c->occ_prefix); cudaFree(c->block_sums); cudaFree(c->counters);
-    cudaFree(c->brick_mask); cudaFree(c->slab_ids); cudaFree(c->slab_recs); cudaFree(c->slab_count); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->shadow_owned); cudaFree(c->stage);
+    cudaFree(c->brick_mask); cudaFree(c->slab_ids); cudaFree(c->slab_recs); cudaFree(c->slab_count); cudaFree(c->visit_list); cudaFree(c->footprint); cudaFree(c->nz[0]); cudaFree(c->nz[1]); cudaFree(c->spec_list); cudaFree(c->spec_tab); cudaFree(c->spec_cnt); cudaFree(c->spec_coeff); cudaFree(c->shadow_owned); cudaFree(c->stage);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_inputs); cudaEventDestroy(c->ev_main_done); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_copy_done); }
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch); cudaFree(c->raster_keys);
     peer_close(c);
@@ -742,9 +742,62 @@ static int fill_trace_params(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffe
     tp.spec_list = c->spec_list + 2;
     tp.spec_count = c->spec_list;
     tp.spec_cursor = c->spec_list + 1;
+    tp.spec_tab = c->spec_tab; tp.spec_cnt = c->spec_cnt; tp.spec_coeff = c->spec_coeff; tp.spec_stride = c->spec_stride;
     // ref: voxelConeTracing.frag:80,117,344 — coneCoefficient = 2 tan(aperture / 2)
     tp.diffuse_aperture = prm->enable_32_cones ? 0.628319f : 0.872665f;
     tp.cone_coeff_diffuse = 2.0f * tanf(tp.diffuse_aperture * 0.5f);
+    return VGI_OK;
+}
+
+// Step tables of the specular cones (ref: voxelConeTracing.frag:205-216, 341-392). aperture = max(roughness, 0.05) with
+// the roughness an 8-bit G-buffer value, stepFactor = uVoxelSize (Q12), so the sequence step_0 = 0,
+// step_{k+1} = step_k + max(diameter_k, voxelSize) * voxelSize, diameter = step * 2 tan(aperture / 2) takes one of 256
+// forms. Iterated here in binary32 exactly as the shader does (this file is compiled without FMA contraction); the warp-
+// per-cone marcher reads 32 consecutive steps per batch from it.
+static int ensure_spec_tables(vgi_ctx* c, const vgi_vct_params* prm, cudaStream_t s)
+{
+    const float vs = prm->voxel_size;
+    if (c->spec_tab_voxel_size == vs && (c->spec_tab || c->spec_tab_unfit)) return VGI_OK;
+    const float maxDistance = 30.0f;     // MAX_TRACE_DISTANCE
+    std::vector<float> coeff(256);
+    std::vector<uint32_t> cnt(256);
+    std::vector<std::vector<float2>> seq(256);
+    uint32_t stride = 0;
+    bool unfit = !(vs > 0.0f);
+    for (int rb = 0; rb < 256 && !unfit; ++rb) {
+        const float rough = (float)rb / 255.0f;
+        const float aperture = rough > 0.05f ? rough : 0.05f;          // MIN_SPECULAR_APERTURE
+        const float cc = 2.0f * tanf(aperture * 0.5f);
+        coeff[rb] = cc;
+        if (rb > 0 && cc == coeff[rb - 1]) { seq[rb] = seq[rb - 1]; cnt[rb] = cnt[rb - 1]; continue; }
+        float step = 0.0f;
+        float diameter = step * cc > vs ? step * cc : vs;
+        while (step < maxDistance) {
+            seq[rb].push_back(make_float2(step, log2f(diameter / vs)));
+            if (seq[rb].size() > (1u << 15)) { unfit = true; break; }
+            step += (diameter > vs ? diameter : vs) * vs;
+            diameter = step * cc;
+        }
+        cnt[rb] = (uint32_t)seq[rb].size();
+        if (cnt[rb] > stride) stride = cnt[rb];
+    }
+    CK(c, cudaStreamSynchronize(c->last_stream));      // a trace in flight may still read the old tables
+    CK(c, cudaStreamSynchronize(s));
+    cudaFree(c->spec_tab); cudaFree(c->spec_cnt); cudaFree(c->spec_coeff);
+    c->spec_tab = nullptr; c->spec_cnt = nullptr; c->spec_coeff = nullptr;
+    c->spec_tab_voxel_size = vs;
+    c->spec_tab_unfit = unfit;
+    if (unfit) return VGI_OK;
+    stride = (stride + 31u) & ~31u;
+    std::vector<float2> flat((size_t)256 * stride, make_float2(3.0e38f, 0.0f));
+    for (int rb = 0; rb < 256; ++rb) std::copy(seq[rb].begin(), seq[rb].end(), flat.begin() + (size_t)rb * stride);
+    CK(c, cudaMalloc(&c->spec_tab, flat.size() * sizeof(float2)));
+    CK(c, cudaMalloc(&c->spec_cnt, 256 * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->spec_coeff, 256 * sizeof(float)));
+    CK(c, cudaMemcpy(c->spec_tab, flat.data(), flat.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->spec_cnt, cnt.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->spec_coeff, coeff.data(), 256 * sizeof(float), cudaMemcpyHostToDevice));
+    c->spec_stride = stride;
     return VGI_OK;
 }
 
@@ -778,6 +831,7 @@ int vgi_cone_trace_rows(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g,
         CK(c, cudaMalloc(&c->spec_list, need * sizeof(uint32_t)));
         c->spec_capacity = need;
     }
+    if (prm->rendering_mode == 6 || prm->rendering_mode == 8) { r = ensure_spec_tables(c, prm, s); if (r != VGI_OK) return r; }
     TraceParams tp;
     fill_trace_params(c, cam, g, prm, out_diffuse, out_specular, y0, y1, tp);
     c->launches += vgi_launch_trace(c, tp, s);
@@ -804,6 +858,7 @@ int vgi_cone_trace_interleaved(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuf
         CK(c, cudaMalloc(&c->spec_list, need * sizeof(uint32_t)));
         c->spec_capacity = need;
     }
+    if (prm->rendering_mode == 6 || prm->rendering_mode == 8) { r = ensure_spec_tables(c, prm, s); if (r != VGI_OK) return r; }
     TraceParams tp;
     fill_trace_params(c, cam, g, prm, out_diffuse, out_specular, 0, g->height, tp);
     tp.tile_stride = (int)parts;
@@ -1177,6 +1232,87 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
     return report_overflow(c, "vgi_frame_host");
 }
 
+// Whole frame of ONE VIEW with device-rendered inputs (batched / headless views: only the camera goes up, the two
+// images come home). The shadow map (when `shadow` is given) and the G-buffer are rasterised from the ctx's scene by
+// vgi_render_shadow_map / vgi_render_gbuffer — bit-identical to the host rasteriser the parity tests pin — so nothing
+// but this call's small structs crosses PCIe on the way in.
+int vgi_frame_view_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                        uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
+                        const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular, void* stream)
+{
+    if (!c || !camera_pos || !cam || !host_out_diffuse || !host_out_specular || !width || !height)
+        return fail(c, VGI_E_INVALID, "vgi_frame_view_host: bad argument");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_frame_view_host: call vgi_set_light first");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t npx = (size_t)width * height;
+    const size_t need = npx * 60;
+    if (c->stage_bytes < need) {
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        cudaFree(c->stage);
+        c->stage = nullptr;
+        c->stage_bytes = 0;
+        CK(c, cudaMalloc(&c->stage, need));
+        c->stage_bytes = need;
+    }
+    uint8_t* d_out_d = c->stage;
+    uint8_t* d_out_s = d_out_d + npx * 16;
+    uint8_t* d_nrm = d_out_s + npx * 16;
+    uint8_t* d_emi = d_nrm + npx * 8;
+    uint8_t* d_dif = d_emi + npx * 8;
+    uint8_t* d_spc = d_dif + npx * 4;
+    uint8_t* d_dep = d_spc + npx * 4;
+    if (!c->copy_stream) {
+        CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_main_done, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = c->copy_stream;
+    int r;
+    if (shadow) {
+        const size_t sb = (size_t)c->light.sw * c->light.sh * sizeof(float);
+        if (!c->shadow_owned || c->shadow_owned_bytes < sb) {
+            CK(c, cudaStreamSynchronize(c->last_stream));
+            cudaFree(c->shadow_owned);
+            c->shadow_owned = nullptr;
+            CK(c, cudaMalloc(&c->shadow_owned, sb));
+            c->shadow_owned_bytes = sb;
+        }
+        r = vgi_render_shadow_map(c, shadow, (uint32_t)c->light.sw, (uint32_t)c->light.sh, c->shadow_owned, stream);
+        if (r != VGI_OK) return r;
+        c->light.depth = c->shadow_owned;
+        memcpy(c->light.view, shadow->view, sizeof c->light.view);
+        memcpy(c->light.proj, shadow->proj, sizeof c->light.proj);
+        c->light.z_near = shadow->z_near; c->light.z_far = shadow->z_far;
+    }
+    vgi_gbuffer dg;
+    dg.diffuse_rgba8 = d_dif; dg.normal_rgba16f = d_nrm; dg.specular_rgba8 = d_spc; dg.emission_rgba16f = d_emi;
+    dg.depth_f32 = (const float*)d_dep; dg.width = width; dg.height = height;
+    r = vgi_render_gbuffer(c, cam, &dg, stream);
+    if (r != VGI_OK) return r;
+    CK(c, cudaMemsetAsync(d_out_d, 0, npx * 32, s));
+    r = vgi_update_regions(c, camera_pos);
+    if (r != VGI_OK) return r;
+    r = vgi_build_clipmap(c, frame_index, stream);
+    if (r != VGI_OK) return r;
+    vgi_vct_params prm;
+    if (params) prm = *params;
+    else vgi_default_vct_params(c, &prm);
+    c->mark_main_done = c->ev_main_done;
+    r = vgi_cone_trace(c, cam, &dg, &prm, d_out_d, d_out_s, stream);
+    c->mark_main_done = nullptr;
+    if (r != VGI_OK) return r;
+    CK(c, cudaStreamWaitEvent(cs, c->ev_main_done, 0));
+    CK(c, cudaMemcpyAsync(host_out_diffuse, d_out_d, npx * 16, cudaMemcpyDeviceToHost, cs));
+    CK(c, cudaEventRecord(c->ev_copy_done, cs));
+    CK(c, cudaMemcpyAsync(host_out_specular, d_out_s, npx * 16, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamWaitEvent(s, c->ev_copy_done, 0));
+    CK(c, cudaStreamSynchronize(s));
+    return report_overflow(c, "vgi_frame_view_host");
+}
+
 // ---- Vulkan interop (VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd) --------------------
 
 int vgi_import_vk_memory(vgi_ctx* c, int fd, size_t size, void** dev_ptr, void** handle)
@@ -1251,6 +1387,14 @@ int vgi_release_vk_semaphore(vgi_ctx* c, void* handle)
 {
     if (!c || !handle) return fail(c, VGI_E_INVALID, "vgi_release_vk_semaphore: bad argument");
     CK(c, cudaDestroyExternalSemaphore((cudaExternalSemaphore_t)handle));
+    return VGI_OK;
+}
+
+int vgi_synchronize(vgi_ctx* c, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_synchronize: null ctx");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize((cudaStream_t)stream));
     return VGI_OK;
 }
 

@@ -113,6 +113,12 @@ struct TraceParams {
     float    svo_center[3], svo_extent, svo_max_level;
     float    cone_coeff_diffuse;  // 2*tan(aperture/2), evaluated on the host
     float    diffuse_aperture;
+    // specular marches (k_trace_specular_warp): the step sequence depends on the roughness byte alone, so the host
+    // tabulates it per byte value: spec_tab[rb * spec_stride + k] = (step_k, log2(diameter_k / voxel_size))
+    const float2* spec_tab;       // nullptr -> per-lane marcher (k_trace_specular)
+    const uint32_t* spec_cnt;     // [256] steps until MAX_TRACE_DISTANCE
+    const float* spec_coeff;      // [256] 2*tan(max(roughness, 0.05)/2)
+    uint32_t spec_stride;
 };
 
 // optional per-kernel CUDA-event timing (vgi_set_timing): events are recorded on the launching stream
@@ -205,6 +211,13 @@ struct vgi_ctx {
     // cone trace scratch
     uint32_t* spec_list = nullptr;
     size_t spec_capacity = 0;
+    // specular step tables (see TraceParams::spec_tab), rebuilt when the voxel size changes
+    float2* spec_tab = nullptr;
+    uint32_t* spec_cnt = nullptr;
+    float* spec_coeff = nullptr;
+    uint32_t spec_stride = 0;
+    float spec_tab_voxel_size = 0.0f;
+    bool spec_tab_unfit = false;      // table would be too large for this voxel size: per-lane marcher
 
     // build: the empty-space / visit-list masks depend on the occupancy alone, so they run on a side stream next to
     // the injection and the record pass (created on first use)

@@ -1348,6 +1348,206 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Specular cones, one WARP per cone (ref: voxelConeTracing.frag:205-216, 341-392; Q12: stepFactor = uVoxelSize, so a
+// cone advances 1/16 of a voxel of its level per step and ~8 consecutive samples fall into the same cell).
+// The step sequence does not depend on what is sampled and takes one of 256 forms (8-bit roughness): the host
+// tabulates it (TraceParams::spec_tab) and the 32 lanes of a warp evaluate 32 CONSECUTIVE steps of one cone:
+//   * every lane computes where its two level samples lie (cell key + tri-linear weights);
+//   * consecutive lanes with equal keys form runs (about four per level and batch); lane 8 r + c tests the brick bit
+//     and the footprint byte of run r's cell and fetches corner record c, blended with the cone's face weights,
+//     into shared memory — once per cell instead of once per step; a batch whose cells are all empty ends here;
+//   * every lane sums the non-zero corners of its cell with its own weights;
+//   * front-to-back accumulation is a prefix product over the batch: 1 - alpha' = (1 - alpha)(1 - o) and
+//     1 - occ' = (1 - occ)(1 - o / (1 + (step + voxelSize) decay)) are the shader's updates :380-388 in product form.
+// The march ends like the shader's when the occlusion saturates (binary32: 1 - occ below 2^-25), and also once the
+// transmittance 1 - alpha is below 1e-10: only rgb leaves this pass, and every later contribution is scaled by it.
+// ---------------------------------------------------------------------------------------------------
+#ifndef VGI_TRACE_SPEC_WARP
+#define VGI_TRACE_SPEC_WARP 1
+#endif
+#ifndef VGI_TRACE_SPECW_MINBLOCKS
+#define VGI_TRACE_SPECW_MINBLOCKS 8
+#endif
+
+struct SpecWarpShared {
+    float4   val[32];     // 4 runs x 8 pre-blended corner records
+    uint32_t key[64];     // run keys of the current pass (a pass has at most 32 runs)
+};
+
+// one level sample of the batch for every lane that wants one; false when every cell is empty
+DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const float* w, unsigned lane,
+                           uint32_t ox, uint32_t oy, uint32_t oz, float kx, float ky, float kz,
+                           SpecWarpShared& sh, float* out)
+{
+    const unsigned wantMask = __ballot_sync(FULL_MASK, want);
+    if (!wantMask) return false;
+    const uint32_t k2 = want ? key : 0xffffffffu;
+    const uint32_t prev = __shfl_up_sync(FULL_MASK, k2, 1);
+    const bool head = want && (lane == 0u || k2 != prev);
+    const unsigned heads = __ballot_sync(FULL_MASK, head);
+    const int nRuns = __popc(heads);
+    const int myRun = __popc(heads & (0xffffffffu >> (31u - lane))) - 1;
+    if (head) sh.key[myRun] = key;
+    __syncwarp();
+    bool any = false;
+    const int R = tp.R, Rm = R - 1, logR = tp.logR;
+    const unsigned corner = lane & 7u;
+    for (int r0 = 0; r0 < nRuns; r0 += 4) {
+        const int r = r0 + (int)(lane >> 3);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool nz = false;
+        if (r < nRuns) {
+            const uint32_t vox = sh.key[r];
+            const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
+            const uint32_t level = vox >> (3 * logR);
+            const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
+            const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
+            const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
+            const uint32_t m = __ldg(tp.footprint + vox);   // meaningful only where the brick bit is set
+            STAT(1, 1);
+            if (((bbyte >> ((ix >> 2) & 7u)) & 1u) && ((m >> corner) & 1u)) {
+                int off = 0;
+                if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
+                if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
+                if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+                const uint32_t tx = __ldg(rec + ox), ty = __ldg(rec + oy), tz = __ldg(rec + oz);
+                STAT(4, 1);
+                const float2 kx2 = make_float2(kx, kx), ky2 = make_float2(ky, ky), kz2 = make_float2(kz, kz);
+                float2 lo = __fmul2_rn(kx2, unpack2(tx, 0x7540u, 0x7541u)), hi = __fmul2_rn(kx2, unpack2(tx, 0x7542u, 0x7543u));
+                lo = __ffma2_rn(ky2, unpack2(ty, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(ky2, unpack2(ty, 0x7542u, 0x7543u), hi);
+                lo = __ffma2_rn(kz2, unpack2(tz, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(kz2, unpack2(tz, 0x7542u, 0x7543u), hi);
+                v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                nz = true;
+            }
+        }
+        const unsigned nzMask = __ballot_sync(FULL_MASK, nz);
+        if (nzMask) {
+            if (nz) sh.val[lane] = v;
+            __syncwarp();
+            const int q = myRun - r0;
+            if (want && q >= 0 && q < 4) {
+                const uint32_t m = (nzMask >> (8 * q)) & 0xffu;
+                if (m) { coop_gather_w(w, m, sh.val + 8 * q, out); any = true; }
+            }
+            __syncwarp();
+        }
+    }
+    return any;
+}
+
+__global__ void __launch_bounds__(128, VGI_TRACE_SPECW_MINBLOCKS) k_trace_specular_warp(const __grid_constant__ TraceParams tp)
+{
+    __shared__ SpecWarpShared s_sh[4];
+    const uint32_t n = *tp.spec_count;
+    const unsigned lane = threadIdx.x & 31u;
+    SpecWarpShared& sh = s_sh[threadIdx.x >> 5];
+    const vgi_vct_params& p = tp.p;
+    const float topLevel = (float)(tp.L - 1);
+    for (;;) {
+        uint32_t item = 0u;
+        if (lane == 0u) item = atomicAdd(tp.spec_cursor, 1u);
+        item = __shfl_sync(FULL_MASK, item, 0);
+        if (item >= n) break;
+        const uint32_t pi = tp.spec_list[item];
+        const int px = (int)(pi % (uint32_t)tp.width), py = (int)(pi / (uint32_t)tp.width);
+        PixelSetup s;
+        if (!pixel_setup(tp, px, py, s)) continue;       // cannot happen: listed pixels are covered
+        float dir[3], startPos[3], spec[3];
+        {
+            const float I[3] = { -s.view[0], -s.view[1], -s.view[2] };   // reflect(-view, normal) = I - 2 dot(N, I) N
+            const float dn = dot3(s.normal, I);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dir[k] = I[k] - 2.0f * dn * s.normal[k];
+        }
+        const uint32_t rb = (uint32_t)(s.perceptualRoughness * 255.0f + 0.5f) & 255u;
+        const float coneCoefficient = __ldg(tp.spec_coeff + rb);
+        const uint32_t nSteps = __ldg(tp.spec_cnt + rb);
+        const float2* tab = tp.spec_tab + (size_t)rb * tp.spec_stride;
+        const float startLevel = s.minLevel;
+        const float voxelSize0 = p.voxel_size * exp2f(startLevel);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            startPos[k] = s.startPos[k] + dir[k] * voxelSize0 * p.trace_start_offset * 0.5f;
+            spec[k] = s.specularColor[k] * p.indirect_specular_intensity;
+        }
+        (void)coneCoefficient;
+        const ConeFaces cf = cone_faces(dir);
+        const uint32_t ox = cf.negX ? 1u : 0u, oy = cf.negY ? 3u : 2u, oz = cf.negZ ? 5u : 4u;
+        float acc[3] = { 0.f, 0.f, 0.f };
+        float carryA = 1.0f, carryO = 1.0f;       // 1 - result.a, 1 - occlusion before the batch
+        for (uint32_t base = 0u; base < nSteps; base += 32u) {
+            const uint32_t k = base + lane;
+            const bool valid = k < nSteps;
+            const float2 sl = __ldg(tab + k);       // rows are padded to a multiple of 32
+            const float step = sl.x, lodk = sl.y;
+            float prevStep = __shfl_up_sync(FULL_MASK, step, 1);
+            if (lane == 0u) prevStep = base ? __ldg(&tab[base - 1u].x) : 0.0f;
+            const float seg = k == 0u ? voxelSize0 : step - prevStep;
+            uint32_t keyLo = 0u, keyHi = 0u;
+            float wLo[3] = { 0.f, 0.f, 0.f }, wHi[3] = { 0.f, 0.f, 0.f };
+            float curLevel = 0.0f, fr = 0.0f;
+            if (valid) {
+                STAT(0, 1);
+                float position[3], d[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    position[a] = startPos[a] + dir[a] * step;
+                    d[a] = p.volume_center[a] - position[a];
+                }
+                const float minLevel = min_level_from_dd(tp, dot3(d, d));
+                curLevel = fminf(fmaxf(fmaxf(startLevel, lodk), minLevel), topLevel);
+                const float fl = floorf(curLevel);
+                fr = curLevel - fl;
+                const float posV[3] = { position[0] * tp.vox_scale0, position[1] * tp.vox_scale0, position[2] * tp.vox_scale0 };
+                keyLo = level_cell(tp, posV, (int)fl, wLo);
+                if (fr > 0.0f) keyHi = level_cell(tp, posV, (int)fl + 1, wHi); // Q17
+            }
+            float smp[4] = { 0.f, 0.f, 0.f, 0.f }, up[4] = { 0.f, 0.f, 0.f, 0.f };
+            const bool anyLo = spec_level_pass(tp, valid, keyLo, wLo, lane, ox, oy, oz, cf.kx, cf.ky, cf.kz, sh, smp);
+            const bool anyHi = spec_level_pass(tp, valid && fr > 0.0f, keyHi, wHi, lane, ox, oy, oz, cf.kx, cf.ky, cf.kz, sh, up);
+            const bool any = anyLo || anyHi;
+            if (!__any_sync(FULL_MASK, any)) { STAT(2, 1); continue; }        // the whole batch is empty space
+            float fa = 1.0f, fo = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (any) {
+                if (fr > 0.0f) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) smp[c] = smp[c] * (1.0f - fr) + up[c] * fr;
+                }
+                const float voxelSize = p.voxel_size * exp2f(curLevel);
+                const float correction = __fdividef(seg, voxelSize);
+                float opacity = 0.0f;
+                if (smp[3] > 0.0f) opacity = f_clamp(1.0f - exp2f(correction * __log2f(1.0f - smp[3])), 0.0f, 1.0f);
+                cr = smp[0] * correction; cg = smp[1] * correction; cb = smp[2] * correction;
+                fa = 1.0f - opacity;
+                fo = 1.0f - __fdividef(opacity, 1.0f + (step + voxelSize) * p.occlusion_decay);
+            }
+            // inclusive prefix products over the batch
+            float pa = fa, po = fo;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const float ta = __shfl_up_sync(FULL_MASK, pa, dlt), to = __shfl_up_sync(FULL_MASK, po, dlt);
+                if (lane >= (unsigned)dlt) { pa *= ta; po *= to; }
+            }
+            float ea = __shfl_up_sync(FULL_MASK, pa, 1);
+            if (lane == 0u) ea = 1.0f;
+            const float k1 = carryA * ea;               // clamp(1 - result.a, 0, 1) before this lane's step
+            acc[0] += k1 * cr; acc[1] += k1 * cg; acc[2] += k1 * cb;
+            carryA *= __shfl_sync(FULL_MASK, pa, 31);
+            carryO *= __shfl_sync(FULL_MASK, po, 31);
+            if (carryO < 2.98023224e-8f || carryA < 1e-10f) break;
+        }
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) {
+            acc[0] += __shfl_xor_sync(FULL_MASK, acc[0], dlt);
+            acc[1] += __shfl_xor_sync(FULL_MASK, acc[1], dlt);
+            acc[2] += __shfl_xor_sync(FULL_MASK, acc[2], dlt);
+        }
+        if (lane == 0u) tp.out_specular[pi] = make_float4(acc[0] * spec[0], acc[1] * spec[1], acc[2] * spec[2], 1.0f);
+    }
+}
+
 int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
 {
     const int rows = tp.y1 - tp.y0;
@@ -1380,17 +1580,24 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     if (c->mark_main_done) cudaEventRecord(c->mark_main_done, s); // the diffuse image is complete here
     const uint32_t mode = tp.p.rendering_mode;
     if (mode == 6 || mode == 8) {
-        c->timer.begin("k_trace_specular", s);
-        // persistent kernel: exactly as many blocks as fit on the device at once
-        static int specBlocks = 0;
+        // persistent kernels: exactly as many blocks as fit on the device at once
+        static int specBlocks = 0, specWarpBlocks = 0;
         if (!specBlocks) {
-            int perSm = 0, dev = 0, sms = 148;
+            int perSm = 0, perSmW = 0, dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace_specular, 128, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmW, k_trace_specular_warp, 128, 0);
             specBlocks = sms * (perSm > 0 ? perSm : 4);
+            specWarpBlocks = sms * (perSmW > 0 ? perSmW : 4);
         }
-        k_trace_specular<<<specBlocks, 128, 0, s>>>(tp); ++n;
+        if (VGI_TRACE_SPEC_WARP && tp.spec_tab) {
+            c->timer.begin("k_trace_specular_warp", s);
+            k_trace_specular_warp<<<specWarpBlocks, 128, 0, s>>>(tp); ++n;
+        } else {
+            c->timer.begin("k_trace_specular", s);
+            k_trace_specular<<<specBlocks, 128, 0, s>>>(tp); ++n;
+        }
         c->timer.end(s);
     }
     return n;
