@@ -103,6 +103,24 @@ def inject_level(cfg, regs, level, osc, light, shadow, shadow_depth, radiance):
                            _p(radiance))
 
 
+def literal_voxelize_level(cfg, regs, level, osc, opacity, samples=8, shade_at=0, q2_fixed=False):
+    """Opacity of one level with the MODELLED raster coverage of the reference (vgi_oracle_literal.inc, quirk Q3)."""
+    fn = lib().vgo_literal_voxelize_level
+    fn.restype = C.c_uint64
+    return int(fn(C.byref(cfg), regs, C.c_uint32(level), C.byref(osc.tris), C.c_int(samples), C.c_int(shade_at),
+                  C.c_int(1 if q2_fixed else 0), _p(opacity)))
+
+
+def literal_inject_level(cfg, regs, level, osc, light, shadow, shadow_depth, radiance, samples=8, shade_at=0, q2_fixed=False):
+    """Radiance of one level with the modelled raster coverage (exact-mean accumulation, R <= 128)."""
+    h, w = shadow_depth.shape
+    fn = lib().vgo_literal_inject_level
+    fn.restype = C.c_uint64
+    return int(fn(C.byref(cfg), regs, C.c_uint32(level), C.byref(osc.tris), _p(osc.materials), C.byref(light), C.byref(shadow),
+                  _p(shadow_depth), C.c_uint32(w), C.c_uint32(h), C.c_int(samples), C.c_int(shade_at),
+                  C.c_int(1 if q2_fixed else 0), _p(radiance)))
+
+
 def inject_fragments(cfg, regs, level, osc, light, shadow, shadow_depth):
     """The samples inject_level shades + their shading results (vgo_inject_fragments); dict of numpy arrays."""
     h, w = shadow_depth.shape

@@ -1276,3 +1276,4 @@ int vgo_set_threads(int n)
 }
 
 #include "vgi_oracle_svo.inc"
+#include "vgi_oracle_literal.inc"

@@ -67,6 +67,19 @@ void vgo_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uin
                       const vgo_tris* tris, const vgi_material* materials,
                       const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
                       const float* shadow_depth, uint32_t sw, uint32_t sh, uint8_t* radiance);
+/* Q3 quantified (vgi_oracle_literal.inc): a MODEL of the reference's own raster coverage — (R+2)-pixel orthographic
+ * viewports in which a pixel spans two voxels (Voxelizer.cpp:266-318), n-sample MSAA at the Vulkan standard locations
+ * (Utils.cpp:8-20), sample shading 0.25 (VoxelizationPass.cpp:409-413), near plane 0.1, the literal texel addressing of
+ * msaaVoxelizer.frag:43-73. samples: 8 | 4 | 1; shade_at: 0 = first covered sample of the invocation, 1 = pixel centre;
+ * q2_fixed: per-axis clamp bounds. Return value: fragment-shader invocations that stored. Not used by any parity test:
+ * the canonical mode stays the contract; these exist to measure how far the two are apart. */
+uint64_t vgo_literal_voxelize_level(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level, const vgo_tris* tris,
+                                    int samples, int shade_at, int q2_fixed, uint8_t* opacity);
+uint64_t vgo_literal_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level, const vgo_tris* tris,
+                                  const vgi_material* materials, const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
+                                  const float* shadow_depth, uint32_t sw, uint32_t sh, int samples, int shade_at, int q2_fixed,
+                                  uint8_t* radiance);
+
 /* test aid: the samples vgo_inject_level shades (position, un-normalised normal, material, unwrapped voxel) and their
  * shading results (faces, 16-bit fixed-point rgb); capacity == 0 counts only. Returns the number of samples. */
 uint64_t vgo_inject_fragments(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,

@@ -1367,15 +1367,20 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
 #define VGI_TRACE_SPEC_WARP 1
 #endif
 #ifndef VGI_TRACE_SPECW_MINBLOCKS
-#define VGI_TRACE_SPECW_MINBLOCKS 8
+#define VGI_TRACE_SPECW_MINBLOCKS 6      // measured: 8 (64 registers, spills) 1.70 ms, 6 (80) 1.59 ms, 4 1.69 ms
 #endif
 
 struct SpecWarpShared {
-    float4   val[32];     // 4 runs x 8 pre-blended corner records
-    uint32_t key[64];     // run keys of the current pass (a pass has at most 32 runs)
+    float4 val[32];     // 4 cells x 8 pre-blended corner records
+    uint2  cell[32];    // non-empty cells of the current pass: (key, mask of the records that can be non-zero)
 };
 
-// one level sample of the batch for every lane that wants one; false when every cell is empty
+// One level sample of the batch for every lane that wants one; false when every cell is empty.
+//  A. run heads (first lane of each group of consecutive lanes with the same cell) test their cell's brick bit and
+//     footprint byte: one probe per CELL, not per step; a pass whose cells are all empty ends with one ballot;
+//  B. the non-empty cells are numbered compactly; lane 8 c + corner fetches corner `corner` of compact cell c (its three
+//     face texels blended with the cone's weights) into shared memory, four cells per round;
+//  C. every lane sums the non-zero corners of its cell with its own tri-linear weights.
 DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const float* w, unsigned lane,
                            uint32_t ox, uint32_t oy, uint32_t oz, float kx, float ky, float kz,
                            SpecWarpShared& sh, float* out)
@@ -1386,27 +1391,37 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
     const uint32_t prev = __shfl_up_sync(FULL_MASK, k2, 1);
     const bool head = want && (lane == 0u || k2 != prev);
     const unsigned heads = __ballot_sync(FULL_MASK, head);
-    const int nRuns = __popc(heads);
-    const int myRun = __popc(heads & (0xffffffffu >> (31u - lane))) - 1;
-    if (head) sh.key[myRun] = key;
-    __syncwarp();
-    bool any = false;
     const int R = tp.R, Rm = R - 1, logR = tp.logR;
+    // ---- A
+    uint32_t cellMask = 0u;
+    if (head) {
+        const uint32_t ix = key & (uint32_t)Rm, iy = (key >> logR) & (uint32_t)Rm, iz = (key >> (2 * logR)) & (uint32_t)Rm;
+        const uint32_t level = key >> (3 * logR);
+        const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
+        const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
+        const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
+        const uint32_t m = __ldg(tp.footprint + key);   // meaningful only where the brick bit is set
+        STAT(1, 1);
+        cellMask = ((bbyte >> ((ix >> 2) & 7u)) & 1u) ? m : 0u;
+    }
+    const unsigned live = __ballot_sync(FULL_MASK, cellMask != 0u);
+    if (!live) return false;
+    // ---- B: my run's head lane, its mask and its compact number
+    const int hl = (31 - __clz((int)(heads & (0xffffffffu >> (31u - lane))))) & 31;
+    const uint32_t headMask = __shfl_sync(FULL_MASK, cellMask, hl);
+    const uint32_t myMask = want ? headMask : 0u;
+    const int myCell = __popc(live & ((1u << hl) - 1u));
+    const int nCells = __popc(live);
+    if (cellMask) sh.cell[myCell] = make_uint2(key, cellMask);     // head lanes of non-empty cells (hl == lane)
+    __syncwarp();
     const unsigned corner = lane & 7u;
-    for (int r0 = 0; r0 < nRuns; r0 += 4) {
-        const int r = r0 + (int)(lane >> 3);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool nz = false;
-        if (r < nRuns) {
-            const uint32_t vox = sh.key[r];
-            const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
-            const uint32_t level = vox >> (3 * logR);
-            const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
-            const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
-            const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
-            const uint32_t m = __ldg(tp.footprint + vox);   // meaningful only where the brick bit is set
-            STAT(1, 1);
-            if (((bbyte >> ((ix >> 2) & 7u)) & 1u) && ((m >> corner) & 1u)) {
+    for (int c0 = 0; c0 < nCells; c0 += 4) {
+        const int c = c0 + (int)(lane >> 3);
+        if (c < nCells) {
+            const uint2 cm = sh.cell[c];
+            if ((cm.y >> corner) & 1u) {
+                const uint32_t vox = cm.x;
+                const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
                 int off = 0;
                 if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
                 if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
@@ -1418,23 +1433,16 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
                 float2 lo = __fmul2_rn(kx2, unpack2(tx, 0x7540u, 0x7541u)), hi = __fmul2_rn(kx2, unpack2(tx, 0x7542u, 0x7543u));
                 lo = __ffma2_rn(ky2, unpack2(ty, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(ky2, unpack2(ty, 0x7542u, 0x7543u), hi);
                 lo = __ffma2_rn(kz2, unpack2(tz, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(kz2, unpack2(tz, 0x7542u, 0x7543u), hi);
-                v = make_float4(lo.x, lo.y, hi.x, hi.y);
-                nz = true;
+                sh.val[lane] = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
         }
-        const unsigned nzMask = __ballot_sync(FULL_MASK, nz);
-        if (nzMask) {
-            if (nz) sh.val[lane] = v;
-            __syncwarp();
-            const int q = myRun - r0;
-            if (want && q >= 0 && q < 4) {
-                const uint32_t m = (nzMask >> (8 * q)) & 0xffu;
-                if (m) { coop_gather_w(w, m, sh.val + 8 * q, out); any = true; }
-            }
-            __syncwarp();
-        }
+        __syncwarp();
+        // ---- C
+        const int q = myCell - c0;
+        if (myMask && q >= 0 && q < 4) coop_gather_w(w, myMask, sh.val + 8 * q, out);
+        __syncwarp();
     }
-    return any;
+    return myMask != 0u;
 }
 
 __global__ void __launch_bounds__(128, VGI_TRACE_SPECW_MINBLOCKS) k_trace_specular_warp(const __grid_constant__ TraceParams tp)
@@ -1502,7 +1510,8 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPECW_MINBLOCKS) k_trace_specul
                 fr = curLevel - fl;
                 const float posV[3] = { position[0] * tp.vox_scale0, position[1] * tp.vox_scale0, position[2] * tp.vox_scale0 };
                 keyLo = level_cell(tp, posV, (int)fl, wLo);
-                if (fr > 0.0f) keyHi = level_cell(tp, posV, (int)fl + 1, wHi); // Q17
+                // Q17: no second sample when the level is integral (computed unconditionally: no divergent branch)
+                keyHi = level_cell(tp, posV, min((int)fl + 1, tp.L - 1), wHi);
             }
             float smp[4] = { 0.f, 0.f, 0.f, 0.f }, up[4] = { 0.f, 0.f, 0.f, 0.f };
             const bool anyLo = spec_level_pass(tp, valid, keyLo, wLo, lane, ox, oy, oz, cf.kx, cf.ky, cf.kz, sh, smp);
