@@ -566,6 +566,32 @@ def run_vgi(args):
                           "traffic": (ncu_traffic("k_trace_main") or 0) + (ncu_traffic("k_trace_specular") or 0) or None,
                           "note": "A_cone = 32 B x tri-linear taps (counted by the oracle on the sampled rows, scaled) + 60 B x pixels"}
 
+    # ---- every view of the fixed list on ONE GPU (N = 1 only): with `per_rank` of the N > 1 lines this separates the
+    # machine's scaling from the cameras' different costs (rank r renders view r; the slowest view sets `value`)
+    per_view = None
+    if rank == 0 and world == 1:
+        from vk_voxel_cone_tracing_b200 import raster as _raster, synth as _synth
+        per_view = []
+        ve = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        for v in range(N_VIEWS):
+            pos, dirv = view_camera(v)
+            cam_v = _synth.make_camera(pos, dirv, aspect=WIDTH / HEIGHT)
+            gb_v = gi.render_gbuffer(cam_v, WIDTH, HEIGHT)      # bit-identical to the host rasteriser (tests/test_gpu_raster.py)
+            acc_ms = 0.0
+            for i in range(5):
+                flush.zero_()
+                ve[0].record()
+                gi.update_regions(pos)
+                gi.build_clipmap(0)
+                gi.cone_trace(cam_v, gb_v, prm, out=out)
+                ve[1].record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    acc_ms += ve[0].elapsed_time(ve[1])
+            per_view.append(acc_ms / 3)
+        frame()
+        torch.cuda.synchronize()
+
     # ---- configs[2] beside it: 512^3 octree (level 9) fragment list + build + 1080p octree cone trace
     svo = None
     if rank == 0 and not args.no_svo:
@@ -676,7 +702,7 @@ def run_vgi(args):
                                  "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_hg_ms,
                                  "call": "vgi_frame_host: host G-buffer uploaded every step (shadow map of the static light "
                                          "uploaded once, outside), both float4 images down"},
-            "per_rank": per_rank,
+            "per_rank": per_rank, "per_view_ms_on_one_gpu": per_view,
             "gpu_launches": int(launches) * args.steps,
             "gpu_launches_per_step": int(launches),
             # `roofline` = the dominant kernel of the step (k_trace_main, bounded by L1 / issue rate per SURVEY 8d); without
@@ -696,6 +722,146 @@ def run_vgi(args):
         raise SystemExit(3)
 
 
+# ---------------------------------------------------------------------------------------------------
+# --config 4: BASELINE configs[4] — 512^3 volume, slab-voxelized across the GPUs and exchanged, 64 camera views at 4K
+# sharded by view. Not the headline metric (the driver runs the default); run under gpurun --gpus N and kept in profiles/.
+# ---------------------------------------------------------------------------------------------------
+def run_config4(args):
+    import torch
+    import torch.distributed as dist
+    from vk_voxel_cone_tracing_b200 import multigpu as M, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libvgi has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    R4, W4, H4, NV = 512, 3840, 2160, 64
+    scene = synth.atrium()
+    cfg = S.default_config(R4, 1, extent_level0=32.0)
+    light, shadow = synth.make_light()
+    lo, hi = scene.world_bbox()
+    centre = tuple(float(x) for x in (np.asarray(lo) + np.asarray(hi)) * 0.5)
+
+    def make():
+        g = VoxelGI(cfg, device=local)
+        g.set_scene(scene)
+        g.update_regions(centre)
+        return g
+
+    gi = make()
+    sm = gi.render_shadow_map(shadow, SHADOW)
+    gi.set_light(light, shadow, sm)
+    rng = np.random.RandomState(5)
+    cams = []
+    for v in range(NV):
+        ang = 2.0 * np.pi * v / NV
+        pos = np.asarray(centre) + np.array([rng.uniform(6, 12) * np.cos(ang), rng.uniform(2, 8) - centre[1], rng.uniform(6, 12) * np.sin(ang)])
+        d = np.asarray(centre) - pos
+        cams.append(synth.make_camera(tuple(pos), tuple(d / np.linalg.norm(d)), aspect=W4 / H4))
+    mine = list(M.views_for_rank(NV, rank, world))
+    prm = gi.default_vct_params(8)
+    out = (torch.zeros((H4, W4, 4), dtype=torch.float32, device=dev), torch.zeros((H4, W4, 4), dtype=torch.float32, device=dev))
+    gbuf = gi.render_gbuffer(cams[0], W4, H4)
+    hout = (torch.empty((H4, W4, 4), dtype=torch.float32).pin_memory(), torch.empty((H4, W4, 4), dtype=torch.float32).pin_memory())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    builders = {"replicated": lambda: gi.build_clipmap(0)}
+    keep = []
+    if world > 1:
+        gs, gp = make(), make()
+        for g in (gs, gp):
+            g.set_light(light, shadow, sm)
+        sb, pb = M.SlabBuild(gs), M.PeerBuild(gp)
+        keep += [pb]
+        builders["slab_nccl_allgather"] = lambda: sb.build(0)
+        builders["peer_nvlink_stores"] = lambda: pb.build(0)
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    build_ms = {k: timed(f, 10) for k, f in builders.items()}
+    # the sharded builds equal the replicated one bit for bit (checked on the store itself: 4.3 GB per GPU, no export)
+    same = True
+    if world > 1:
+        from vk_voxel_cone_tracing_b200 import api as _api
+
+        def store(g):
+            ptr, nbytes = g.voxel_store()
+            return torch.as_tensor(_api._DevView(ptr, (nbytes // 4,), "<i4"), device=dev)
+
+        gi.build_clipmap(0)
+        torch.cuda.synchronize()
+        ref = store(gi)
+        for g in (gs, gp):
+            same = same and bool(torch.equal(ref, store(g)))
+        flag = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item())
+    best = min(build_ms, key=build_ms.get)
+    build = builders[best]
+    src = gi if best == "replicated" else (gs if best.startswith("slab") else gp)
+
+    def step(download):
+        build()
+        for v in mine:
+            src.render_gbuffer(cams[v], W4, H4, out=gbuf)
+            src.cone_trace(cams[v], gbuf, prm, out=out)
+            if download:
+                hout[0].copy_(out[0], non_blocking=True)
+                hout[1].copy_(out[1], non_blocking=True)
+        if download:
+            torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(lambda: step(False), args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e = timed(lambda: step(True), args.steps)
+    if rank == 0:
+        line = {"metric": "configs[4]: 4K 16-cone GI views/s over 64 views sharded by view; 512^3 volume build ms (1/2/4/8 B200)",
+                "value": NV * 1e3 / ms, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": 2, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 texels)", "data": "synthetic",
+                "config": {"workload": "configs[4]: batched 64 camera views at 3840x2160 sharded by view across the GPUs, one 512^3 "
+                                       "volume (single level, extent 32) built per step from the 262144-triangle atrium",
+                           "resolution": R4, "levels": 1, "image": [W4, H4], "views": NV, "views_per_gpu": len(mine),
+                           "build": best, "parallelism": f"{world} GPU(s): views round-robin, volume built by '{best}'"},
+                "stages": {"build_ms": build_ms, "sharded_builds_equal_replicated_store": same,
+                           "ms_per_view": (ms - build_ms[best]) / max(len(mine), 1)},
+                "e2e": {"value": NV * 1e3 / ms_e2e, "unit": "views/s", "h2d_bytes_per_step": 344 * len(mine),
+                        "d2h_bytes_per_step": 2 * H4 * W4 * 16 * len(mine), "ms_per_step": ms_e2e,
+                        "call": "per view: camera up, G-buffer rasterised on the device, cone trace, both float4 images to pinned host memory"},
+                "clocks": clk, "kernel_source_hash": kernel_source_hash()}
+        print(json.dumps(line), flush=True)
+    for k in keep:
+        if hasattr(k, "close"):
+            k.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -704,9 +870,13 @@ def main():
     ap.add_argument("--impl", default="vgi", choices=["vgi", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-svo", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 4],
+                    help="1 = the headline workload (BASELINE configs[1]); 4 = configs[4], 64 views at 4K + 512^3 slab build")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 4:
+        run_config4(args)
     else:
         run_vgi(args)
 

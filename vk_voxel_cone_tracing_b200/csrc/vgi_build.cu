@@ -7,6 +7,12 @@
 // reference checkout; this file restates behaviour, it does not share code with the GLSL.
 #include "vgi_device.cuh"
 
+// shadow taps of the injection: 1 = one lane per pair with aligned float4 row loads (lane_visibility), 0 = the quad-
+// cooperative version of round 1 (warp_visibility). Measured on B200, 3.4 M pairs: see DESIGN.md section 4.
+#ifndef VGI_INJECT_LANE_VIS
+#define VGI_INJECT_LANE_VIS 1
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // K1: voxelize — occupancy bits + (triangle, level, texel) pair list
 // ---------------------------------------------------------------------------------------------------
@@ -230,7 +236,12 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
         }
         // quad phase: round r serves the pairs of lanes 8r..8r+7, quad q serves lane 8r+q
         const unsigned lit = __ballot_sync(0xffffffffu, ps.kind == 2);
+#if VGI_INJECT_LANE_VIS
+        (void)lit;
+        const float vis = ps.kind == 2 ? lane_visibility(lp, ps.px, ps.py, ps.cmpz, compare) : 0.0f;
+#else
         const float vis = warp_visibility(lp, ps.px, ps.py, ps.cmpz, compare, lit);
+#endif
         // contribution of this lane: up to 6 faces x (r, g, b) in 16.16 fixed point
         const vgi_material* m = materials + ps.mat;
         uint32_t q[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
@@ -768,9 +779,35 @@ static void launch_brick(vgi_ctx* c, const BuildParams& bp, int cur, cudaStream_
     LAUNCH("k_brick_mask", k_brick_mask<<<cdiv(nbytes, 128), 128, 0, s>>>(bp.R, bp.L, bp.logR, c->nz[cur], c->brick_mask, c->footprint));
 }
 
+#ifdef VGI_INJECT_SORT_EXPERIMENT
+#include <cub/device/device_radix_sort.cuh>
+// development experiment (tools/build_variant.py -DVGI_INJECT_SORT_EXPERIMENT): pairs sorted by (level, z, y, x) with a
+// library sort and a host read-back of the count, ONLY to measure what k_inject gains from voxel-ordered pairs
+static void experiment_sort_pairs(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
+{
+    static vgi_pair_t* alt = nullptr;
+    static void* tmp = nullptr;
+    static size_t tmpBytes = 0;
+    uint32_t count = 0;
+    cudaMemcpyAsync(&count, &c->counters->pairs, 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (count > bp.max_pairs) count = bp.max_pairs;
+    if (!count) return;
+    if (!alt) cudaMalloc(&alt, (size_t)bp.max_pairs * sizeof(vgi_pair_t));
+    size_t need = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, c->pairs, alt, (int)count, 0, 30, s);
+    if (need > tmpBytes) { cudaFree(tmp); cudaMalloc(&tmp, need); tmpBytes = need; }
+    cub::DeviceRadixSort::SortKeys(tmp, need, c->pairs, alt, (int)count, 0, 30, s);
+    cudaMemcpyAsync(c->pairs, alt, (size_t)count * sizeof(vgi_pair_t), cudaMemcpyDeviceToDevice, s);
+}
+#endif
+
 static int launch_inject(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
     int n = 0;
+#ifdef VGI_INJECT_SORT_EXPERIMENT
+    experiment_sort_pairs(c, bp, s);
+#endif
     LAUNCH("k_zero_acc", k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ));
     if (bp.ntri && bp.level_mask) {
         LAUNCH("k_inject", k_inject<<<148 * 8, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,

@@ -372,6 +372,78 @@ DEVFN float warp_visibility(const LightParams& lp, float px, float py, float cmp
     return vis;
 }
 
+// Visibility of ONE pair on ONE lane (shipped since round 2; the quad-cooperative version above is kept for reference and
+// A/B: it needs 45 warp instructions per pair, two thirds of them shuffles and replicated coordinate arithmetic, and was
+// 67 % of k_inject). The 16 bilinear footprints of shadow.glsl:14-26 tile a 5 x 5 texel block whenever the tap coordinates
+// round consistently; its rows are fetched as two ALIGNED float4 loads each (a row of five starting at x0 lies inside the
+// eight texels from x0 & ~3: ten 16-byte loads instead of twenty-five scalar ones, one or two sectors per row) and the five
+// texels are picked out of the eight registers with two rounds of selects on x0 & 3. Every tap keeps its own (a, b) and the
+// taps are summed in the shader's order, so the result is bit-identical to calc_visibility(); pairs whose taps do not tile
+// (rounding at a texel boundary) or maps whose width is not a multiple of four take the scalar path.
+DEVFN float4 shadow_row4(const LightParams& lp, int x, int y)
+{
+    if (y < 0 || y >= lp.sh || x < 0 || x >= lp.sw) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // aligned chunk: all in or all out
+    return __ldg(reinterpret_cast<const float4*>(lp.depth + (size_t)y * lp.sw + x));
+}
+
+DEVFN float lane_visibility(const LightParams& lp, float px, float py, float cmpz, bool compare)
+{
+    const float sx = 1.0f / (float)lp.sw, sy = 1.0f / (float)lp.sh;
+    float a[4], b[4];
+    int ix[4], iy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float o = -1.5f + (float)k;
+        const float x = (px + o * sx) * (float)lp.sw - 0.5f;
+        const float fx = floorf(x);
+        a[k] = x - fx;
+        ix[k] = (int)f_clamp(fx, -4.0f, (float)lp.sw + 4.0f);
+        const float y = (py + o * sy) * (float)lp.sh - 0.5f;
+        const float fy = floorf(y);
+        b[k] = y - fy;
+        iy[k] = (int)f_clamp(fy, -4.0f, (float)lp.sh + 4.0f);
+    }
+    const bool tiles = ix[1] == ix[0] + 1 && ix[2] == ix[0] + 2 && ix[3] == ix[0] + 3 &&
+                       iy[1] == iy[0] + 1 && iy[2] == iy[0] + 2 && iy[3] == iy[0] + 3 && (lp.sw & 3) == 0 &&
+                       ((reinterpret_cast<size_t>(lp.depth) & 15) == 0);
+    float sum = 0.0f;
+    if (tiles) {
+        const int cx = ix[0] & ~3, sft = ix[0] - cx;
+        float t[5][5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const float4 lo = shadow_row4(lp, cx, iy[0] + r), hi = shadow_row4(lp, cx + 4, iy[0] + r);
+            const float v[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+            float w[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) w[k] = (sft & 1) ? v[k + 1] : v[k];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                float x = (sft & 2) ? w[k + 2] : w[k];
+                if (compare) x = x >= cmpz ? 1.0f : 0.0f;
+                t[r][k] = x;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                sum += bilinear_mix(t[j][i], t[j][i + 1], t[j + 1][i], t[j + 1][i + 1], a[i], b[j]);
+    } else {
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) {
+                float t00 = shadow_texel(lp, ix[i], iy[j]), t10 = shadow_texel(lp, ix[i] + 1, iy[j]);
+                float t01 = shadow_texel(lp, ix[i], iy[j] + 1), t11 = shadow_texel(lp, ix[i] + 1, iy[j] + 1);
+                if (compare) {
+                    t00 = t00 >= cmpz ? 1.0f : 0.0f; t10 = t10 >= cmpz ? 1.0f : 0.0f;
+                    t01 = t01 >= cmpz ? 1.0f : 0.0f; t11 = t11 >= cmpz ? 1.0f : 0.0f;
+                }
+                sum += bilinear_mix(t00, t10, t01, t11, a[i], b[j]);
+            }
+    }
+    return sum * 0.0625f;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2: exclusive prefix sum of the occupancy popcounts (compact accumulator index per occupied voxel)
 // ---------------------------------------------------------------------------------------------------

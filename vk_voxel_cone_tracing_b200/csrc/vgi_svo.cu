@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256) k_svo_shade(SvoGrid g, LightParams lp, in
             }
         }
         const unsigned lit = __ballot_sync(0xffffffffu, kind == 2);
-        const float vis = warp_visibility(lp, spx, spy, scz, compare, lit);
+        (void)lit;
+        const float vis = kind == 2 ? lane_visibility(lp, spx, spy, scz, compare) : 0.0f;
         float radiance[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
         bool emit = kind != 0;
         if (kind == 1) {
