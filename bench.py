@@ -366,6 +366,7 @@ def algorithmic_bytes(name, st, cfg, launches_per_step=1):
     V, P, T = st.occupied_voxels, st.clip_pairs, st.triangles
     table = {
         "k_voxelize": T * 48 + P * 8,
+        # compulsory bytes: pairs + triangle data + every shadow texel once + read-modify-write of the 96-byte accumulator rows
         "k_inject": P * 8 + T * 96 + 4 * SHADOW * SHADOW + 2 * 96 * V,
         "k_level_masks": 3 * 4 * (nvox // 32),                       # per level launch
         "k_level_records": 32 * 3 * (2 * V) // max(L, 1),            # per level launch: ~2V visited, own + ~2 children
@@ -563,7 +564,7 @@ def run_vgi(args):
             roof_trace = {"kernels": sorted(trace_k), "bound": "l1", "ms_per_step": tms, "peak": l1_peak, "unit": "GB/s",
                           "peak_source": f"{nsm} SMs x 128 B/clk x {sm_mhz:.0f} MHz (clock sampled during the run)",
                           "achieved": None, "frac": None,
-                          "traffic": (ncu_traffic("k_trace_main") or 0) + (ncu_traffic("k_trace_specular") or 0) or None,
+                          "traffic": (ncu_traffic("k_trace_main") or 0) + (ncu_traffic("k_trace_specular_warp") or ncu_traffic("k_trace_specular") or 0) or None,
                           "note": "A_cone = 32 B x tri-linear taps (counted by the oracle on the sampled rows, scaled) + 60 B x pixels"}
 
     # ---- every view of the fixed list on ONE GPU (N = 1 only): with `per_rank` of the N > 1 lines this separates the

@@ -128,8 +128,20 @@ typedef struct vgi_node_matrix {
     float it_model[16];
 } vgi_node_matrix;
 
+/* One material texture as GLTFScene::uploadImage creates it (VFS/GLTFScene.cpp:196-260): RGBA8 UNORM, row-major, sampled
+ * with REPEAT addressing and LINEAR filtering at mip level 0 only (the reference builds a mip chain but creates its samplers
+ * with maxLod = 0, GLTFScene.cpp:339 / Sampler.cpp:46, so every texture() / textureLod() of the path is a bi-linear read
+ * of level 0: quirk Q23). HOST pointer; vgi_set_textures copies. */
+typedef struct vgi_texture {
+    const void* rgba8;
+    uint32_t    width, height;
+} vgi_texture;
+
 /* Scene buffers in the SoA layout GLTFScene uploads (VFS/GLTFScene.cpp:55-93). HOST pointers;
- * vgi_set_scene copies what it needs. Textured materials (any *_texture > -1) -> VGI_E_UNSUPPORTED. */
+ * vgi_set_scene copies what it needs. Materials may reference textures (base_color_texture, emissive_texture,
+ * occlusion_texture index into the array given to vgi_set_textures): the voxelization and injection stages use them as
+ * msaaVoxelizer.frag:64, msaaInjectRadiance.frag:73-82,131-136 and voxelizer.frag:52-76 do. texcoords may be NULL when no
+ * material is textured. vgi_render_gbuffer (an adjacent pass) still takes factor-only materials. */
 typedef struct vgi_scene_desc {
     const float*           positions;   /* vec3 f32 x vertex_count */
     const float*           normals;     /* vec3 f32 x vertex_count */
@@ -205,6 +217,9 @@ int         vgi_reset_timings(vgi_ctx* ctx);
 /* ---- inputs --------------------------------------------------------------------------------- */
 /* replaces: GLTFScene vertex/index/matrix/material uploads consumed by msaaVoxelizer.vert:31-36 */
 int vgi_set_scene(vgi_ctx* ctx, const vgi_scene_desc* scene);
+/* replaces: GLTFScene::uploadImage + the uTextures[] descriptor array (set 1, binding 2). May be called before or after
+ * vgi_set_scene; a build whose materials reference a texture index >= count fails with VGI_E_STATE. count 0 clears. */
+int vgi_set_textures(vgi_ctx* ctx, const vgi_texture* textures, uint32_t count);
 /* replaces: light UBOs + shadow-map binding of RadianceInjectionPass (set 4) and
  * VoxelConeTracingPass (set 3). shadow_depth: w*h f32 (D32), device pointer borrowed until replaced
  * (is_host != 0: copied). */

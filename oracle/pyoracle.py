@@ -26,7 +26,8 @@ def build(force=False):
 
 
 class Tris(C.Structure):
-    _fields_ = [("count", C.c_uint32), ("pos", C.c_void_p), ("nrm", C.c_void_p), ("mat", C.c_void_p)]
+    _fields_ = [("count", C.c_uint32), ("pos", C.c_void_p), ("nrm", C.c_void_p), ("mat", C.c_void_p),
+                ("uv", C.c_void_p), ("materials", C.c_void_p)]
 
 
 def lib():
@@ -66,8 +67,37 @@ class OracleScene:
         self.nrm = np.zeros((n, 3, 3), dtype=np.float32)
         self.mat = np.zeros(n, dtype=np.int32)
         lib().vgo_scene_triangles(C.byref(d), _p(self.pos), _p(self.nrm), _p(self.mat))
-        self.tris = Tris(n, self.pos.ctypes.data, self.nrm.ctypes.data, self.mat.ctypes.data)
         self.materials = np.ascontiguousarray(scene.materials)
+        # per-triangle texture coordinates in draw order (GLTFScene.cpp:457-490), only for textured scenes
+        self.uv = None
+        textured = any(int(m[k]) > -1 for m in self.materials for k in ("base_color_texture", "emissive_texture", "occlusion_texture"))
+        if textured:
+            uv = []
+            for p in scene.primitives:
+                idx = scene.indices[p["first_index"]:p["first_index"] + p["index_count"]].astype(np.int64) + int(p["vertex_offset"])
+                uv.append(scene.texcoords[idx].reshape(-1, 3, 2))
+            self.uv = np.ascontiguousarray(np.concatenate(uv, axis=0), dtype=np.float32)
+            assert self.uv.shape[0] == n
+        self.tris = Tris(n, self.pos.ctypes.data, self.nrm.ctypes.data, self.mat.ctypes.data,
+                         self.uv.ctypes.data if textured else None, self.materials.ctypes.data if textured else None)
+
+
+_tex_keep = None
+
+
+def set_textures(images):
+    """The scene's texture array for the oracle (vgo_set_textures borrows the pointers: kept alive here)."""
+    global _tex_keep
+    from vk_voxel_cone_tracing_b200 import structs as S2
+    arr, keep = S2.texture_array(images or [])
+    _tex_keep = (arr, keep)
+    lib().vgo_set_textures(arr, C.c_uint32(len(keep)))
+
+
+def texture_fetch(texture, u, v):
+    out = (C.c_float * 4)()
+    lib().vgo_texture_fetch(C.c_uint32(texture), C.c_float(u), C.c_float(v), out)
+    return np.array(out[:], dtype=np.float32)
 
 
 def regions(cfg, cam_pos):
@@ -129,11 +159,11 @@ def inject_fragments(cfg, regs, level, osc, light, shadow, shadow_depth):
     head = (C.byref(cfg), regs, C.c_uint32(level), C.byref(osc.tris), _p(osc.materials), C.byref(light), C.byref(shadow),
             _p(shadow_depth), C.c_uint32(w), C.c_uint32(h))
     nul = C.c_void_p(0)
-    n = int(fn(*head, C.c_uint64(0), nul, nul, nul, nul, nul, nul, nul))
+    n = int(fn(*head, C.c_uint64(0), nul, nul, nul, nul, nul, nul, nul, nul))
     out = dict(pos=np.zeros((n, 3), np.float32), nrm=np.zeros((n, 3), np.float32), mat=np.zeros(n, np.int32),
                voxel=np.zeros((n, 3), np.int32), nfaces=np.zeros(n, np.int32), faces=np.zeros((n, 6), np.int32),
-               q=np.zeros((n, 6, 3), np.uint32))
-    fn(*head, C.c_uint64(n), *(_p(out[k]) for k in ("pos", "nrm", "mat", "voxel", "nfaces", "faces", "q")))
+               q=np.zeros((n, 6, 3), np.uint32), uv=np.zeros((n, 2), np.float32))
+    fn(*head, C.c_uint64(n), *(_p(out[k]) for k in ("pos", "nrm", "mat", "voxel", "nfaces", "faces", "q", "uv")))
     return out
 
 

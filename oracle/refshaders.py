@@ -221,6 +221,7 @@ class _InjectArgs(C.Structure):
         ("shadow_view", C.c_void_p), ("shadow_proj", C.c_void_p), ("z_near", C.c_float), ("z_far", C.c_float),
         ("W", C.c_int), ("H", C.c_int), ("D", C.c_int),
         ("out_count", C.c_void_p), ("out_coords", C.c_void_p), ("out_values", C.c_void_p),
+        ("texcoord", C.c_void_p), ("n_textures", C.c_int), ("tex_data", C.c_void_p), ("tex_w", C.c_void_p), ("tex_h", C.c_void_p),
     ]
 
 
@@ -234,7 +235,7 @@ def voxelization_desc(region):
 
 
 def inject_fragments(cfg, regs, level, position, normal, material_index, materials, light, shadow, shadow_depth,
-                     accumulate=False):
+                     accumulate=False, texcoord=None, textures=None):
     """msaaInjectRadiance.frag, one invocation per given fragment on a cleared r32ui image.
     Returns (count[n], coords[n, 6, 3] atlas texel, values[n, 6] packed RGBA8 word).
     accumulate=True: all fragments in the given order on ONE image (the reference's CAS running average for that order, Q10);
@@ -251,6 +252,16 @@ def inject_fragments(cfg, regs, level, position, normal, material_index, materia
                 out_count=np.zeros(n, np.int32), out_coords=np.zeros((n, 6, 3), np.int32), out_values=np.zeros((n, 6), np.uint32))
     for k, v in keep.items():
         setattr(a, k, v.ctypes.data)
+    if textures:
+        # uTextures[]: float RGBA = byte / 255 in binary32 (what a UNORM8 image returns), REPEAT + LINEAR in the driver
+        tex_f = [np.ascontiguousarray(t.astype(np.float32) / np.float32(255.0)) for t in textures]
+        ptrs = (C.c_void_p * len(tex_f))(*[t.ctypes.data for t in tex_f])
+        tw = np.array([t.shape[1] for t in tex_f], np.int32)
+        th = np.array([t.shape[0] for t in tex_f], np.int32)
+        tc = np.ascontiguousarray(texcoord, np.float32)
+        keep.update(_tex_f=tex_f, _ptrs=ptrs, _tw=tw, _th=th, _tc=tc)
+        a.texcoord, a.n_textures, a.tex_data = tc.ctypes.data, len(tex_f), C.cast(ptrs, C.c_void_p).value
+        a.tex_w, a.tex_h = tw.ctypes.data, th.ctypes.data
     a.n, a.clip_level, a.clip_max_extent, a.voxel_size, a.resolution = n, level, ext, vs, cfg.resolution
     a.sh, a.sw = sd.shape
     a.light_intensity, a.z_near, a.z_far = light.intensity, shadow.z_near, shadow.z_far

@@ -124,6 +124,48 @@ void vgo_scene_triangles(const vgi_scene_desc* s, float* pos, float* nrm, int32_
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Material textures. ref: texture() / textureLod() of msaaVoxelizer.frag:64, msaaInjectRadiance.frag:73-82,131-136,
+ * voxelizer.frag:52-76 on samplers created with REPEAT + LINEAR and maxLod = 0 (GLTFScene.cpp:339, Sampler.cpp:46): a
+ * bi-linear read of level 0 — the same rule oracle/glsl_shim's sampler2D applies when the shaders themselves run.
+ * ---------------------------------------------------------------------------------------------- */
+static const vgi_texture* g_textures = NULL;
+static uint32_t g_texture_count = 0;
+
+void vgo_set_textures(const vgi_texture* textures, uint32_t count)
+{
+    g_textures = textures;
+    g_texture_count = count;
+}
+
+static int tex_wrap(long long i, int n)
+{
+    if (i >= 0 && i < n) return (int)i;
+    const long long m = i % n;
+    return (int)(m < 0 ? m + n : m);
+}
+
+static void tex_fetch(int tex, float u, float v, float* o)
+{
+    const vgi_texture* t = &g_textures[tex];
+    const int W = (int)t->width, H = (int)t->height;
+    const uint8_t* d = (const uint8_t*)t->rgba8;
+    const float ux = u * (float)W - 0.5f, uy = v * (float)H - 0.5f;
+    const float fx = floorf(ux), fy = floorf(uy);
+    const float wx = ux - fx, wy = uy - fy;
+    const long long ix = (long long)fx, iy = (long long)fy;
+    const int x0 = tex_wrap(ix, W), x1 = tex_wrap(ix + 1, W), y0 = tex_wrap(iy, H), y1 = tex_wrap(iy + 1, H);
+    const uint8_t* t00 = d + ((size_t)y0 * W + x0) * 4, *t10 = d + ((size_t)y0 * W + x1) * 4;
+    const uint8_t* t01 = d + ((size_t)y1 * W + x0) * 4, *t11 = d + ((size_t)y1 * W + x1) * 4;
+    for (int k = 0; k < 4; ++k) {
+        const float r0 = unorm8_to_f(t00[k]) * (1.0f - wx) + unorm8_to_f(t10[k]) * wx;
+        const float r1 = unorm8_to_f(t01[k]) * (1.0f - wx) + unorm8_to_f(t11[k]) * wx;
+        o[k] = r0 * (1.0f - wy) + r1 * wy;
+    }
+}
+
+void vgo_texture_fetch(uint32_t texture, float u, float v, float* rgba) { tex_fetch((int)texture, u, v, rgba); }
+
+/* ------------------------------------------------------------------------------------------------
  * Canonical conservative coverage: a voxel of level l is covered by a triangle iff
  * the triangle overlaps the voxel's cube, evaluated with the Schwarz-Seidel (2010) triangle/box
  * test in voxel units (q = p / voxelSize, unit cubes at integer coordinates), binary32, in exactly
@@ -235,6 +277,10 @@ static inline int tri_overlaps_voxel(const tri_setup* ts, int vx, int vy, int vz
 /* A4. ref: VoxelizationPass.cpp:104-126 */
 void vgo_clear_atlas(const vgi_config* cfg, uint8_t* atlas) { memset(atlas, 0, vgo_atlas_bytes(cfg)); }
 
+/* alpha-tested materials: is the (triangle, voxel) pair discarded by the occlusion texture at its canonical sample? A pair
+ * without a sample (degenerate projection) is kept by the coverage stage and skipped by the injection. */
+static int pair_alpha_discarded(const vgo_tris* tris, int64_t t, const tri_setup* ts, float voxelSize, int x, int y, int z);
+
 /* A3. ref: msaaVoxelizer.frag:43-73 — texel = (v mod R) + 1 (+ level*(R+2) in y), imageStore(vec4(1)) to 6 faces */
 uint64_t vgo_voxelize_level(const vgi_config* cfg, const vgi_clip_region* regions, uint32_t level,
                             const vgo_tris* tris, uint8_t* opacity)
@@ -251,6 +297,7 @@ uint64_t vgo_voxelize_level(const vgi_config* cfg, const vgi_clip_region* region
             for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
                 for (int x = ts.lo[0]; x <= ts.hi[0]; ++x) {
                     if (!tri_overlaps_voxel(&ts, x, y, z)) continue;
+                    if (pair_alpha_discarded(tris, t, &ts, rg->voxel_size, x, y, z)) continue;
                     ++pairs;
                     const size_t tx = (size_t)(x & (int)(R - 1)) + 1;
                     const size_t ty = (size_t)(y & (int)(R - 1)) + 1 + (size_t)(R + 2) * level;
@@ -356,6 +403,8 @@ static float calc_visibility(const shadow_ctx* s, const float* worldPos)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct inject_sample {
     float pos[3], nrm[3];
+    float b[3];         /* barycentric weights of the sample (after clamping into the triangle) */
+    float uv[2];        /* texture coordinate, valid when the caller interpolated it (sample_uv) */
 } inject_sample;
 
 static int inject_sample_at(const tri_setup* ts, const float* p, const float* n9, float* c, inject_sample* o);
@@ -394,7 +443,44 @@ static int inject_sample_at(const tri_setup* ts, const float* p, const float* n9
         o->pos[k] = (p[k] * b0 + p[3 + k] * b1) + p[6 + k] * b2;
         o->nrm[k] = (n9[k] * b0 + n9[3 + k] * b1) + n9[6 + k] * b2;
     }
+    o->b[0] = b0; o->b[1] = b1; o->b[2] = b2;
+    o->uv[0] = o->uv[1] = 0.0f;
     return 1;
+}
+
+/* material of triangle t when it samples any texture of the path, else NULL */
+static const vgi_material* textured_material(const vgo_tris* tris, int64_t t)
+{
+    if (!tris->uv || !tris->materials || !g_texture_count) return NULL;
+    const vgi_material* m = &tris->materials[tris->mat[t]];
+    return (m->base_color_texture > -1 || m->emissive_texture > -1 || m->occlusion_texture > -1) ? m : NULL;
+}
+
+static void sample_uv(const vgo_tris* tris, int64_t t, inject_sample* s)
+{
+    const float* uv = tris->uv + t * 6;
+    s->uv[0] = (uv[0] * s->b[0] + uv[2] * s->b[1]) + uv[4] * s->b[2];
+    s->uv[1] = (uv[1] * s->b[0] + uv[3] * s->b[1]) + uv[5] * s->b[2];
+}
+
+/* ref: msaaVoxelizer.frag:64 / msaaInjectRadiance.frag:73 / voxelizer.frag:52 — occlusion texture .r < 0.1 -> discard,
+ * at the canonical sample of the pair. s->uv must be set. */
+static int alpha_discard(const vgi_material* m, const inject_sample* s)
+{
+    if (!m || m->occlusion_texture < 0) return 0;
+    float t[4];
+    tex_fetch(m->occlusion_texture, s->uv[0], s->uv[1], t);
+    return t[0] < 0.1f;
+}
+
+static int pair_alpha_discarded(const vgo_tris* tris, int64_t t, const tri_setup* ts, float voxelSize, int x, int y, int z)
+{
+    const vgi_material* m = textured_material(tris, t);
+    if (!m || m->occlusion_texture < 0) return 0;
+    inject_sample s;
+    if (!inject_sample_point(ts, tris->pos + t * 9, tris->nrm + t * 9, voxelSize, x, y, z, &s)) return 0;
+    sample_uv(tris, t, &s);
+    return alpha_discard(m, &s);
 }
 
 /* returns number of faces written (0 = discarded); faces[i], q[i][3] */
@@ -403,10 +489,16 @@ static int shade_fragment(const vgi_material* m, const vgi_dir_light* light, con
 {
     if (m->emissive_factor[0] > 0.0f || m->emissive_factor[1] > 0.0f || m->emissive_factor[2] > 0.0f) {
         /* ref msaaInjectRadiance.frag:76-86 */
+        float em[3] = { m->emissive_factor[0], m->emissive_factor[1], m->emissive_factor[2] };
+        if (g_texture_count && m->emissive_texture > -1) {     /* :79-82 */
+            float t[4];
+            tex_fetch(m->emissive_texture, s->uv[0], s->uv[1], t);
+            for (int k = 0; k < 3; ++k) em[k] = em[k] + t[k];
+        }
         for (int f = 0; f < 6; ++f) {
             faces[f] = f;
             for (int k = 0; k < 3; ++k)
-                q[f][k] = (uint32_t)(f_clamp(m->emissive_factor[k], 0.0f, 1.0f) * 65536.0f + 0.5f);
+                q[f][k] = (uint32_t)(f_clamp(em[k], 0.0f, 1.0f) * 65536.0f + 0.5f);
         }
         return 6;
     }
@@ -419,9 +511,15 @@ static int shade_fragment(const vgi_material* m, const vgi_dir_light* light, con
     float lc[3];
     for (int k = 0; k < 3; ++k) lc[k] = ((NdotL * vis) * light->color[k]) * light->intensity;
     if (lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f) return 0;
+    float col[4] = { m->base_color_factor[0], m->base_color_factor[1], m->base_color_factor[2], m->base_color_factor[3] };
+    if (g_texture_count && m->base_color_texture > -1) {        /* :131-136 */
+        float t[4];
+        tex_fetch(m->base_color_texture, s->uv[0], s->uv[1], t);
+        for (int k = 0; k < 4; ++k) col[k] = col[k] * t[k];
+    }
     float rad[3];
     for (int k = 0; k < 3; ++k)
-        rad[k] = f_clamp((lc[k] * m->base_color_factor[k]) * m->base_color_factor[3], 0.0f, 1.0f);
+        rad[k] = f_clamp((lc[k] * col[k]) * col[3], 0.0f, 1.0f);
     /* calculateVoxelFaceIndex(-normal) */
     faces[0] = (-n[0] > 0.0f) ? 0 : 1;
     faces[1] = (-n[1] > 0.0f) ? 2 : 3;
@@ -464,7 +562,7 @@ void vgo_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uin
         for (int z = ts.lo[2]; z <= ts.hi[2]; ++z)
             for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
                 for (int x = ts.lo[0]; x <= ts.hi[0]; ++x)
-                    if (tri_overlaps_voxel(&ts, x, y, z)) {
+                    if (tri_overlaps_voxel(&ts, x, y, z) && !pair_alpha_discarded(tris, t, &ts, rg->voxel_size, x, y, z)) {
                         const size_t v = (((size_t)(z & (int)(R - 1)) * R) + (size_t)(y & (int)(R - 1))) * R + (size_t)(x & (int)(R - 1));
                         __atomic_store_n(&occ[v], 1, __ATOMIC_RELAXED);
                     }
@@ -487,6 +585,11 @@ void vgo_inject_level(const vgi_config* cfg, const vgi_clip_region* regions, uin
                     if (!tri_overlaps_voxel(&ts, x, y, z)) continue;
                     inject_sample s;
                     if (!inject_sample_point(&ts, p, tris->nrm + t * 9, rg->voxel_size, x, y, z, &s)) continue;
+                    const vgi_material* tm = textured_material(tris, t);
+                    if (tm) {
+                        sample_uv(tris, t, &s);
+                        if (alpha_discard(tm, &s)) continue;
+                    }
                     int faces[6];
                     uint32_t q[6][3];
                     const int nf = shade_fragment(m, light, lightDir, &sc, &s, faces, q);
@@ -535,7 +638,7 @@ uint64_t vgo_inject_fragments(const vgi_config* cfg, const vgi_clip_region* regi
                               const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
                               const float* shadow_depth, uint32_t sw, uint32_t sh_, uint64_t capacity,
                               float* pos, float* nrm, int32_t* mat, int32_t* voxel, int32_t* nfaces,
-                              int32_t* faces, uint32_t* q)
+                              int32_t* faces, uint32_t* q, float* uv)
 {
     const uint32_t R = cfg_R(cfg);
     const vgi_clip_region* rg = &regions[level];
@@ -555,12 +658,18 @@ uint64_t vgo_inject_fragments(const vgi_config* cfg, const vgi_clip_region* regi
                     if (!tri_overlaps_voxel(&ts, x, y, z)) continue;
                     inject_sample s;
                     if (!inject_sample_point(&ts, p, tris->nrm + (size_t)t * 9, rg->voxel_size, x, y, z, &s)) continue;
+                    const vgi_material* tm = textured_material(tris, (int64_t)t);
+                    if (tm) {
+                        sample_uv(tris, (int64_t)t, &s);
+                        if (alpha_discard(tm, &s)) continue;
+                    }
                     if (n < capacity) {
                         int fc[6];
                         uint32_t qq[6][3];
                         const int nf = shade_fragment(m, light, lightDir, &sc, &s, fc, qq);
                         memcpy(pos + n * 3, s.pos, sizeof s.pos);
                         memcpy(nrm + n * 3, s.nrm, sizeof s.nrm);
+                        if (uv) memcpy(uv + n * 2, s.uv, sizeof s.uv);
                         mat[n] = tris->mat[t];
                         voxel[n * 3] = x; voxel[n * 3 + 1] = y; voxel[n * 3 + 2] = z;
                         nfaces[n] = nf;

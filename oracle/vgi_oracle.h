@@ -38,7 +38,17 @@ typedef struct vgo_tris {
     float*   pos;   /* count*9: p0 p1 p2 (world) */
     float*   nrm;   /* count*9: world normals (itModel * n), NOT normalised */
     int32_t* mat;   /* count: material index */
+    /* textured materials (both NULL for factor-only scenes): per-triangle texture coordinates and the material array the
+     * coverage stage needs for the occlusion-texture alpha test (msaaVoxelizer.frag:64) */
+    const float* uv;                    /* count*6: uv0 uv1 uv2 */
+    const vgi_material* materials;
 } vgo_tris;
+
+/* the texture array of the scene (uTextures[]); pointers are borrowed. ref: GLTFScene::uploadImage, REPEAT + LINEAR,
+ * level 0 only (Q23) */
+void vgo_set_textures(const vgi_texture* textures, uint32_t count);
+/* test aid: one bi-linear REPEAT read of level 0, as every texture() / textureLod() of the path evaluates */
+void vgo_texture_fetch(uint32_t texture, float u, float v, float* rgba);
 
 size_t vgo_atlas_bytes(const vgi_config* cfg);
 /* sets (n > 0) and returns the number of OpenMP threads the oracle loops use */
@@ -87,7 +97,7 @@ uint64_t vgo_inject_fragments(const vgi_config* cfg, const vgi_clip_region* regi
                               const vgi_dir_light* light, const vgi_dir_light_shadow* shadow,
                               const float* shadow_depth, uint32_t sw, uint32_t sh, uint64_t capacity,
                               float* pos, float* nrm, int32_t* mat, int32_t* voxel, int32_t* nfaces,
-                              int32_t* faces, uint32_t* q);
+                              int32_t* faces, uint32_t* q, float* uv /* n*2, may be NULL: texture coordinate of each sample */);
 /* ref: copyAlphaImage.comp:16-29 */
 void vgo_copy_alpha(const vgi_config* cfg, uint32_t level, uint8_t* dst, const uint8_t* src);
 /* ref: opacityDownSample.comp:28-138 (which=0), radianceDownSample.comp:28-139 with Q6 repaired (which=1) */

@@ -48,6 +48,22 @@ def test_atrium_1080p_bit_exact_with_large_and_clipped_triangles():
     _same_gbuffer(gi.render_gbuffer(cam, 301, 173), raster.gbuffer(inp["scene"], cam, 301, 173))
 
 
+def test_triangles_crossing_the_camera_plane_bit_exact():
+    """A hall of two triangles per wall seen from inside: every wall has a vertex behind the camera plane and takes the
+    homogeneous edge-function path; device and host rasterisers agree bit for bit, and nothing is dropped."""
+    from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    scene = synth.coarse_room(1)
+    gi = VoxelGI(S.default_config(32, 2))
+    gi.set_scene(scene)
+    for pos, dirv, (w, h) in (((2.0, 1.7, -3.0), (1.0, -0.15, 0.4), (320, 180)), ((-9.0, 4.5, 8.0), (0.3, -0.6, -1.0), (301, 173))):
+        d = np.array(dirv) / np.linalg.norm(dirv)
+        cam = synth.make_camera(pos, tuple(d), aspect=w / h)
+        host = raster.gbuffer(scene, cam, w, h)
+        assert (host["depth"] < 1.0).all()
+        _same_gbuffer(gi.render_gbuffer(cam, w, h), host)
+
+
 def test_rendered_inputs_drive_the_path():
     """The device-rendered shadow map and G-buffer feed vgi_set_light / vgi_cone_trace directly (no host copy) and
     give the image the host-rendered inputs give."""

@@ -397,6 +397,34 @@ def test_live_injection_fragments(oracle, refshaders, level):
     _check_injection(cfg, level, fr, sel, cnt, coords, vals)
 
 
+@pytest.mark.parametrize("level", [0, 1])
+def test_live_textured_injection(oracle, refshaders, level):
+    """Textured materials (base-colour, emissive, occlusion alpha test; REPEAT coordinates beyond [0, 1]; a 3 x 5 texture):
+    every sample the oracle shades, with its interpolated texture coordinate, through the reference's own
+    msaaInjectRadiance.frag with the same textures bound — same faces, same colours (the 16-bit fixed-point cell rule of
+    _check_injection), and no sample the oracle kept is discarded by the shader's alpha test."""
+    from vk_voxel_cone_tracing_b200 import raster, synth
+    scene = synth.textured_cornell()
+    tex = synth.procedural_textures()
+    cfg = S.default_config(32, 2)
+    light, shadow = synth.make_light(origin=(0.0, 20.0, -3.5))
+    depth = raster.shadow_depth(scene, shadow, 256)
+    regs = oracle.regions(cfg, (0.0, 0.0, 0.0))
+    oracle.set_textures(tex)
+    try:
+        osc = oracle.OracleScene(scene)
+        fr = oracle.inject_fragments(cfg, regs, level, osc, light, shadow, depth)
+    finally:
+        oracle.set_textures([])
+    textured = np.isin(fr["mat"], [i for i, m in enumerate(osc.materials)
+                                   if max(int(m["base_color_texture"]), int(m["emissive_texture"]), int(m["occlusion_texture"])) > -1])
+    assert textured.sum() > 200 and (fr["uv"][textured] != 0).any()
+    sel = np.arange(fr["pos"].shape[0])
+    cnt, coords, vals = refshaders.inject_fragments(cfg, regs, level, fr["pos"], fr["nrm"], fr["mat"], osc.materials,
+                                                    light, shadow, depth, texcoord=fr["uv"], textures=tex)
+    _check_injection(cfg, level, fr, sel, cnt, coords, vals)
+
+
 def test_live_voxelizer_geometry_axis(oracle, refshaders):
     gen = _gen()
     for seed in (1, 2):

@@ -93,6 +93,11 @@ class VoxelGI:
         self._ck(lib().vgi_set_scene(self._h, C.byref(d)))
         self.scene = scene
 
+    def set_textures(self, images):
+        """images: list of (H, W, 4) uint8 arrays (the scene's uTextures[]); copied by the library."""
+        arr, keep = S.texture_array(images)
+        self._ck(lib().vgi_set_textures(self._h, arr, C.c_uint32(len(keep))))
+
     def set_light(self, light, shadow, shadow_depth):
         """shadow_depth: numpy (H,W) float32 (copied) or a CUDA torch tensor (borrowed)."""
         torch = self._torch

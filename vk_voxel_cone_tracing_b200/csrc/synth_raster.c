@@ -7,7 +7,8 @@
  * build identical inputs for the CUDA path and the CPU oracle. Plain C + OpenMP, no CUDA.
  *
  * Rasterisation: pixel-centre sampling, depth test LESS with ties broken by the lower triangle
- * index, triangles with a vertex at w <= 1e-4 are skipped (synthetic cameras sit in open space),
+ * index; a triangle with a vertex at or behind the camera plane (clip w <= 1e-4) is rasterised with 2-D homogeneous edge
+ * functions inside the pixel box of its part in front of the plane (same rule and arithmetic as csrc/vgi_raster.cu),
  * fragments with z outside [0,1] are clipped. Factor-only materials (texture indices -1).
  */
 #include "../../include/vgi.h"
@@ -84,25 +85,103 @@ static tri_world* world_tris(const vgi_scene_desc* s, uint32_t* count)
     return out;
 }
 
+#define RASTER_W_EPS 1e-4
+
 typedef struct proj_tri {
-    double x[3], y[3], z[3], iw[3]; /* pixel coords, ndc depth, 1/w */
+    /* ok == 1: pixel coords, ndc depth, 1/w. ok == 2 (crosses the camera plane): e_i = x[i]*px + y[i]*py + z[i],
+     * iw[] = clip z, wc[] = clip w of the vertices, box = pixel box of the part in front (x0, x1, y0, y1) */
+    double x[3], y[3], z[3], iw[3];
+    double wc[3];
+    int box[4];
     int ok;
 } proj_tri;
 
 static void project(const float* M, const tri_world* t, uint32_t w, uint32_t h, proj_tri* o)
 {
-    o->ok = 1;
+    double c[3][4];
+    int behind = 0;
     for (int k = 0; k < 3; ++k) {
         const float* p = t->p[k];
-        double c[4];
         for (int r = 0; r < 4; ++r)
-            c[r] = (double)M[r] * p[0] + (double)M[4 + r] * p[1] + (double)M[8 + r] * p[2] + (double)M[12 + r];
-        if (c[3] <= 1e-4) { o->ok = 0; return; }
-        o->iw[k] = 1.0 / c[3];
-        o->x[k] = (c[0] * o->iw[k] * 0.5 + 0.5) * (double)w;
-        o->y[k] = (c[1] * o->iw[k] * 0.5 + 0.5) * (double)h;
-        o->z[k] = c[2] * o->iw[k];
+            c[k][r] = (double)M[r] * p[0] + (double)M[4 + r] * p[1] + (double)M[8 + r] * p[2] + (double)M[12 + r];
+        behind += c[k][3] <= RASTER_W_EPS ? 1 : 0;
     }
+    o->box[0] = o->box[2] = 0; o->box[1] = o->box[3] = -1;
+    o->wc[0] = o->wc[1] = o->wc[2] = 0.0;
+    if (behind == 3) { o->ok = 0; return; }
+    if (behind == 0) {
+        o->ok = 1;
+        for (int k = 0; k < 3; ++k) {
+            o->iw[k] = 1.0 / c[k][3];
+            o->x[k] = (c[k][0] * o->iw[k] * 0.5 + 0.5) * (double)w;
+            o->y[k] = (c[k][1] * o->iw[k] * 0.5 + 0.5) * (double)h;
+            o->z[k] = c[k][2] * o->iw[k];
+        }
+        return;
+    }
+    o->ok = 2;
+    double X[3], Y[3], W[3];
+    for (int k = 0; k < 3; ++k) {
+        X[k] = (c[k][0] * 0.5 + c[k][3] * 0.5) * (double)w;
+        Y[k] = (c[k][1] * 0.5 + c[k][3] * 0.5) * (double)h;
+        W[k] = c[k][3];
+        o->iw[k] = c[k][2];
+        o->wc[k] = c[k][3];
+    }
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        o->x[i] = Y[j] * W[k] - W[j] * Y[k];
+        o->y[i] = W[j] * X[k] - X[j] * W[k];
+        o->z[i] = X[j] * Y[k] - Y[j] * X[k];
+        if (W[i] > RASTER_W_EPS) {
+            const double px = X[i] / W[i], py = Y[i] / W[i];
+            xmin = fmin(xmin, px); xmax = fmax(xmax, px); ymin = fmin(ymin, py); ymax = fmax(ymax, py);
+        }
+        if ((W[i] > RASTER_W_EPS) != (W[j] > RASTER_W_EPS)) {
+            const double u = (RASTER_W_EPS - W[i]) / (W[j] - W[i]);
+            const double px = (X[i] + u * (X[j] - X[i])) / RASTER_W_EPS, py = (Y[i] + u * (Y[j] - Y[i])) / RASTER_W_EPS;
+            xmin = fmin(xmin, px); xmax = fmax(xmax, px); ymin = fmin(ymin, py); ymax = fmax(ymax, py);
+        }
+    }
+    if (ymax < 0 || ymin > h || xmax < 0 || xmin > w) return;
+    xmin = fmax(xmin, -1.0); ymin = fmax(ymin, -1.0); xmax = fmin(xmax, (double)w + 1.0); ymax = fmin(ymax, (double)h + 1.0);
+    o->box[0] = (int)floor(xmin - 0.5) > 0 ? (int)floor(xmin - 0.5) : 0;
+    o->box[1] = (int)ceil(xmax - 0.5) < (int)w - 1 ? (int)ceil(xmax - 0.5) : (int)w - 1;
+    o->box[2] = (int)floor(ymin - 0.5) > 0 ? (int)floor(ymin - 0.5) : 0;
+    o->box[3] = (int)ceil(ymax - 0.5) < (int)h - 1 ? (int)ceil(ymax - 0.5) : (int)h - 1;
+}
+
+static int hom_bary(const proj_tri* q, double px, double py, double* b, double* z)
+{
+    const double e0 = (q->x[0] * px + q->y[0] * py) + q->z[0];
+    const double e1 = (q->x[1] * px + q->y[1] * py) + q->z[1];
+    const double e2 = (q->x[2] * px + q->y[2] * py) + q->z[2];
+    const double s = (e0 + e1) + e2;
+    if (s == 0.0) return 0;
+    b[0] = e0 / s; b[1] = e1 / s; b[2] = e2 / s;
+    if (b[0] < 0 || b[1] < 0 || b[2] < 0) return 0;
+    const double wc = (b[0] * q->wc[0] + b[1] * q->wc[1]) + b[2] * q->wc[2];
+    if (!(wc > RASTER_W_EPS)) return 0;
+    *z = ((b[0] * q->iw[0] + b[1] * q->iw[1]) + b[2] * q->iw[2]) / wc;
+    return 1;
+}
+
+/* perspective-correct barycentric weights of the pixel centre on its winning triangle (both kinds) */
+static void pixel_bary(const proj_tri* q, double px, double py, double* b)
+{
+    if (q->ok == 2) {
+        double z;
+        hom_bary(q, px, py, b, &z);
+        return;
+    }
+    const double area = (q->x[1] - q->x[0]) * (q->y[2] - q->y[0]) - (q->x[2] - q->x[0]) * (q->y[1] - q->y[0]);
+    double b0 = ((q->x[1] - px) * (q->y[2] - py) - (q->x[2] - px) * (q->y[1] - py)) / area;
+    double b1 = ((q->x[2] - px) * (q->y[0] - py) - (q->x[0] - px) * (q->y[2] - py)) / area;
+    double b2 = 1.0 - b0 - b1;
+    b0 *= q->iw[0]; b1 *= q->iw[1]; b2 *= q->iw[2];
+    const double bs = b0 + b1 + b2;
+    b[0] = b0 / bs; b[1] = b1 / bs; b[2] = b2 / bs;
 }
 
 /* depth + winning triangle id per pixel */
@@ -122,6 +201,19 @@ static void raster_ids(const float* M, const tri_world* tris, uint32_t ntri, uin
         for (uint32_t t = 0; t < ntri; ++t) {
             const proj_tri* q = &pt[t];
             if (!q->ok) continue;
+            if (q->ok == 2) {
+                const int hy0 = q->box[2] > by0 ? q->box[2] : by0, hy1 = q->box[3] < by1 - 1 ? q->box[3] : by1 - 1;
+                for (int y = hy0; y <= hy1; ++y)
+                    for (int x = q->box[0]; x <= q->box[1]; ++x) {
+                        double b[3], z;
+                        if (!hom_bary(q, x + 0.5, y + 0.5, b, &z)) continue;
+                        if (z < 0.0 || z > 1.0) continue;
+                        const float zf = (float)z;
+                        const size_t pi = (size_t)y * w + x;
+                        if (zf < depth[pi]) { depth[pi] = zf; ids[pi] = (int32_t)t; }
+                    }
+                continue;
+            }
             const double ymin = fmin(q->y[0], fmin(q->y[1], q->y[2])), ymax = fmax(q->y[0], fmax(q->y[1], q->y[2]));
             if (ymax < by0 || ymin > by1) continue;
             const double xmin = fmin(q->x[0], fmin(q->x[1], q->x[2])), xmax = fmax(q->x[0], fmax(q->x[1], q->x[2]));
@@ -191,15 +283,9 @@ int vgs_gbuffer(const vgi_scene_desc* scene, const vgi_camera* cam, uint32_t w, 
             const tri_world* t = &tris[ids[pi]];
             proj_tri q;
             project(cam->view_proj, t, w, h, &q);
-            const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
-            const double px = x + 0.5, py = y + 0.5;
-            double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
-            double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
-            double b2 = 1.0 - b0 - b1;
-            /* perspective-correct attribute interpolation */
-            b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2];
-            const double bs = b0 + b1 + b2;
-            b0 /= bs; b1 /= bs; b2 /= bs;
+            double bb[3];
+            pixel_bary(&q, x + 0.5, y + 0.5, bb);
+            const double b0 = bb[0], b1 = bb[1], b2 = bb[2];
             double n[3];
             for (int k = 0; k < 3; ++k) n[k] = b0 * t->n[0][k] + b1 * t->n[1][k] + b2 * t->n[2][k];
             const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
@@ -245,14 +331,9 @@ int vgs_gbuffer_attributes(const vgi_scene_desc* scene, const vgi_camera* cam, u
             const tri_world* t = &tris[ids[pi]];
             proj_tri q;
             project(cam->view_proj, t, w, h, &q);
-            const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
-            const double px = x + 0.5, py = y + 0.5;
-            double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
-            double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
-            double b2 = 1.0 - b0 - b1;
-            b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2];
-            const double bs = b0 + b1 + b2;
-            b0 /= bs; b1 /= bs; b2 /= bs;
+            double bb[3];
+            pixel_bary(&q, x + 0.5, y + 0.5, bb);
+            const double b0 = bb[0], b1 = bb[1], b2 = bb[2];
             for (int k = 0; k < 3; ++k) normal[pi * 3 + k] = (float)(b0 * t->n[0][k] + b1 * t->n[1][k] + b2 * t->n[2][k]);
             material[pi] = t->mat;
         }

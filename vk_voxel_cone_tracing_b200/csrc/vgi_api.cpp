@@ -51,7 +51,8 @@ static void peer_close(vgi_ctx* c);
 
 static void free_scene(vgi_ctx* c)
 {
-    cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials);
+    cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials); cudaFree(c->tri_uv);
+    c->tri_uv = nullptr; c->scene_max_texture = -1;
     cudaFree(c->pairs); cudaFree(c->large); cudaFree(c->acc);
     cudaFree(c->raster_proj); cudaFree(c->raster_large);
     c->raster_proj = nullptr; c->raster_large = nullptr; c->raster_tri_cap = 0;
@@ -281,11 +282,13 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     if (!c || !s) return fail(c, VGI_E_INVALID, "vgi_set_scene: null argument");
     if (!s->positions || !s->normals || !s->indices || !s->primitives || !s->nodes || !s->materials)
         return fail(c, VGI_E_INVALID, "vgi_set_scene: missing buffer");
+    int32_t maxTex = -1;
     for (uint32_t m = 0; m < s->material_count; ++m) {
         const vgi_material& mt = s->materials[m];
-        if (mt.base_color_texture > -1 || mt.emissive_texture > -1 || mt.occlusion_texture > -1)
-            return fail(c, VGI_E_UNSUPPORTED, "vgi_set_scene: textured materials are outside the hot path (factor-only materials)");
+        const int32_t used[3] = { mt.base_color_texture, mt.emissive_texture, mt.occlusion_texture };
+        for (int k = 0; k < 3; ++k) maxTex = used[k] > maxTex ? used[k] : maxTex;
     }
+    if (maxTex > -1 && !s->texcoords) return fail(c, VGI_E_INVALID, "vgi_set_scene: textured materials need texcoords");
     uint64_t ntri = 0;
     for (uint32_t p = 0; p < s->primitive_count; ++p) {
         const vgi_primitive& pr = s->primitives[p];
@@ -299,6 +302,7 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     CK(c, cudaStreamSynchronize(c->last_stream));
     free_scene(c);
     std::vector<float4> pos(ntri * 3), nrm(ntri * 3);
+    std::vector<float2> uv(maxTex > -1 ? ntri * 3 : 0);
     float bbmin[3] = { INFINITY, INFINITY, INFINITY }, bbmax[3] = { -INFINITY, -INFINITY, -INFINITY };
     size_t t = 0;
     // world transform: ref msaaVoxelizer.vert:31-36; draw order: GLTFScene.cpp:457-490
@@ -317,6 +321,7 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
                 memcpy(&matf, &mat, 4);
                 pos[t * 3 + k] = make_float4(w[0], w[1], w[2], matf);
                 nrm[t * 3 + k] = make_float4(n[0], n[1], n[2], 0.f);
+                if (maxTex > -1) uv[t * 3 + k] = make_float2(s->texcoords[2 * vi], s->texcoords[2 * vi + 1]);
                 for (int a = 0; a < 3; ++a) {
                     bbmin[a] = w[a] < bbmin[a] ? w[a] : bbmin[a];
                     bbmax[a] = w[a] > bbmax[a] ? w[a] : bbmax[a];
@@ -328,6 +333,11 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     memcpy(c->scene_bb_min, bbmin, sizeof bbmin);
     memcpy(c->scene_bb_max, bbmax, sizeof bbmax);
     c->nmat = s->material_count;
+    c->scene_max_texture = maxTex;
+    if (ntri && maxTex > -1) {
+        CK(c, cudaMalloc(&c->tri_uv, uv.size() * sizeof(float2)));
+        CK(c, cudaMemcpy(c->tri_uv, uv.data(), uv.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     if (ntri) {
         CK(c, cudaMalloc(&c->tri_pos, pos.size() * sizeof(float4)));
         CK(c, cudaMalloc(&c->tri_nrm, nrm.size() * sizeof(float4)));
@@ -362,6 +372,36 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     c->visit_cap = c->max_occ;
     CK(c, cudaMalloc(&c->visit_list, (size_t)c->visit_cap * L * sizeof(uint32_t)));
     c->voxelized = c->built = false;
+    return VGI_OK;
+}
+
+int vgi_set_textures(vgi_ctx* c, const vgi_texture* tex, uint32_t count)
+{
+    if (!c || (count && !tex)) return fail(c, VGI_E_INVALID, "vgi_set_textures: null argument");
+    size_t total = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        if (!tex[i].rgba8 || !tex[i].width || !tex[i].height) return fail(c, VGI_E_INVALID, "vgi_set_textures: empty texture");
+        total += (size_t)tex[i].width * tex[i].height;
+    }
+    if (total > 0xffffffffull) return fail(c, VGI_E_INVALID, "vgi_set_textures: more than 2^32 texels");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    cudaFree(c->tex_data); cudaFree(c->tex_table);
+    c->tex_data = nullptr; c->tex_table = nullptr; c->ntex = 0;
+    c->voxelized = c->built = false;
+    if (!count) return VGI_OK;
+    std::vector<uint4> table(count);
+    CK(c, cudaMalloc(&c->tex_data, total * sizeof(uint32_t)));
+    size_t off = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        const size_t n = (size_t)tex[i].width * tex[i].height;
+        CK(c, cudaMemcpy(c->tex_data + off, tex[i].rgba8, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        table[i] = make_uint4((uint32_t)off, tex[i].width, tex[i].height, 0u);
+        off += n;
+    }
+    CK(c, cudaMalloc(&c->tex_table, count * sizeof(uint4)));
+    CK(c, cudaMemcpy(c->tex_table, table.data(), count * sizeof(uint4), cudaMemcpyHostToDevice));
+    c->ntex = count;
     return VGI_OK;
 }
 
@@ -488,6 +528,7 @@ int vgi_voxelize_opacity(vgi_ctx* c, void* stream)
 {
     if (!c) return fail(c, VGI_E_INVALID, "vgi_voxelize_opacity: null ctx");
     if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_voxelize_opacity: call vgi_set_scene first");
+    if (c->scene_max_texture >= (int32_t)c->ntex) return fail(c, VGI_E_STATE, "vgi_voxelize_opacity: a material references a texture that vgi_set_textures has not provided");
     CK(c, cudaSetDevice(c->device));
     BuildParams bp;
     build_params_from_ctx(c, 0, &bp);
@@ -585,6 +626,7 @@ int vgi_slab_build_begin(vgi_ctx* c, uint32_t frame_index, void* stream)
 {
     if (!c) return fail(c, VGI_E_INVALID, "vgi_slab_build_begin: null ctx");
     if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_slab_build_begin: call vgi_set_scene first");
+    if (c->scene_max_texture >= (int32_t)c->ntex) return fail(c, VGI_E_STATE, "vgi_slab_build_begin: a material references a texture that vgi_set_textures has not provided");
     if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_slab_build_begin: call vgi_set_light first");
     CK(c, cudaSetDevice(c->device));
     if (!c->slab_ids) {
@@ -1034,6 +1076,7 @@ int vgi_peer_build_clipmap(vgi_ctx* c, uint32_t frame_index, void* stream)
     if (!c) return fail(c, VGI_E_INVALID, "vgi_peer_build_clipmap: null ctx");
     if (!c->peers_attached) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: call vgi_peer_attach first");
     if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: call vgi_set_scene first");
+    if (c->scene_max_texture >= (int32_t)c->ntex) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: a material references a texture that vgi_set_textures has not provided");
     if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_peer_build_clipmap: call vgi_set_light first");
     CK(c, cudaSetDevice(c->device));
     BuildParams bp;
@@ -1101,6 +1144,8 @@ int vgi_render_gbuffer(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* tar
         !target->depth_f32 || !target->width || !target->height)
         return fail(c, VGI_E_INVALID, "vgi_render_gbuffer: incomplete target");
     if (!c->materials) return fail(c, VGI_E_STATE, "vgi_render_gbuffer: call vgi_set_scene first");
+    if (c->scene_max_texture > -1)
+        return fail(c, VGI_E_UNSUPPORTED, "vgi_render_gbuffer: textured materials (the host's own G-buffer pass supplies these images)");
     CK(c, cudaSetDevice(c->device));
     int r = raster_scratch(c, (size_t)target->width * target->height);
     if (r != VGI_OK) return r;

@@ -44,7 +44,8 @@ DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair
 
 __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* __restrict__ tri_pos,
                                                    uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
-                                                   uint2* __restrict__ large, Counters* __restrict__ cnt)
+                                                   uint2* __restrict__ large, Counters* __restrict__ cnt,
+                                                   const vgi_material* __restrict__ materials, TexSet tex)
 {
     // One thread per (level, triangle), level-major: neighbouring lanes are neighbouring triangles at the same
     // level. A thread first tests its (at most 64) candidate voxels into a 64-bit hit mask; then the warp
@@ -58,8 +59,11 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
     int lo0 = 0, lo1 = 0, lo2 = 0, nx = 1, ny = 1;
     if (inRange) {
         float p[9], N[3];
-        load_tri(tri_pos, t, p, nullptr);
-        cross_and_axis(p, N);
+        int mat = 0;
+        load_tri(tri_pos, t, p, &mat);
+        const int axis = cross_and_axis(p, N);
+        // alpha-tested materials (msaaVoxelizer.frag:64): the pair exists only where the occlusion texture passes
+        const int occTex = tex.count ? materials[mat].occlusion_texture : -1;
         TriSetup ts;
         tri_setup_level(ts, p, N, bp.lv[l], bp.R);
         if (ts.valid && ts.lo[0] <= ts.hi[0] && ts.lo[1] <= ts.hi[1] && ts.lo[2] <= ts.hi[2]) {
@@ -86,7 +90,14 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
                     if (slab && !owns_plane(bp, z & Rm)) { i += nx * ny; continue; }
                     for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
                         for (int x = ts.lo[0]; x <= ts.hi[0]; ++x, ++i)
-                            if (tri_overlaps_voxel(ts, x, y, z)) hits |= 1ull << i;
+                            if (tri_overlaps_voxel(ts, x, y, z)) {
+                                if (occTex > -1) {
+                                    const float vs = bp.lv[l].voxel_size;
+                                    float c[3] = { ((float)x + 0.5f) * vs, ((float)y + 0.5f) * vs, ((float)z + 0.5f) * vs };
+                                    if (!alpha_test_pair(tex, occTex, t, axis, N, p, c)) continue;
+                                }
+                                hits |= 1ull << i;
+                            }
                 }
             }
         }
@@ -122,15 +133,18 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
 // one warp per big (triangle, level) item; lanes stride over the clipped bounding box
 __global__ void __launch_bounds__(256) k_voxelize_large(BuildParams bp, const float4* __restrict__ tri_pos,
                                                          uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
-                                                         const uint2* __restrict__ large, Counters* __restrict__ cnt)
+                                                         const uint2* __restrict__ large, Counters* __restrict__ cnt,
+                                                         const vgi_material* __restrict__ materials, TexSet tex)
 {
     const uint32_t nitems = min(cnt->large, bp.max_large);
     const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += warpsPerGrid) {
         const uint2 it = large[item];
         float p[9], N[3];
-        load_tri(tri_pos, it.x, p, nullptr);
-        cross_and_axis(p, N);
+        int mat = 0;
+        load_tri(tri_pos, it.x, p, &mat);
+        const int axis = cross_and_axis(p, N);
+        const int occTex = tex.count ? materials[mat].occlusion_texture : -1;
         TriSetup ts;
         tri_setup_level(ts, p, N, bp.lv[it.y], bp.R);
         const int nx = ts.hi[0] - ts.lo[0] + 1, ny = ts.hi[1] - ts.lo[1] + 1, nz = ts.hi[2] - ts.lo[2] + 1;
@@ -141,7 +155,13 @@ __global__ void __launch_bounds__(256) k_voxelize_large(BuildParams bp, const fl
                 const int x = ts.lo[0] + (int)(i % nx);
                 const int y = ts.lo[1] + (int)((i / nx) % ny);
                 const int z = ts.lo[2] + (int)(i / ((long long)nx * ny));
-                if (tri_overlaps_voxel(ts, x, y, z)) emit_pair(bp, occ, pairs, cnt, it.x, (int)it.y, x, y, z);
+                bool hit = tri_overlaps_voxel(ts, x, y, z);
+                if (hit && occTex > -1) {
+                    const float vs = bp.lv[it.y].voxel_size;
+                    float c[3] = { ((float)x + 0.5f) * vs, ((float)y + 0.5f) * vs, ((float)z + 0.5f) * vs };
+                    hit = alpha_test_pair(tex, occTex, it.x, axis, N, p, c);
+                }
+                if (hit) emit_pair(bp, occ, pairs, cnt, it.x, (int)it.y, x, y, z);
             }
         }
     }
@@ -164,11 +184,14 @@ __global__ void k_zero_acc(uint32_t* __restrict__ acc, const Counters* __restric
 // (measured: 2, 3 or 4 resident blocks per SM give 429 / 421 / 420 us, and plain stores instead of the 64-bit
 // reductions 340 us: the kernel is bound by the L2 -> L1 sector traffic of the shadow taps, 25 texels per pair
 // with no overlap between neighbouring voxels, not by occupancy or by the atomics)
-__global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, const float4* __restrict__ tri_pos,
+#ifndef VGI_INJECT_MINBLOCKS
+#define VGI_INJECT_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, VGI_INJECT_MINBLOCKS) k_inject(BuildParams bp, LightParams lp, const float4* __restrict__ tri_pos,
                                                  const float4* __restrict__ tri_nrm, const vgi_material* __restrict__ materials,
                                                  const vgi_pair_t* __restrict__ pairs, const uint32_t* __restrict__ occ,
                                                  const uint32_t* __restrict__ occ_prefix, uint32_t* __restrict__ acc,
-                                                 Counters* __restrict__ cnt)
+                                                 Counters* __restrict__ cnt, TexSet tex)
 {
     const uint32_t npairs = min(cnt->pairs, bp.max_pairs);
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -184,6 +207,7 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
         ps.n[0] = ps.n[1] = ps.n[2] = 0.0f;
         ps.mat = 0;
         ps.cell = 0;
+        float uv[2] = { 0.0f, 0.0f };       // texture coordinate of the sample (textured materials only)
         if (i < npairs) {
             const vgi_pair_t pr = pairs[i];
             const uint32_t tri = (uint32_t)(pr >> 32);
@@ -204,8 +228,20 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
                 }
                 const int axis = cross_and_axis(p, N);
                 float c[3] = { ((float)vx + 0.5f) * lv.voxel_size, ((float)vy + 0.5f) * lv.voxel_size, ((float)vz + 0.5f) * lv.voxel_size };
-                float pos[3], nrm[3];
-                if (inject_sample_at(axis, N, p, n9, c, pos, nrm)) {
+                float pos[3], nrm[3], bary[3];
+                bool sampled = inject_sample_at(axis, N, p, n9, c, pos, nrm, bary);
+                if (sampled && tex.count) {
+                    const vgi_material* mt = materials + ps.mat;
+                    if (mt->base_color_texture > -1 || mt->emissive_texture > -1 || mt->occlusion_texture > -1) {
+                        tri_uv_at(tex, tri, bary, uv);
+                        if (mt->occlusion_texture > -1) {       // ref: msaaInjectRadiance.frag:73
+                            float t[4];
+                            tex_fetch(tex, mt->occlusion_texture, uv[0], uv[1], t);
+                            if (t[0] < 0.1f) sampled = false;
+                        }
+                    }
+                }
+                if (sampled) {
                     const vgi_material* m = materials + ps.mat;
                     const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
                     const size_t w = (size_t)level * wordsPerLevel + (((((size_t)tz << bp.logR) + ty) << bp.logR) + tx) / 32;
@@ -248,9 +284,15 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
         uint32_t fcode = 0u;            // lit: sign bits of the three faces; emissive: 8
         bool contrib = false;
         if (ps.kind == 1) {
-            q[0][0] = (uint32_t)(f_clamp(m->emissive_factor[0], 0.0f, 1.0f) * 65536.0f + 0.5f);
-            q[0][1] = (uint32_t)(f_clamp(m->emissive_factor[1], 0.0f, 1.0f) * 65536.0f + 0.5f);
-            q[0][2] = (uint32_t)(f_clamp(m->emissive_factor[2], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            float em[3] = { m->emissive_factor[0], m->emissive_factor[1], m->emissive_factor[2] };
+            if (tex.count && m->emissive_texture > -1) {    // ref: msaaInjectRadiance.frag:79-82
+                float t[4];
+                tex_fetch(tex, m->emissive_texture, uv[0], uv[1], t);
+                em[0] = em[0] + t[0]; em[1] = em[1] + t[1]; em[2] = em[2] + t[2];
+            }
+            q[0][0] = (uint32_t)(f_clamp(em[0], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            q[0][1] = (uint32_t)(f_clamp(em[1], 0.0f, 1.0f) * 65536.0f + 0.5f);
+            q[0][2] = (uint32_t)(f_clamp(em[2], 0.0f, 1.0f) * 65536.0f + 0.5f);
             fcode = 8u;
             contrib = true;
         } else if (ps.kind == 2) {
@@ -258,10 +300,17 @@ __global__ void __launch_bounds__(256) k_inject(BuildParams bp, LightParams lp, 
 #pragma unroll
             for (int k = 0; k < 3; ++k) lc[k] = ((ps.NdotL * vis) * lp.color[k]) * lp.intensity;
             if (!(lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f)) {
+                float col[4] = { m->base_color_factor[0], m->base_color_factor[1], m->base_color_factor[2], m->base_color_factor[3] };
+                if (tex.count && m->base_color_texture > -1) {  // ref: msaaInjectRadiance.frag:131-136
+                    float t[4];
+                    tex_fetch(tex, m->base_color_texture, uv[0], uv[1], t);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) col[k] = col[k] * t[k];
+                }
                 float rad[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    rad[k] = f_clamp((lc[k] * m->base_color_factor[k]) * m->base_color_factor[3], 0.0f, 1.0f);
+                    rad[k] = f_clamp((lc[k] * col[k]) * col[3], 0.0f, 1.0f);
                 // faces selected by -normal (ref: msaaInjectRadiance.frag:152-153): 0/1 = +X/-X, ...
                 fcode = ((-ps.n[0] > 0.0f) ? 0u : 1u) | ((-ps.n[1] > 0.0f) ? 0u : 2u) | ((-ps.n[2] > 0.0f) ? 0u : 4u);
 #pragma unroll
@@ -755,8 +804,8 @@ int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
     cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
     if (bp.ntri) {
-        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
-        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
+        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
     }
     const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
     LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));
@@ -810,8 +859,8 @@ static int launch_inject(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 #endif
     LAUNCH("k_zero_acc", k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ));
     if (bp.ntri && bp.level_mask) {
-        LAUNCH("k_inject", k_inject<<<148 * 8, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
-                                                            c->occ, c->occ_prefix, c->acc, c->counters));
+        LAUNCH("k_inject", k_inject<<<148 * VGI_INJECT_MINBLOCKS * 2, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
+                                                            c->occ, c->occ_prefix, c->acc, c->counters, c->texset()));
     }
     return n;
 }
@@ -969,8 +1018,8 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
     LAUNCH("k_peer_clear_occ", k_peer_own_planes<false><<<148 * 4, 256, 0, s>>>(ps, bp, c->occ));
     if (bp.ntri) {
-        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
-        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters));
+        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
     }
     const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
     LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));

@@ -187,7 +187,7 @@ DEVFN float calc_visibility(const LightParams& lp, const float* worldPos, bool c
 
 // voxel centre projected along the dominant axis onto the triangle plane, clamped into the triangle
 DEVFN bool inject_sample_at(int a, const float N[3], const float p[9], const float n9[9], float c[3],
-                            float pos[3], float nrm[3])
+                            float pos[3], float nrm[3], float* bary = nullptr)
 {
     // component selects instead of dynamic indexing keep the vertex arrays in registers
 #define SEL3(arr, base, i) ((i) == 0 ? (arr)[(base)] : ((i) == 1 ? (arr)[(base) + 1] : (arr)[(base) + 2]))
@@ -211,12 +211,68 @@ DEVFN bool inject_sample_at(int a, const float N[3], const float p[9], const flo
     b0 = f_max(b0, 0.0f); b1 = f_max(b1, 0.0f); b2 = f_max(b2, 0.0f);
     const float sum = (b0 + b1) + b2;
     b0 = b0 / sum; b1 = b1 / sum; b2 = b2 / sum;
+    if (bary) { bary[0] = b0; bary[1] = b1; bary[2] = b2; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         pos[k] = (p[k] * b0 + p[3 + k] * b1) + p[6 + k] * b2;
-        nrm[k] = (n9[k] * b0 + n9[3 + k] * b1) + n9[6 + k] * b2;
+        if (n9) nrm[k] = (n9[k] * b0 + n9[3 + k] * b1) + n9[6 + k] * b2;
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Material textures. ref: texture() / textureLod() of msaaVoxelizer.frag:64, msaaInjectRadiance.frag:73-82,131-136 and
+// voxelizer.frag:52-76 on samplers created with REPEAT + LINEAR and maxLod = 0 (GLTFScene.cpp:339): a bi-linear read
+// of level 0 with exact binary32 weights (unnormalised coordinate u * W - 0.5, texel = byte / 255).
+// ---------------------------------------------------------------------------------------------------
+DEVFN int tex_wrap(long long i, int n)
+{
+    if (i >= 0 && i < n) return (int)i;
+    const long long m = i % n;
+    return (int)(m < 0 ? m + n : m);
+}
+
+DEVFN void tex_fetch(const TexSet& ts, int tex, float u, float v, float o[4])
+{
+    const uint4 t = __ldg(ts.table + tex);
+    const int W = (int)t.y, H = (int)t.z;
+    const uint32_t* d = ts.data + t.x;
+    const float ux = u * (float)W - 0.5f, uy = v * (float)H - 0.5f;
+    const float fx = floorf(ux), fy = floorf(uy);
+    const float wx = ux - fx, wy = uy - fy;
+    const long long ix = (long long)fx, iy = (long long)fy;
+    const int x0 = tex_wrap(ix, W), x1 = tex_wrap(ix + 1, W), y0 = tex_wrap(iy, H), y1 = tex_wrap(iy + 1, H);
+    const uint32_t t00 = __ldg(d + (size_t)y0 * W + x0), t10 = __ldg(d + (size_t)y0 * W + x1);
+    const uint32_t t01 = __ldg(d + (size_t)y1 * W + x0), t11 = __ldg(d + (size_t)y1 * W + x1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = (float)((t00 >> (8 * k)) & 0xffu) / 255.0f, b = (float)((t10 >> (8 * k)) & 0xffu) / 255.0f;
+        const float c = (float)((t01 >> (8 * k)) & 0xffu) / 255.0f, e = (float)((t11 >> (8 * k)) & 0xffu) / 255.0f;
+        const float r0 = a * (1.0f - wx) + b * wx;
+        const float r1 = c * (1.0f - wx) + e * wx;
+        o[k] = r0 * (1.0f - wy) + r1 * wy;
+    }
+}
+
+// texture coordinate of a canonical sample: the vertices' coordinates weighted like its position
+DEVFN void tri_uv_at(const TexSet& ts, uint32_t tri, const float* bary, float* uv)
+{
+    const float2 a = __ldg(ts.tri_uv + 3 * (size_t)tri), b = __ldg(ts.tri_uv + 3 * (size_t)tri + 1), c = __ldg(ts.tri_uv + 3 * (size_t)tri + 2);
+    uv[0] = (a.x * bary[0] + b.x * bary[1]) + c.x * bary[2];
+    uv[1] = (a.y * bary[0] + b.y * bary[1]) + c.y * bary[2];
+}
+
+// ref: msaaVoxelizer.frag:64 / msaaInjectRadiance.frag:73 / voxelizer.frag:52 — "occlusion texture .r < 0.1 -> discard",
+// evaluated at the canonical sample of the (triangle, voxel) pair: the voxel centre c projected onto the triangle.
+// false = the pair is discarded (also when the sample does not exist: degenerate projection).
+DEVFN bool alpha_test_pair(const TexSet& ts, int occlusionTexture, uint32_t tri, int axis, const float N[3], const float p[9],
+                           float c[3])
+{
+    float pos[3], bary[3], uv[2], t[4];
+    if (!inject_sample_at(axis, N, p, nullptr, c, pos, nullptr, bary)) return true;    // no sample: nothing to test, the injection skips it too
+    tri_uv_at(ts, tri, bary, uv);
+    tex_fetch(ts, occlusionTexture, uv[0], uv[1], t);
+    return !(t[0] < 0.1f);
 }
 
 // Per-pair shading state produced by the lane-per-pair phase of k_inject.

@@ -47,6 +47,15 @@ struct BuildParams {
     int      shadow_compare;
 };
 
+// material textures (vgi_set_textures): RGBA8 texels of all textures back to back + one (offset, width, height) row each;
+// tri_uv = 3 texture coordinates per triangle (nullptr when the scene has none)
+struct TexSet {
+    const uint32_t* data;
+    const uint4*    table;
+    const float2*   tri_uv;
+    uint32_t        count;
+};
+
 struct LightParams {
     float view[16], proj[16];
     float dir_to_light[3];  // normalize(-direction)
@@ -155,6 +164,12 @@ struct vgi_ctx {
     float4*  tri_nrm = nullptr;   // 3 per triangle
     vgi_material* materials = nullptr;
     uint32_t nmat = 0;
+    float2*  tri_uv = nullptr;    // 3 per triangle, only when a material is textured
+    uint32_t* tex_data = nullptr;
+    uint4*    tex_table = nullptr;
+    uint32_t  ntex = 0;
+    int32_t   scene_max_texture = -1;   // highest texture index a material of the scene references
+    TexSet texset() const { return TexSet{ tex_data, tex_table, tri_uv, ntex }; }
     std::vector<float> h_tri_pos; // host copies for debugging / multi-GPU culling
     float scene_bb_min[3], scene_bb_max[3];
 

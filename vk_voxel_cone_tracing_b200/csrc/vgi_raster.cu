@@ -5,8 +5,13 @@
 // (factor-only materials), formats VFS/RenderPass/GBufferPass.cpp:177-194.
 //
 // Rasterisation rule (the software definition the test producers pin: pixel-centre sampling, depth test LESS with ties
-// to the lower triangle index, z clipped to [0,1], triangles with a vertex at w <= 1e-4 skipped): visibility is one
-// 64-bit atomicMin per fragment on (depth bits << 32 | triangle), then a resolve pass shades the winning triangle.
+// to the lower triangle index, z clipped to [0,1]): visibility is one 64-bit atomicMin per fragment on
+// (depth bits << 32 | triangle), then a resolve pass shades the winning triangle. A triangle with a vertex at or behind the
+// camera plane (clip w <= 1e-4: floors and walls next to the viewer) is NOT dropped: it is rasterised with 2-D homogeneous
+// edge functions (Olano & Greer 1997) — e_i(px, py) = det[V_j; V_k; (px, py, 1)] on V = (x_h, y_h, w), whose ratios
+// e_i / (e_0 + e_1 + e_2) are the perspective-correct barycentric weights of the point the pixel's ray hits on the
+// triangle's plane, valid on both sides of w = 0 — inside the pixel box of its part in front of the plane; the hardware
+// rasteriser of the reference clips such triangles against the frustum and shades the same pixels.
 // Edge functions and interpolation are evaluated in binary64 without FMA contraction (this file is compiled with
 // -fmad=false), so depth and every quantised attribute equal the host producer bit for bit.
 #include <cuda_fp16.h>
@@ -16,7 +21,11 @@
 #define DEVFN static __device__ __forceinline__
 
 struct ProjTri {
-    double x[3], y[3], z[3], iw[3]; // pixel coordinates, NDC depth, 1 / w
+    // ok == 1: pixel coordinates, NDC depth, 1 / w of the vertices.
+    // ok == 2 (crosses the camera plane): e_i = x[i] * px + y[i] * py + z[i]; iw[] = clip z, wc[] = clip w of the vertices
+    double x[3], y[3], z[3], iw[3];
+    double wc[3];
+    int box[4];                     // ok == 2: pixel box of the part in front of the plane (x0, x1, y0, y1), may be empty
     int ok;
     int pad;
 };
@@ -24,22 +33,87 @@ struct ProjTri {
 #define RASTER_SMALL_MAX 256   // bounding boxes up to this many pixels are walked by one thread
 #define RASTER_HUGE_MIN (128 * 128)    // boxes above this many pixels are spread over the whole grid
 
+#define RASTER_W_EPS 1e-4
+
 DEVFN void project_tri(const float* M, const float4* tri_pos, uint32_t t, int w, int h, ProjTri& o)
 {
-    o.ok = 1;
+    double c[3][4];
+    int behind = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float4 p = tri_pos[(size_t)t * 3 + k];
-        double c[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-            c[r] = (double)M[r] * p.x + (double)M[4 + r] * p.y + (double)M[8 + r] * p.z + (double)M[12 + r];
-        if (c[3] <= 1e-4) { o.ok = 0; return; }
-        o.iw[k] = 1.0 / c[3];
-        o.x[k] = (c[0] * o.iw[k] * 0.5 + 0.5) * (double)w;
-        o.y[k] = (c[1] * o.iw[k] * 0.5 + 0.5) * (double)h;
-        o.z[k] = c[2] * o.iw[k];
+            c[k][r] = (double)M[r] * p.x + (double)M[4 + r] * p.y + (double)M[8 + r] * p.z + (double)M[12 + r];
+        behind += c[k][3] <= RASTER_W_EPS ? 1 : 0;
     }
+    o.box[0] = o.box[2] = 0; o.box[1] = o.box[3] = -1;
+    o.wc[0] = o.wc[1] = o.wc[2] = 0.0;
+    if (behind == 3) { o.ok = 0; return; }
+    if (behind == 0) {
+        o.ok = 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            o.iw[k] = 1.0 / c[k][3];
+            o.x[k] = (c[k][0] * o.iw[k] * 0.5 + 0.5) * (double)w;
+            o.y[k] = (c[k][1] * o.iw[k] * 0.5 + 0.5) * (double)h;
+            o.z[k] = c[k][2] * o.iw[k];
+        }
+        return;
+    }
+    // crosses the camera plane: homogeneous pixel coordinates V = (x_h, y_h, w) with x_h / w = pixel x
+    o.ok = 2;
+    double X[3], Y[3], W[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        X[k] = (c[k][0] * 0.5 + c[k][3] * 0.5) * (double)w;
+        Y[k] = (c[k][1] * 0.5 + c[k][3] * 0.5) * (double)h;
+        W[k] = c[k][3];
+        o.iw[k] = c[k][2];
+        o.wc[k] = c[k][3];
+    }
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        o.x[i] = Y[j] * W[k] - W[j] * Y[k];
+        o.y[i] = W[j] * X[k] - X[j] * W[k];
+        o.z[i] = X[j] * Y[k] - Y[j] * X[k];
+        // pixel box of the polygon in front of w = eps: its vertices are the triangle's vertices in front and the points
+        // where an edge crosses the plane
+        if (W[i] > RASTER_W_EPS) {
+            const double px = X[i] / W[i], py = Y[i] / W[i];
+            xmin = fmin(xmin, px); xmax = fmax(xmax, px); ymin = fmin(ymin, py); ymax = fmax(ymax, py);
+        }
+        if ((W[i] > RASTER_W_EPS) != (W[j] > RASTER_W_EPS)) {
+            const double u = (RASTER_W_EPS - W[i]) / (W[j] - W[i]);
+            const double px = (X[i] + u * (X[j] - X[i])) / RASTER_W_EPS, py = (Y[i] + u * (Y[j] - Y[i])) / RASTER_W_EPS;
+            xmin = fmin(xmin, px); xmax = fmax(xmax, px); ymin = fmin(ymin, py); ymax = fmax(ymax, py);
+        }
+    }
+    if (ymax < 0 || ymin > h || xmax < 0 || xmin > w) return;       // empty box
+    xmin = fmax(xmin, -1.0); ymin = fmax(ymin, -1.0); xmax = fmin(xmax, (double)w + 1.0); ymax = fmin(ymax, (double)h + 1.0);
+    o.box[0] = max((int)floor(xmin - 0.5), 0);
+    o.box[1] = min((int)ceil(xmax - 0.5), w - 1);
+    o.box[2] = max((int)floor(ymin - 0.5), 0);
+    o.box[3] = min((int)ceil(ymax - 0.5), h - 1);
+}
+
+// ok == 2: perspective-correct barycentric weights and NDC depth of pixel centre (px, py); false outside the triangle
+// or at / behind the camera plane
+DEVFN bool hom_bary(const ProjTri& q, double px, double py, double* b, double* z)
+{
+    const double e0 = (q.x[0] * px + q.y[0] * py) + q.z[0];
+    const double e1 = (q.x[1] * px + q.y[1] * py) + q.z[1];
+    const double e2 = (q.x[2] * px + q.y[2] * py) + q.z[2];
+    const double s = (e0 + e1) + e2;
+    if (s == 0.0) return false;
+    b[0] = e0 / s; b[1] = e1 / s; b[2] = e2 / s;
+    if (b[0] < 0 || b[1] < 0 || b[2] < 0) return false;
+    const double wc = (b[0] * q.wc[0] + b[1] * q.wc[1]) + b[2] * q.wc[2];
+    if (!(wc > RASTER_W_EPS)) return false;
+    *z = ((b[0] * q.iw[0] + b[1] * q.iw[1]) + b[2] * q.iw[2]) / wc;
+    return true;
 }
 
 struct RasterParams {
@@ -61,7 +135,13 @@ DEVFN Box tri_box(const ProjTri& q, int w, int h)
 {
     Box b;
     b.any = false;
+    b.area = 1.0;
     if (!q.ok) return b;
+    if (q.ok == 2) {
+        b.x0 = q.box[0]; b.x1 = q.box[1]; b.y0 = q.box[2]; b.y1 = q.box[3];
+        b.any = b.x0 <= b.x1 && b.y0 <= b.y1;
+        return b;
+    }
     const double ymin = fmin(q.y[0], fmin(q.y[1], q.y[2])), ymax = fmax(q.y[0], fmax(q.y[1], q.y[2]));
     const double xmin = fmin(q.x[0], fmin(q.x[1], q.x[2])), xmax = fmax(q.x[0], fmax(q.x[1], q.x[2]));
     if (ymax < 0 || ymin > h || xmax < 0 || xmin > w) return b;
@@ -78,6 +158,15 @@ DEVFN Box tri_box(const ProjTri& q, int w, int h)
 DEVFN void raster_pixel(const RasterParams& rp, const ProjTri& q, double area, uint32_t t, int x, int y)
 {
     const double px = x + 0.5, py = y + 0.5;
+    if (q.ok == 2) {
+        double b[3], z;
+        if (!hom_bary(q, px, py, b, &z)) return;
+        if (z < 0.0 || z > 1.0) return;
+        const float zf = (float)z;
+        if (!(zf < 1.0f)) return;
+        atomicMin(rp.keys + (size_t)y * rp.w + x, ((unsigned long long)__float_as_uint(zf) << 32) | t);
+        return;
+    }
     const double e0 = (q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py);
     const double e1 = (q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py);
     // e / area < 0 <=> the signs differ (e != 0): most pixels of a bounding box leave before the two divisions
@@ -200,14 +289,21 @@ __global__ void __launch_bounds__(256) k_raster_resolve_gbuffer(const __grid_con
     g.depth[pi] = __uint_as_float((uint32_t)(k >> 32));
     const uint32_t t = (uint32_t)k;
     const ProjTri q = rp.proj[t];
-    const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
     const double px = x + 0.5, py = y + 0.5;
-    double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
-    double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
-    double b2 = 1.0 - b0 - b1;
-    b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2]; // perspective-correct attribute interpolation
-    const double bs = b0 + b1 + b2;
-    b0 /= bs; b1 /= bs; b2 /= bs;
+    double b0, b1, b2;
+    if (q.ok == 2) {
+        double b[3], z;
+        hom_bary(q, px, py, b, &z);     // the weights of the homogeneous edge functions are perspective-correct already
+        b0 = b[0]; b1 = b[1]; b2 = b[2];
+    } else {
+        const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
+        b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
+        b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
+        b2 = 1.0 - b0 - b1;
+        b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2]; // perspective-correct attribute interpolation
+        const double bs = b0 + b1 + b2;
+        b0 /= bs; b1 /= bs; b2 /= bs;
+    }
     const float4 n0 = rp.tri_nrm[(size_t)t * 3], n1 = rp.tri_nrm[(size_t)t * 3 + 1], n2 = rp.tri_nrm[(size_t)t * 3 + 2];
     const double n[3] = { b0 * n0.x + b1 * n1.x + b2 * n2.x, b0 * n0.y + b1 * n1.y + b2 * n2.y, b0 * n0.z + b1 * n1.z + b2 * n2.z };
     const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(256) k_svo_shade(SvoGrid g, LightParams lp, in
                                                     const float4* __restrict__ tri_pos, const float4* __restrict__ tri_nrm,
                                                     const vgi_material* __restrict__ materials,
                                                     const svo_pair_t* __restrict__ pairs, uint32_t max_pairs,
-                                                    uint2* __restrict__ frags, uint32_t max_frags, Counters* __restrict__ cnt)
+                                                    uint2* __restrict__ frags, uint32_t max_frags, Counters* __restrict__ cnt,
+                                                    TexSet tex)
 {
     const uint32_t npairs = min(cnt->pairs, max_pairs);
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(256) k_svo_shade(SvoGrid g, LightParams lp, in
         float spx = 0.0f, spy = 0.0f, scz = 0.0f, NdotL = 0.0f;
         int mat = 0;
         uint32_t vx = 0, vy = 0, vz = 0;
+        float uv[2] = { 0.0f, 0.0f };
         if (i < npairs) {
             const svo_pair_t pr = pairs[i];
             const uint32_t tri = (uint32_t)(pr >> 36);
@@ -186,8 +188,20 @@ __global__ void __launch_bounds__(256) k_svo_shade(SvoGrid g, LightParams lp, in
             float c[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) c[k] = ((((float)v3[k] + 0.5f) / (float)g.res) * 2.0f - 1.0f) * g.extentValue + g.center[k];
-            float pos[3], nrm[3];
-            if (inject_sample_at(axis, N, p, n9, c, pos, nrm)) {
+            float pos[3], nrm[3], bary[3];
+            bool sampled = inject_sample_at(axis, N, p, n9, c, pos, nrm, bary);
+            if (sampled && tex.count) {
+                const vgi_material* mt = materials + mat;
+                if (mt->base_color_texture > -1 || mt->emissive_texture > -1 || mt->occlusion_texture > -1) {
+                    tri_uv_at(tex, tri, bary, uv);
+                    if (mt->occlusion_texture > -1) {       // ref: voxelizer.frag:52
+                        float t[4];
+                        tex_fetch(tex, mt->occlusion_texture, uv[0], uv[1], t);
+                        if (t[0] < 0.1f) sampled = false;
+                    }
+                }
+            }
+            if (sampled) {
                 const vgi_material* m = materials + mat;
                 if (m->emissive_factor[0] > 0.0f || m->emissive_factor[1] > 0.0f || m->emissive_factor[2] > 0.0f) {
                     kind = 1;
@@ -222,12 +236,23 @@ __global__ void __launch_bounds__(256) k_svo_shade(SvoGrid g, LightParams lp, in
         bool emit = kind != 0;
         if (kind == 1) {
             const vgi_material* m = materials + mat;
+            float em[3] = { m->emissive_factor[0], m->emissive_factor[1], m->emissive_factor[2] };
+            if (tex.count && m->emissive_texture > -1) {    // ref: voxelizer.frag:63-67
+                float t[4];
+                tex_fetch(tex, m->emissive_texture, uv[0], uv[1], t);
+                em[0] = em[0] + t[0]; em[1] = em[1] + t[1]; em[2] = em[2] + t[2];
+            }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) radiance[k] = f_clamp(m->emissive_factor[k], 0.0f, 1.0f);
+            for (int k = 0; k < 3; ++k) radiance[k] = f_clamp(em[k], 0.0f, 1.0f);
         } else if (kind == 2) {
             const vgi_material* m = materials + mat;
             float color[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
-            if (!literal) { color[0] = m->base_color_factor[0]; color[1] = m->base_color_factor[1]; color[2] = m->base_color_factor[2]; color[3] = m->base_color_factor[3]; } // Q21
+            if (tex.count && m->base_color_texture > -1) {  // ref: voxelizer.frag:72-77 — texture * factor (both modes)
+                float t[4];
+                tex_fetch(tex, m->base_color_texture, uv[0], uv[1], t);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) color[k] = t[k] * m->base_color_factor[k];
+            } else if (!literal) { color[0] = m->base_color_factor[0]; color[1] = m->base_color_factor[1]; color[2] = m->base_color_factor[2]; color[3] = m->base_color_factor[3]; } // Q21
             float lc[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) lc[k] = ((NdotL * vis) * lp.color[k]) * lp.intensity;
@@ -502,6 +527,8 @@ int vgi_svo_voxelize(vgi_ctx* c, uint32_t level, const float bb_min[3], const fl
     if (level < 1 || level > 10) return svo_fail(c, VGI_E_INVALID, "vgi_svo_voxelize: level must be in [1,10]"); // EngineConfig.h:19-21 allows 11; the dense path masks stop at 10
     if (!c->tri_pos && c->ntri) return svo_fail(c, VGI_E_STATE, "vgi_svo_voxelize: call vgi_set_scene first");
     if (!c->pairs) return svo_fail(c, VGI_E_STATE, "vgi_svo_voxelize: call vgi_set_scene first");
+    if (c->scene_max_texture >= (int32_t)c->ntex)
+        return svo_fail(c, VGI_E_STATE, "vgi_svo_voxelize: a material references a texture that vgi_set_textures has not provided");
     if (!c->light_set) return svo_fail(c, VGI_E_STATE, "vgi_svo_voxelize: call vgi_set_light first");
     for (int k = 0; k < 3; ++k)
         if (!(bb_max[k] >= bb_min[k])) return svo_fail(c, VGI_E_INVALID, "vgi_svo_voxelize: empty bounding box");
@@ -526,7 +553,7 @@ int vgi_svo_voxelize(vgi_ctx* c, uint32_t level, const float bb_min[3], const fl
         LAUNCH("k_svo_voxelize_large", k_svo_voxelize_large<<<148 * 4, 256, 0, s>>>(g, c->tri_pos, pairs, c->max_pairs, c->large, c->max_large, c->counters));
         LAUNCH("k_svo_shade", k_svo_shade<<<148 * 8, 256, 0, s>>>(g, c->light, (c->cfg.mode_flags & VGI_MODE_SHADOW_COMPARE) ? 1 : 0,
                                                                    (c->cfg.mode_flags & VGI_MODE_SVO_LITERAL) ? 1 : 0, c->tri_pos, c->tri_nrm,
-                                                                   c->materials, pairs, c->max_pairs, c->svo_frags, c->svo_frag_capacity, c->counters));
+                                                                   c->materials, pairs, c->max_pairs, c->svo_frags, c->svo_frag_capacity, c->counters, c->texset()));
     }
     SCK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     c->last_stream = s;

@@ -56,6 +56,22 @@ def default_config(resolution=128, level_count=6, **kw):
     return c
 
 
+class Texture(C.Structure):
+    """vgi_texture — one RGBA8 material texture (ref: GLTFScene::uploadImage; REPEAT + LINEAR, level 0 only, Q23)"""
+    _fields_ = [("rgba8", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+def texture_array(images):
+    """list of (H, W, 4) uint8 arrays -> (ctypes array of vgi_texture, keep-alive list)."""
+    keep = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    arr = (Texture * max(len(keep), 1))()
+    for i, im in enumerate(keep):
+        assert im.ndim == 3 and im.shape[2] == 4
+        arr[i].rgba8 = im.ctypes.data
+        arr[i].height, arr[i].width = im.shape[:2]
+    return arr, keep
+
+
 class ClipRegion(C.Structure):
     """vgi_clip_region — ref: VFS/RenderPass/Clipmap/ClipmapRegion.h:8-18"""
     _fields_ = [("min_corner", C.c_int32 * 3), ("extent", C.c_uint32 * 3), ("voxel_size", C.c_float)]

@@ -188,6 +188,86 @@ def cornell_box(wall_quads=32, box_quads=10):
     return b.build("cornell")
 
 
+def coarse_room(quads=1, half=12.0, height=6.0):
+    """A hall whose floor, ceiling and four walls are `quads` x `quads` grids (2 triangles each at quads = 1): for a camera
+    inside, most of these triangles have a vertex BEHIND the camera plane — the case a hardware rasteriser clips and the
+    software rasterisers must not drop (near-plane handling)."""
+    b = _Builder()
+    node = b.node(np.eye(4, dtype=np.float32))
+    cols = [(0.8, 0.8, 0.8, 1.0), (0.7, 0.3, 0.2, 1.0), (0.2, 0.6, 0.3, 1.0), (0.3, 0.3, 0.8, 1.0), (0.8, 0.7, 0.2, 1.0),
+            (0.6, 0.6, 0.6, 1.0)]
+    m = [b.material(c) for c in cols]
+    h, y0, y1, n = half, 0.0, height, quads
+    b.grid((-h, y0, -h), (2 * h, 0, 0), (0, 0, 2 * h), n, n, (0, 1, 0), m[0], node)       # floor
+    b.grid((-h, y1, -h), (0, 0, 2 * h), (2 * h, 0, 0), n, n, (0, -1, 0), m[5], node)      # ceiling
+    b.grid((-h, y0, -h), (2 * h, 0, 0), (0, y1 - y0, 0), n, n, (0, 0, 1), m[1], node)     # z = -h
+    b.grid((-h, y0, h), (0, y1 - y0, 0), (2 * h, 0, 0), n, n, (0, 0, -1), m[2], node)     # z = +h
+    b.grid((-h, y0, -h), (0, y1 - y0, 0), (0, 0, 2 * h), n, n, (1, 0, 0), m[3], node)     # x = -h
+    b.grid((h, y0, -h), (0, 0, 2 * h), (0, y1 - y0, 0), n, n, (-1, 0, 0), m[4], node)     # x = +h
+    return b.build("coarse_room")
+
+
+def procedural_textures(seed=7):
+    """Four small RGBA8 textures for the textured fixtures: [0] base colour (coloured checker with a smooth gradient, alpha
+    0.6-1), [1] emissive pattern (dim stripes), [2] occlusion mask (.r = 0 inside round holes, 1 elsewhere: alpha test),
+    [3] a 3 x 5 non-power-of-two noise image (REPEAT wrap on awkward sizes)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:64, 0:64]
+    base = np.zeros((64, 64, 4), np.uint8)
+    chk = ((xx // 8 + yy // 8) % 2).astype(np.float64)
+    base[..., 0] = (90 + 150 * chk).astype(np.uint8)
+    base[..., 1] = (40 + 3 * xx).astype(np.uint8)
+    base[..., 2] = (250 - 3 * yy).astype(np.uint8)
+    base[..., 3] = (153 + 102 * (1 - chk)).astype(np.uint8)
+    emis = np.zeros((32, 16, 4), np.uint8)
+    yy2, xx2 = np.mgrid[0:32, 0:16]
+    emis[..., 0] = (40 * ((yy2 // 4) % 2)).astype(np.uint8)
+    emis[..., 1] = (25 * ((xx2 // 2) % 2)).astype(np.uint8)
+    emis[..., 2] = 10
+    emis[..., 3] = 255
+    occ = np.full((48, 48, 4), 255, np.uint8)
+    yy3, xx3 = np.mgrid[0:48, 0:48]
+    holes = (((xx3 % 16) - 8) ** 2 + ((yy3 % 16) - 8) ** 2) < 20
+    occ[holes, 0] = 0
+    noise = rng.randint(0, 256, (5, 3, 4)).astype(np.uint8)
+    return [base, emis, occ, noise]
+
+
+def textured_cornell(wall_quads=12, box_quads=4):
+    """The Cornell box with textured materials (texture indices into procedural_textures()): textured floor (base colour),
+    alpha-tested back wall (occlusion mask: holes), a wall whose base colour uses the 3 x 5 texture with repeated
+    coordinates, an emissive quad with an emissive texture, one box that combines all three."""
+    b = _Builder()
+    node = b.node(np.eye(4, dtype=np.float32).reshape(4, 4))
+
+    def mat(base=(1, 1, 1, 1), emissive=(0, 0, 0), bt=-1, et=-1, ot=-1, **kw):
+        i = b.material(base, emissive=emissive, **kw)
+        b.mats[i]["base_color_texture"] = bt
+        b.mats[i]["emissive_texture"] = et
+        b.mats[i]["occlusion_texture"] = ot
+        return i
+
+    floor = mat((0.9, 0.9, 0.9, 1.0), bt=0)
+    back = mat((0.725, 0.725, 0.725, 1.0), ot=2)
+    left = mat((0.63, 0.3, 0.25, 0.9), bt=3)
+    right = mat((0.14, 0.45, 0.091, 1.0))
+    combo = mat((0.8, 0.8, 0.8, 1.0), bt=0, ot=2)
+    light = mat((1.0, 1.0, 1.0, 1.0), emissive=(0.6, 0.7, 0.8), et=1)
+    n = wall_quads
+    b.grid((-4, -4, -4), (8, 0, 0), (0, 0, 8), n, n, (0, 1, 0), floor, node)
+    b.grid((-4, -4, -4), (8, 0, 0), (0, 8, 0), n, n, (0, 0, 1), back, node)
+    b.grid((-4, -4, -4), (0, 0, 8), (0, 8, 0), n, n, (1, 0, 0), left, node)
+    b.grid((4, -4, -4), (0, 8, 0), (0, 0, 8), n, n, (-1, 0, 0), right, node)
+    _box(b, (1.7, -2.8, -1.7), (1.2, 1.2, 1.2), 18.0, box_quads, combo, node)
+    b.grid((-1, 3.6, -2.5), (2, 0, 0), (0, 0, 2), 2, 2, (0, -1, 0), light, node)
+    sc = b.build("textured_cornell")
+    # texture coordinates beyond [0, 1] and negative on the left wall (primitive 2): REPEAT addressing
+    v0 = int(sc.primitives[2]["vertex_offset"])
+    v1 = int(sc.primitives[3]["vertex_offset"])
+    sc.texcoords[v0:v1] = (sc.texcoords[v0:v1] * np.float32(3.3) - np.float32(1.2)).astype(np.float32)
+    return sc
+
+
 def atrium(seed=1234):
     """Config 2: "Sponza-scale" procedural atrium, exactly 262 144 triangles inside the
     Sponza world bounding box [-15.4,-1.0,-9.5]..[14.4,11.4,8.8]: floor, walls,
