@@ -42,6 +42,9 @@ DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair
         atomicOr(&cnt->overflow, 1u);
 }
 
+// TEX = the scene has textured materials (occlusion-texture alpha test per candidate pair); the untextured instantiation
+// carries none of that code (measured: the shared kernel cost the factor-only scene 0.111 -> 0.138 ms)
+template <bool TEX>
 __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* __restrict__ tri_pos,
                                                    uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
                                                    uint2* __restrict__ large, Counters* __restrict__ cnt,
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
         load_tri(tri_pos, t, p, &mat);
         const int axis = cross_and_axis(p, N);
         // alpha-tested materials (msaaVoxelizer.frag:64): the pair exists only where the occlusion texture passes
-        const int occTex = tex.count ? materials[mat].occlusion_texture : -1;
+        const int occTex = TEX ? materials[mat].occlusion_texture : -1;
         TriSetup ts;
         tri_setup_level(ts, p, N, bp.lv[l], bp.R);
         if (ts.valid && ts.lo[0] <= ts.hi[0] && ts.lo[1] <= ts.hi[1] && ts.lo[2] <= ts.hi[2]) {
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
                     for (int y = ts.lo[1]; y <= ts.hi[1]; ++y)
                         for (int x = ts.lo[0]; x <= ts.hi[0]; ++x, ++i)
                             if (tri_overlaps_voxel(ts, x, y, z)) {
-                                if (occTex > -1) {
+                                if (TEX && occTex > -1) {
                                     const float vs = bp.lv[l].voxel_size;
                                     float c[3] = { ((float)x + 0.5f) * vs, ((float)y + 0.5f) * vs, ((float)z + 0.5f) * vs };
                                     if (!alpha_test_pair(tex, occTex, t, axis, N, p, c)) continue;
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
 }
 
 // one warp per big (triangle, level) item; lanes stride over the clipped bounding box
+template <bool TEX>
 __global__ void __launch_bounds__(256) k_voxelize_large(BuildParams bp, const float4* __restrict__ tri_pos,
                                                          uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
                                                          const uint2* __restrict__ large, Counters* __restrict__ cnt,
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) k_voxelize_large(BuildParams bp, const fl
         int mat = 0;
         load_tri(tri_pos, it.x, p, &mat);
         const int axis = cross_and_axis(p, N);
-        const int occTex = tex.count ? materials[mat].occlusion_texture : -1;
+        const int occTex = TEX ? materials[mat].occlusion_texture : -1;
         TriSetup ts;
         tri_setup_level(ts, p, N, bp.lv[it.y], bp.R);
         const int nx = ts.hi[0] - ts.lo[0] + 1, ny = ts.hi[1] - ts.lo[1] + 1, nz = ts.hi[2] - ts.lo[2] + 1;
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(256) k_voxelize_large(BuildParams bp, const fl
                 const int y = ts.lo[1] + (int)((i / nx) % ny);
                 const int z = ts.lo[2] + (int)(i / ((long long)nx * ny));
                 bool hit = tri_overlaps_voxel(ts, x, y, z);
-                if (hit && occTex > -1) {
+                if (TEX && hit && occTex > -1) {
                     const float vs = bp.lv[it.y].voxel_size;
                     float c[3] = { ((float)x + 0.5f) * vs, ((float)y + 0.5f) * vs, ((float)z + 0.5f) * vs };
                     hit = alpha_test_pair(tex, occTex, it.x, axis, N, p, c);
@@ -187,6 +191,7 @@ __global__ void k_zero_acc(uint32_t* __restrict__ acc, const Counters* __restric
 #ifndef VGI_INJECT_MINBLOCKS
 #define VGI_INJECT_MINBLOCKS 4
 #endif
+template <bool TEX>
 __global__ void __launch_bounds__(256, VGI_INJECT_MINBLOCKS) k_inject(BuildParams bp, LightParams lp, const float4* __restrict__ tri_pos,
                                                  const float4* __restrict__ tri_nrm, const vgi_material* __restrict__ materials,
                                                  const vgi_pair_t* __restrict__ pairs, const uint32_t* __restrict__ occ,
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(256, VGI_INJECT_MINBLOCKS) k_inject(BuildParam
                 float c[3] = { ((float)vx + 0.5f) * lv.voxel_size, ((float)vy + 0.5f) * lv.voxel_size, ((float)vz + 0.5f) * lv.voxel_size };
                 float pos[3], nrm[3], bary[3];
                 bool sampled = inject_sample_at(axis, N, p, n9, c, pos, nrm, bary);
-                if (sampled && tex.count) {
+                if (TEX && sampled) {
                     const vgi_material* mt = materials + ps.mat;
                     if (mt->base_color_texture > -1 || mt->emissive_texture > -1 || mt->occlusion_texture > -1) {
                         tri_uv_at(tex, tri, bary, uv);
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(256, VGI_INJECT_MINBLOCKS) k_inject(BuildParam
         bool contrib = false;
         if (ps.kind == 1) {
             float em[3] = { m->emissive_factor[0], m->emissive_factor[1], m->emissive_factor[2] };
-            if (tex.count && m->emissive_texture > -1) {    // ref: msaaInjectRadiance.frag:79-82
+            if (TEX && m->emissive_texture > -1) {    // ref: msaaInjectRadiance.frag:79-82
                 float t[4];
                 tex_fetch(tex, m->emissive_texture, uv[0], uv[1], t);
                 em[0] = em[0] + t[0]; em[1] = em[1] + t[1]; em[2] = em[2] + t[2];
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(256, VGI_INJECT_MINBLOCKS) k_inject(BuildParam
             for (int k = 0; k < 3; ++k) lc[k] = ((ps.NdotL * vis) * lp.color[k]) * lp.intensity;
             if (!(lc[0] == 0.0f && lc[1] == 0.0f && lc[2] == 0.0f)) {
                 float col[4] = { m->base_color_factor[0], m->base_color_factor[1], m->base_color_factor[2], m->base_color_factor[3] };
-                if (tex.count && m->base_color_texture > -1) {  // ref: msaaInjectRadiance.frag:131-136
+                if (TEX && m->base_color_texture > -1) {  // ref: msaaInjectRadiance.frag:131-136
                     float t[4];
                     tex_fetch(tex, m->base_color_texture, uv[0], uv[1], t);
 #pragma unroll
@@ -804,8 +809,13 @@ int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
     cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
     if (bp.ntri) {
-        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
-        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        if (c->scene_max_texture > -1) {
+            LAUNCH("k_voxelize", k_voxelize<true><<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+            LAUNCH("k_voxelize_large", k_voxelize_large<true><<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        } else {
+            LAUNCH("k_voxelize", k_voxelize<false><<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+            LAUNCH("k_voxelize_large", k_voxelize_large<false><<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        }
     }
     const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
     LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));
@@ -859,8 +869,13 @@ static int launch_inject(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 #endif
     LAUNCH("k_zero_acc", k_zero_acc<<<148 * 8, 256, 0, s>>>(c->acc, c->counters, bp.max_occ));
     if (bp.ntri && bp.level_mask) {
-        LAUNCH("k_inject", k_inject<<<148 * VGI_INJECT_MINBLOCKS * 2, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
-                                                            c->occ, c->occ_prefix, c->acc, c->counters, c->texset()));
+        if (c->scene_max_texture > -1) {
+            LAUNCH("k_inject", k_inject<true><<<148 * VGI_INJECT_MINBLOCKS * 2, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
+                                                                                        c->occ, c->occ_prefix, c->acc, c->counters, c->texset()));
+        } else {
+            LAUNCH("k_inject", k_inject<false><<<148 * VGI_INJECT_MINBLOCKS * 2, 256, 0, s>>>(bp, c->light, c->tri_pos, c->tri_nrm, c->materials, c->pairs,
+                                                                                         c->occ, c->occ_prefix, c->acc, c->counters, c->texset()));
+        }
     }
     return n;
 }
@@ -1018,8 +1033,13 @@ int vgi_launch_peer_build(vgi_ctx* c, const BuildParams& bp, const PeerSet& ps, 
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
     LAUNCH("k_peer_clear_occ", k_peer_own_planes<false><<<148 * 4, 256, 0, s>>>(ps, bp, c->occ));
     if (bp.ntri) {
-        LAUNCH("k_voxelize", k_voxelize<<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
-        LAUNCH("k_voxelize_large", k_voxelize_large<<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        if (c->scene_max_texture > -1) {
+            LAUNCH("k_voxelize", k_voxelize<true><<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+            LAUNCH("k_voxelize_large", k_voxelize_large<true><<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        } else {
+            LAUNCH("k_voxelize", k_voxelize<false><<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+            LAUNCH("k_voxelize_large", k_voxelize_large<false><<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+        }
     }
     const unsigned nblk = cdiv(nwords, SCAN_BLOCK * SCAN_ITEMS);
     LAUNCH("k_scan_block_sums", k_scan_block_sums<<<nblk, SCAN_BLOCK, 0, s>>>(c->occ, nwords, c->block_sums));
