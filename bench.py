@@ -36,7 +36,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "1080p 16-cone GI frames/s; voxelize+inject+mip ms @256^3 (1/2/4/8 B200)"
 WORKLOAD = ("configs[1]: Sponza-scale synthetic atrium (262144 tris), 6-level 256^3 clipmap voxelize+inject+mip "
-            "(frame 0: all levels) + 1920x1080 16-cone diffuse/specular GI (mode 8)")
+            "(frame 0: all levels) + 1920x1080 16-cone diffuse/specular GI (mode 8), one frame per step along a fixed "
+            "8-camera path")
 RES, LEVELS, SHADOW, WIDTH, HEIGHT = 256, 6, 4096, 1920, 1080
 TRACE_ROW_STRIDE = 32          # reference arm: every 32nd row block of the image per sample
 
@@ -137,13 +138,16 @@ def config_dict(world, triangles=262144):
     """The `config` object of the JSON line: identical for both arms (the reference arm runs the same workload on the CPU)."""
     return {"workload": WORKLOAD, "resolution": RES, "levels": LEVELS, "triangles": int(triangles),
             "image": [WIDTH, HEIGHT], "cones": 16, "shadow_map": SHADOW,
-            "parallelism": f"{world} view(s) of the fixed {N_VIEWS}-view list, one per GPU (rank r = view r), replicated clipmap build",
+            "parallelism": f"{world} GPU(s); every step renders the next camera of a fixed {N_VIEWS}-view path (rank r starts at "
+                           f"view r, so all ranks do the same work over a cycle), clipmap rebuilt for every frame",
             "l2": "256 MB flush between timed steps"}
 
 
-# The batched-view list is FIXED (it does not depend on the number of ranks): view 0 is the headline camera of
-# configs[1], views 1..7 orbit the atrium. Rank r renders view r, so the N = 1, 2, 4, 8 runs time the same views and the
-# scaling curve measures the machine, not a different set of cameras per N.
+# The camera path is FIXED (it does not depend on the number of ranks): view 0 is the camera of round 1's headline frame,
+# views 1..7 orbit the atrium. A step renders ONE frame: step i of rank r uses view (r + i) mod 8, so every rank — at
+# N = 1, 2, 4, 8 alike — cycles through the same eight cameras and does the same work over a cycle: the scaling curve
+# measures the machine, not the cameras (measured on 8 GPUs with one fixed view per rank the views cost 3.6 .. 5.8 ms and
+# the slowest one set the "efficiency"). The clip regions move with the camera, so every frame is a full rebuild.
 N_VIEWS = 8
 
 
@@ -314,10 +318,10 @@ class CpuFrameSampler:
                   "reference's own GLSL compiled for the CPU (oracle/_ref/libvgi_refshaders.so: clipmapCleaning, copyAlphaImage, "
                   "opacity/radianceDownSample .comp and voxelConeTracing.frag); triangle coverage (fixed-function in the reference) "
                   "and the injection loop come from the oracle port (port_share = their share of the time); frame time = sum of "
-                  "per-level means + 32 x mean row-sample time")
+                  "per-level means + 32 x mean row-sample time; sampled on view 0 of the camera path")
     SAMPLE = ("per step: oracle clipmap build of ONE level (cycling 0..5: clear, voxelize, inject, copy-alpha, "
               "opacity+radiance down-sample) + cone trace of 1/32 of the 1080 rows; frame time = sum of per-level "
-              "means + 32 x mean row-sample time")
+              "means + 32 x mean row-sample time; sampled on view 0 of the camera path")
 
 
 def cpu_cores():
@@ -420,14 +424,36 @@ def run_vgi(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def frame():
-        gi.update_regions(inp["cam_pos"])
+    # the camera path: G-buffers rasterised on the device (bit-identical to the host rasteriser: tests/test_gpu_raster.py and
+    # `device_rendered_inputs_equal_host_rendered` below), resident before the timed region like the uploaded one was
+    from vk_voxel_cone_tracing_b200 import synth as _synth
+    views = []
+    for v in range(N_VIEWS):
+        pos, dirv = view_camera(v)
+        cam_v = _synth.make_camera(pos, dirv, aspect=WIDTH / HEIGHT)
+        views.append((pos, cam_v, gi.render_gbuffer(cam_v, WIDTH, HEIGHT)))
+    for k in dgb:
+        assert torch.equal(dgb[k], views[rank % N_VIEWS][2][k]), f"device-rendered G-buffer differs from the host's ({k})"
+    step_no = [0]
+
+    def next_view():
+        v = views[(rank + step_no[0]) % N_VIEWS]
+        step_no[0] += 1
+        return v
+
+    def frame():        # view 0: the frame the per-kernel pass, the roofline (oracle-counted taps) and the parity check use
+        out[0].zero_()  # pixels the view does not cover are left untouched by the tracer: no leftovers of other views
+        out[1].zero_()
+        gi.update_regions(views[0][0])
         gi.build_clipmap(0)
-        gi.cone_trace(inp["cam"], dgb, prm, out=out)
+        gi.cone_trace(views[0][1], views[0][2], prm, out=out)
 
     # ---- device-resident timing
     for _ in range(max(args.warmup, 3)):
-        frame()
+        pos, cam_v, g_v = next_view()
+        gi.update_regions(pos)
+        gi.build_clipmap(0)
+        gi.cone_trace(cam_v, g_v, prm, out=out)
     barrier()
     l0 = gi.stats().kernel_launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
@@ -437,12 +463,13 @@ def run_vgi(args):
         clocks.start()
     barrier()
     for a, m, b in ev:
+        pos, cam_v, g_v = next_view()
         flush.zero_()                       # evict the previous frame from L2 (outside the timed events)
         a.record()
-        gi.update_regions(inp["cam_pos"])
+        gi.update_regions(pos)
         gi.build_clipmap(0)
         m.record()
-        gi.cone_trace(inp["cam"], dgb, prm, out=out)
+        gi.cone_trace(cam_v, g_v, prm, out=out)
         b.record()
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -482,14 +509,28 @@ def run_vgi(args):
     import ctypes as C
     from vk_voxel_cone_tracing_b200 import structs as S0
     h2d_view = C.sizeof(S0.Camera) + C.sizeof(S0.DirLightShadow) + C.sizeof(S0.VctParams) + 12
-    e2e_ms, t_wall = timed(lambda: gi.frame_view_host(0, inp["cam_pos"], inp["cam"], WIDTH, HEIGHT, inp["shadow"], prm,
-                                                      hout[0], hout[1]))
+    def e2e_view():
+        pos, cam_v, _ = next_view()
+        gi.frame_view_host(0, pos, cam_v, WIDTH, HEIGHT, inp["shadow"], prm, hout[0], hout[1])
+
+    e2e_ms, t_wall = timed(e2e_view)
     # the host copy of the result must equal the device-resident path's (whose inputs were rendered on the host)
+    frame()
+    gi.frame_view_host(0, views[0][0], views[0][1], WIDTH, HEIGHT, inp["shadow"], prm, hout[0], hout[1])
     assert torch.equal(hout[0], out[0].cpu()) and torch.equal(hout[1], out[1].cpu()), \
         "vgi_frame_view_host result differs from the device-resident path"
-    h2d_host = sum(t.numel() * t.element_size() for t in hgb.values())
+    # the host-G-buffer variant: every view's G-buffer in pinned host memory (copies of the device-rendered, bit-identical ones)
+    hviews = [{k: t.cpu().pin_memory() for k, t in g_v.items()} for _, _, g_v in views]
+    h2d_host = sum(t.numel() * t.element_size() for t in hviews[0].values())
     gi.frame_host(0, inp["cam_pos"], inp["cam"], hgb, hshadow, prm, hout[0], hout[1])     # static light: uploaded once
-    e2e_hg_ms, hg_wall = timed(lambda: gi.frame_host(0, inp["cam_pos"], inp["cam"], hgb, None, prm, hout[0], hout[1]))
+
+    def e2e_host():
+        i = (rank + step_no[0]) % N_VIEWS
+        step_no[0] += 1
+        gi.frame_host(0, views[i][0], views[i][1], hviews[i], None, prm, hout[0], hout[1])
+
+    e2e_hg_ms, hg_wall = timed(e2e_host)
+    gi.frame_host(0, views[0][0], views[0][1], hviews[0], None, prm, hout[0], hout[1])
     assert torch.equal(hout[0], out[0].cpu()), "vgi_frame_host result differs from the device-resident path"
 
     # ---- max over ranks (and every rank's own times: efficiency must be read from the machine, not from the views)
@@ -498,7 +539,7 @@ def run_vgi(args):
     if world > 1:
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = {"view": [r % N_VIEWS for r in range(world)],
+        per_rank = {"first_view": [r % N_VIEWS for r in range(world)],
                     "ms_per_step": [float(x[0]) for x in allr], "e2e_ms_per_step": [float(x[3]) for x in allr]}
         t = torch.stack(allr).max(dim=0).values
     else:

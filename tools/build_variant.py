@@ -8,8 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from vk_voxel_cone_tracing_b200 import build as B  # noqa: E402
 
-name, flags = sys.argv[1], sys.argv[2:]
-B.build_libvgi()
+name, flags = sys.argv[1], [a for a in sys.argv[2:] if a != "--keep-main"]
+if "--keep-main" not in sys.argv:      # --keep-main: do not touch csrc/libvgi.so (a queued gpurun call may snapshot the tree)
+    B.build_libvgi()
 dev = os.path.join(ROOT, "tools", "_dev")
 os.makedirs(dev, exist_ok=True)
 obj = os.path.join(dev, f"vgi_trace_{name}.o")

@@ -1372,8 +1372,12 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
 
 struct SpecWarpShared {
     float4 val[32];     // 4 cells x 8 pre-blended corner records
-    uint2  cell[32];    // non-empty cells of the current pass: (key, mask of the records that can be non-zero)
+    uint2  cell[64];    // non-empty cells of the current batch: (key, mask of the records that can be non-zero)
 };
+
+#ifndef VGI_TRACE_SPEC_MERGED
+#define VGI_TRACE_SPEC_MERGED 1
+#endif
 
 // One level sample of the batch for every lane that wants one; false when every cell is empty.
 //  A. run heads (first lane of each group of consecutive lanes with the same cell) test their cell's brick bit and
@@ -1445,6 +1449,81 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
     return myMask != 0u;
 }
 
+// brick bit + footprint byte of a cell (0 = every record of its footprint is zero)
+DEVFN uint32_t spec_probe_cell(const TraceParams& tp, uint32_t key)
+{
+    const int Rm = tp.R - 1, logR = tp.logR;
+    const uint32_t ix = key & (uint32_t)Rm, iy = (key >> logR) & (uint32_t)Rm, iz = (key >> (2 * logR)) & (uint32_t)Rm;
+    const uint32_t level = key >> (3 * logR);
+    const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
+    const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
+    const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
+    const uint32_t m = __ldg(tp.footprint + key);   // meaningful only where the brick bit is set
+    STAT(1, 1);
+    return ((bbyte >> ((ix >> 2) & 7u)) & 1u) ? m : 0u;
+}
+
+// Both level samples of the batch in ONE pass (spec_level_pass twice, merged): the run heads of both levels probe their
+// cells together (four mask loads in flight instead of two dependent pairs), the non-empty cells of both levels share one
+// compact numbering (lo cells first) and therefore the fetch rounds: typically one round of four cells instead of one per
+// level. Returns per lane whether its lo / hi sample is non-zero.
+DEVFN void spec_both_levels(const TraceParams& tp, bool wantLo, uint32_t keyLo, const float* wLo, bool wantHi, uint32_t keyHi,
+                            const float* wHi, unsigned lane, uint32_t ox, uint32_t oy, uint32_t oz, float kx, float ky, float kz,
+                            SpecWarpShared& sh, float* smpLo, float* smpHi, bool& anyLo, bool& anyHi)
+{
+    anyLo = anyHi = false;
+    if (!__ballot_sync(FULL_MASK, wantLo || wantHi)) return;
+    const uint32_t kL = wantLo ? keyLo : 0xffffffffu, kH = wantHi ? keyHi : 0xffffffffu;
+    const uint32_t pL = __shfl_up_sync(FULL_MASK, kL, 1), pH = __shfl_up_sync(FULL_MASK, kH, 1);
+    const bool headL = wantLo && (lane == 0u || kL != pL), headH = wantHi && (lane == 0u || kH != pH);
+    const unsigned headsL = __ballot_sync(FULL_MASK, headL), headsH = __ballot_sync(FULL_MASK, headH);
+    uint32_t maskL = 0u, maskH = 0u;
+    if (headL) maskL = spec_probe_cell(tp, keyLo);
+    if (headH) maskH = spec_probe_cell(tp, keyHi);
+    const unsigned liveL = __ballot_sync(FULL_MASK, maskL != 0u), liveH = __ballot_sync(FULL_MASK, maskH != 0u);
+    if (!(liveL | liveH)) return;
+    const unsigned le = 0xffffffffu >> (31u - lane);
+    const int hlL = (31 - __clz((int)(headsL & le))) & 31, hlH = (31 - __clz((int)(headsH & le))) & 31;
+    const uint32_t mL = __shfl_sync(FULL_MASK, maskL, hlL), mH = __shfl_sync(FULL_MASK, maskH, hlH);
+    const uint32_t myL = wantLo ? mL : 0u, myH = wantHi ? mH : 0u;
+    const int nL = __popc(liveL), nCells = nL + __popc(liveH);
+    const int cellL = __popc(liveL & ((1u << hlL) - 1u)), cellH = nL + __popc(liveH & ((1u << hlH) - 1u));
+    if (maskL) sh.cell[cellL] = make_uint2(keyLo, maskL);      // head lanes of non-empty cells (their hl is their own lane)
+    if (maskH) sh.cell[cellH] = make_uint2(keyHi, maskH);
+    __syncwarp();
+    const int R = tp.R, Rm = R - 1, logR = tp.logR;
+    const unsigned corner = lane & 7u;
+    for (int c0 = 0; c0 < nCells; c0 += 4) {
+        const int c = c0 + (int)(lane >> 3);
+        if (c < nCells) {
+            const uint2 cm = sh.cell[c];
+            if ((cm.y >> corner) & 1u) {
+                const uint32_t vox = cm.x;
+                const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
+                int off = 0;
+                if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
+                if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
+                if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+                const uint32_t tx = __ldg(rec + ox), ty = __ldg(rec + oy), tz = __ldg(rec + oz);
+                STAT(4, 1);
+                const float2 kx2 = make_float2(kx, kx), ky2 = make_float2(ky, ky), kz2 = make_float2(kz, kz);
+                float2 lo = __fmul2_rn(kx2, unpack2(tx, 0x7540u, 0x7541u)), hi = __fmul2_rn(kx2, unpack2(tx, 0x7542u, 0x7543u));
+                lo = __ffma2_rn(ky2, unpack2(ty, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(ky2, unpack2(ty, 0x7542u, 0x7543u), hi);
+                lo = __ffma2_rn(kz2, unpack2(tz, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(kz2, unpack2(tz, 0x7542u, 0x7543u), hi);
+                sh.val[lane] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+        }
+        __syncwarp();
+        const int qL = cellL - c0, qH = cellH - c0;
+        if (myL && qL >= 0 && qL < 4) coop_gather_w(wLo, myL, sh.val + 8 * qL, smpLo);
+        if (myH && qH >= 0 && qH < 4) coop_gather_w(wHi, myH, sh.val + 8 * qH, smpHi);
+        __syncwarp();
+    }
+    anyLo = myL != 0u;
+    anyHi = myH != 0u;
+}
+
 __global__ void __launch_bounds__(128, VGI_TRACE_SPECW_MINBLOCKS) k_trace_specular_warp(const __grid_constant__ TraceParams tp)
 {
     __shared__ SpecWarpShared s_sh[4];
@@ -1514,8 +1593,14 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPECW_MINBLOCKS) k_trace_specul
                 keyHi = level_cell(tp, posV, min((int)fl + 1, tp.L - 1), wHi);
             }
             float smp[4] = { 0.f, 0.f, 0.f, 0.f }, up[4] = { 0.f, 0.f, 0.f, 0.f };
+#if VGI_TRACE_SPEC_MERGED
+            bool anyLo, anyHi;
+            spec_both_levels(tp, valid, keyLo, wLo, valid && fr > 0.0f, keyHi, wHi, lane, ox, oy, oz, cf.kx, cf.ky, cf.kz, sh, smp, up,
+                             anyLo, anyHi);
+#else
             const bool anyLo = spec_level_pass(tp, valid, keyLo, wLo, lane, ox, oy, oz, cf.kx, cf.ky, cf.kz, sh, smp);
             const bool anyHi = spec_level_pass(tp, valid && fr > 0.0f, keyHi, wHi, lane, ox, oy, oz, cf.kx, cf.ky, cf.kz, sh, up);
+#endif
             const bool any = anyLo || anyHi;
             if (!__any_sync(FULL_MASK, any)) { STAT(2, 1); continue; }        // the whole batch is empty space
             float fa = 1.0f, fo = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f;
