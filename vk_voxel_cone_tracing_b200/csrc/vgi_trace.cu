@@ -419,8 +419,14 @@ DEVFN bool coop_try(const TraceParams& tp, const Footprint& fp, int cone, const 
 
 // The diffuse march of one warp: 32 (cone, pixel) items advance through the tabulated steps together so that the
 // two level samples of a step can be filtered cooperatively. Per-lane arithmetic is that of cone_step.
+DEVFN bool coop_try3(const TraceParams& tp, const Footprint& fp, uint32_t secBit, int c0, int c1, const float4* s_face,
+                     float4* s_corner, unsigned lane, float* out);
+
+// v3cone: c0 / c1 = first / last cone of the warp's slice of the work list, multi = more than two cones in it,
+// s_face = per-block face table (nullptr: the original vote, coop_try)
 DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have, int cone, const float (*cones)[3], const float* startPos_,
-                            const float* dir, float startLevel, float4* s_corner, unsigned lane, float* out)
+                            const float* dir, float startLevel, float4* s_corner, unsigned lane, float* out,
+                            int c0 = 0, int c1 = 0, bool multi = true, const float4* s_face = nullptr)
 {
     const vgi_vct_params& p = tp.p;
     ConeState cs = { { 0.f, 0.f, 0.f, 0.f }, 0.0f };
@@ -461,8 +467,14 @@ DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have
         }
         float smp[4] = { 0.f, 0.f, 0.f, 0.f }, up[4] = { 0.f, 0.f, 0.f, 0.f };
         const bool vote = t.lod[k] >= VGI_TRACE_COOP_MIN_LOD;
+        if (s_face) {
+            const uint32_t secBit = (cone != c0) ? 0x80000000u : 0u;
+            if (!(vote && !multi && coop_try3(tp, f0, secBit, c0, c1, s_face, s_corner, lane, smp)) && f0.mask) filter_footprint(tp, f0, cf, smp);
+            if (!(vote && !multi && coop_try3(tp, f1, secBit, c0, c1, s_face, s_corner, lane, up)) && f1.mask) filter_footprint(tp, f1, cf, up);
+        } else {
         if (!(vote && coop_try(tp, f0, cone, cones, s_corner, lane, smp)) && f0.mask) filter_footprint(tp, f0, cf, smp);
         if (!(vote && coop_try(tp, f1, cone, cones, s_corner, lane, up)) && f1.mask) filter_footprint(tp, f1, cf, up);
+        }
         if ((f0.mask | f1.mask) != 0u) { // implies alive
             if (fr > 0.0f) {
 #pragma unroll
@@ -496,7 +508,7 @@ DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have
 // the non-zero corners of its cell. Steps whose lanes are more scattered take the per-lane path of v1.
 // ---------------------------------------------------------------------------------------------------
 #ifndef VGI_TRACE_V2
-#define VGI_TRACE_V2 0      // measured on B200: v2 2.94 ms, v1 (march_warp_table) 2.84 ms per 1080p frame
+#define VGI_TRACE_V2 3      // measured on B200, ms per 1080p frame: 0 = round-1 march 2.845, 1 = v2 2.94, 3 = v3 (round-1 march, one-key vote + face table) 2.825
 #endif
 
 // per-cone constants of the fetch lanes, two float4 per cone in shared memory:
@@ -704,6 +716,56 @@ DEVFN void march_warp_v2(const TraceParams& tp, const StepTable& t, bool have, i
     }
     out[0] = cs.result[0]; out[1] = cs.result[1]; out[2] = cs.result[2];
     out[3] = 1.0f - cs.occlusion;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// v3 = the shipped march (per-lane probes, vote among the lanes with a non-empty footprint) with a cheaper vote and fetch:
+// (cell, "second cone of the warp's slice") travel as ONE 32-bit key (two shuffles instead of four), and the fetch lanes
+// read their cone's face-word offsets and direction weights from the per-block table of v2 instead of re-deriving them
+// (cone_faces was 2.5 % of the kernel's instructions, the vote 12 %). Slices with more than two cones filter per lane.
+// ---------------------------------------------------------------------------------------------------
+DEVFN bool coop_try3(const TraceParams& tp, const Footprint& fp, uint32_t secBit, int c0, int c1, const float4* s_face,
+                     float4* s_corner /* 16 */, unsigned lane, float* out)
+{
+    const bool wanted = fp.mask != 0u;
+    const unsigned want = __ballot_sync(FULL_MASK, wanted);
+    if (!want) return true;
+    const int la = __ffs(want) - 1, lb = 31 - __clz(want);
+    const uint32_t key = fp.vox | secBit;
+    const uint32_t keyA = __shfl_sync(FULL_MASK, key, la), keyB = __shfl_sync(FULL_MASK, key, lb);
+    const bool inA = key == keyA;
+    if (__ballot_sync(FULL_MASK, wanted && !(inA || key == keyB))) return false;
+    STAT(7, 1);
+    const uint32_t mA = __shfl_sync(FULL_MASK, fp.mask, la), mB = __shfl_sync(FULL_MASK, fp.mask, lb); // mask = f(cell)
+    if (lane < (keyA != keyB ? 16u : 8u)) {
+        const bool second = lane >= 8u;
+        const uint32_t k = second ? keyB : keyA, m = second ? mB : mA;
+        const unsigned corner = lane & 7u;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((m >> corner) & 1u) {
+            const uint32_t vox = k & 0x7fffffffu;
+            const int R = tp.R, Rm = R - 1, logR = tp.logR;
+            const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
+            int off = 0;
+            if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
+            if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
+            if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
+            const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+            const int sc = (k >> 31) ? c1 : c0;
+            const float4 fo = s_face[2 * sc], fk = s_face[2 * sc + 1];
+            const uint32_t tx = __ldg(rec + __float_as_uint(fo.x)), ty = __ldg(rec + __float_as_uint(fo.y)), tz = __ldg(rec + __float_as_uint(fo.z));
+            const float2 kx2 = make_float2(fk.x, fk.x), ky2 = make_float2(fk.y, fk.y), kz2 = make_float2(fk.z, fk.z);
+            float2 lo = __fmul2_rn(kx2, unpack2(tx, 0x7540u, 0x7541u)), hi = __fmul2_rn(kx2, unpack2(tx, 0x7542u, 0x7543u));
+            lo = __ffma2_rn(ky2, unpack2(ty, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(ky2, unpack2(ty, 0x7542u, 0x7543u), hi);
+            lo = __ffma2_rn(kz2, unpack2(tz, 0x7540u, 0x7541u), lo); hi = __ffma2_rn(kz2, unpack2(tz, 0x7542u, 0x7543u), hi);
+            v = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        s_corner[lane] = v;
+    }
+    __syncwarp();
+    if (wanted) coop_gather(fp, fp.mask, s_corner + (inA ? 0 : 8), out);
+    __syncwarp(); // the slots are rewritten by the next sample
+    return true;
 }
 
 // ref: voxelConeTracing.frag:394-414
@@ -1080,9 +1142,12 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     __shared__ uint16_t s_list[NCONES * TILE_PIX];
     __shared__ int s_warp_count[4];
     __shared__ StepTable s_table;
-#if VGI_TRACE_V2
+#if VGI_TRACE_V2 == 1
     __shared__ float4 s_coop[4][64];                // per warp, double-buffered: 4 groups x 8 pre-blended corner records
     __shared__ float4 s_face[2 * NCONES];           // per cone: face-texel word offsets, direction weights (fetch lanes)
+#elif VGI_TRACE_V2 == 3
+    __shared__ float4 s_coop[4][16];
+    __shared__ float4 s_face[2 * NCONES];
 #else
     __shared__ float4 s_coop[4][16];                // per warp: the eight pre-blended corner records of a shared cell
 #endif
@@ -1110,7 +1175,7 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     }
     if (tid == 127 && needCones && !SVO)
         build_step_table(tp, s_table, tp.cone_coeff_diffuse, fmaxf(MIN_TRACE_STEP_FACTOR, tp.p.min_trace_step_factor));
-#if VGI_TRACE_V2
+#if VGI_TRACE_V2 == 1 || VGI_TRACE_V2 == 3
     if (!SVO && needCones && tid >= 64 && tid < 64 + NCONES) {
         const float fdir[3] = { cones[tid - 64][0], cones[tid - 64][1], cones[tid - 64][2] };
         cone_face_table(fdir, s_face + 2 * (tid - 64));
@@ -1163,12 +1228,16 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
                 const float sp[3] = { s_pix[0][pix], s_pix[1][pix], s_pix[2][pix] };
                 const float cosTheta = s_pix[3][pix] * dir[0] + s_pix[4][pix] * dir[1] + s_pix[5][pix] * dir[2];
                 float c[4];
-#if VGI_TRACE_V2
+#if VGI_TRACE_V2 == 1 || VGI_TRACE_V2 == 3
                 // the warp's slice of the cone-major list: first and last cone; more than two -> per-lane path
                 const unsigned haveMask = __ballot_sync(FULL_MASK, have);
                 const int c0 = __shfl_sync(FULL_MASK, cone, 0), c1 = __shfl_sync(FULL_MASK, cone, 31 - __clz(haveMask | 1u));
                 const bool multi = __any_sync(FULL_MASK, have && cone != c0 && cone != c1);
+#if VGI_TRACE_V2 == 1
                 march_warp_v2(tp, s_table, have, cone, c0, c1, multi, sp, dir, s_pix[6][pix], s_face, s_coop[warp], (unsigned)lane, c);
+#else
+                march_warp_table(tp, s_table, have, cone, cones, sp, dir, s_pix[6][pix], s_coop[warp], (unsigned)lane, c, c0, c1, multi, s_face);
+#endif
 #else
                 march_warp_table(tp, s_table, have, cone, cones, sp, dir, s_pix[6][pix], s_coop[warp], (unsigned)lane, c);
 #endif
