@@ -60,6 +60,16 @@ namespace vfs
 			++instanceIndex;
 		}
 
+		// the images GLTFScene::uploadImage turns into uTextures[] (RGBA8, sampled REPEAT + LINEAR at level 0)
+		std::vector<vgi_texture> textures;
+		textures.reserve(_images.size());
+		for (const GLTFImage& image : _images)
+		{
+			textures.push_back({ image.data.data(), image.width, image.height });
+		}
+		if (!bridge->setTextures(textures.data(), static_cast<uint32_t>(textures.size())))
+			return false;
+
 		vgi_scene_desc desc = {};
 		desc.positions	= reinterpret_cast<const float*>(_positions.data());
 		desc.normals	= reinterpret_cast<const float*>(_normals.data());

@@ -97,6 +97,16 @@ namespace vfs
 							VK_BUFFER_USAGE_TRANSFER_DST_BIT);
 	}
 
+	bool VgiBridge::setTextures(const vgi_texture* textures, uint32_t count)
+	{
+		if (vgi_set_textures(_ctx, textures, count) != VGI_OK)
+		{
+			VFS_ERROR << "libvgi : " << vgi_last_error(_ctx);
+			return false;
+		}
+		return true;
+	}
+
 	bool VgiBridge::setScene(const vgi_scene_desc& sceneDesc)
 	{
 		if (vgi_set_scene(_ctx, &sceneDesc) != VGI_OK)

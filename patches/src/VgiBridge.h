@@ -19,6 +19,7 @@
 
 struct vgi_ctx;
 struct vgi_scene_desc;
+struct vgi_texture;
 
 namespace vfs
 {
@@ -39,6 +40,7 @@ namespace vfs
 		const char* lastError(void) const;
 
 		// GLTFScene::initialize, before releaseSourceData()
+		bool setTextures(const vgi_texture* textures, uint32_t count);
 		bool setScene(const vgi_scene_desc& sceneDesc);
 
 		// pre-pass command buffer, after "GBuffer" and "RSMPass": attachments -> shared linear buffers

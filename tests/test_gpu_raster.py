@@ -90,3 +90,27 @@ def test_raster_error_paths():
         gi.render_shadow_map(inp["shadow"], 64)              # no scene yet
     with pytest.raises(VgiError):
         gi.render_gbuffer(inp["cam"], 16, 16)
+
+
+def test_frame_view_host_equals_the_device_resident_path():
+    """vgi_frame_view_host (the batched / headless view: camera up, shadow map + G-buffer rasterised on the device, build,
+    trace, both images down) gives exactly what the separate calls give on host-rendered inputs — the e2e call of bench.py."""
+    import torch
+    inp = common.cornell_inputs(64, 1024, 128, 128)
+    a, b = _ctx(inp), _ctx(inp)
+    a.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
+    a.update_regions(inp["cam_pos"])
+    a.build_clipmap(0)
+    prm = a.default_vct_params(8)
+    want = a.cone_trace(inp["cam"], a.upload_gbuffer(inp["gbuffer"]), prm)
+    # b never sees a host image: the light's depth buffer is a placeholder that the call replaces with its own render
+    b.set_light(inp["light"], inp["shadow"], torch.ones((1024, 1024), dtype=torch.float32, device="cuda"))
+    out = (torch.empty((128, 128, 4), dtype=torch.float32).pin_memory(), torch.empty((128, 128, 4), dtype=torch.float32).pin_memory())
+    for _ in range(2):      # twice: the second call reuses the staging buffers
+        b.frame_view_host(0, inp["cam_pos"], inp["cam"], 128, 128, inp["shadow"], prm, out[0], out[1])
+    cov = torch.from_numpy(inp["gbuffer"]["depth"] < 1.0)
+    assert torch.equal(out[0][cov], want[0].cpu()[cov]) and torch.equal(out[1][cov], want[1].cpu()[cov])
+    assert float(out[0][cov][:, :3].max()) > 0.05
+    # shadow = None keeps the current shadow map
+    b.frame_view_host(0, inp["cam_pos"], inp["cam"], 128, 128, None, prm, out[0], out[1])
+    assert torch.equal(out[0][cov], want[0].cpu()[cov])
