@@ -217,6 +217,10 @@ int         vgi_reset_timings(vgi_ctx* ctx);
 /* ---- inputs --------------------------------------------------------------------------------- */
 /* replaces: GLTFScene vertex/index/matrix/material uploads consumed by msaaVoxelizer.vert:31-36 */
 int vgi_set_scene(vgi_ctx* ctx, const vgi_scene_desc* scene);
+/* replaces: the per-frame world transform of msaaVoxelizer.vert:31-36 / voxelizer.vert for ANIMATED nodes: new node matrices
+ * (same count and order as in vgi_set_scene) re-transform the object-space vertices on the device — no re-upload of the
+ * mesh. The result equals vgi_set_scene with those matrices bit for bit. nodes: HOST pointer, copied. */
+int vgi_update_nodes(vgi_ctx* ctx, const vgi_node_matrix* nodes, uint32_t count, void* stream);
 /* replaces: GLTFScene::uploadImage + the uTextures[] descriptor array (set 1, binding 2). May be called before or after
  * vgi_set_scene; a build whose materials reference a texture index >= count fails with VGI_E_STATE. count 0 clears. */
 int vgi_set_textures(vgi_ctx* ctx, const vgi_texture* textures, uint32_t count);

@@ -298,3 +298,41 @@ def test_peer_build_single_rank_equals_build_clipmap(oracle):
     finally:
         if own_group:
             dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_update_nodes_equals_a_fresh_upload():
+    """vgi_update_nodes (animated nodes: the world transform of msaaVoxelizer.vert:31-36 on the device) gives the triangle
+    soup vgi_set_scene computes on the host for the same matrices: same pairs, same atlases, same octree fragments."""
+    import copy
+    import torch
+    from vk_voxel_cone_tracing_b200 import glm, raster, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VgiError, VoxelGI
+    scene = synth.atrium()
+    cfg = S.default_config(64, 3)
+    light, shadow = synth.make_light()
+    depth = raster.shadow_depth(scene, shadow, 512)
+    moved = copy.deepcopy(scene)
+    # every node gets another rigid motion + non-uniform scale (the inverse-transpose matters for the normals)
+    for i in range(moved.nodes.shape[0]):
+        m = moved.nodes[i]["model"].reshape(4, 4).T.astype(np.float64)
+        a = 0.3 + 0.2 * i
+        rot = np.array([[np.cos(a), 0, np.sin(a), 0.4 * i], [0, 1.0 + 0.1 * i, 0, -0.2], [-np.sin(a), 0, np.cos(a), 0.3], [0, 0, 0, 1]])
+        new = (rot @ m)
+        moved.nodes[i]["model"] = new.T.astype(np.float32).reshape(16)
+        moved.nodes[i]["it_model"] = np.linalg.inv(new).astype(np.float32).reshape(16)      # (inverse transpose) stored [col][row]
+    cam = (1.0, 3.0, -2.0)
+    outs = []
+    for mode in ("fresh", "updated"):
+        gi = VoxelGI(cfg)
+        gi.set_scene(moved if mode == "fresh" else scene)
+        if mode == "updated":
+            with pytest.raises(VgiError):
+                gi.update_nodes(moved.nodes[:1])            # wrong count
+            gi.update_nodes(moved.nodes)
+        gi.set_light(light, shadow, depth)
+        gi.update_regions(cam)
+        gi.build_clipmap(0)
+        outs.append((gi.stats().clip_pairs, gi.export_atlas(0).cpu(), gi.export_atlas(1).cpu()))
+    assert outs[0][0] == outs[1][0] and outs[0][0] > 10000
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])

@@ -126,3 +126,37 @@ def test_cornell_svo_cone_trace(oracle, mode):
     assert np.abs(s - ref_s)[covered].max() <= 1e-3
     assert common.psnr(d[..., :3], ref_d[..., :3]) >= 50.0 and common.psnr(s[..., :3], ref_s[..., :3]) >= 50.0
     assert ref_d[covered][:, :3].std() > 0.01
+
+
+def test_cornell_svo_cone_trace_literal_sampling(oracle):
+    """VGI_MODE_SVO_LITERAL end to end: fragments and build as shipped (Q21 / Q22 / Q13) AND the un-halved sample positions
+    of voxelConeTracing_Octree.frag:330-333 in the tracer — the variant the oracle compares with the reference's shader
+    text bit for bit (tests/test_ref_shaders.py)."""
+    from vk_voxel_cone_tracing_b200 import structs as S
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    inp = common.cornell_inputs()
+    cfg = S.default_config(inp["cfg"].resolution, inp["cfg"].level_count, mode_flags=S.VGI_MODE_SVO_LITERAL)
+    gi = VoxelGI(cfg)
+    gi.set_scene(inp["scene"])
+    gi.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
+    level = 6
+    lo, hi = inp["scene"].world_bbox()
+    gi.svo_voxelize(level, lo, hi)
+    gi.svo_build()
+    nodes = gi.svo_nodes().cpu().numpy().view(np.uint32)
+    prm = gi.default_vct_params(8)
+    prm.volume_dimension = float(1 << level)
+    prm.voxel_size = float((np.float32(hi) - np.float32(lo)).max() / np.float32(1 << level))
+    prm.indirect_diffuse_intensity = 15.0
+    prm.occlusion_decay = 3.0
+    gb = inp["gbuffer"]
+    hg = oracle.HostGBuffer(gb["diffuse"], gb["normal"], gb["specular"], gb["emission"], gb["depth"])
+    ref_d, ref_s = oracle.svo_cone_trace(inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], nodes, lo, hi,
+                                         cfg.level_count, mode_flags=S.VGI_MODE_SVO_LITERAL)
+    can_d, _ = oracle.svo_cone_trace(inp["cam"], hg, prm, inp["light"], inp["shadow"], inp["shadow_depth"], nodes, lo, hi,
+                                     cfg.level_count)
+    d, s = gi.svo_cone_trace(inp["cam"], gi.upload_gbuffer(gb), prm)
+    d, s = d.cpu().numpy(), s.cpu().numpy()
+    covered = gb["depth"] < 1.0
+    assert np.abs(d - ref_d)[covered].max() <= 1e-3 and np.abs(s - ref_s)[covered].max() <= 1e-3
+    assert np.abs(ref_d - can_d)[covered].max() > 1.2e-3        # the two sampling rules differ by more than the tolerance

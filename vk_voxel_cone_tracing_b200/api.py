@@ -93,6 +93,11 @@ class VoxelGI:
         self._ck(lib().vgi_set_scene(self._h, C.byref(d)))
         self.scene = scene
 
+    def update_nodes(self, nodes, stream=None):
+        """New node matrices (structured array like Scene.nodes, same count): the scene is re-transformed on the device."""
+        arr = np.ascontiguousarray(nodes)
+        self._ck(lib().vgi_update_nodes(self._h, C.c_void_p(arr.ctypes.data), C.c_uint32(arr.shape[0]), _stream(stream)))
+
     def set_textures(self, images):
         """images: list of (H, W, 4) uint8 arrays (the scene's uTextures[]); copied by the library."""
         arr, keep = S.texture_array(images)

@@ -52,6 +52,8 @@ static void peer_close(vgi_ctx* c);
 static void free_scene(vgi_ctx* c)
 {
     cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials); cudaFree(c->tri_uv);
+    cudaFree(c->obj_pos); cudaFree(c->obj_nrm); cudaFree(c->d_nodes);
+    c->obj_pos = c->obj_nrm = nullptr; c->d_nodes = nullptr; c->nnodes = 0;
     c->tri_uv = nullptr; c->scene_max_texture = -1;
     cudaFree(c->pairs); cudaFree(c->large); cudaFree(c->acc);
     cudaFree(c->raster_proj); cudaFree(c->raster_large);
@@ -301,7 +303,7 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->last_stream));
     free_scene(c);
-    std::vector<float4> pos(ntri * 3), nrm(ntri * 3);
+    std::vector<float4> pos(ntri * 3), nrm(ntri * 3), opos(ntri * 3), onrm(ntri * 3);
     std::vector<float2> uv(maxTex > -1 ? ntri * 3 : 0);
     float bbmin[3] = { INFINITY, INFINITY, INFINITY }, bbmax[3] = { -INFINITY, -INFINITY, -INFINITY };
     size_t t = 0;
@@ -320,6 +322,13 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
                 float matf;
                 memcpy(&matf, &mat, 4);
                 pos[t * 3 + k] = make_float4(w[0], w[1], w[2], matf);
+                {   // object-space copy: the node index rides in w (vgi_update_nodes)
+                    const uint32_t ni = pr.node_index;
+                    float nif;
+                    memcpy(&nif, &ni, 4);
+                    opos[t * 3 + k] = make_float4(s->positions[3 * vi], s->positions[3 * vi + 1], s->positions[3 * vi + 2], nif);
+                    onrm[t * 3 + k] = make_float4(s->normals[3 * vi], s->normals[3 * vi + 1], s->normals[3 * vi + 2], matf);
+                }
                 nrm[t * 3 + k] = make_float4(n[0], n[1], n[2], 0.f);
                 if (maxTex > -1) uv[t * 3 + k] = make_float2(s->texcoords[2 * vi], s->texcoords[2 * vi + 1]);
                 for (int a = 0; a < 3; ++a) {
@@ -343,7 +352,14 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
         CK(c, cudaMalloc(&c->tri_nrm, nrm.size() * sizeof(float4)));
         CK(c, cudaMemcpy(c->tri_pos, pos.data(), pos.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CK(c, cudaMemcpy(c->tri_nrm, nrm.data(), nrm.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(c, cudaMalloc(&c->obj_pos, opos.size() * sizeof(float4)));
+        CK(c, cudaMalloc(&c->obj_nrm, onrm.size() * sizeof(float4)));
+        CK(c, cudaMemcpy(c->obj_pos, opos.data(), opos.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->obj_nrm, onrm.data(), onrm.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
+    c->nnodes = s->node_count;
+    CK(c, cudaMalloc(&c->d_nodes, (s->node_count ? s->node_count : 1) * sizeof(vgi_node_matrix)));
+    CK(c, cudaMemcpy(c->d_nodes, s->nodes, s->node_count * sizeof(vgi_node_matrix), cudaMemcpyHostToDevice));
     CK(c, cudaMalloc(&c->materials, (s->material_count ? s->material_count : 1) * sizeof(vgi_material)));
     CK(c, cudaMemcpy(c->materials, s->materials, s->material_count * sizeof(vgi_material), cudaMemcpyHostToDevice));
 
@@ -373,6 +389,25 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     CK(c, cudaMalloc(&c->visit_list, (size_t)c->visit_cap * L * sizeof(uint32_t)));
     c->voxelized = c->built = false;
     return VGI_OK;
+}
+
+static int check_launch(vgi_ctx* c, const char* what);
+
+int vgi_update_nodes(vgi_ctx* c, const vgi_node_matrix* nodes, uint32_t count, void* stream)
+{
+    if (!c || !nodes) return fail(c, VGI_E_INVALID, "vgi_update_nodes: null argument");
+    if (!c->materials) return fail(c, VGI_E_STATE, "vgi_update_nodes: call vgi_set_scene first");
+    if (count != c->nnodes) return fail(c, VGI_E_INVALID, "vgi_update_nodes: node count differs from the scene's");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // the matrices are read by the transform kernel on `s`: a synchronous copy keeps the caller's buffer free on return
+    CK(c, cudaStreamSynchronize(c->last_stream));
+    CK(c, cudaMemcpy(c->d_nodes, nodes, (size_t)count * sizeof(vgi_node_matrix), cudaMemcpyHostToDevice));
+    if (c->ntri) c->launches += vgi_launch_transform_scene(c, s);
+    c->voxelized = c->built = false;
+    c->svo_voxelized = false;
+    c->last_stream = s;
+    return check_launch(c, "vgi_update_nodes");
 }
 
 int vgi_set_textures(vgi_ctx* c, const vgi_texture* tex, uint32_t count)
@@ -930,6 +965,7 @@ int vgi_svo_cone_trace(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* g, 
         tp.svo_extent = m * 0.5f;
         for (int k = 0; k < 3; ++k) tp.svo_center[k] = (c->svo_bb_min[k] + c->svo_bb_max[k]) * 0.5f;
         tp.svo_max_level = (float)((int)c->cfg.level_count - 1);
+        tp.svo_literal = (c->cfg.mode_flags & VGI_MODE_SVO_LITERAL) ? 1 : 0;
     }
     c->launches += vgi_launch_trace_svo(c, tp, s);
     c->last_stream = s;

@@ -802,6 +802,36 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 // launch + optional per-kernel event timing (vgi_set_timing)
 #define LAUNCH(name, ...) do { c->timer.begin(name, s); __VA_ARGS__; c->timer.end(s); ++n; } while (0)
 
+// world transform of the scene on the device (vgi_update_nodes). ref: msaaVoxelizer.vert:31-36 — position = model * p,
+// normal = itModel * n; same binary32 expression order as vgi_set_scene's host loop, so the triangle soup is identical
+__global__ void __launch_bounds__(256) k_transform_scene(uint32_t nvert, const float4* __restrict__ obj_pos, const float4* __restrict__ obj_nrm,
+                                                          const vgi_node_matrix* __restrict__ nodes, float4* __restrict__ tri_pos,
+                                                          float4* __restrict__ tri_nrm)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvert) return;
+    const float4 p = obj_pos[i], n = obj_nrm[i];
+    const vgi_node_matrix& nm = nodes[__float_as_uint(p.w)];
+    const float* m = nm.model;
+    const float* it = nm.it_model;
+    float w[3], d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        w[r] = ((m[r] * p.x + m[4 + r] * p.y) + m[8 + r] * p.z) + m[12 + r];
+        d[r] = (it[r] * n.x + it[4 + r] * n.y) + it[8 + r] * n.z;
+    }
+    tri_pos[i] = make_float4(w[0], w[1], w[2], n.w);     // w keeps the material index
+    tri_nrm[i] = make_float4(d[0], d[1], d[2], 0.0f);
+}
+
+int vgi_launch_transform_scene(vgi_ctx* c, cudaStream_t s)
+{
+    int n = 0;
+    const uint32_t nvert = c->ntri * 3u;
+    LAUNCH("k_transform_scene", k_transform_scene<<<cdiv(nvert, 256), 256, 0, s>>>(nvert, c->obj_pos, c->obj_nrm, c->d_nodes, c->tri_pos, c->tri_nrm));
+    return n;
+}
+
 int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
     int n = 0;

@@ -120,6 +120,7 @@ struct TraceParams {
     uint32_t* spec_cursor;        // next unclaimed entry of spec_list (k_trace_specular)
     const uint2* svo_nodes;       // SVO tracer: node pool, grid of the fragment voxelizer
     float    svo_center[3], svo_extent, svo_max_level;
+    int      svo_literal;         // VGI_MODE_SVO_LITERAL: sample positions are not halved (voxelConeTracing_Octree.frag:330-333 as shipped, Q13)
     float    cone_coeff_diffuse;  // 2*tan(aperture/2), evaluated on the host
     float    diffuse_aperture;
     // specular marches (k_trace_specular_warp): the step sequence depends on the roughness byte alone, so the host
@@ -165,6 +166,11 @@ struct vgi_ctx {
     vgi_material* materials = nullptr;
     uint32_t nmat = 0;
     float2*  tri_uv = nullptr;    // 3 per triangle, only when a material is textured
+    // object-space copies for vgi_update_nodes (animated nodes): xyz + node index in w / normal xyz
+    float4*  obj_pos = nullptr;
+    float4*  obj_nrm = nullptr;
+    vgi_node_matrix* d_nodes = nullptr;
+    uint32_t nnodes = 0;
     uint32_t* tex_data = nullptr;
     uint4*    tex_table = nullptr;
     uint32_t  ntex = 0;
@@ -262,6 +268,7 @@ struct vgi_ctx {
 };
 
 // ---- launch wrappers implemented in the .cu files (return number of kernels launched) ------------
+int vgi_launch_transform_scene(vgi_ctx* c, cudaStream_t s);
 int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);
 int vgi_launch_slab_begin(vgi_ctx* c, const BuildParams& bp, cudaStream_t s);

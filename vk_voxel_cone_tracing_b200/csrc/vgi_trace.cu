@@ -920,7 +920,7 @@ DEVFN void sample_svo(const TraceParams& tp, const float* position, uint32_t lev
         const float scaled = (position[k] - tp.svo_center[k]) / tp.svo_extent;
         float g = ((scaled + 1.0f) * 0.5f) * (float)resolution;
         g = f_clamp(g, 0.0f, (float)resolution);
-        fp[k] = ((uint32_t)g) >> 1;
+        fp[k] = tp.svo_literal ? (uint32_t)g : ((uint32_t)g) >> 1;     // canonical: the same halving as the build (Q13)
     }
     const uint32_t targetLo = 1u << level;
     const uint32_t targetFirst = two ? targetLo << 1 : targetLo;
