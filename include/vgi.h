@@ -138,10 +138,12 @@ typedef struct vgi_texture {
 } vgi_texture;
 
 /* Scene buffers in the SoA layout GLTFScene uploads (VFS/GLTFScene.cpp:55-93). HOST pointers;
- * vgi_set_scene copies what it needs. Materials may reference textures (base_color_texture, emissive_texture,
- * occlusion_texture index into the array given to vgi_set_textures): the voxelization and injection stages use them as
- * msaaVoxelizer.frag:64, msaaInjectRadiance.frag:73-82,131-136 and voxelizer.frag:52-76 do. texcoords may be NULL when no
- * material is textured. vgi_render_gbuffer (an adjacent pass) still takes factor-only materials. */
+ * vgi_set_scene copies what it needs. Materials may reference textures (indices into the array given to vgi_set_textures):
+ * the voxelization and injection stages use base_color_texture, emissive_texture and occlusion_texture as
+ * msaaVoxelizer.frag:64, msaaInjectRadiance.frag:73-82,131-136 and voxelizer.frag:52-76 do; vgi_render_gbuffer uses
+ * base colour, metallic-roughness, emissive and normal textures and the alpha cutoff as gBufferPass.frag:62-116 does.
+ * texcoords may be NULL when no material is textured; tangents (gBufferPass.vert:40, xyz transformed by itModel, w the
+ * handedness) may be NULL unless vgi_render_gbuffer is asked to shade a material with normal_texture > -1. */
 typedef struct vgi_scene_desc {
     const float*           positions;   /* vec3 f32 x vertex_count */
     const float*           normals;     /* vec3 f32 x vertex_count */
@@ -151,6 +153,7 @@ typedef struct vgi_scene_desc {
     const vgi_node_matrix* nodes;
     const vgi_material*    materials;
     uint32_t vertex_count, index_count, primitive_count, node_count, material_count;
+    const float*           tangents;    /* vec4 f32 x vertex_count, may be NULL */
 } vgi_scene_desc;
 
 /* G-buffer in the reference formats (ref: VFS/RenderPass/GBufferPass.cpp:177-194), linear row-major
@@ -320,9 +323,11 @@ int vgi_default_vct_params(vgi_ctx* ctx, vgi_vct_params* out);
  * shadow_depth of vgi_set_light. Pixel-centre sampling, depth test LESS. */
 int vgi_render_shadow_map(vgi_ctx* ctx, const vgi_dir_light_shadow* shadow, uint32_t width, uint32_t height,
                           float* depth, void* stream);
-/* replaces: GBufferPass::onUpdate (gBufferPass.vert:45, gBufferPass.frag:62-116, factor-only materials; formats
- * GBufferPass.cpp:177-194). target: a vgi_gbuffer whose five DEVICE buffers are WRITTEN (width*height texels
- * each); uncovered pixels get depth 1 and zero attributes. */
+/* replaces: GBufferPass::onUpdate (gBufferPass.vert:38-45, gBufferPass.frag:39-116: factors, base-colour /
+ * metallic-roughness / emissive / normal textures, alpha cutoff; formats GBufferPass.cpp:177-194). target: a vgi_gbuffer
+ * whose five DEVICE buffers are WRITTEN (width*height texels each); uncovered pixels get depth 1 and zero attributes.
+ * VGI_E_STATE: a material references a texture vgi_set_textures has not provided, or is normal-mapped while the scene
+ * came without tangents. */
 int vgi_render_gbuffer(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gbuffer* target, void* stream);
 
 /* ---- the pass after cone tracing ------------------------------------------ */

@@ -352,6 +352,26 @@ def gbuffer_fragments(normal, material_index, materials):
     return (*outs, disc)
 
 
+def gbuffer_fragments_tex(normal, texcoord, tangent, material_index, materials, textures):
+    """gBufferPass.frag with the whole fs_in block and the scene's textures (list of (H, W, 4) uint8); same returns."""
+    nrm = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    n = nrm.shape[0]
+    tc = np.ascontiguousarray(texcoord, np.float32).reshape(-1, 2)
+    tg = np.ascontiguousarray(tangent, np.float32).reshape(-1, 4)
+    assert tc.shape[0] == n and tg.shape[0] == n
+    mi = np.ascontiguousarray(material_index, np.int32)
+    mats = np.ascontiguousarray(materials)
+    tex_f = [np.ascontiguousarray(t.astype(np.float32) / np.float32(255.0)) for t in textures]
+    ptrs = (C.c_void_p * max(len(tex_f), 1))(*[t.ctypes.data for t in tex_f])
+    tw = np.array([t.shape[1] for t in tex_f] or [0], np.int32)
+    th = np.array([t.shape[0] for t in tex_f] or [0], np.int32)
+    outs = [np.zeros((n, 4), np.float32) for _ in range(4)]
+    disc = np.zeros(n, np.uint8)
+    lib().ref_gbuffer_fragments_tex(C.c_int(n), _p(nrm), _p(tc), _p(tg), _p(mi), _p(mats), C.c_int(len(tex_f)), ptrs, _p(tw), _p(th),
+                                    *(_p(o) for o in outs), _p(disc))
+    return (*outs, disc)
+
+
 # ---- vertex stage of the voxelization passes -------------------------------------------------------
 
 def voxelizer_vertices(scene):

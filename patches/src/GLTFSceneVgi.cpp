@@ -83,6 +83,7 @@ namespace vfs
 		desc.primitive_count = static_cast<uint32_t>(primitives.size());
 		desc.node_count		 = static_cast<uint32_t>(matrices.size());
 		desc.material_count	 = static_cast<uint32_t>(materials.size());
+		desc.tangents	= _tangents.empty() ? nullptr : reinterpret_cast<const float*>(_tangents.data());
 		return bridge->setScene(desc);
 	}
 }

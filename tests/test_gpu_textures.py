@@ -102,6 +102,105 @@ def test_missing_textures_fail_loudly():
     gi.set_textures(tex)
     gi.build_clipmap(0)
     assert gi.stats().clip_pairs > 0
-    with pytest.raises(VgiError):           # the G-buffer producer (adjacent pass) stays factor-only
-        from vk_voxel_cone_tracing_b200 import synth
-        gi.render_gbuffer(synth.make_camera((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), aspect=1.0), 32, 32)
+    from vk_voxel_cone_tracing_b200 import synth
+    cam = synth.make_camera((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), aspect=1.0)
+    gi.render_gbuffer(cam, 32, 32)          # textured G-buffer with all textures present
+    gi.set_textures(tex[:2])
+    with pytest.raises(VgiError):           # ... and not with some missing
+        gi.render_gbuffer(cam, 32, 32)
+    # a normal-mapped material without tangents: the build stages do not care, the G-buffer producer refuses
+    nm = synth.textured_cornell(gbuffer_maps=True)
+    nm.tangents = None
+    gi.set_textures(synth.procedural_textures())
+    gi.set_scene(nm)
+    gi.build_clipmap(0)
+    with pytest.raises(VgiError):
+        gi.render_gbuffer(cam, 32, 32)
+
+
+def _same(dev, host):
+    for k in ("depth", "diffuse", "specular", "normal", "emission"):
+        a = dev[k].cpu().numpy()
+        b = host[k]
+        if b.dtype == np.uint16:
+            a = a.view(np.uint16)
+        assert a.shape == b.shape and np.array_equal(a, b), (k, int((a != b).sum()))
+
+
+@pytest.mark.gpu
+def test_textured_gbuffer_bit_exact_with_the_host_producer():
+    """vgi_render_gbuffer with textured materials (base colour, metallic-roughness, emissive, normal map + tangents, alpha
+    cutoff in the visibility pass) against csrc/synth_raster.c, which tests/test_ref_shaders.py::test_live_textured_gbuffer
+    pins on the reference's gBufferPass.frag: every attachment bit for bit, from two cameras (one next to the floor, so
+    alpha-tested triangles cross the camera plane), and again after vgi_update_nodes rotated the scene (tangents follow)."""
+    from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    scene = synth.textured_cornell(gbuffer_maps=True)
+    tex = synth.procedural_textures()
+    gi = VoxelGI(S.default_config(32, 2))
+    gi.set_textures(tex)
+    gi.set_scene(scene)
+    w, h = 320, 200
+    for eye, look in (((0.0, -1.0, 3.5), (0.0, 0.45, -1.0)), ((-2.0, 1.0, 3.0), (0.9, -0.6, -1.0)), ((0.5, -3.7, 1.0), (0.3, -0.1, -1.0))):
+        cam = synth.make_camera(eye, look, aspect=w / h)
+        host = raster.gbuffer(scene, cam, w, h, textures=tex)
+        assert (host["depth"] < 1.0).mean() > 0.5
+        _same(gi.render_gbuffer(cam, w, h), host)
+    # the alpha cutoff really removes floor fragments
+    opaque = synth.textured_cornell(gbuffer_maps=True)
+    opaque.materials["alpha_mode"] = 0
+    assert (raster.gbuffer(opaque, cam, w, h, textures=tex)["depth"] != host["depth"]).sum() > 500
+    # a factor-only material below its cutoff vanishes as a whole (gBufferPass.frag:96 with no base-colour texture)
+    gone = synth.textured_cornell(gbuffer_maps=True)
+    back = 1
+    gone.materials[back]["alpha_mode"], gone.materials[back]["alpha_cutoff"] = 1, 0.9
+    gone.materials[back]["base_color_factor"][3] = 0.5
+    gi2 = VoxelGI(S.default_config(32, 2))
+    gi2.set_textures(tex)
+    gi2.set_scene(gone)
+    hg = raster.gbuffer(gone, cam, w, h, textures=tex)
+    assert (hg["depth"] != host["depth"]).sum() > 500
+    _same(gi2.render_gbuffer(cam, w, h), hg)
+    gi2.close()
+    # animated node: rotate about y and shift; normals and tangents go through itModel on the device
+    a = np.deg2rad(25.0)
+    m = np.array([[np.cos(a), 0, np.sin(a), 0.3], [0, 1, 0, 0.1], [-np.sin(a), 0, np.cos(a), -0.2], [0, 0, 0, 1]], np.float64)
+    moved = synth.textured_cornell(gbuffer_maps=True)
+    moved.nodes[0]["model"] = m.T.astype(np.float32).reshape(-1)
+    moved.nodes[0]["it_model"] = np.linalg.inv(m).astype(np.float32).reshape(-1)      # (M^-1)^T column-major = M^-1 row-major
+    gi.update_nodes(moved.nodes)
+    cam = synth.make_camera((-2.0, 1.0, 3.0), (0.9, -0.6, -1.0), aspect=w / h)
+    _same(gi.render_gbuffer(cam, w, h), raster.gbuffer(moved, cam, w, h, textures=tex))
+
+
+@pytest.mark.gpu
+def test_frame_view_host_on_a_textured_scene():
+    """The headless view call (device-rendered shadow map + G-buffer, build, trace) on textured materials equals the separate
+    calls on host-rendered inputs."""
+    import torch
+    from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
+    from vk_voxel_cone_tracing_b200.api import VoxelGI
+    scene = synth.textured_cornell(gbuffer_maps=True)
+    tex = synth.procedural_textures()
+    cfg = S.default_config(64, 3)
+    light, shadow = synth.make_light(origin=(0.0, 20.0, -3.5))
+    depth = raster.shadow_depth(scene, shadow, 512)
+    w, h = 160, 120
+    eye = (-2.0, 1.0, 3.0)
+    cam = synth.make_camera(eye, (0.9, -0.6, -1.0), aspect=w / h)
+    a, b = VoxelGI(cfg), VoxelGI(cfg)
+    for gi in (a, b):
+        gi.set_textures(tex)
+        gi.set_scene(scene)
+    a.set_light(light, shadow, depth)
+    a.update_regions(eye)
+    a.build_clipmap(0)
+    prm = a.default_vct_params(8)
+    hostgb = raster.gbuffer(scene, cam, w, h, textures=tex)
+    want = a.cone_trace(cam, a.upload_gbuffer(hostgb), prm)
+    b.set_light(light, shadow, torch.ones((512, 512), dtype=torch.float32, device="cuda"))
+    out = (torch.empty((h, w, 4), dtype=torch.float32).pin_memory(), torch.empty((h, w, 4), dtype=torch.float32).pin_memory())
+    b.frame_view_host(0, eye, cam, w, h, shadow, prm, out[0], out[1])
+    cov = torch.from_numpy(hostgb["depth"] < 1.0)
+    assert torch.equal(out[0][cov], want[0].cpu()[cov]) and torch.equal(out[1][cov], want[1].cpu()[cov])
+    assert float(out[0][cov][:, :3].max()) > 0.05

@@ -711,3 +711,59 @@ def test_refshader_library_is_test_infrastructure_only():
                 with open(os.path.join(root, f), errors="replace") as fh:
                     text = fh.read()
                 assert "refshaders" not in text and "glsl_shim" not in text and "oracle/_ref" not in text, f
+
+
+def _half_ulps(x, ref16):
+    return np.abs(x.astype(np.float16).view(np.uint16).astype(np.int32) - ref16.astype(np.int32))
+
+
+@pytest.mark.parametrize("eye,look,needs", [
+    ((0.0, -1.0, 3.5), (0.0, 0.45, -1.0), ("normal_texture", "metallic_roughness_texture", "emissive_texture")),
+    ((-2.0, 1.0, 3.0), (0.9, -0.6, -1.0), ("normal_texture", "metallic_roughness_texture", "base_color_texture", "alpha"))])
+def test_live_textured_gbuffer(refshaders, eye, look, needs):
+    """The G-buffer producer with textured materials (base colour, metallic-roughness with its unclamped branch, emissive
+    through SRGBtoLinear, tangent-space normal map, alpha cutoff) against the reference's own gBufferPass.frag: every covered
+    pixel's fs_in block (normal, texture coordinate, tangent as the rasteriser interpolates them) goes through the shader with
+    the same textures bound. 8-bit attachments identical, binary16 ones within one ulp; the fragments the shader discards are
+    exactly the ones the producer's visibility pass dropped."""
+    from vk_voxel_cone_tracing_b200 import raster, synth
+    scene = synth.textured_cornell(gbuffer_maps=True)
+    tex = synth.procedural_textures()
+    w, h = 160, 120
+    cam = synth.make_camera(eye, look, aspect=w / h)
+    gb = raster.gbuffer(scene, cam, w, h, textures=tex)
+    mat, nrm, uv, tg = raster.gbuffer_attributes(scene, cam, w, h, textures=tex, full=True)
+    cov = mat >= 0
+    assert np.array_equal(cov, gb["depth"] < 1.0) and cov.sum() > 10000
+    mats = np.ascontiguousarray(scene.materials)
+    d, n, s, e, disc = refshaders.gbuffer_fragments_tex(nrm[cov], uv[cov], tg[cov], mat[cov], mats, tex)
+    assert not disc.any()
+    to8 = lambda x: np.floor(np.clip(x, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)  # noqa: E731
+    assert np.array_equal(to8(d), gb["diffuse"][cov]) and np.array_equal(to8(s), gb["specular"][cov])
+    de, dn = _half_ulps(e, gb["emission"][cov]), _half_ulps(n, gb["normal"][cov])
+    assert de.max() <= 1 and (de == 0).mean() > 0.99
+    assert dn.max() <= 1 and (dn == 0).mean() > 0.97
+    # every kind of material is in view: normal-mapped, metallic-roughness-mapped, base-colour, emissive texture
+    seen = set(np.unique(mat[cov]).tolist())
+    for name in needs:
+        assert name == "alpha" or any(mats[i][name] > -1 for i in seen), name
+    nm = np.isin(mat, [i for i in seen if mats[i]["normal_texture"] > -1])
+    flat = scene.materials.copy()
+    flat["normal_texture"] = -1
+    scene_flat = synth.textured_cornell(gbuffer_maps=True)
+    scene_flat.materials[:] = flat
+    gb_flat = raster.gbuffer(scene_flat, cam, w, h, textures=tex)
+    assert (gb_flat["normal"][nm] != gb["normal"][nm]).any(axis=-1).mean() > 0.5      # the map really bends the normals
+    assert np.array_equal(gb_flat["normal"][~nm], gb["normal"][~nm])
+
+    # alpha cutoff: without it the floor covers more pixels; the shader discards exactly the difference
+    opaque = synth.textured_cornell(gbuffer_maps=True)
+    opaque.materials["alpha_mode"] = 0
+    mat0, nrm0, uv0, tg0 = raster.gbuffer_attributes(opaque, cam, w, h, textures=tex, full=True)
+    cov0 = mat0 >= 0
+    disc0 = refshaders.gbuffer_fragments_tex(nrm0[cov0], uv0[cov0], tg0[cov0], mat0[cov0], mats, tex)[4].astype(bool)
+    dropped = np.zeros((h, w), bool)
+    dropped[cov0] = disc0
+    assert dropped.sum() > (200 if "alpha" in needs else -1)
+    assert np.array_equal(mat[~dropped], mat0[~dropped])            # nothing else changed
+    assert (mat[dropped] != mat0[dropped]).all() or (gb["depth"][dropped] > raster.gbuffer(opaque, cam, w, h, textures=tex)["depth"][dropped]).all()

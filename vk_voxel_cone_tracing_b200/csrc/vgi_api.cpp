@@ -54,7 +54,9 @@ static void free_scene(vgi_ctx* c)
     cudaFree(c->tri_pos); cudaFree(c->tri_nrm); cudaFree(c->materials); cudaFree(c->tri_uv);
     cudaFree(c->obj_pos); cudaFree(c->obj_nrm); cudaFree(c->d_nodes);
     c->obj_pos = c->obj_nrm = nullptr; c->d_nodes = nullptr; c->nnodes = 0;
-    c->tri_uv = nullptr; c->scene_max_texture = -1;
+    cudaFree(c->tri_tan); cudaFree(c->obj_tan);
+    c->tri_tan = c->obj_tan = nullptr;
+    c->tri_uv = nullptr; c->scene_max_texture = c->scene_max_texture_all = -1; c->scene_normal_mapped = c->scene_alpha_tested = false;
     cudaFree(c->pairs); cudaFree(c->large); cudaFree(c->acc);
     cudaFree(c->raster_proj); cudaFree(c->raster_large);
     c->raster_proj = nullptr; c->raster_large = nullptr; c->raster_tri_cap = 0;
@@ -284,13 +286,19 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     if (!c || !s) return fail(c, VGI_E_INVALID, "vgi_set_scene: null argument");
     if (!s->positions || !s->normals || !s->indices || !s->primitives || !s->nodes || !s->materials)
         return fail(c, VGI_E_INVALID, "vgi_set_scene: missing buffer");
-    int32_t maxTex = -1;
+    int32_t maxTex = -1, maxTexAll = -1;
+    bool normalMapped = false, alphaTested = false;
     for (uint32_t m = 0; m < s->material_count; ++m) {
         const vgi_material& mt = s->materials[m];
-        const int32_t used[3] = { mt.base_color_texture, mt.emissive_texture, mt.occlusion_texture };
+        const int32_t used[5] = { mt.base_color_texture, mt.emissive_texture, mt.occlusion_texture,
+                                  mt.metallic_roughness_texture, mt.normal_texture };
         for (int k = 0; k < 3; ++k) maxTex = used[k] > maxTex ? used[k] : maxTex;
+        for (int k = 0; k < 5; ++k) maxTexAll = used[k] > maxTexAll ? used[k] : maxTexAll;
+        normalMapped = normalMapped || mt.normal_texture > -1;
+        alphaTested = alphaTested || mt.alpha_mode > 0;
     }
-    if (maxTex > -1 && !s->texcoords) return fail(c, VGI_E_INVALID, "vgi_set_scene: textured materials need texcoords");
+    if (maxTexAll > -1 && !s->texcoords) return fail(c, VGI_E_INVALID, "vgi_set_scene: textured materials need texcoords");
+    const bool withTan = normalMapped && s->tangents;
     uint64_t ntri = 0;
     for (uint32_t p = 0; p < s->primitive_count; ++p) {
         const vgi_primitive& pr = s->primitives[p];
@@ -304,7 +312,8 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     CK(c, cudaStreamSynchronize(c->last_stream));
     free_scene(c);
     std::vector<float4> pos(ntri * 3), nrm(ntri * 3), opos(ntri * 3), onrm(ntri * 3);
-    std::vector<float2> uv(maxTex > -1 ? ntri * 3 : 0);
+    std::vector<float2> uv(maxTexAll > -1 ? ntri * 3 : 0);
+    std::vector<float4> tan(withTan ? ntri * 3 : 0), otan(withTan ? ntri * 3 : 0);
     float bbmin[3] = { INFINITY, INFINITY, INFINITY }, bbmax[3] = { -INFINITY, -INFINITY, -INFINITY };
     size_t t = 0;
     // world transform: ref msaaVoxelizer.vert:31-36; draw order: GLTFScene.cpp:457-490
@@ -330,7 +339,13 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
                     onrm[t * 3 + k] = make_float4(s->normals[3 * vi], s->normals[3 * vi + 1], s->normals[3 * vi + 2], matf);
                 }
                 nrm[t * 3 + k] = make_float4(n[0], n[1], n[2], 0.f);
-                if (maxTex > -1) uv[t * 3 + k] = make_float2(s->texcoords[2 * vi], s->texcoords[2 * vi + 1]);
+                if (maxTexAll > -1) uv[t * 3 + k] = make_float2(s->texcoords[2 * vi], s->texcoords[2 * vi + 1]);
+                if (withTan) {      // ref: gBufferPass.vert:40
+                    float tg[3];
+                    xform_dir(nm.it_model, s->tangents + 4 * vi, tg);
+                    tan[t * 3 + k] = make_float4(tg[0], tg[1], tg[2], s->tangents[4 * vi + 3]);
+                    otan[t * 3 + k] = make_float4(s->tangents[4 * vi], s->tangents[4 * vi + 1], s->tangents[4 * vi + 2], s->tangents[4 * vi + 3]);
+                }
                 for (int a = 0; a < 3; ++a) {
                     bbmin[a] = w[a] < bbmin[a] ? w[a] : bbmin[a];
                     bbmax[a] = w[a] > bbmax[a] ? w[a] : bbmax[a];
@@ -343,9 +358,18 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     memcpy(c->scene_bb_max, bbmax, sizeof bbmax);
     c->nmat = s->material_count;
     c->scene_max_texture = maxTex;
-    if (ntri && maxTex > -1) {
+    c->scene_max_texture_all = maxTexAll;
+    c->scene_normal_mapped = normalMapped;
+    c->scene_alpha_tested = alphaTested;
+    if (ntri && maxTexAll > -1) {
         CK(c, cudaMalloc(&c->tri_uv, uv.size() * sizeof(float2)));
         CK(c, cudaMemcpy(c->tri_uv, uv.data(), uv.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    if (ntri && withTan) {
+        CK(c, cudaMalloc(&c->tri_tan, tan.size() * sizeof(float4)));
+        CK(c, cudaMemcpy(c->tri_tan, tan.data(), tan.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(c, cudaMalloc(&c->obj_tan, otan.size() * sizeof(float4)));
+        CK(c, cudaMemcpy(c->obj_tan, otan.data(), otan.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
     if (ntri) {
         CK(c, cudaMalloc(&c->tri_pos, pos.size() * sizeof(float4)));
@@ -1180,8 +1204,10 @@ int vgi_render_gbuffer(vgi_ctx* c, const vgi_camera* cam, const vgi_gbuffer* tar
         !target->depth_f32 || !target->width || !target->height)
         return fail(c, VGI_E_INVALID, "vgi_render_gbuffer: incomplete target");
     if (!c->materials) return fail(c, VGI_E_STATE, "vgi_render_gbuffer: call vgi_set_scene first");
-    if (c->scene_max_texture > -1)
-        return fail(c, VGI_E_UNSUPPORTED, "vgi_render_gbuffer: textured materials (the host's own G-buffer pass supplies these images)");
+    if (c->scene_max_texture_all >= (int32_t)c->ntex)
+        return fail(c, VGI_E_STATE, "vgi_render_gbuffer: a material references a texture that vgi_set_textures has not provided");
+    if (c->scene_normal_mapped && !c->tri_tan)
+        return fail(c, VGI_E_STATE, "vgi_render_gbuffer: normal-mapped materials need vgi_scene_desc.tangents");
     CK(c, cudaSetDevice(c->device));
     int r = raster_scratch(c, (size_t)target->width * target->height);
     if (r != VGI_OK) return r;

@@ -806,7 +806,8 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 // normal = itModel * n; same binary32 expression order as vgi_set_scene's host loop, so the triangle soup is identical
 __global__ void __launch_bounds__(256) k_transform_scene(uint32_t nvert, const float4* __restrict__ obj_pos, const float4* __restrict__ obj_nrm,
                                                           const vgi_node_matrix* __restrict__ nodes, float4* __restrict__ tri_pos,
-                                                          float4* __restrict__ tri_nrm)
+                                                          float4* __restrict__ tri_nrm, const float4* __restrict__ obj_tan,
+                                                          float4* __restrict__ tri_tan)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvert) return;
@@ -822,13 +823,20 @@ __global__ void __launch_bounds__(256) k_transform_scene(uint32_t nvert, const f
     }
     tri_pos[i] = make_float4(w[0], w[1], w[2], n.w);     // w keeps the material index
     tri_nrm[i] = make_float4(d[0], d[1], d[2], 0.0f);
+    if (obj_tan) {      // ref: gBufferPass.vert:40
+        const float4 t = obj_tan[i];
+        float g[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) g[r] = (it[r] * t.x + it[4 + r] * t.y) + it[8 + r] * t.z;
+        tri_tan[i] = make_float4(g[0], g[1], g[2], t.w);
+    }
 }
 
 int vgi_launch_transform_scene(vgi_ctx* c, cudaStream_t s)
 {
     int n = 0;
     const uint32_t nvert = c->ntri * 3u;
-    LAUNCH("k_transform_scene", k_transform_scene<<<cdiv(nvert, 256), 256, 0, s>>>(nvert, c->obj_pos, c->obj_nrm, c->d_nodes, c->tri_pos, c->tri_nrm));
+    LAUNCH("k_transform_scene", k_transform_scene<<<cdiv(nvert, 256), 256, 0, s>>>(nvert, c->obj_pos, c->obj_nrm, c->d_nodes, c->tri_pos, c->tri_nrm, c->obj_tan, c->tri_tan));
     return n;
 }
 

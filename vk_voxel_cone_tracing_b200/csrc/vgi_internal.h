@@ -166,6 +166,8 @@ struct vgi_ctx {
     vgi_material* materials = nullptr;
     uint32_t nmat = 0;
     float2*  tri_uv = nullptr;    // 3 per triangle, only when a material is textured
+    float4*  tri_tan = nullptr;   // 3 per triangle (itModel * tangent.xyz, handedness), only for normal-mapped scenes with tangents
+    float4*  obj_tan = nullptr;
     // object-space copies for vgi_update_nodes (animated nodes): xyz + node index in w / normal xyz
     float4*  obj_pos = nullptr;
     float4*  obj_nrm = nullptr;
@@ -174,7 +176,10 @@ struct vgi_ctx {
     uint32_t* tex_data = nullptr;
     uint4*    tex_table = nullptr;
     uint32_t  ntex = 0;
-    int32_t   scene_max_texture = -1;   // highest texture index a material of the scene references
+    int32_t   scene_max_texture = -1;   // highest texture index the build stages read (base colour, emissive, occlusion)
+    int32_t   scene_max_texture_all = -1;   // ... and the G-buffer producer (also metallic-roughness, normal)
+    bool      scene_normal_mapped = false;  // a material has normal_texture > -1
+    bool      scene_alpha_tested = false;   // a material has alpha_mode > 0 (gBufferPass.frag:96)
     TexSet texset() const { return TexSet{ tex_data, tex_table, tri_uv, ntex }; }
     std::vector<float> h_tri_pos; // host copies for debugging / multi-GPU culling
     float scene_bb_min[3], scene_bb_max[3];

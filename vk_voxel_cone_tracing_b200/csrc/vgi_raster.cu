@@ -1,8 +1,9 @@
 // vgi_raster.cu — producers of the hot path's image inputs: the directional light's shadow
 // depth map and the camera G-buffer, rendered from the ctx's scene without Vulkan so that batched-view runs
 // (BASELINE configs[4]: 64 cameras at 4K) need no host rasteriser.
-// ref: VFS/Shaders/shadowPass.vert:33 (depth-only, proj * view * model), gBufferPass.vert:45, gBufferPass.frag:62-116
-// (factor-only materials), formats VFS/RenderPass/GBufferPass.cpp:177-194.
+// ref: VFS/Shaders/shadowPass.vert:33 (depth-only, proj * view * model), gBufferPass.vert:38-42, gBufferPass.frag:39-116
+// (factors and textures: base colour, metallic-roughness, emissive, tangent-space normal map, alpha cutoff), formats
+// VFS/RenderPass/GBufferPass.cpp:177-194.
 //
 // Rasterisation rule (the software definition the test producers pin: pixel-centre sampling, depth test LESS with ties
 // to the lower triangle index, z clipped to [0,1]): visibility is one 64-bit atomicMin per fragment on
@@ -16,9 +17,7 @@
 // -fmad=false), so depth and every quantised attribute equal the host producer bit for bit.
 #include <cuda_fp16.h>
 
-#include "vgi_internal.h"
-
-#define DEVFN static __device__ __forceinline__
+#include "vgi_device.cuh"
 
 struct ProjTri {
     // ok == 1: pixel coordinates, NDC depth, 1 / w of the vertices.
@@ -27,7 +26,7 @@ struct ProjTri {
     double wc[3];
     int box[4];                     // ok == 2: pixel box of the part in front of the plane (x0, x1, y0, y1), may be empty
     int ok;
-    int pad;
+    int alpha;                      // G-buffer pass: 1 = every fragment takes the alpha-cutoff test against the base-colour texture
 };
 
 #define RASTER_SMALL_MAX 256   // bounding boxes up to this many pixels are walked by one thread
@@ -120,7 +119,9 @@ struct RasterParams {
     float M[16];
     const float4* tri_pos;
     const float4* tri_nrm;
+    const float4* tri_tan;      // nullptr unless the scene is normal-mapped
     const vgi_material* materials;
+    TexSet tex;
     uint32_t ntri;
     int w, h;
     ProjTri* proj;
@@ -155,6 +156,45 @@ DEVFN Box tri_box(const ProjTri& q, int w, int h)
     return b;
 }
 
+// perspective-correct barycentric weights of pixel centre (px, py) on a triangle that covers it (both kinds)
+DEVFN void persp_bary(const ProjTri& q, double px, double py, double* b)
+{
+    if (q.ok == 2) {
+        double z;
+        hom_bary(q, px, py, b, &z);     // the weights of the homogeneous edge functions are perspective-correct already
+        return;
+    }
+    const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
+    double b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
+    double b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
+    double b2 = 1.0 - b0 - b1;
+    b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2];
+    const double bs = b0 + b1 + b2;
+    b[0] = b0 / bs; b[1] = b1 / bs; b[2] = b2 / bs;
+}
+
+// the interpolated texture coordinate the fragment stage receives (gBufferPass.vert:38)
+DEVFN void frag_uv(const RasterParams& rp, uint32_t t, const double* b, float* uv)
+{
+    const float2 a = rp.tex.tri_uv[3 * (size_t)t], c = rp.tex.tri_uv[3 * (size_t)t + 1], e = rp.tex.tri_uv[3 * (size_t)t + 2];
+    uv[0] = (float)((b[0] * a.x + b[1] * c.x) + b[2] * e.x);
+    uv[1] = (float)((b[0] * a.y + b[1] * c.y) + b[2] * e.y);
+}
+
+// ref: gBufferPass.frag:88-99 — alphaMode > 0 and baseColorFactor.a * texture.a < alphaCutoff: the fragment is discarded
+// before it writes depth. true = keep.
+DEVFN bool alpha_keep(const RasterParams& rp, const ProjTri& q, uint32_t t, double px, double py)
+{
+    double b[3];
+    float uv[2], tx[4];
+    persp_bary(q, px, py, b);
+    frag_uv(rp, t, b, uv);
+    const vgi_material& m = rp.materials[__float_as_int(rp.tri_pos[(size_t)t * 3].w)];
+    tex_fetch(rp.tex, m.base_color_texture, uv[0], uv[1], tx);
+    return !(m.base_color_factor[3] * tx[3] < m.alpha_cutoff);
+}
+
+template <bool ALPHA>
 DEVFN void raster_pixel(const RasterParams& rp, const ProjTri& q, double area, uint32_t t, int x, int y)
 {
     const double px = x + 0.5, py = y + 0.5;
@@ -164,6 +204,7 @@ DEVFN void raster_pixel(const RasterParams& rp, const ProjTri& q, double area, u
         if (z < 0.0 || z > 1.0) return;
         const float zf = (float)z;
         if (!(zf < 1.0f)) return;
+        if (ALPHA && q.alpha && !alpha_keep(rp, q, t, px, py)) return;
         atomicMin(rp.keys + (size_t)y * rp.w + x, ((unsigned long long)__float_as_uint(zf) << 32) | t);
         return;
     }
@@ -179,6 +220,7 @@ DEVFN void raster_pixel(const RasterParams& rp, const ProjTri& q, double area, u
     if (z < 0.0 || z > 1.0) return;
     const float zf = (float)z;
     if (!(zf < 1.0f)) return; // the cleared depth is 1 and the test is LESS
+    if (ALPHA && q.alpha && !alpha_keep(rp, q, t, px, py)) return;
     const unsigned long long key = ((unsigned long long)__float_as_uint(zf) << 32) | t;
     atomicMin(rp.keys + (size_t)y * rp.w + x, key);
 }
@@ -190,12 +232,21 @@ __global__ void __launch_bounds__(256) k_raster_clear(unsigned long long* keys, 
     if (i == 0) { large_count[0] = 0u; large_count[1] = 0u; }
 }
 
+template <bool ALPHA>
 __global__ void __launch_bounds__(128) k_raster_small(const __grid_constant__ RasterParams rp)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rp.ntri) return;
     ProjTri q;
     project_tri(rp.M, rp.tri_pos, t, rp.w, rp.h, q);
+    q.alpha = 0;
+    if (ALPHA) {
+        const vgi_material& m = rp.materials[__float_as_int(rp.tri_pos[(size_t)t * 3].w)];
+        if (m.alpha_mode > 0) {
+            if (m.base_color_texture > -1) q.alpha = 1;
+            else if (m.base_color_factor[3] < m.alpha_cutoff) q.ok = 0;     // every fragment of it is discarded
+        }
+    }
     rp.proj[t] = q;
     const Box b = tri_box(q, rp.w, rp.h);
     if (!b.any) return;
@@ -209,10 +260,11 @@ __global__ void __launch_bounds__(128) k_raster_small(const __grid_constant__ Ra
         return;
     }
     for (int y = b.y0; y <= b.y1; ++y)
-        for (int x = b.x0; x <= b.x1; ++x) raster_pixel(rp, q, b.area, t, x, y);
+        for (int x = b.x0; x <= b.x1; ++x) raster_pixel<ALPHA>(rp, q, b.area, t, x, y);
 }
 
 // medium boxes (257 .. RASTER_HUGE_MIN pixels): one warp per triangle, lanes stride over the box row-major
+template <bool ALPHA>
 __global__ void __launch_bounds__(256) k_raster_large(const __grid_constant__ RasterParams rp)
 {
     const uint32_t n = *rp.large_count;
@@ -223,11 +275,12 @@ __global__ void __launch_bounds__(256) k_raster_large(const __grid_constant__ Ra
         const ProjTri& q = rp.proj[t];
         const Box b = tri_box(q, rp.w, rp.h);
         const int bw = b.x1 - b.x0 + 1, bh = b.y1 - b.y0 + 1;
-        for (int p = (int)lane; p < bw * bh; p += 32) raster_pixel(rp, q, b.area, t, b.x0 + p % bw, b.y0 + p / bw);
+        for (int p = (int)lane; p < bw * bh; p += 32) raster_pixel<ALPHA>(rp, q, b.area, t, b.x0 + p % bw, b.y0 + p / bw);
     }
 }
 
 // the few triangles that cover a large part of the image (floors, walls): every block of the grid takes pieces
+template <bool ALPHA>
 __global__ void __launch_bounds__(256) k_raster_huge(const __grid_constant__ RasterParams rp)
 {
     const uint32_t n = rp.large_count[1];
@@ -240,7 +293,7 @@ __global__ void __launch_bounds__(256) k_raster_huge(const __grid_constant__ Ras
             const int tx = b.x0 + (tile % tilesX) * 32, ty = b.y0 + (tile / tilesX) * 32;
             const int tw = min(32, b.x1 - tx + 1), th = min(32, b.y1 - ty + 1);
             for (int p = threadIdx.x; p < tw * th; p += 256)
-                raster_pixel(rp, q, b.area, t, tx + p % tw, ty + p / tw);
+                raster_pixel<ALPHA>(rp, q, b.area, t, tx + p % tw, ty + p / tw);
         }
     }
 }
@@ -271,7 +324,8 @@ DEVFN uint2 pack_half4(float a, float b, float c, float d)
     return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
 }
 
-// ref: gBufferPass.frag:62-116 for factor-only materials
+// ref: gBufferPass.frag:62-116; TEX = false: factor-only scene
+template <bool TEX>
 __global__ void __launch_bounds__(256) k_raster_resolve_gbuffer(const __grid_constant__ RasterParams rp, const GBufferTarget g)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -290,43 +344,69 @@ __global__ void __launch_bounds__(256) k_raster_resolve_gbuffer(const __grid_con
     const uint32_t t = (uint32_t)k;
     const ProjTri q = rp.proj[t];
     const double px = x + 0.5, py = y + 0.5;
-    double b0, b1, b2;
-    if (q.ok == 2) {
-        double b[3], z;
-        hom_bary(q, px, py, b, &z);     // the weights of the homogeneous edge functions are perspective-correct already
-        b0 = b[0]; b1 = b[1]; b2 = b[2];
-    } else {
-        const double area = (q.x[1] - q.x[0]) * (q.y[2] - q.y[0]) - (q.x[2] - q.x[0]) * (q.y[1] - q.y[0]);
-        b0 = ((q.x[1] - px) * (q.y[2] - py) - (q.x[2] - px) * (q.y[1] - py)) / area;
-        b1 = ((q.x[2] - px) * (q.y[0] - py) - (q.x[0] - px) * (q.y[2] - py)) / area;
-        b2 = 1.0 - b0 - b1;
-        b0 *= q.iw[0]; b1 *= q.iw[1]; b2 *= q.iw[2]; // perspective-correct attribute interpolation
-        const double bs = b0 + b1 + b2;
-        b0 /= bs; b1 /= bs; b2 /= bs;
-    }
+    double b[3];
+    persp_bary(q, px, py, b);
+    const double b0 = b[0], b1 = b[1], b2 = b[2];
     const float4 n0 = rp.tri_nrm[(size_t)t * 3], n1 = rp.tri_nrm[(size_t)t * 3 + 1], n2 = rp.tri_nrm[(size_t)t * 3 + 2];
-    const double n[3] = { b0 * n0.x + b1 * n1.x + b2 * n2.x, b0 * n0.y + b1 * n1.y + b2 * n2.y, b0 * n0.z + b1 * n1.z + b2 * n2.z };
-    const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    double n[3] = { b0 * n0.x + b1 * n1.x + b2 * n2.x, b0 * n0.y + b1 * n1.y + b2 * n2.y, b0 * n0.z + b1 * n1.z + b2 * n2.z };
+    double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
     const int mi = __float_as_int(rp.tri_pos[(size_t)t * 3].w);
     const vgi_material& m = rp.materials[mi];
+    float uv[2] = { 0.0f, 0.0f }, tx[4];
+    if (TEX) frag_uv(rp, t, b, uv);
     float rough = m.roughness_factor, metal = m.metallic_factor;
-    rough = rough < 0.04f ? 0.04f : (rough > 1.0f ? 1.0f : rough); // MIN_ROUGHNESS clamp, untextured
-    metal = metal < 0.0f ? 0.0f : (metal > 1.0f ? 1.0f : metal);
+    if (TEX && m.metallic_roughness_texture > -1) {        // g = roughness, b = metallic; this branch does not clamp (gBufferPass.frag:77-82)
+        tex_fetch(rp.tex, m.metallic_roughness_texture, uv[0], uv[1], tx);
+        rough *= tx[1];
+        metal *= tx[2];
+    } else {
+        rough = rough < 0.04f ? 0.04f : (rough > 1.0f ? 1.0f : rough); // MIN_ROUGHNESS clamp
+        metal = metal < 0.0f ? 0.0f : (metal > 1.0f ? 1.0f : metal);
+    }
+    float base[3] = { m.base_color_factor[0], m.base_color_factor[1], m.base_color_factor[2] };
+    if (TEX && m.base_color_texture > -1) {
+        tex_fetch(rp.tex, m.base_color_texture, uv[0], uv[1], tx);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) base[c] *= tx[c];
+    }
+    if (TEX && m.normal_texture > -1) {
+        // ref: gBufferPass.frag:39-60 — tangent-space sample, bitangent = cross(N, T) * handedness, each axis normalised
+        tex_fetch(rp.tex, m.normal_texture, uv[0], uv[1], tx);
+        const float4 t0 = rp.tri_tan[(size_t)t * 3], t1 = rp.tri_tan[(size_t)t * 3 + 1], t2 = rp.tri_tan[(size_t)t * 3 + 2];
+        const double T[3] = { b0 * t0.x + b1 * t1.x + b2 * t2.x, b0 * t0.y + b1 * t1.y + b2 * t2.y, b0 * t0.z + b1 * t1.z + b2 * t2.z };
+        const double hw = b0 * t0.w + b1 * t1.w + b2 * t2.w;
+        const double B[3] = { (n[1] * T[2] - n[2] * T[1]) * hw, (n[2] * T[0] - n[0] * T[2]) * hw, (n[0] * T[1] - n[1] * T[0]) * hw };
+        const double lt = sqrt(T[0] * T[0] + T[1] * T[1] + T[2] * T[2]);
+        const double lb = sqrt(B[0] * B[0] + B[1] * B[1] + B[2] * B[2]);
+        const double sx = (double)(2.0f * tx[0] - 1.0f), sy = (double)(2.0f * tx[1] - 1.0f), sz = (double)(2.0f * tx[2] - 1.0f);
+        double r[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            r[c] = (sx * (lt > 0 ? T[c] / lt : 0.0) + sy * (lb > 0 ? B[c] / lb : 0.0)) + sz * (ln > 0 ? n[c] / ln : 0.0);
+        n[0] = r[0]; n[1] = r[1]; n[2] = r[2];
+        ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    }
+    float emi[3] = { m.emissive_factor[0], m.emissive_factor[1], m.emissive_factor[2] };
+    if (TEX && m.emissive_texture > -1) {      // SRGBtoLinear(texel, 2.2), gBufferPass.frag:111-114; binary64 pow on both producers
+        tex_fetch(rp.tex, m.emissive_texture, uv[0], uv[1], tx);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) emi[c] *= (float)pow((double)tx[c], 2.2);
+    }
     uint8_t dif[3], spc[3];
     float nn[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float base = m.base_color_factor[c];
-        dif[c] = to_unorm8(base * (1.0f - 0.04f) * (1.0f - metal));
-        spc[c] = to_unorm8(0.04f * (1.0f - metal) + base * metal);
+        dif[c] = to_unorm8(base[c] * (1.0f - 0.04f) * (1.0f - metal));
+        spc[c] = to_unorm8(0.04f * (1.0f - metal) + base[c] * metal);
         nn[c] = (float)((ln > 0 ? n[c] / ln : 0.0) * 0.5 + 0.5);
     }
     g.diffuse[pi] = make_uchar4(dif[0], dif[1], dif[2], to_unorm8(rough));
     g.specular[pi] = make_uchar4(spc[0], spc[1], spc[2], to_unorm8(metal));
     g.normal[pi] = pack_half4(nn[0], nn[1], nn[2], 1.0f);
-    g.emission[pi] = pack_half4(m.emissive_factor[0], m.emissive_factor[1], m.emissive_factor[2], 1.0f);
+    g.emission[pi] = pack_half4(emi[0], emi[1], emi[2], 1.0f);
 }
 
+template <bool ALPHA>
 static int launch_visibility(vgi_ctx* c, const RasterParams& rp, cudaStream_t s)
 {
     const size_t npx = (size_t)rp.w * rp.h;
@@ -336,13 +416,13 @@ static int launch_visibility(vgi_ctx* c, const RasterParams& rp, cudaStream_t s)
     int n = 1;
     if (rp.ntri) {
         c->timer.begin("k_raster_small", s);
-        k_raster_small<<<(rp.ntri + 127) / 128, 128, 0, s>>>(rp);
+        k_raster_small<ALPHA><<<(rp.ntri + 127) / 128, 128, 0, s>>>(rp);
         c->timer.end(s);
         c->timer.begin("k_raster_large", s);
-        k_raster_large<<<148 * 8, 256, 0, s>>>(rp);
+        k_raster_large<ALPHA><<<148 * 8, 256, 0, s>>>(rp);
         c->timer.end(s);
         c->timer.begin("k_raster_huge", s);
-        k_raster_huge<<<148 * 8, 256, 0, s>>>(rp);
+        k_raster_huge<ALPHA><<<148 * 8, 256, 0, s>>>(rp);
         c->timer.end(s);
         n += 3;
     }
@@ -353,10 +433,11 @@ int vgi_launch_render_shadow(vgi_ctx* c, const float* M, uint32_t w, uint32_t h,
 {
     RasterParams rp;
     memcpy(rp.M, M, sizeof rp.M);
-    rp.tri_pos = c->tri_pos; rp.tri_nrm = c->tri_nrm; rp.materials = c->materials; rp.ntri = c->ntri;
+    rp.tri_pos = c->tri_pos; rp.tri_nrm = c->tri_nrm; rp.tri_tan = nullptr; rp.materials = c->materials; rp.ntri = c->ntri;
+    rp.tex = c->texset();
     rp.w = (int)w; rp.h = (int)h;
     rp.proj = (ProjTri*)c->raster_proj; rp.keys = c->raster_keys; rp.large = c->raster_large; rp.large_count = c->raster_large + c->ntri;
-    int n = launch_visibility(c, rp, s);
+    int n = launch_visibility<false>(c, rp, s);     // no fragment shader in the shadow pass: nothing is discarded
     const size_t npx = (size_t)w * h;
     c->timer.begin("k_raster_resolve_depth", s);
     k_raster_resolve_depth<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(rp.keys, npx, depth);
@@ -368,16 +449,19 @@ int vgi_launch_render_gbuffer(vgi_ctx* c, const float* M, const vgi_gbuffer* tar
 {
     RasterParams rp;
     memcpy(rp.M, M, sizeof rp.M);
-    rp.tri_pos = c->tri_pos; rp.tri_nrm = c->tri_nrm; rp.materials = c->materials; rp.ntri = c->ntri;
+    rp.tri_pos = c->tri_pos; rp.tri_nrm = c->tri_nrm; rp.tri_tan = c->tri_tan; rp.materials = c->materials; rp.ntri = c->ntri;
+    rp.tex = c->texset();
     rp.w = (int)target->width; rp.h = (int)target->height;
     rp.proj = (ProjTri*)c->raster_proj; rp.keys = c->raster_keys; rp.large = c->raster_large; rp.large_count = c->raster_large + c->ntri;
-    int n = launch_visibility(c, rp, s);
+    // gBufferPass.frag:96 discards by alpha cutoff: only scenes with such a material pay for the test
+    int n = c->scene_alpha_tested ? launch_visibility<true>(c, rp, s) : launch_visibility<false>(c, rp, s);
     GBufferTarget g;
     g.diffuse = (uchar4*)target->diffuse_rgba8; g.normal = (uint2*)target->normal_rgba16f;
     g.specular = (uchar4*)target->specular_rgba8; g.emission = (uint2*)target->emission_rgba16f;
     g.depth = (float*)target->depth_f32;
     c->timer.begin("k_raster_resolve_gbuffer", s);
-    k_raster_resolve_gbuffer<<<dim3((rp.w + 31) / 32, (rp.h + 7) / 8), 256, 0, s>>>(rp, g);
+    if (c->scene_max_texture_all > -1) k_raster_resolve_gbuffer<true><<<dim3((rp.w + 31) / 32, (rp.h + 7) / 8), 256, 0, s>>>(rp, g);
+    else k_raster_resolve_gbuffer<false><<<dim3((rp.w + 31) / 32, (rp.h + 7) / 8), 256, 0, s>>>(rp, g);
     c->timer.end(s);
     return n + 1;
 }

@@ -29,28 +29,37 @@ def shadow_depth(scene, shadow_desc, size=4096):
     return depth
 
 
-def gbuffer(scene, camera, width, height):
+def gbuffer(scene, camera, width, height, textures=None):
     """G-buffer in the reference formats: diffuse RGBA8, normal RGBA16F, specular RGBA8,
-    emission RGBA16F, depth D32 (ref: GBufferPass.cpp:177-194)."""
+    emission RGBA16F, depth D32 (ref: GBufferPass.cpp:177-194). textures: list of (H, W, 4) uint8 images the materials'
+    texture indices refer to (gBufferPass.frag: base colour, metallic-roughness, emissive, normal map, alpha cutoff)."""
+    from .structs import texture_array
     diffuse = np.empty((height, width, 4), dtype=np.uint8)
     specular = np.empty((height, width, 4), dtype=np.uint8)
     normal = np.empty((height, width, 4), dtype=np.uint16)
     emission = np.empty((height, width, 4), dtype=np.uint16)
     depth = np.empty((height, width), dtype=np.float32)
     d = scene.desc()
-    lib().vgs_gbuffer(C.byref(d), C.byref(camera), C.c_uint32(width), C.c_uint32(height),
-                      C.c_void_p(diffuse.ctypes.data), C.c_void_p(normal.ctypes.data),
-                      C.c_void_p(specular.ctypes.data), C.c_void_p(emission.ctypes.data),
-                      C.c_void_p(depth.ctypes.data))
+    arr, keep = texture_array(textures or [])
+    lib().vgs_gbuffer_tex(C.byref(d), arr, C.c_uint32(len(keep)), C.byref(camera), C.c_uint32(width), C.c_uint32(height),
+                          C.c_void_p(diffuse.ctypes.data), C.c_void_p(normal.ctypes.data),
+                          C.c_void_p(specular.ctypes.data), C.c_void_p(emission.ctypes.data),
+                          C.c_void_p(depth.ctypes.data))
     return dict(diffuse=diffuse, normal=normal, specular=specular, emission=emission, depth=depth)
 
 
-def gbuffer_attributes(scene, camera, width, height):
+def gbuffer_attributes(scene, camera, width, height, textures=None, full=False):
     """Test aid: per pixel the material index (-1 = not covered) and the interpolated, un-normalised world normal the
-    G-buffer fragment stage receives (vgs_gbuffer_attributes)."""
+    G-buffer fragment stage receives (vgs_gbuffer_attributes_tex); full=True adds the interpolated texture coordinate and
+    tangent (the whole `fs_in` block of gBufferPass.frag)."""
+    from .structs import texture_array
     material = np.empty((height, width), dtype=np.int32)
     normal = np.empty((height, width, 3), dtype=np.float32)
+    uv = np.empty((height, width, 2), dtype=np.float32)
+    tangent = np.empty((height, width, 4), dtype=np.float32)
     d = scene.desc()
-    lib().vgs_gbuffer_attributes(C.byref(d), C.byref(camera), C.c_uint32(width), C.c_uint32(height),
-                                 C.c_void_p(material.ctypes.data), C.c_void_p(normal.ctypes.data))
-    return material, normal
+    arr, keep = texture_array(textures or [])
+    lib().vgs_gbuffer_attributes_tex(C.byref(d), arr, C.c_uint32(len(keep)), C.byref(camera), C.c_uint32(width),
+                                     C.c_uint32(height), C.c_void_p(material.ctypes.data), C.c_void_p(normal.ctypes.data),
+                                     C.c_void_p(uv.ctypes.data), C.c_void_p(tangent.ctypes.data))
+    return (material, normal, uv, tangent) if full else (material, normal)

@@ -149,6 +149,7 @@ class SceneDesc(C.Structure):
         ("materials", C.c_void_p),
         ("vertex_count", C.c_uint32), ("index_count", C.c_uint32), ("primitive_count", C.c_uint32),
         ("node_count", C.c_uint32), ("material_count", C.c_uint32),
+        ("tangents", C.c_void_p),
     ]
 
 

@@ -26,6 +26,7 @@ class Scene:
     materials: np.ndarray
     name: str = "scene"
     _keep: list = field(default_factory=list)
+    tangents: np.ndarray = None     # vec4 per vertex (xyz, handedness), only the G-buffer's normal mapping reads them
 
     @property
     def triangle_count(self):
@@ -48,6 +49,10 @@ class Scene:
         d.primitive_count = self.primitives.shape[0]
         d.node_count = self.nodes.shape[0]
         d.material_count = self.materials.shape[0]
+        if self.tangents is not None:
+            tg = np.ascontiguousarray(self.tangents, np.float32)
+            self._keep.append(tg)
+            d.tangents = tg.ctypes.data
         return d
 
     def world_bbox(self):
@@ -230,13 +235,63 @@ def procedural_textures(seed=7):
     holes = (((xx3 % 16) - 8) ** 2 + ((yy3 % 16) - 8) ** 2) < 20
     occ[holes, 0] = 0
     noise = rng.randint(0, 256, (5, 3, 4)).astype(np.uint8)
-    return [base, emis, occ, noise]
+    # [4] tangent-space normal map (egg-crate bumps), [5] metallic-roughness map (g = roughness ramp, b = metallic patches):
+    # read by the G-buffer producer only (gBufferPass.frag)
+    yy4, xx4 = np.mgrid[0:32, 0:32]
+    sx = 0.6 * np.cos(2 * np.pi * xx4 / 16.0)
+    sy = 0.6 * np.cos(2 * np.pi * yy4 / 8.0)
+    nz = np.sqrt(np.maximum(1.0 - 0.5 * (sx * sx + sy * sy), 0.0))
+    nmap = np.zeros((32, 32, 4), np.uint8)
+    nmap[..., 0] = np.round((sx * 0.5 + 0.5) * 255)
+    nmap[..., 1] = np.round((sy * 0.5 + 0.5) * 255)
+    nmap[..., 2] = np.round((nz * 0.5 + 0.5) * 255)
+    nmap[..., 3] = 255
+    mr = np.zeros((16, 24, 4), np.uint8)
+    yy5, xx5 = np.mgrid[0:16, 0:24]
+    mr[..., 0] = 255
+    mr[..., 1] = (20 + 9 * xx5).astype(np.uint8)
+    mr[..., 2] = (255 * ((xx5 // 6 + yy5 // 4) % 2)).astype(np.uint8)
+    mr[..., 3] = 255
+    return [base, emis, occ, noise, nmap, mr]
 
 
-def textured_cornell(wall_quads=12, box_quads=4):
+def compute_tangents(scene):
+    """Per-vertex tangents (xyz, handedness) of a Scene from its positions, normals and texture coordinates: the usual
+    accumulation of per-triangle dP/du, Gram-Schmidt against the normal, handedness from dP/dv."""
+    pos = scene.positions.astype(np.float64)
+    uv = scene.texcoords.astype(np.float64)
+    nrm = scene.normals.astype(np.float64)
+    tan = np.zeros_like(pos)
+    bit = np.zeros_like(pos)
+    for pr in scene.primitives:
+        idx = scene.indices[int(pr["first_index"]):int(pr["first_index"]) + int(pr["index_count"])].astype(np.int64)
+        idx = idx.reshape(-1, 3) + int(pr["vertex_offset"])
+        e1, e2 = pos[idx[:, 1]] - pos[idx[:, 0]], pos[idx[:, 2]] - pos[idx[:, 0]]
+        d1, d2 = uv[idx[:, 1]] - uv[idx[:, 0]], uv[idx[:, 2]] - uv[idx[:, 0]]
+        det = d1[:, 0] * d2[:, 1] - d2[:, 0] * d1[:, 1]
+        det = np.where(np.abs(det) < 1e-20, 1.0, det)
+        tt = (e1 * d2[:, 1:2] - e2 * d1[:, 1:2]) / det[:, None]
+        bb = (e2 * d1[:, 0:1] - e1 * d2[:, 0:1]) / det[:, None]
+        for k in range(3):
+            np.add.at(tan, idx[:, k], tt)
+            np.add.at(bit, idx[:, k], bb)
+    tan = tan - nrm * np.sum(tan * nrm, axis=1, keepdims=True)
+    ln = np.linalg.norm(tan, axis=1, keepdims=True)
+    fallback = np.cross(nrm, np.array([0.0, 1.0, 0.0])[None, :])
+    fb2 = np.cross(nrm, np.array([1.0, 0.0, 0.0])[None, :])
+    fallback = np.where(np.linalg.norm(fallback, axis=1, keepdims=True) < 1e-6, fb2, fallback)
+    tan = np.where(ln < 1e-12, fallback, tan)
+    tan = tan / np.maximum(np.linalg.norm(tan, axis=1, keepdims=True), 1e-30)
+    hand = np.where(np.sum(np.cross(nrm, tan) * bit, axis=1) < 0.0, -1.0, 1.0)
+    return np.concatenate([tan, hand[:, None]], axis=1).astype(np.float32)
+
+
+def textured_cornell(wall_quads=12, box_quads=4, gbuffer_maps=False):
     """The Cornell box with textured materials (texture indices into procedural_textures()): textured floor (base colour),
     alpha-tested back wall (occlusion mask: holes), a wall whose base colour uses the 3 x 5 texture with repeated
-    coordinates, an emissive quad with an emissive texture, one box that combines all three."""
+    coordinates, an emissive quad with an emissive texture, one box that combines all three. gbuffer_maps=True adds what only
+    the G-buffer pass reads: a normal map + metallic-roughness map on the right wall, a normal map on the box, an alpha cutoff
+    on the floor (its base-colour texture has alpha 0.6 / 1 in a checker) and per-vertex tangents."""
     b = _Builder()
     node = b.node(np.eye(4, dtype=np.float32).reshape(4, 4))
 
@@ -265,6 +320,15 @@ def textured_cornell(wall_quads=12, box_quads=4):
     v0 = int(sc.primitives[2]["vertex_offset"])
     v1 = int(sc.primitives[3]["vertex_offset"])
     sc.texcoords[v0:v1] = (sc.texcoords[v0:v1] * np.float32(3.3) - np.float32(1.2)).astype(np.float32)
+    if gbuffer_maps:
+        sc.materials[right]["normal_texture"] = 4
+        sc.materials[right]["metallic_roughness_texture"] = 5
+        sc.materials[right]["metallic_factor"] = 0.9
+        sc.materials[right]["roughness_factor"] = 0.8
+        sc.materials[combo]["normal_texture"] = 4
+        sc.materials[floor]["alpha_mode"] = 1
+        sc.materials[floor]["alpha_cutoff"] = 0.8
+        sc.tangents = compute_tangents(sc)
     return sc
 
 
