@@ -248,6 +248,16 @@ int vgi_voxelize_opacity(vgi_ctx* ctx, void* stream);
 int vgi_inject_radiance(vgi_ctx* ctx, uint32_t frame_index, void* stream);
 /* both of the above in one call (the fused fast path; identical results). */
 int vgi_build_clipmap(vgi_ctx* ctx, uint32_t frame_index, void* stream);
+/* replaces: the `_fullRevoxelization = false` branch of VoxelizationPass (VoxelizationPass.cpp:81-99,127-150 with
+ * fillRevoxelizationRegions :450-494 — present in the reference, never taken): the same frame as vgi_build_clipmap, but only
+ * what a moved clip region invalidates is rebuilt. Granularity is the clip level: a level whose region, children and radiance
+ * are current keeps its records in the toroidal store; a level whose region moved — or whose cadence frame arrives while its
+ * radiance is stale — is rebuilt together with every coarser level (their centre halves are down-samples of it). Scene, light
+ * and textures must be unchanged since the previous build; their setters (and every full or sharded build) invalidate, after
+ * which the next call rebuilds everything. Called on every frame of a sequence, the store equals the one vgi_build_clipmap
+ * leaves on the same sequence bit for bit. first_level_rebuilt (may be NULL): the finest level that was rebuilt, level_count
+ * when nothing had to be. vgi_get_stats then describes the rebuilt levels only. */
+int vgi_build_clipmap_incremental(vgi_ctx* ctx, uint32_t frame_index, uint32_t* first_level_rebuilt, void* stream);
 
 /* Export one atlas in the reference image layout: RGBA8, x-fastest,
  * W=(R+2)*6, H=(R+2)*L, D=R+2 (ref: Voxelizer.h:40-52), borders per mode_flags.

@@ -92,6 +92,46 @@ def test_cadence_and_moving_camera_bit_exact(oracle):
         assert np.array_equal(g_rad, rad), f"frame {frame}: radiance differs in {(g_rad != rad).sum()} bytes"
 
 
+def test_incremental_build_equals_full_rebuild_over_a_camera_path():
+    """vgi_build_clipmap_incremental on every frame of a 24-frame camera walk (regions of different levels move on
+    different frames, cadence frames come and go) against vgi_build_clipmap on every frame of the same walk: opacity and
+    radiance atlases bit for bit on every frame, the traced images at the end, and the call really skips work — frames with
+    nothing to rebuild, frames that rebuild only the coarse levels' tail, frames that rebuild everything. The full build is
+    compared with the oracle on such a walk by test_cadence_and_moving_camera_bit_exact."""
+    import torch
+    inp = common.cornell_inputs()
+    cfg = inp["cfg"]
+    full, inc = _gi_for(inp), _gi_for(inp)
+    firsts = []
+    for frame in range(24):
+        cam = (0.11 * frame, -0.03 * frame, 0.07 * frame)
+        for gi in (full, inc):
+            gi.update_regions(cam)
+        full.build_clipmap(frame)
+        firsts.append(inc.build_clipmap_incremental(frame))
+        for which in (0, 1):
+            a, b = full.export_atlas(which), inc.export_atlas(which)
+            assert torch.equal(a, b), f"frame {frame}: atlas {which} differs in {int((a != b).sum())} bytes (first level rebuilt {firsts[-1]})"
+    L = cfg.level_count
+    assert firsts[0] == 0
+    assert firsts.count(L) >= 4, firsts                 # nothing moved, no stale radiance due
+    assert any(0 < f < L for f in firsts), firsts       # only coarser levels
+    assert firsts.count(0) >= 3, firsts                 # the finest region moved
+    prm = full.default_vct_params(8)
+    cam = inp["cam"]
+    gb = full.upload_gbuffer(inp["gbuffer"])
+    d0, s0 = full.cone_trace(cam, gb, prm)
+    d1, s1 = inc.cone_trace(cam, inc.upload_gbuffer(inp["gbuffer"]), prm)
+    assert torch.equal(d0, d1) and torch.equal(s0, s1)
+    # a setter invalidates: the next call rebuilds everything
+    inc.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
+    assert inc.build_clipmap_incremental(24) == 0
+    # ... and so does a full build in between
+    assert inc.build_clipmap_incremental(25) == L        # odd frame, same regions: only level 0 is on cadence and it is current
+    inc.build_clipmap(26)
+    assert inc.build_clipmap_incremental(27) == 0
+
+
 def test_scene_change_clears_stale_records(oracle):
     """Replace the scene by a much smaller one: every record of the old scene must be cleared."""
     from vk_voxel_cone_tracing_b200 import synth

@@ -136,6 +136,13 @@ class VoxelGI:
     def build_clipmap(self, frame_index=0, stream=None):
         self._ck(lib().vgi_build_clipmap(self._h, C.c_uint32(frame_index), _stream(stream)))
 
+    def build_clipmap_incremental(self, frame_index=0, stream=None):
+        """vgi_build_clipmap_incremental: rebuild only the clip levels a moved region (or a due cadence frame) invalidates.
+        Returns the finest level that was rebuilt (level_count: nothing had to be)."""
+        first = C.c_uint32(0)
+        self._ck(lib().vgi_build_clipmap_incremental(self._h, C.c_uint32(frame_index), C.byref(first), _stream(stream)))
+        return int(first.value)
+
     def export_atlas(self, which, out=None, stream=None):
         """which: 0 opacity, 1 radiance -> uint8 tensor (D, H, W, 4) in the reference image layout."""
         torch = self._torch

@@ -412,6 +412,7 @@ int vgi_set_scene(vgi_ctx* c, const vgi_scene_desc* s)
     c->visit_cap = c->max_occ;
     CK(c, cudaMalloc(&c->visit_list, (size_t)c->visit_cap * L * sizeof(uint32_t)));
     c->voxelized = c->built = false;
+    c->inc_valid = false;
     return VGI_OK;
 }
 
@@ -429,6 +430,7 @@ int vgi_update_nodes(vgi_ctx* c, const vgi_node_matrix* nodes, uint32_t count, v
     CK(c, cudaMemcpy(c->d_nodes, nodes, (size_t)count * sizeof(vgi_node_matrix), cudaMemcpyHostToDevice));
     if (c->ntri) c->launches += vgi_launch_transform_scene(c, s);
     c->voxelized = c->built = false;
+    c->inc_valid = false;
     c->svo_voxelized = false;
     c->last_stream = s;
     return check_launch(c, "vgi_update_nodes");
@@ -448,6 +450,7 @@ int vgi_set_textures(vgi_ctx* c, const vgi_texture* tex, uint32_t count)
     cudaFree(c->tex_data); cudaFree(c->tex_table);
     c->tex_data = nullptr; c->tex_table = nullptr; c->ntex = 0;
     c->voxelized = c->built = false;
+    c->inc_valid = false;
     if (!count) return VGI_OK;
     std::vector<uint4> table(count);
     CK(c, cudaMalloc(&c->tex_data, total * sizeof(uint32_t)));
@@ -493,6 +496,7 @@ int vgi_set_light(vgi_ctx* c, const vgi_dir_light* light, const vgi_dir_light_sh
         lp.depth = depth;
     }
     c->light_set = true;
+    c->inc_valid = false;
     return VGI_OK;
 }
 
@@ -572,6 +576,8 @@ void build_params_from_ctx(const vgi_ctx* c, uint32_t frame_index, BuildParams* 
         if (frame_index % (1u << l) == 0) mask |= 1u << l; // ref: RadianceInjectionPass.cpp:36-38,75
     }
     bp->level_mask = mask;
+    bp->vox_levels = 0x76543210u;
+    bp->vox_nlev = bp->L;
 }
 
 extern "C" {
@@ -617,6 +623,7 @@ int vgi_inject_radiance(vgi_ctx* c, uint32_t frame_index, void* stream)
     c->last_stream = s;
     c->voxelized = false; // the pair list is consumed: the next frame re-voxelizes (Q8/Q9)
     c->built = true;
+    c->inc_valid = false;   // a full rebuild: vgi_build_clipmap_incremental starts over
     return check_launch(c, "vgi_inject_radiance");
 }
 
@@ -625,6 +632,67 @@ int vgi_build_clipmap(vgi_ctx* c, uint32_t frame_index, void* stream)
     int r = vgi_voxelize_opacity(c, stream);
     if (r != VGI_OK) return r;
     return vgi_inject_radiance(c, frame_index, stream);
+}
+
+// The reference's `_fullRevoxelization = false` branch (VoxelizationPass.cpp:81-99,127-150, fillRevoxelizationRegions
+// :450-494), which it never takes: rebuild only what a moved clip region invalidates. Granularity here is the clip level:
+// the toroidal store keeps every record of a level whose region, children and radiance are current, and a level is rebuilt
+// as a whole — together with every coarser one, whose centre half is a down-sample of it — when its region moved, or when
+// its cadence frame arrives while its radiance is stale. Scene, light and textures are assumed unchanged since the last
+// build (their setters invalidate). The store after this call equals the store after vgi_build_clipmap(frame) called on
+// every frame of the same sequence, bit for bit.
+int vgi_build_clipmap_incremental(vgi_ctx* c, uint32_t frame_index, uint32_t* first_level_rebuilt, void* stream)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_build_clipmap_incremental: null ctx");
+    if (!c->pairs) return fail(c, VGI_E_STATE, "vgi_build_clipmap_incremental: call vgi_set_scene first");
+    if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_build_clipmap_incremental: call vgi_set_light first");
+    if (!c->regions_set) return fail(c, VGI_E_STATE, "vgi_build_clipmap_incremental: call vgi_update_regions first");
+    if (c->scene_max_texture >= (int32_t)c->ntex) return fail(c, VGI_E_STATE, "vgi_build_clipmap_incremental: a material references a texture that vgi_set_textures has not provided");
+    if (c->z0 != 0 || c->z1 != (int)c->cfg.resolution || c->z_mask != 0)
+        return fail(c, VGI_E_STATE, "vgi_build_clipmap_incremental: not with a slab-sharded context");
+    CK(c, cudaSetDevice(c->device));
+    BuildParams bp;
+    build_params_from_ctx(c, frame_index, &bp);
+    int first = bp.L;
+    if (!c->inc_valid) first = 0;
+    else
+        for (int l = 0; l < bp.L && first == bp.L; ++l) {
+            const bool moved = c->inc_corner[l][0] != bp.lv[l].min_corner[0] || c->inc_corner[l][1] != bp.lv[l].min_corner[1] ||
+                               c->inc_corner[l][2] != bp.lv[l].min_corner[2];
+            const bool onCadence = (bp.level_mask >> l) & 1u;
+            if (moved || (onCadence && !c->inc_radiance_current[l])) first = l;
+        }
+    if (first_level_rebuilt) *first_level_rebuilt = (uint32_t)first;
+    if (first == bp.L) return VGI_OK;       // every record is current
+    bp.level_first = first;
+    // occupancy bits persist per level: a level from `first` up is voxelized again only if its region moved (new occupancy)
+    // or it is on its cadence frame (the injection needs its pair list); the others only re-run their mask / record passes
+    bp.vox_levels = 0u;
+    bp.vox_nlev = 0;
+    for (int l = first; l < bp.L; ++l) {
+        const bool moved = !c->inc_valid || c->inc_corner[l][0] != bp.lv[l].min_corner[0] || c->inc_corner[l][1] != bp.lv[l].min_corner[1] ||
+                           c->inc_corner[l][2] != bp.lv[l].min_corner[2];
+        if (moved || ((bp.level_mask >> l) & 1u)) bp.vox_levels |= (uint32_t)l << (4 * bp.vox_nlev++);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->svo_counters_fresh && c->svo_built) {    // as in vgi_voxelize_opacity: the counters block is shared with the octree path
+        cudaStreamSynchronize(c->last_stream);
+        c->svo_nnodes = c->h_counters->svo_counter;
+    }
+    c->svo_counters_fresh = false;
+    c->svo_voxelized = false;
+    c->launches += vgi_launch_voxelize(c, bp, s);
+    c->launches += vgi_launch_inject_finalize(c, bp, s);
+    c->last_stream = s;
+    for (int l = first; l < bp.L; ++l) {
+        for (int k = 0; k < 3; ++k) c->inc_corner[l][k] = bp.lv[l].min_corner[k];
+        // rebuilt off its cadence frame: opacity is current, the radiance texels are last frame's (as in the full build)
+        c->inc_radiance_current[l] = (bp.level_mask >> l) & 1u;
+    }
+    c->inc_valid = true;
+    c->voxelized = false;
+    c->built = true;
+    return check_launch(c, "vgi_build_clipmap_incremental");
 }
 
 size_t vgi_atlas_bytes(const vgi_ctx* c)
@@ -667,6 +735,7 @@ int vgi_bind_voxel_store(vgi_ctx* c, void* dev_ptr, size_t bytes)
     const size_t nwords = (((size_t)c->cfg.resolution * c->cfg.resolution * c->cfg.resolution) >> 5) * c->cfg.level_count;
     for (int k = 0; k < 2; ++k) CK(c, cudaMemset(c->nz[k], 0, nwords * sizeof(uint32_t)));
     c->built = false;
+    c->inc_valid = false;
     return VGI_OK;
 }
 
@@ -771,6 +840,7 @@ int vgi_slab_build_end(vgi_ctx* c, uint32_t frame_index, void* stream)
     c->slab_phase = 0;
     c->voxelized = false;
     c->built = true;
+    c->inc_valid = false;
     return check_launch(c, "vgi_slab_build_end");
 }
 
@@ -1152,6 +1222,7 @@ int vgi_peer_build_clipmap(vgi_ctx* c, uint32_t frame_index, void* stream)
     c->last_stream = s;
     c->voxelized = false;
     c->built = true;
+    c->inc_valid = false;
     return check_launch(c, "vgi_peer_build_clipmap");
 }
 

@@ -55,9 +55,10 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
     // reserves the space for all its pairs with ONE atomic (warp prefix sum of the popcounts) and every lane
     // writes its pairs to consecutive slots. The single global pair counter is no longer hit once per voxel row.
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inRange = gid < bp.ntri * (uint32_t)bp.L;
-    const int l = inRange ? (int)(gid / bp.ntri) : 0;
-    const uint32_t t = inRange ? gid - (uint32_t)l * bp.ntri : 0u;
+    const bool inRange = gid < bp.ntri * (uint32_t)bp.vox_nlev;
+    const int lrel = inRange ? (int)(gid / bp.ntri) : 0;
+    const int l = (int)((bp.vox_levels >> (4 * lrel)) & 15u);   // incremental build: only the levels whose occupancy or pairs are needed
+    const uint32_t t = inRange ? gid - (uint32_t)lrel * bp.ntri : 0u;
     unsigned long long hits = 0ull;
     int lo0 = 0, lo1 = 0, lo2 = 0, nx = 1, ny = 1;
     if (inRange) {
@@ -843,15 +844,20 @@ int vgi_launch_transform_scene(vgi_ctx* c, cudaStream_t s)
 int vgi_launch_voxelize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s)
 {
     int n = 0;
-    const size_t nwords = ((size_t)bp.R * bp.R * bp.R >> 5) * bp.L;
+    const size_t wordsPerLevel = (size_t)bp.R * bp.R * bp.R >> 5;
+    const size_t nwords = wordsPerLevel * bp.L;
+    const int nlev = bp.vox_nlev;
     cudaMemsetAsync(c->counters, 0, sizeof(Counters), s);
-    cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
-    if (bp.ntri) {
+    if (nlev == bp.L) cudaMemsetAsync(c->occ, 0, nwords * sizeof(uint32_t), s);
+    else
+        for (int i = 0; i < nlev; ++i)
+            cudaMemsetAsync(c->occ + wordsPerLevel * ((bp.vox_levels >> (4 * i)) & 15u), 0, wordsPerLevel * sizeof(uint32_t), s);
+    if (bp.ntri && nlev > 0) {
         if (c->scene_max_texture > -1) {
-            LAUNCH("k_voxelize", k_voxelize<true><<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+            LAUNCH("k_voxelize", k_voxelize<true><<<cdiv((size_t)bp.ntri * nlev, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
             LAUNCH("k_voxelize_large", k_voxelize_large<true><<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
         } else {
-            LAUNCH("k_voxelize", k_voxelize<false><<<cdiv((size_t)bp.ntri * bp.L, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
+            LAUNCH("k_voxelize", k_voxelize<false><<<cdiv((size_t)bp.ntri * nlev, 128), 128, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
             LAUNCH("k_voxelize_large", k_voxelize_large<false><<<148 * 4, 256, 0, s>>>(bp, c->tri_pos, c->occ, c->pairs, c->large, c->counters, c->materials, c->texset()));
         }
     }
@@ -866,7 +872,11 @@ static void launch_masks(vgi_ctx* c, const BuildParams& bp, int cur, cudaStream_
 {
     const uint32_t chunks = (uint32_t)((((size_t)bp.R * bp.R * bp.R) >> 5) >> 5);
     const unsigned grid = min(cdiv(chunks, 8), 148u * 16u);
-    for (int l = 0; l < bp.L; ++l)
+    if (bp.level_first > 0) {   // untouched levels: their masks are last build's
+        const size_t bytes = (((size_t)bp.R * bp.R * bp.R) >> 5) * bp.level_first * sizeof(uint32_t);
+        cudaMemcpyAsync(c->nz[cur], c->nz[cur ^ 1], bytes, cudaMemcpyDeviceToDevice, s);
+    }
+    for (int l = bp.level_first; l < bp.L; ++l)
         LAUNCH("k_level_masks", k_level_masks<<<grid, 256, 0, s>>>(bp, l, c->occ, c->nz[cur ^ 1], c->nz[cur], c->visit_list, c->visit_cap, c->counters));
 }
 
@@ -947,7 +957,7 @@ int vgi_launch_inject_finalize(vgi_ctx* c, const BuildParams& bp, cudaStream_t s
     n += launch_inject(c, bp, s);
     if (side != s) cudaStreamWaitEvent(s, c->ev_side_masks, 0);
     const SlabPack none = { nullptr, nullptr, nullptr, 0u };
-    for (int l = 0; l < bp.L; ++l)
+    for (int l = bp.level_first; l < bp.L; ++l)
         LAUNCH("k_level_records", k_level_records<0><<<148 * 8, 128, 0, s>>>(bp, l, c->occ, c->occ_prefix, c->acc, c->nz[cur], c->visit_list, c->visit_cap, c->counters, c->store, none));
     if (side != s) cudaStreamWaitEvent(s, c->ev_side_done, 0);
     c->nz_cur = cur;

@@ -42,6 +42,9 @@ struct BuildParams {
     uint32_t max_occ;       // capacity of the accumulator table (occupied voxels)
     uint32_t max_large;
     uint32_t level_mask;    // levels whose radiance is (re)injected this frame (cadence)
+    int      level_first;   // incremental build: levels below this one are current and stay untouched (0 = rebuild all)
+    uint32_t vox_levels;    // the levels k_voxelize visits, 4 bits each, finest first (full build: 0x..543210)
+    int      vox_nlev;      // ... and how many
     int      z0, z1;        // slab of records this GPU writes: texel planes z in [z0, z1) ...
     int      z_mask, z_rem; // ... with (z & z_mask) == z_rem (peer build: planes dealt round-robin; 0, 0 = every plane)
     int      shadow_compare;
@@ -201,6 +204,10 @@ struct vgi_ctx {
     uint2* large = nullptr;         // (triangle, level) work items for big triangles
     uint32_t* nz[2] = { nullptr, nullptr }; // non-zero-record masks, ping-pong between frames (L * R^3/32 words each)
     int nz_cur = 0;
+    // vgi_build_clipmap_incremental: what the store currently holds, per level
+    bool    inc_valid = false;
+    int32_t inc_corner[VGI_MAX_LEVELS][3] = {};
+    bool    inc_radiance_current[VGI_MAX_LEVELS] = {};
     uint8_t* brick_mask = nullptr;
     // slab-sharded build: exchange buffer of this GPU's finalized records
     uint32_t* slab_ids = nullptr;
