@@ -105,6 +105,31 @@ DEVFN ConeFaces cone_faces(const float* dir)
     return f;
 }
 
+// Layout experiment (development builds only, tools/build_variant.py -DVGI_TRACE_BRICK_STORE=1|2): the tracer reads a copy of
+// the voxel store whose records are grouped in 4^3 bricks (2 KB, brick-major; inside a brick 1 = z, y, x order, 2 = Morton
+// order so that an aligned 2x2x2 block is 256 contiguous bytes). The copy is made by k_brick_copy before every trace and is
+// not part of any reported time; DESIGN.md section 4 has the A/B. 0 = the shipped linear (level, z, y, x) layout.
+#ifndef VGI_TRACE_BRICK_STORE
+#define VGI_TRACE_BRICK_STORE 0
+#endif
+DEVFN uint32_t rec_index(uint32_t lin, int logR)
+{
+#if VGI_TRACE_BRICK_STORE
+    const uint32_t Rm = (1u << logR) - 1u, nb = (uint32_t)logR - 2u;
+    const uint32_t x = lin & Rm, y = (lin >> logR) & Rm, zl = lin >> (2 * logR);    // zl = level << logR | z
+    const uint32_t brick = ((((zl >> 2) << nb) + (y >> 2)) << nb) + (x >> 2);
+#if VGI_TRACE_BRICK_STORE == 2
+    const uint32_t in = (x & 1u) | ((y & 1u) << 1) | ((zl & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3) | ((zl & 2u) << 4);
+#else
+    const uint32_t in = ((zl & 3u) << 4) | ((y & 3u) << 2) | (x & 3u);
+#endif
+    return (brick << 6) | in;
+#else
+    (void)logR;
+    return lin;
+#endif
+}
+
 // Where a tri-linear footprint lies: texel index of its low corner, the fractional weights and the mask of
 // the records that can be non-zero (0 = nothing to fetch).
 struct Footprint {
@@ -153,7 +178,9 @@ DEVFN void filter_footprint(const TraceParams& tp, const Footprint& fp, const Co
     const int R = tp.R, Rm = R - 1, logR = tp.logR;
     const uint32_t m = fp.mask;
     const uint32_t ix = fp.vox & (uint32_t)Rm, iy = (fp.vox >> logR) & (uint32_t)Rm, iz = (fp.vox >> (2 * logR)) & (uint32_t)Rm;
+#if !VGI_TRACE_BRICK_STORE
     const VoxelRecord* base = tp.store + fp.vox;
+#endif
     // record offsets of the +1 neighbours (toroidal); in records, not bytes: -(R-1) * R^2 * 32 overflows int at R = 512
     const int dx = (ix == (uint32_t)Rm) ? -Rm : 1;
     const int dy = ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
@@ -172,7 +199,11 @@ DEVFN void filter_footprint(const TraceParams& tp, const Footprint& fp, const Co
         if (!((m >> c) & 1u)) continue;
         const int off = oxy[c & 3] + ((c & 4) ? dz : 0);
         const float wc = wxy[c & 3] * ((c & 4) ? w[2] : wz0);
+#if VGI_TRACE_BRICK_STORE
+        const uint2* rec = reinterpret_cast<const uint2*>(tp.store + rec_index(fp.vox + (uint32_t)off, logR));
+#else
         const uint2* rec = reinterpret_cast<const uint2*>(base + off);   // base is a VoxelRecord*: off counts records
+#endif
         const uint2 fx = __ldg(rec), fy = __ldg(rec + 1), fz = __ldg(rec + 2);
         const uint32_t tx = cf.negX ? fx.y : fx.x;
         const uint32_t ty = cf.negY ? fy.y : fy.x;
@@ -355,7 +386,7 @@ DEVFN float4 coop_corner(const TraceParams& tp, uint32_t vox, uint32_t mask, uns
     if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
     if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
     if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
-    const uint2* rec = reinterpret_cast<const uint2*>(tp.store + vox + off);
+    const uint2* rec = reinterpret_cast<const uint2*>(tp.store + rec_index(vox + (uint32_t)off, logR));
     const uint2 fx = __ldg(rec), fy = __ldg(rec + 1), fz = __ldg(rec + 2);
     const uint32_t tx = cf.negX ? fx.y : fx.x;
     const uint32_t ty = cf.negY ? fy.y : fy.x;
@@ -554,7 +585,7 @@ DEVFN bool coop_fetch(const TraceParams& tp, uint32_t vox, unsigned corner, cons
     if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
     if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
     if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
-    const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + rec_index(vox + (uint32_t)off, logR));
     const float4 fo = s_face[2 * cone], fk = s_face[2 * cone + 1];
     const uint32_t tx = __ldg(rec + __float_as_uint(fo.x));
     const uint32_t ty = __ldg(rec + __float_as_uint(fo.y));
@@ -750,7 +781,7 @@ DEVFN bool coop_try3(const TraceParams& tp, const Footprint& fp, uint32_t secBit
             if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
             if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
             if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
-            const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+            const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + rec_index(vox + (uint32_t)off, logR));
             const int sc = (k >> 31) ? c1 : c0;
             const float4 fo = s_face[2 * sc], fk = s_face[2 * sc + 1];
             const uint32_t tx = __ldg(rec + __float_as_uint(fo.x)), ty = __ldg(rec + __float_as_uint(fo.y)), tz = __ldg(rec + __float_as_uint(fo.z));
@@ -1499,7 +1530,7 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
                 if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
                 if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
                 if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
-                const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + rec_index(vox + (uint32_t)off, logR));
                 const uint32_t tx = __ldg(rec + ox), ty = __ldg(rec + oy), tz = __ldg(rec + oz);
                 STAT(4, 1);
                 const float2 kx2 = make_float2(kx, kx), ky2 = make_float2(ky, ky), kz2 = make_float2(kz, kz);
@@ -1573,7 +1604,7 @@ DEVFN void spec_both_levels(const TraceParams& tp, bool wantLo, uint32_t keyLo, 
                 if (corner & 1u) off += (ix == (uint32_t)Rm) ? -Rm : 1;
                 if (corner & 2u) off += ((iy == (uint32_t)Rm) ? -Rm : 1) << logR;
                 if (corner & 4u) off += ((iz == (uint32_t)Rm) ? -Rm : 1) << (2 * logR);
-                const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + vox + off);
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(tp.store + rec_index(vox + (uint32_t)off, logR));
                 const uint32_t tx = __ldg(rec + ox), ty = __ldg(rec + oy), tz = __ldg(rec + oz);
                 STAT(4, 1);
                 const float2 kx2 = make_float2(kx, kx), ky2 = make_float2(ky, ky), kz2 = make_float2(kz, kz);
@@ -1724,9 +1755,37 @@ int vgi_launch_trace_svo(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
     return 1;
 }
 
-int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp, cudaStream_t s)
+#if VGI_TRACE_BRICK_STORE
+__global__ void __launch_bounds__(256) k_brick_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nrec, int logR)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = rec_index((uint32_t)i, logR);
+        dst[2 * j] = src[2 * i];
+        dst[2 * j + 1] = src[2 * i + 1];
+    }
+}
+static VoxelRecord* g_brick_store = nullptr;
+static size_t g_brick_records = 0;
+#endif
+
+int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp_in, cudaStream_t s)
 {
     int n = 0;
+#if VGI_TRACE_BRICK_STORE
+    TraceParams tp = tp_in;
+    {
+        const size_t nrec = ((size_t)tp.R * tp.R * tp.R) * tp.L;
+        if (g_brick_records != nrec) {
+            cudaFree(g_brick_store);
+            cudaMalloc(&g_brick_store, nrec * sizeof(VoxelRecord));
+            g_brick_records = nrec;
+        }
+        k_brick_copy<<<148 * 16, 256, 0, s>>>(reinterpret_cast<const uint4*>(tp.store), reinterpret_cast<uint4*>(g_brick_store), nrec, tp.logR);
+        tp.store = g_brick_store;
+    }
+#else
+    const TraceParams& tp = tp_in;
+#endif
     cudaMemsetAsync(tp.spec_count, 0, 2 * sizeof(uint32_t), s); // list length + work cursor
     const int rows = tp.y1 - tp.y0;
     if (rows <= 0 || tp.width <= 0) return 0;
