@@ -161,6 +161,7 @@ static int report_overflow(vgi_ctx* c, const char* who)
 {
     const uint32_t m = c->h_counters->overflow;
     if (!m) return VGI_OK;
+    c->inc_valid = false;       // an overflowed build left records unwritten: the next incremental build starts over
     char buf[320];
     int n = snprintf(buf, sizeof buf, "%s: device list overflow (mask 0x%x):", who, m);
     auto add = [&](const char* fmt, unsigned a, unsigned b) { if (n < (int)sizeof buf) n += snprintf(buf + n, sizeof buf - n, fmt, a, b); };
