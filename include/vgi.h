@@ -372,6 +372,16 @@ int vgi_frame_view_host(vgi_ctx* ctx, uint32_t frame_index, const float camera_p
                         uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
                         const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular,
                         void* stream);
+/* The same frame split in two so that a sequence of views is pipelined: _begin enqueues everything (both downloads ride a
+ * copy stream) and returns; _end waits until the OLDEST frame begun has both images in its host buffers and reports its list
+ * overflows. At most two frames may be in flight: begin(i), begin(i + 1), end() [= frame i], begin(i + 2), end() ... — the
+ * download of frame i then overlaps the rasterisation and build of frame i + 1. Host buffers should be pinned.
+ * vgi_frame_view_host = _begin + _end + a synchronise of `stream`. */
+int vgi_frame_view_host_begin(vgi_ctx* ctx, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                              uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
+                              const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular,
+                              void* stream);
+int vgi_frame_view_host_end(vgi_ctx* ctx);
 
 /* ---- sparse voxel octree -------------------------------------------------------------------- */
 /* replaces: SparseVoxelizer::preVoxelize + cmdVoxelize (SparseVoxelizer.cpp:248-326) — one pass,

@@ -114,3 +114,43 @@ def test_frame_view_host_equals_the_device_resident_path():
     # shadow = None keeps the current shadow map
     b.frame_view_host(0, inp["cam_pos"], inp["cam"], 128, 128, None, prm, out[0], out[1])
     assert torch.equal(out[0][cov], want[0].cpu()[cov])
+
+
+def test_pipelined_view_frames_equal_the_synchronous_call():
+    """vgi_frame_view_host_begin / _end with two frames in flight over a six-camera sequence: every frame's images equal what
+    the synchronous call delivers for the same camera, and the call order is enforced (a third begin, an end with nothing
+    in flight, a synchronous call in between fail with VGI_E_STATE)."""
+    import torch
+    from vk_voxel_cone_tracing_b200 import synth
+    from vk_voxel_cone_tracing_b200.api import VgiError
+    inp = common.cornell_inputs(64, 1024, 128, 128)
+    a, b = _ctx(inp), _ctx(inp)
+    for gi in (a, b):
+        gi.set_light(inp["light"], inp["shadow"], torch.ones((1024, 1024), dtype=torch.float32, device="cuda"))
+    prm = a.default_vct_params(8)
+    cams = []
+    for i in range(6):
+        eye = (0.4 * i - 1.0, 0.2 * i - 0.5, 0.3 * i)
+        cams.append((eye, synth.make_camera(eye, (0.1 * i, -0.05 * i, -1.0), aspect=1.0)))
+    pin = lambda: (torch.empty((128, 128, 4), dtype=torch.float32).pin_memory(), torch.empty((128, 128, 4), dtype=torch.float32).pin_memory())  # noqa: E731
+    want = []
+    for i, (eye, cam) in enumerate(cams):
+        o = pin()
+        a.frame_view_host(i, eye, cam, 128, 128, inp["shadow"], prm, o[0], o[1])
+        want.append((o[0].clone(), o[1].clone()))
+    outs = [pin() for _ in cams]
+    with pytest.raises(VgiError):
+        b.frame_view_host_end()
+    b.frame_view_host_begin(0, cams[0][0], cams[0][1], 128, 128, inp["shadow"], prm, outs[0][0], outs[0][1])
+    for i in range(1, len(cams)):
+        b.frame_view_host_begin(i, cams[i][0], cams[i][1], 128, 128, inp["shadow"], prm, outs[i][0], outs[i][1])
+        if i == 1:
+            with pytest.raises(VgiError):       # two in flight already
+                b.frame_view_host_begin(9, cams[0][0], cams[0][1], 128, 128, inp["shadow"], prm, outs[0][0], outs[0][1])
+            with pytest.raises(VgiError):
+                b.frame_view_host(9, cams[0][0], cams[0][1], 128, 128, inp["shadow"], prm, outs[0][0], outs[0][1])
+        b.frame_view_host_end()                 # frame i - 1 is home
+        assert torch.equal(outs[i - 1][0], want[i - 1][0]) and torch.equal(outs[i - 1][1], want[i - 1][1]), i - 1
+    b.frame_view_host_end()
+    assert torch.equal(outs[-1][0], want[-1][0]) and torch.equal(outs[-1][1], want[-1][1])
+    assert float(want[0][0][..., :3].max()) > 0.05

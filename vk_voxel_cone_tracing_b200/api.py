@@ -336,6 +336,21 @@ class VoxelGI:
                                            C.c_uint32(width), C.c_uint32(height), sh, prm,
                                            C.c_void_p(ptr(out_diffuse)), C.c_void_p(ptr(out_specular)), _stream(stream)))
 
+    def frame_view_host_begin(self, frame_index, camera_pos, camera, width, height, shadow, params, out_diffuse, out_specular,
+                              stream=None):
+        """vgi_frame_view_host_begin: enqueue the frame and return; at most two frames in flight (frame_view_host_end)."""
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        prm = C.byref(params) if params is not None else None
+        sh = C.byref(shadow) if shadow is not None else None
+        self._ck(lib().vgi_frame_view_host_begin(self._h, C.c_uint32(frame_index), _f3(camera_pos), C.byref(camera),
+                                                 C.c_uint32(width), C.c_uint32(height), sh, prm,
+                                                 C.c_void_p(ptr(out_diffuse)), C.c_void_p(ptr(out_specular)), _stream(stream)))
+
+    def frame_view_host_end(self):
+        """Wait for the oldest frame begun: its images are in their host buffers on return."""
+        self._ck(lib().vgi_frame_view_host_end(self._h))
+
     # -- per-kernel timing
     def set_timing(self, enable=True):
         self._ck(lib().vgi_set_timing(self._h, C.c_int(1 if enable else 0)))

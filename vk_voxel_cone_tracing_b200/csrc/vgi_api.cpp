@@ -149,6 +149,9 @@ int vgi_destroy(vgi_ctx* c)
     cudaFree(c->sync_flags);
     if (c->side_stream) { cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->ev_side_fork); cudaEventDestroy(c->ev_side_masks); cudaEventDestroy(c->ev_side_done); }
     cudaFreeHost(c->h_counters);
+    cudaFreeHost(c->h_view_counters);
+    for (int k = 0; k < 2; ++k) { cudaFree(c->view_stage[k]); if (c->ev_view_done[k]) cudaEventDestroy(c->ev_view_done[k]); }
+    if (c->ev_view_traced) cudaEventDestroy(c->ev_view_traced);
     c->timer.resolve();
     for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
     delete c;
@@ -157,19 +160,20 @@ int vgi_destroy(vgi_ctx* c)
 
 // The bounded device lists report overflow through Counters::overflow (h_counters is refreshed by every build). One message
 // per bit, so that a peer-barrier timeout is not reported as a pair-list problem. Call only after the build's stream was synchronised.
-static int report_overflow(vgi_ctx* c, const char* who)
+static int report_overflow(vgi_ctx* c, const char* who, const Counters* counters = nullptr)
 {
-    const uint32_t m = c->h_counters->overflow;
+    const Counters* hc = counters ? counters : c->h_counters;
+    const uint32_t m = hc->overflow;
     if (!m) return VGI_OK;
     c->inc_valid = false;       // an overflowed build left records unwritten: the next incremental build starts over
     char buf[320];
     int n = snprintf(buf, sizeof buf, "%s: device list overflow (mask 0x%x):", who, m);
     auto add = [&](const char* fmt, unsigned a, unsigned b) { if (n < (int)sizeof buf) n += snprintf(buf + n, sizeof buf - n, fmt, a, b); };
-    if (m & 1u) add(" (triangle, voxel) pair list full, %u capacity %u - raise vgi_config.max_fragments;", c->h_counters->pairs, c->max_pairs);
+    if (m & 1u) add(" (triangle, voxel) pair list full, %u capacity %u - raise vgi_config.max_fragments;", hc->pairs, c->max_pairs);
     if (m & 2u) add(" large-triangle queue full (capacity %u)%.0u;", c->max_large, 0u);
-    if (m & 4u) add(" accumulator / visit / exchange list full, %u occupied voxels, capacity %u - raise vgi_config.max_fragments;", c->h_counters->occ_total, c->max_occ);
-    if (m & 8u) add(" octree fragment list full, %u capacity %u;", c->h_counters->svo_frags, c->svo_frag_capacity);
-    if (m & 16u) add(" octree node pool full, %u capacity %u;", c->h_counters->svo_counter, c->svo_node_capacity);
+    if (m & 4u) add(" accumulator / visit / exchange list full, %u occupied voxels, capacity %u - raise vgi_config.max_fragments;", hc->occ_total, c->max_occ);
+    if (m & 8u) add(" octree fragment list full, %u capacity %u;", hc->svo_frags, c->svo_frag_capacity);
+    if (m & 16u) add(" octree node pool full, %u capacity %u;", hc->svo_counter, c->svo_node_capacity);
     if (m & 32u) add(" peer build: a barrier timed out waiting for another GPU (epoch %u)%.0u;", c->peer_epoch, 0u);
     return fail(c, VGI_E_OVERFLOW, buf);
 }
@@ -1415,32 +1419,18 @@ int vgi_frame_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], 
 // images come home). The shadow map (when `shadow` is given) and the G-buffer are rasterised from the ctx's scene by
 // vgi_render_shadow_map / vgi_render_gbuffer — bit-identical to the host rasteriser the parity tests pin — so nothing
 // but this call's small structs crosses PCIe on the way in.
-int vgi_frame_view_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
-                        uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
-                        const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular, void* stream)
+int vgi_frame_view_host_begin(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                              uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
+                              const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular, void* stream)
 {
     if (!c || !camera_pos || !cam || !host_out_diffuse || !host_out_specular || !width || !height)
         return fail(c, VGI_E_INVALID, "vgi_frame_view_host: bad argument");
     if (!c->light_set) return fail(c, VGI_E_STATE, "vgi_frame_view_host: call vgi_set_light first");
+    if (c->view_pending >= 2) return fail(c, VGI_E_STATE, "vgi_frame_view_host_begin: two frames are in flight - call vgi_frame_view_host_end first");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t npx = (size_t)width * height;
     const size_t need = npx * 60;
-    if (c->stage_bytes < need) {
-        CK(c, cudaStreamSynchronize(c->last_stream));
-        cudaFree(c->stage);
-        c->stage = nullptr;
-        c->stage_bytes = 0;
-        CK(c, cudaMalloc(&c->stage, need));
-        c->stage_bytes = need;
-    }
-    uint8_t* d_out_d = c->stage;
-    uint8_t* d_out_s = d_out_d + npx * 16;
-    uint8_t* d_nrm = d_out_s + npx * 16;
-    uint8_t* d_emi = d_nrm + npx * 8;
-    uint8_t* d_dif = d_emi + npx * 8;
-    uint8_t* d_spc = d_dif + npx * 4;
-    uint8_t* d_dep = d_spc + npx * 4;
     if (!c->copy_stream) {
         CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CK(c, cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming));
@@ -1449,6 +1439,29 @@ int vgi_frame_view_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos
         CK(c, cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     }
     cudaStream_t cs = c->copy_stream;
+    if (!c->ev_view_traced) {
+        CK(c, cudaEventCreateWithFlags(&c->ev_view_traced, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) CK(c, cudaEventCreateWithFlags(&c->ev_view_done[k], cudaEventDisableTiming));
+        CK(c, cudaMallocHost(&c->h_view_counters, 2 * sizeof(Counters)));
+        memset(c->h_view_counters, 0, 2 * sizeof(Counters));
+    }
+    if (c->view_stage_bytes < need) {
+        if (c->view_pending) return fail(c, VGI_E_STATE, "vgi_frame_view_host_begin: the image size changed while a frame is in flight");
+        CK(c, cudaStreamSynchronize(c->last_stream));
+        CK(c, cudaStreamSynchronize(cs));
+        for (int k = 0; k < 2; ++k) { cudaFree(c->view_stage[k]); c->view_stage[k] = nullptr; }
+        c->view_stage_bytes = 0;
+        for (int k = 0; k < 2; ++k) CK(c, cudaMalloc(&c->view_stage[k], need));
+        c->view_stage_bytes = need;
+    }
+    const int slot = c->view_next;
+    uint8_t* d_out_d = c->view_stage[slot];
+    uint8_t* d_out_s = d_out_d + npx * 16;
+    uint8_t* d_nrm = d_out_s + npx * 16;
+    uint8_t* d_emi = d_nrm + npx * 8;
+    uint8_t* d_dif = d_emi + npx * 8;
+    uint8_t* d_spc = d_dif + npx * 4;
+    uint8_t* d_dep = d_spc + npx * 4;
     int r;
     if (shadow) {
         const size_t sb = (size_t)c->light.sw * c->light.sh * sizeof(float);
@@ -1476,6 +1489,8 @@ int vgi_frame_view_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos
     if (r != VGI_OK) return r;
     r = vgi_build_clipmap(c, frame_index, stream);
     if (r != VGI_OK) return r;
+    // this frame's own copy of the list counters: the next frame's build overwrites the shared block
+    CK(c, cudaMemcpyAsync(c->h_view_counters + slot, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     vgi_vct_params prm;
     if (params) prm = *params;
     else vgi_default_vct_params(c, &prm);
@@ -1483,13 +1498,41 @@ int vgi_frame_view_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos
     r = vgi_cone_trace(c, cam, &dg, &prm, d_out_d, d_out_s, stream);
     c->mark_main_done = nullptr;
     if (r != VGI_OK) return r;
+    // both downloads ride the copy stream: the diffuse image leaves while the specular cones still march, the specular
+    // image while the NEXT frame's rasterisation and build run on `stream`
+    CK(c, cudaEventRecord(c->ev_view_traced, s));
     CK(c, cudaStreamWaitEvent(cs, c->ev_main_done, 0));
     CK(c, cudaMemcpyAsync(host_out_diffuse, d_out_d, npx * 16, cudaMemcpyDeviceToHost, cs));
-    CK(c, cudaEventRecord(c->ev_copy_done, cs));
-    CK(c, cudaMemcpyAsync(host_out_specular, d_out_s, npx * 16, cudaMemcpyDeviceToHost, s));
-    CK(c, cudaStreamWaitEvent(s, c->ev_copy_done, 0));
-    CK(c, cudaStreamSynchronize(s));
-    return report_overflow(c, "vgi_frame_view_host");
+    CK(c, cudaStreamWaitEvent(cs, c->ev_view_traced, 0));
+    CK(c, cudaMemcpyAsync(host_out_specular, d_out_s, npx * 16, cudaMemcpyDeviceToHost, cs));
+    CK(c, cudaEventRecord(c->ev_view_done[slot], cs));
+    c->view_next = slot ^ 1;
+    ++c->view_pending;
+    return VGI_OK;
+}
+
+int vgi_frame_view_host_end(vgi_ctx* c)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_frame_view_host_end: null ctx");
+    if (!c->view_pending) return fail(c, VGI_E_STATE, "vgi_frame_view_host_end: no frame in flight");
+    CK(c, cudaSetDevice(c->device));
+    const int slot = c->view_pending == 2 ? c->view_next : (c->view_next ^ 1);     // the oldest frame in flight
+    CK(c, cudaEventSynchronize(c->ev_view_done[slot]));
+    --c->view_pending;
+    return report_overflow(c, "vgi_frame_view_host", c->h_view_counters + slot);
+}
+
+int vgi_frame_view_host(vgi_ctx* c, uint32_t frame_index, const float camera_pos[3], const vgi_camera* cam,
+                        uint32_t width, uint32_t height, const vgi_dir_light_shadow* shadow,
+                        const vgi_vct_params* params, void* host_out_diffuse, void* host_out_specular, void* stream)
+{
+    if (c && c->view_pending) return fail(c, VGI_E_STATE, "vgi_frame_view_host: frames begun with vgi_frame_view_host_begin are still in flight");
+    int r = vgi_frame_view_host_begin(c, frame_index, camera_pos, cam, width, height, shadow, params, host_out_diffuse, host_out_specular, stream);
+    if (r != VGI_OK) return r;
+    r = vgi_frame_view_host_end(c);
+    if (r != VGI_OK) return r;
+    CK(c, cudaStreamSynchronize((cudaStream_t)stream));
+    return VGI_OK;
 }
 
 // ---- Vulkan interop (VK_KHR_external_memory_fd / VK_KHR_external_semaphore_fd) --------------------

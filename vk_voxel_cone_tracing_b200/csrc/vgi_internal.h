@@ -264,6 +264,15 @@ struct vgi_ctx {
     // vgi_frame_host staging (device copies of the host G-buffer and of both output images)
     uint8_t* stage = nullptr;
     size_t stage_bytes = 0;
+    // vgi_frame_view_host[_begin/_end]: two device staging sets (G-buffer + both output images) so that the download of
+    // frame i overlaps the work of frame i + 1; a frame's slot is free again after its _end
+    uint8_t* view_stage[2] = { nullptr, nullptr };
+    size_t view_stage_bytes = 0;
+    cudaEvent_t ev_view_done[2] = { nullptr, nullptr };
+    cudaEvent_t ev_view_traced = nullptr;
+    Counters* h_view_counters = nullptr;   // pinned, one block per slot
+    int view_pending = 0;                   // frames begun and not ended (0..2)
+    int view_next = 0;                      // slot the next _begin takes
     size_t shadow_owned_bytes = 0;
 
     // svo
