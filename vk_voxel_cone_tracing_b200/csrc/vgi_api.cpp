@@ -150,6 +150,9 @@ int vgi_destroy(vgi_ctx* c)
     if (c->side_stream) { cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->ev_side_fork); cudaEventDestroy(c->ev_side_masks); cudaEventDestroy(c->ev_side_done); }
     cudaFreeHost(c->h_counters);
     cudaFreeHost(c->h_view_counters);
+    for (int k = 0; k < 2; ++k) cudaFree(c->view_shadow[k]);
+    if (c->raster_stream) { cudaStreamDestroy(c->raster_stream); cudaEventDestroy(c->ev_raster_done); }
+    if (c->ev_scene) cudaEventDestroy(c->ev_scene);
     for (int k = 0; k < 2; ++k) { cudaFree(c->view_stage[k]); if (c->ev_view_done[k]) cudaEventDestroy(c->ev_view_done[k]); }
     if (c->ev_view_traced) cudaEventDestroy(c->ev_view_traced);
     c->timer.resolve();
@@ -434,6 +437,8 @@ int vgi_update_nodes(vgi_ctx* c, const vgi_node_matrix* nodes, uint32_t count, v
     CK(c, cudaStreamSynchronize(c->last_stream));
     CK(c, cudaMemcpy(c->d_nodes, nodes, (size_t)count * sizeof(vgi_node_matrix), cudaMemcpyHostToDevice));
     if (c->ntri) c->launches += vgi_launch_transform_scene(c, s);
+    if (!c->ev_scene) cudaEventCreateWithFlags(&c->ev_scene, cudaEventDisableTiming);
+    cudaEventRecord(c->ev_scene, s);    // rasterisation on another stream (vgi_frame_view_host_begin) waits for the new triangles
     c->voxelized = c->built = false;
     c->inc_valid = false;
     c->svo_voxelized = false;
@@ -1463,27 +1468,42 @@ int vgi_frame_view_host_begin(vgi_ctx* c, uint32_t frame_index, const float came
     uint8_t* d_spc = d_dif + npx * 4;
     uint8_t* d_dep = d_spc + npx * 4;
     int r;
+    // The rasterisation reads the scene only, so it runs on its own stream: with two frames in flight it overlaps the cone
+    // trace of the previous frame, which is still queued on `stream`. Per-kernel timing keeps everything on one stream.
+    if (!c->raster_stream) {
+        CK(c, cudaStreamCreateWithFlags(&c->raster_stream, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&c->ev_raster_done, cudaEventDisableTiming));
+    }
+    cudaStream_t rs = c->timer.enabled ? s : c->raster_stream;
+    if (rs != s && c->ev_scene) CK(c, cudaStreamWaitEvent(rs, c->ev_scene, 0));
     if (shadow) {
         const size_t sb = (size_t)c->light.sw * c->light.sh * sizeof(float);
-        if (!c->shadow_owned || c->shadow_owned_bytes < sb) {
+        if (c->view_shadow_bytes < sb) {
+            if (c->view_pending) return fail(c, VGI_E_STATE, "vgi_frame_view_host_begin: the shadow map size changed while a frame is in flight");
             CK(c, cudaStreamSynchronize(c->last_stream));
-            cudaFree(c->shadow_owned);
-            c->shadow_owned = nullptr;
-            CK(c, cudaMalloc(&c->shadow_owned, sb));
-            c->shadow_owned_bytes = sb;
+            CK(c, cudaStreamSynchronize(rs));
+            for (int k = 0; k < 2; ++k) { cudaFree(c->view_shadow[k]); c->view_shadow[k] = nullptr; }
+            c->view_shadow_bytes = 0;
+            for (int k = 0; k < 2; ++k) CK(c, cudaMalloc(&c->view_shadow[k], sb));
+            c->view_shadow_bytes = sb;
         }
-        r = vgi_render_shadow_map(c, shadow, (uint32_t)c->light.sw, (uint32_t)c->light.sh, c->shadow_owned, stream);
+        r = vgi_render_shadow_map(c, shadow, (uint32_t)c->light.sw, (uint32_t)c->light.sh, c->view_shadow[slot], rs);
         if (r != VGI_OK) return r;
-        c->light.depth = c->shadow_owned;
+        c->light.depth = c->view_shadow[slot];
         memcpy(c->light.view, shadow->view, sizeof c->light.view);
         memcpy(c->light.proj, shadow->proj, sizeof c->light.proj);
         c->light.z_near = shadow->z_near; c->light.z_far = shadow->z_far;
+        c->inc_valid = false;
     }
     vgi_gbuffer dg;
     dg.diffuse_rgba8 = d_dif; dg.normal_rgba16f = d_nrm; dg.specular_rgba8 = d_spc; dg.emission_rgba16f = d_emi;
     dg.depth_f32 = (const float*)d_dep; dg.width = width; dg.height = height;
-    r = vgi_render_gbuffer(c, cam, &dg, stream);
+    r = vgi_render_gbuffer(c, cam, &dg, rs);
     if (r != VGI_OK) return r;
+    if (rs != s) {
+        CK(c, cudaEventRecord(c->ev_raster_done, rs));
+        CK(c, cudaStreamWaitEvent(s, c->ev_raster_done, 0));
+    }
     CK(c, cudaMemsetAsync(d_out_d, 0, npx * 32, s));
     r = vgi_update_regions(c, camera_pos);
     if (r != VGI_OK) return r;

@@ -271,6 +271,13 @@ struct vgi_ctx {
     cudaEvent_t ev_view_done[2] = { nullptr, nullptr };
     cudaEvent_t ev_view_traced = nullptr;
     Counters* h_view_counters = nullptr;   // pinned, one block per slot
+    // ... and its rasterisation (shadow map + G-buffer depend on the scene only) runs on its own stream, beside the previous
+    // frame's cone trace; each slot renders into its own shadow map
+    cudaStream_t raster_stream = nullptr;
+    cudaEvent_t ev_raster_done = nullptr;
+    cudaEvent_t ev_scene = nullptr;         // recorded after the last device-side scene change (vgi_update_nodes)
+    float* view_shadow[2] = { nullptr, nullptr };
+    size_t view_shadow_bytes = 0;
     int view_pending = 0;                   // frames begun and not ended (0..2)
     int view_next = 0;                      // slot the next _begin takes
     size_t shadow_owned_bytes = 0;
