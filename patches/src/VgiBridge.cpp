@@ -171,6 +171,8 @@ namespace vfs
 		// "ClipmapRegions" stays valid for the GUI and for VoxelConeTracingPass::onUpdate (ClipmapRegion == vgi_clip_region)
 		static_assert(sizeof(ClipmapRegion) == sizeof(vgi_clip_region), "ClipmapRegion layout");
 		vgi_get_regions(_ctx, reinterpret_cast<vgi_clip_region*>(regionsOut->data()), DEFAULT_CLIP_REGION_COUNT);
+		if (_incremental)
+			return;		// vgi_build_clipmap_incremental does both halves at once, in coneTrace()
 		if (vgi_voxelize_opacity(_ctx, _cudaStream) != VGI_OK)
 			VFS_ERROR << "libvgi : " << vgi_last_error(_ctx);
 	}
@@ -187,8 +189,17 @@ namespace vfs
 		static_assert(sizeof(vgi_dir_light) == 32 && sizeof(vgi_dir_light_shadow) == 136, "light.glsl:8-20");
 		light->getLightDescBuffer()->downloadData(&lightDesc, sizeof(lightDesc));
 		light->getViewProjectionBuffer()->downloadData(&shadowDesc, sizeof(shadowDesc));
-		vgi_set_light(_ctx, &lightDesc, &shadowDesc, static_cast<const float*>(_shadowDepth.devicePtr),
-					  _shadowResolution.width, _shadowResolution.height, /* is_host */ 0);
+		// vgi_set_light invalidates the incremental build's cache: hand the light over only when it changed (the shadow map
+		// itself lives in the shared buffer and is read at build time; a static scene under a static light renders the same map)
+		if (!_lightValid || std::memcmp(&lightDesc, _lastLight, sizeof(lightDesc)) != 0 ||
+			std::memcmp(&shadowDesc, _lastShadow, sizeof(shadowDesc)) != 0)
+		{
+			vgi_set_light(_ctx, &lightDesc, &shadowDesc, static_cast<const float*>(_shadowDepth.devicePtr),
+						  _shadowResolution.width, _shadowResolution.height, /* is_host */ 0);
+			std::memcpy(_lastLight, &lightDesc, sizeof(lightDesc));
+			std::memcpy(_lastShadow, &shadowDesc, sizeof(shadowDesc));
+			_lightValid = true;
+		}
 		_pendingInjectFrame = frameIndex;
 		_pendingInject = true;
 	}
@@ -210,7 +221,9 @@ namespace vfs
 			vgi_wait_vk_semaphore(_ctx, _cudaInputsReady, _cudaStream);
 		if (_pendingInject)
 		{
-			if (vgi_inject_radiance(_ctx, _pendingInjectFrame, _cudaStream) != VGI_OK)
+			const int built = _incremental ? vgi_build_clipmap_incremental(_ctx, _pendingInjectFrame, nullptr, _cudaStream)
+										   : vgi_inject_radiance(_ctx, _pendingInjectFrame, _cudaStream);
+			if (built != VGI_OK)
 				VFS_ERROR << "libvgi : " << vgi_last_error(_ctx);
 			_pendingInject = false;
 		}

@@ -45,7 +45,9 @@ namespace vfs
 
 		// pre-pass command buffer, after "GBuffer" and "RSMPass": attachments -> shared linear buffers
 		void cmdCopyInputs(VkCommandBuffer cmdBuffer);
-		// VoxelizationPass::onUpdate
+		// VoxelizationPass::onUpdate: incremental = !_fullRevoxelization (VoxelizationPass.h:59) - only the clip levels whose
+		// region moved are rebuilt (vgi_build_clipmap_incremental); the whole build then runs in coneTrace()
+		void setIncremental(bool incremental) { _incremental = incremental; }
 		void voxelizeOpacity(const glm::vec3& cameraPos, std::array<ClipmapRegion, DEFAULT_CLIP_REGION_COUNT>* regionsOut);
 		// RadianceInjectionPass::onUpdate
 		void injectRadiance(uint32_t frameIndex);
@@ -86,6 +88,10 @@ namespace vfs
 		bool				_vctDescValid		{ false };
 		bool				_sceneSet			{ false };
 		bool				_pendingInject		{ false };
+		bool				_incremental		{ false };
+		bool				_lightValid			{ false };
+		unsigned char		_lastLight[32]		{};		// vgi_dir_light / vgi_dir_light_shadow of the last vgi_set_light (light.glsl:8-20)
+		unsigned char		_lastShadow[136]	{};
 		uint32_t			_pendingInjectFrame	{ 0 };
 		Semaphore			_inputsReady, _traceDone;
 		void*				_cudaInputsReady	{ nullptr };

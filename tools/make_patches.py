@@ -247,6 +247,7 @@ def step_passes(t):
          "\t\t(void)frameLayout;\n"
          "\t\tVgiBridge* bridge = _renderPassManager->get<VgiBridge>(\"VgiBridge\");\n"
          "\t\tconst glm::vec3 cameraPos = _renderPassManager->get<Camera>(\"MainCamera\")->getOriginPos();\n"
+         "\t\tbridge->setIncremental(!_fullRevoxelization);\t// the reference's own switch (VoxelizationPass.h:59), never cleared there\n"
          "\t\tbridge->voxelizeOpacity(cameraPos, &_clipmapRegions);\n"
          "\t\treturn;\n"
          "#endif\n"),
