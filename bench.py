@@ -39,6 +39,7 @@ WORKLOAD = ("configs[1]: Sponza-scale synthetic atrium (262144 tris), 6-level 25
             "(frame 0: all levels) + 1920x1080 16-cone diffuse/specular GI (mode 8), one frame per step along a fixed "
             "8-camera path")
 RES, LEVELS, SHADOW, WIDTH, HEIGHT = 256, 6, 4096, 1920, 1080
+TEXTURED = False               # --textured: the same mesh with textured materials (synth.textured_atrium), beside the metric
 TRACE_ROW_STRIDE = 32          # reference arm: every 32nd row block of the image per sample
 
 
@@ -125,7 +126,7 @@ def ncu_traffic(kernel):
     profiles/r2_ncu_traffic.json (written by tools/ncu_traffic.py). The capture names the source hash of the kernels it
     profiled: a capture of another build is not this run's traffic, so None is returned instead of a stale constant."""
     p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
-    if (RES, WIDTH, HEIGHT) != (256, 1920, 1080):   # the capture is of the headline workload
+    if (RES, WIDTH, HEIGHT) != (256, 1920, 1080) or TEXTURED:   # the capture is of the headline workload
         return None
     try:
         d = json.load(open(p))
@@ -166,15 +167,16 @@ def view_camera(v):
 def make_inputs(rank, world):
     """Synthetic inputs of configs[1]; rank r renders view r of the fixed list."""
     from vk_voxel_cone_tracing_b200 import raster, structs as S, synth
-    scene = synth.atrium()
+    scene = synth.textured_atrium() if TEXTURED else synth.atrium()
+    textures = synth.procedural_textures() if TEXTURED else None
     cfg = S.default_config(RES, LEVELS)
     light, shadow = synth.make_light()
     depth = raster.shadow_depth(scene, shadow, SHADOW)
     cam_pos, cam_dir = view_camera(rank)
     cam = synth.make_camera(cam_pos, cam_dir, aspect=WIDTH / HEIGHT)
-    gb = raster.gbuffer(scene, cam, WIDTH, HEIGHT)
+    gb = raster.gbuffer(scene, cam, WIDTH, HEIGHT, textures=textures)
     return dict(scene=scene, cfg=cfg, light=light, shadow=shadow, shadow_depth=depth, cam=cam, gbuffer=gb,
-                cam_pos=cam_pos, view=rank % N_VIEWS)
+                cam_pos=cam_pos, view=rank % N_VIEWS, textures=textures)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -191,6 +193,8 @@ class CpuFrameSampler:
         O.build()
         self.threads = O.set_threads(cpu_cores())   # torchrun exports OMP_NUM_THREADS=1: use every host core
         self.O, self.inp = O, inp
+        if inp.get("textures"):
+            O.set_textures(inp["textures"])     # the oracle's coverage (alpha test) and injection read them like the shaders
         self.cfg = inp["cfg"]
         self.regs = O.regions(self.cfg, inp["cam_pos"])
         self.osc = O.OracleScene(inp["scene"])
@@ -412,6 +416,8 @@ def run_vgi(args):
 
     inp = make_inputs(rank, world)
     gi = VoxelGI(inp["cfg"], device=local)
+    if inp.get("textures"):
+        gi.set_textures(inp["textures"])
     gi.set_scene(inp["scene"])
     gi.set_light(inp["light"], inp["shadow"], inp["shadow_depth"])
     gi.update_regions(inp["cam_pos"])
@@ -985,16 +991,25 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-svo", action="store_true")
     ap.add_argument("--no-incremental", action="store_true")
+    ap.add_argument("--textured", action="store_true",
+                    help="the same mesh with textured materials (base colour, emissive, occlusion alpha test in the build; "
+                         "metallic-roughness, normal map, tangents in the device-rendered G-buffer): a number beside the metric")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4],
                     help="1 = the headline workload (BASELINE configs[1]); 3 = configs[3], the same pipeline on a 6-level 128^3 "
                          "clipmap traced at 3840x2160; 4 = configs[4], 64 views at 4K + 512^3 slab build")
     args = ap.parse_args()
+    if args.textured:
+        global TEXTURED
+        TEXTURED = True
     if args.config == 3:        # same code path as the headline, other sizes (both arms read these module constants)
         global WORKLOAD, RES, WIDTH, HEIGHT
         RES, WIDTH, HEIGHT = 128, 3840, 2160
         WORKLOAD = ("configs[3]: Sponza-scale synthetic atrium (262144 tris), 6-level 128^3 clipmap voxelize+inject+mip "
                     "(frame 0: all levels) + 3840x2160 16-cone diffuse/specular GI (mode 8), one frame per step along a fixed "
                     "8-camera path")
+    if TEXTURED:
+        WORKLOAD += (" [--textured: synth.textured_atrium - base-colour / emissive textures and occlusion-mask alpha test in the "
+                     "build, metallic-roughness + normal map + tangents in the device-rendered G-buffer]")
     if args.impl == "reference":
         run_reference(args)
     elif args.config == 4:

@@ -400,6 +400,46 @@ def atrium(seed=1234):
     return scene
 
 
+def textured_atrium(seed=1234):
+    """The atrium with textured materials (texture indices into procedural_textures()): the same 262 144 triangles, texture
+    coordinates repeated 6-24 times per surface; floor, two walls, half of the columns and the arches take a base-colour
+    texture, the banners an occlusion mask (alpha test: the holes change the occupancy), the emissive banners an emissive
+    texture; for the G-buffer pass the side walls carry the normal map, the metallic columns the metallic-roughness map and
+    the floor an alpha cutoff-free base colour; per-vertex tangents included."""
+    sc = atrium(seed)
+    m = sc.materials
+    rep = np.ones(len(m), np.float32)
+
+    def put(i, r, **kw):
+        for k, v in kw.items():
+            m[i][k] = v
+        rep[i] = r
+    put(0, 24.0, base_color_texture=0)
+    put(1, 8.0, base_color_texture=3)
+    put(2, 8.0, base_color_texture=0)
+    put(3, 6.0, normal_texture=4)
+    put(4, 6.0, normal_texture=4, base_color_texture=3)
+    for i in range(5, 11):
+        if i % 2:
+            put(i, 6.0, base_color_texture=0)
+        if m[i]["metallic_factor"] > 0.5:
+            put(i, 6.0, metallic_roughness_texture=5)
+    for i in range(11, 15):
+        put(i, 4.0, base_color_texture=0)
+    for i in range(17, 23):
+        put(i, 3.0, occlusion_texture=2)
+    put(23, 2.0, emissive_texture=1)
+    put(24, 2.0, emissive_texture=1)
+    for pr in sc.primitives:
+        v0 = int(pr["vertex_offset"])
+        idx = sc.indices[int(pr["first_index"]):int(pr["first_index"]) + int(pr["index_count"])]
+        v1 = v0 + int(idx.max()) + 1
+        sc.texcoords[v0:v1] = (sc.texcoords[v0:v1] * rep[int(pr["material_index"])]).astype(np.float32)
+    sc.tangents = compute_tangents(sc)
+    sc.name = "textured_atrium"
+    return sc
+
+
 def quad_scene(corners, normal=(0, 0, 1), base=(1, 1, 1, 1), emissive=(0, 0, 0)):
     """Two-triangle quad for known-answer tests."""
     b = _Builder()
