@@ -373,7 +373,8 @@ def algorithmic_bytes(name, st, cfg, launches_per_step=1):
     """DESIGN.md section 4. P pairs, T triangles, V occupied voxels, S shadow-map edge."""
     R, L = cfg.resolution, cfg.level_count
     nvox = R ** 3
-    V, P, T = st.occupied_voxels, st.clip_pairs, st.triangles
+    V, T = st.occupied_voxels, st.triangles
+    P = st.shaded_pairs     # the pairs on the work list (clip_pairs counts the unlisted ones, too: occupancy only)
     table = {
         "k_voxelize": T * 48 + P * 8,
         # compulsory bytes: pairs + triangle data + every shadow texel once + read-modify-write of the 96-byte accumulator rows
@@ -809,7 +810,8 @@ def run_vgi(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 texels)", "data": "synthetic",
             "config": config_dict(world, int(st.triangles)),
             "stages": {"build_ms": build_ms, "trace_ms": trace_ms, "trace_fps": 1e3 / trace_ms,
-                       "clip_pairs": int(st.clip_pairs), "occupied_voxels": int(st.occupied_voxels)},
+                       "clip_pairs": int(st.clip_pairs), "shaded_pairs": int(st.shaded_pairs),
+                       "occupied_voxels": int(st.occupied_voxels)},
             "e2e": {"value": world * 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_view),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "wall_ms_per_step": t_wall,
                     "call": "vgi_frame_view_host_begin / _end, two frames in flight: camera + light matrices up; shadow map and "

@@ -198,6 +198,8 @@ typedef struct vgi_stats {
     uint64_t svo_fragments;
     uint64_t svo_nodes;
     uint64_t kernel_launches;       /* kernels launched by this ctx since creation */
+    uint64_t shaded_pairs;          /* the pairs on the injection's work list: clip_pairs minus those whose voxel is
+                                     * overwritten by the down-sample of the finer level (centre half, off the blend band) */
 } vgi_stats;
 
 typedef struct vgi_ctx vgi_ctx;
@@ -326,6 +328,15 @@ int vgi_cone_trace_interleaved(vgi_ctx* ctx, const vgi_camera* cam, const vgi_gb
 /* Fill params with the reference defaults (VoxelConeTracingPass.h:75-82) and the volume fields
  * derived from the ctx's level-0 region (VoxelConeTracingPass.cpp:88-93). */
 int vgi_default_vct_params(vgi_ctx* ctx, vgi_vct_params* out);
+/* How the two marches of one vgi_cone_trace* call share the GPU (modes 6 and 8; the reference runs both inside one
+ * fragment invocation, voxelConeTracing.frag:165-216). 0 (default): the diffuse march, then the specular march, one
+ * after the other on the caller's stream. spec_blocks_per_sm > 0: the pixels that need a specular cone are listed by a
+ * pre-pass, the specular march runs on the ctx's own stream with that many resident blocks per SM BESIDE the diffuse
+ * march, and the caller's stream joins it before the call's work ends (images identical to the serial order).
+ * Measured on B200 (1080p bench frame, tools/overlap_sweep.py): serial 4.17 ms; 1 / 2 / 3 / 4 / 6 blocks beside
+ * 4.68 / 5.56 / 4.92 / 4.47 / 4.19 ms — two large kernels resident on one SM evict each other's instructions, so
+ * the default stays serial; the switch is kept for hosts whose specular share is small. */
+int vgi_set_trace_overlap(vgi_ctx* ctx, uint32_t spec_blocks_per_sm);
 
 /* ---- the passes before the path: image inputs without Vulkan ------------------ */
 /* replaces: the depth attachment of ShadowMapPass / ReflectiveShadowMapPass (shadowPass.vert:33: proj * view *

@@ -176,6 +176,10 @@ class VoxelGI:
         p.rendering_mode = rendering_mode
         return p
 
+    def set_trace_overlap(self, spec_blocks_per_sm):
+        """0 = diffuse march, then specular march; n > 0 = the specular march beside the diffuse one, n blocks per SM."""
+        self._ck(lib().vgi_set_trace_overlap(self._h, C.c_uint32(spec_blocks_per_sm)))
+
     def upload_gbuffer(self, gb):
         """dict of numpy arrays (raster.gbuffer) -> dict of CUDA tensors."""
         torch = self._torch

@@ -147,6 +147,7 @@ int vgi_destroy(vgi_ctx* c)
     cudaFree(c->svo_frags); cudaFree(c->svo_nodes); cudaFree(c->svo_scratch); cudaFree(c->raster_keys);
     peer_close(c);
     cudaFree(c->sync_flags);
+    if (c->spec_stream) { cudaStreamDestroy(c->spec_stream); cudaEventDestroy(c->ev_spec_fork); cudaEventDestroy(c->ev_spec_done); }
     if (c->side_stream) { cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->ev_side_fork); cudaEventDestroy(c->ev_side_masks); cudaEventDestroy(c->ev_side_done); }
     cudaFreeHost(c->h_counters);
     cudaFreeHost(c->h_view_counters);
@@ -188,7 +189,8 @@ int vgi_get_stats(vgi_ctx* c, vgi_stats* out)
     CK(c, cudaStreamSynchronize(c->last_stream));
     CK(c, cudaMemcpy(c->h_counters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
     out->triangles = c->ntri;
-    out->clip_pairs = c->h_counters->pairs;
+    out->clip_pairs = (uint64_t)c->h_counters->pairs + c->h_counters->pairs_unlisted;
+    out->shaded_pairs = c->h_counters->pairs;
     out->occupied_voxels = c->h_counters->occ_total;
     if (c->svo_counters_fresh) { // the device counters still hold the SVO pass (no clipmap build since)
         if (c->svo_voxelized) c->svo_nfrag = c->h_counters->svo_frags;
@@ -873,6 +875,14 @@ int vgi_default_vct_params(vgi_ctx* c, vgi_vct_params* p)
     p->indirect_specular_intensity = 3.0f;
     p->occlusion_decay = 2.0f;
     p->enable_32_cones = 0;
+    return VGI_OK;
+}
+
+int vgi_set_trace_overlap(vgi_ctx* c, uint32_t spec_blocks_per_sm)
+{
+    if (!c) return fail(c, VGI_E_INVALID, "vgi_set_trace_overlap: null ctx");
+    if (spec_blocks_per_sm > 16u) return fail(c, VGI_E_INVALID, "vgi_set_trace_overlap: at most 16 blocks per SM");
+    c->trace_spec_blocks = spec_blocks_per_sm;
     return VGI_OK;
 }
 

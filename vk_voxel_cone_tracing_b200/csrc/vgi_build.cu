@@ -18,6 +18,44 @@
 // ---------------------------------------------------------------------------------------------------
 #define SMALL_BOX_MAX 64
 
+// The blend weight of a level's OWN texel inside its centre half (opacityDownSample.comp / radianceDownSample.comp: the
+// texel is mix(down-sample of the finer level, own value, lerpFactor)); g = the voxel's offset from pm = min_corner of the
+// finer level >> 1, every component < R/2. 0 everywhere but in the band of `band` texels along the centre region's rim.
+DEVFN float mip_lerp_factor(const int* pm, const int* g, int half, int band)
+{
+    float dist[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int cur = pm[k] + g[k];
+        const float center = (float)pm[k] + (float)((uint32_t)half >> 1);
+        dist[k] = fabsf(((float)cur + 0.5f) - center) - 0.5f;
+    }
+    const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)band;
+    const float thr = (float)thrU;
+    const float invBand = 1.0f / ((float)band + 1.0f);
+    float lerpFactor = 0.0f;
+    if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
+        lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
+        lerpFactor = lerpFactor * invBand;
+    }
+    return lerpFactor;
+}
+
+// Is the injected radiance of voxel (x, y, z) of `level` dead on arrival? Inside the centre half and off its blend band
+// the record pass writes mix(down-sample, own, 0) = the down-sample, exactly, whatever the own value: such a (triangle,
+// voxel) pair sets its occupancy bit (the raw opacity flag survives the mip) but is never shaded, so it is counted
+// (Counters::pairs_unlisted) instead of listed. On the bench scene that is every pair of the levels whose finer level
+// already spans the scene: 3.4 M canonical pairs, of which k_inject shades the rest.
+DEVFN bool mip_interior(const BuildParams& bp, int level, int x, int y, int z)
+{
+    if (level == 0) return false;
+    const int Rm = bp.R - 1, half = bp.R >> 1;
+    const int pm[3] = { bp.lv[level - 1].min_corner[0] >> 1, bp.lv[level - 1].min_corner[1] >> 1, bp.lv[level - 1].min_corner[2] >> 1 };
+    const int g[3] = { (x - pm[0]) & Rm, (y - pm[1]) & Rm, (z - pm[2]) & Rm };
+    if (!(g[0] < half && g[1] < half && g[2] < half)) return false;
+    return mip_lerp_factor(pm, g, half, bp.band) == 0.0f;
+}
+
 DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair_t* __restrict__ pairs,
                      Counters* __restrict__ cnt, uint32_t tri, int level, int vx, int vy, int vz)
 {
@@ -28,6 +66,7 @@ DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair
     const size_t w = (size_t)level * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
     const uint32_t bit = 1u << (x & 31u);
     if (!(occ[w] & bit)) atomicOr(&occ[w], bit);
+    if (mip_interior(bp, level, (int)x, (int)y, (int)z)) { atomicAdd(&cnt->pairs_unlisted, 1u); return; }
     // warp-aggregated append
     const unsigned m = __activemask();
     const int leader = __ffs(m) - 1;
@@ -59,7 +98,7 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
     const int lrel = inRange ? (int)(gid / bp.ntri) : 0;
     const int l = (int)((bp.vox_levels >> (4 * lrel)) & 15u);   // incremental build: only the levels whose occupancy or pairs are needed
     const uint32_t t = inRange ? gid - (uint32_t)lrel * bp.ntri : 0u;
-    unsigned long long hits = 0ull;
+    unsigned long long hits = 0ull, dead = 0ull;   // dead: occupancy only, never shaded (mip_interior)
     int lo0 = 0, lo1 = 0, lo2 = 0, nx = 1, ny = 1;
     if (inRange) {
         float p[9], N[3];
@@ -101,34 +140,41 @@ __global__ void __launch_bounds__(128) k_voxelize(BuildParams bp, const float4* 
                                     if (!alpha_test_pair(tex, occTex, t, axis, N, p, c)) continue;
                                 }
                                 hits |= 1ull << i;
+                                if (mip_interior(bp, l, x, y, z)) dead |= 1ull << i;
                             }
                 }
             }
         }
     }
     const int Rm = bp.R - 1;
-    const uint32_t n = (uint32_t)__popcll(hits);
-    uint32_t incl = n;
+    const uint32_t n = (uint32_t)__popcll(hits & ~dead);
+    uint32_t incl = n, nDead = (uint32_t)__popcll(dead);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if ((int)lane_id() >= o) incl += v;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nDead += __shfl_xor_sync(0xffffffffu, nDead, o);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (!total) return;
+    if (!(total | nDead)) return;
     uint32_t base = 0u;
-    if (lane_id() == 31u) base = atomicAdd(&cnt->pairs, total);
+    if (lane_id() == 31u) {
+        if (total) base = atomicAdd(&cnt->pairs, total);
+        if (nDead) atomicAdd(&cnt->pairs_unlisted, nDead);
+    }
     uint32_t slot = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
     const size_t wordsPerLevel = ((size_t)bp.R * bp.R * bp.R) >> 5;
-    for (unsigned long long h = hits; h; h &= h - 1, ++slot) {
+    for (unsigned long long h = hits; h; h &= h - 1) {
         const int i = __ffsll((long long)h) - 1;
         const int vx = lo0 + i % nx, vy = lo1 + (i / nx) % ny, vz = lo2 + i / (nx * ny);
         const uint32_t x = vx & Rm, y = vy & Rm, z = vz & Rm;
         const size_t w = (size_t)l * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
         const uint32_t bit = 1u << (x & 31u);
         if (!(occ[w] & bit)) atomicOr(&occ[w], bit);
-        if (slot < bp.max_pairs)
-            pairs[slot] = ((vgi_pair_t)t << 32) | ((vgi_pair_t)l << 27) | ((vgi_pair_t)z << 18) | ((vgi_pair_t)y << 9) | x;
+        if ((dead >> i) & 1ull) continue;
+        if (slot++ < bp.max_pairs)
+            pairs[slot - 1u] = ((vgi_pair_t)t << 32) | ((vgi_pair_t)l << 27) | ((vgi_pair_t)z << 18) | ((vgi_pair_t)y << 9) | x;
         else
             atomicOr(&cnt->overflow, 1u);
     }
@@ -607,22 +653,9 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
         if (centre) {
             const int g[3] = { g0, g1, g2 };
             int pstart[3];
-            float dist[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int cur = pm[k] + g[k];
-                pstart[k] = (cur << 1) & Rm;
-                const float center = (float)pm[k] + (float)((uint32_t)half >> 1);
-                dist[k] = fabsf(((float)cur + 0.5f) - center) - 0.5f;
-            }
-            const uint32_t thrU = ((uint32_t)half >> 1) - (uint32_t)bp.band;
-            const float thr = (float)thrU;
-            const float invBand = 1.0f / ((float)bp.band + 1.0f);
-            float lerpFactor = 0.0f;
-            if (dist[0] >= thr || dist[1] >= thr || dist[2] >= thr) {
-                lerpFactor = (f_max(dist[0], f_max(dist[1], dist[2])) - thr) + 1.0f;
-                lerpFactor = lerpFactor * invBand;
-            }
+            for (int k = 0; k < 3; ++k) pstart[k] = ((pm[k] + g[k]) << 1) & Rm;
+            const float lerpFactor = mip_lerp_factor(pm, g, half, bp.band);   // 0: the own radiance is not read (mip_interior)
             // children: index i = dx + 2*dy + 4*dz; records whose nz bit is clear are zero
             Rec ch[8];
             uint32_t anyChild = 0u;

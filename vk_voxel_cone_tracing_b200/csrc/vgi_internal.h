@@ -81,7 +81,8 @@ struct Counters {
     uint32_t svo_alloc_begin;
     uint32_t svo_alloc_num;
     uint32_t visit[VGI_MAX_LEVELS]; // entries in each level's visit list (k_level_masks)
-    uint32_t pad[7];
+    uint32_t pairs_unlisted;        // canonical pairs that only set their occupancy bit (mip_interior): stats = pairs + this
+    uint32_t pad[6];
 };
 
 // peer build (vgi_peer_*): device pointers of every GPU's buffers, mapped through CUDA IPC; [rank] = this GPU's own
@@ -121,6 +122,8 @@ struct TraceParams {
     uint32_t* spec_list;          // compacted pixels needing a specular cone
     uint32_t* spec_count;
     uint32_t* spec_cursor;        // next unclaimed entry of spec_list (k_trace_specular)
+    int      spec_presplit;       // 1: spec_list was filled by k_spec_classify and the specular march runs beside k_trace_main,
+                                  //    which then neither appends nor writes out_specular of the listed pixels
     const uint2* svo_nodes;       // SVO tracer: node pool, grid of the fragment voxelizer
     float    svo_center[3], svo_extent, svo_max_level;
     int      svo_literal;         // VGI_MODE_SVO_LITERAL: sample positions are not halved (voxelConeTracing_Octree.frag:330-333 as shipped, Q13)
@@ -251,6 +254,11 @@ struct vgi_ctx {
     uint32_t spec_stride = 0;
     float spec_tab_voxel_size = 0.0f;
     bool spec_tab_unfit = false;      // table would be too large for this voxel size: per-lane marcher
+
+    // cone trace: the specular march on its own stream beside the diffuse march (vgi_set_trace_overlap)
+    uint32_t trace_spec_blocks = 0;   // resident specular blocks per SM while both run; 0 (default) = one kernel after the other
+    cudaStream_t spec_stream = nullptr;
+    cudaEvent_t ev_spec_fork = nullptr, ev_spec_done = nullptr;
 
     // build: the empty-space / visit-list masks depend on the occupancy alone, so they run on a side stream next to
     // the injection and the record pass (created on first use)

@@ -1315,7 +1315,8 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
         for (int k = 0; k < 3; ++k) indirect[k] *= s.diffuseColor[k] * tp.p.indirect_diffuse_intensity;
     }
 
-    if (needSpec && (s.specularColor[0] > 1e-6f || s.specularColor[1] > 1e-6f || s.specularColor[2] > 1e-6f) && s.metallic > 1e-6f) {
+    const bool wantsSpec = needSpec && (s.specularColor[0] > 1e-6f || s.specularColor[1] > 1e-6f || s.specularColor[2] > 1e-6f) && s.metallic > 1e-6f;
+    if (wantsSpec && !tp.spec_presplit) {
         const uint32_t slot = atomicAdd(tp.spec_count, 1u);
         tp.spec_list[slot] = (uint32_t)pi;
     }
@@ -1369,7 +1370,36 @@ __global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(co
     default: break;
     }
     tp.out_diffuse[pi] = dc;
-    tp.out_specular[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+    // a listed pixel's specular texel belongs to the specular march, which may already have written it
+    if (!(wantsSpec && tp.spec_presplit)) tp.out_specular[pi] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+
+// The pixels of this call's tiles that need a specular cone (voxelConeTracing.frag:146-149, 208), listed ahead of both
+// marches so that they can run side by side. Same tile walk as k_trace_main (four 8 x 8 tiles per block, a warp = half
+// a tile) and the same predicate as its phase 3; warp-aggregated append, so the list stays in tile order.
+__global__ void __launch_bounds__(256) k_spec_classify(const __grid_constant__ TraceParams tp)
+{
+    const int tilesX4 = (tp.width + 31) / 32;
+    const int tid = threadIdx.x;
+    const int tx0 = ((int)(blockIdx.x % tilesX4) * 4 + (tid >> 6)) * 8;
+    const int ty0 = tp.y0 + (tp.tile_phase + (int)(blockIdx.x / tilesX4) * tp.tile_stride) * TILE_H;
+    const int px = tx0 + (tid & 7), py = ty0 + ((tid >> 3) & 7);
+    bool want = false;
+    size_t pi = 0;
+    if (px < tp.width && py < tp.y1) {
+        pi = (size_t)py * tp.width + px;
+        if (__ldg(tp.depth + pi) != 1.0f) {
+            const uchar4 spc = __ldg(reinterpret_cast<const uchar4*>(tp.specular) + pi);
+            want = (spc.x / 255.0f > 1e-6f || spc.y / 255.0f > 1e-6f || spc.z / 255.0f > 1e-6f) && spc.w / 255.0f > 1e-6f;
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, want);
+    if (!b) return;
+    const unsigned lane = tid & 31u;
+    uint32_t base = 0u;
+    if (lane == 0u) base = atomicAdd(tp.spec_count, (uint32_t)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (want) tp.spec_list[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)pi;
 }
 
 // ref: voxelConeTracing.frag:205-216 (stepFactor = uVoxelSize, Q12)
@@ -1794,13 +1824,61 @@ int vgi_launch_trace(vgi_ctx* c, const TraceParams& tp_in, cudaStream_t s)
     if (myTileRows <= 0) return 0;
     const int tileW = 8; // 8 x 8 tiles: measured faster than 16 x 8 for the clipmap march (tighter footprints per warp)
     const unsigned grid = (unsigned)(((tp.width + tileW - 1) / tileW) * myTileRows);
+    const uint32_t mode = tp.p.rendering_mode;
+    if ((mode == 6 || mode == 8) && VGI_TRACE_SPEC_WARP && tp.spec_tab && c->trace_spec_blocks > 0u) {
+        // Both marches at once. The diffuse march leaves a third of the issue slots idle and the specular one ends in a
+        // tail of a few long cones; a few resident specular blocks per SM beside the diffuse blocks fill the former, and
+        // a second wave of specular workers behind k_trace_main takes over the SMs for whatever is left of the list.
+        if (!c->spec_stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = served first
+            if (cudaStreamCreateWithPriority(&c->spec_stream, cudaStreamNonBlocking, hi) != cudaSuccess) c->spec_stream = nullptr;
+            else {
+                cudaEventCreateWithFlags(&c->ev_spec_fork, cudaEventDisableTiming);
+                cudaEventCreateWithFlags(&c->ev_spec_done, cudaEventDisableTiming);
+            }
+        }
+        if (c->spec_stream) {
+            static int perSmW = 0, sms = 148;
+            if (!perSmW) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmW, k_trace_specular_warp, 128, 0);
+                if (perSmW <= 0) perSmW = 4;
+            }
+            TraceParams tq = tp;
+            tq.spec_presplit = 1;
+            c->timer.begin("cone_trace(main||specular)", s);
+            cudaEvent_t joint_b = c->timer.enabled && !c->timer.pending.empty() ? c->timer.pending.back().b : nullptr;
+            k_spec_classify<<<(unsigned)(((tp.width + 31) / 32) * myTileRows), 256, 0, s>>>(tq); ++n;
+            cudaEventRecord(c->ev_spec_fork, s);
+            cudaStreamWaitEvent(c->spec_stream, c->ev_spec_fork, 0);
+            const int beside = (int)c->trace_spec_blocks < perSmW ? (int)c->trace_spec_blocks : perSmW;
+            c->timer.begin("k_trace_specular_warp", c->spec_stream);
+            k_trace_specular_warp<<<sms * beside, 128, 0, c->spec_stream>>>(tq); ++n;
+            c->timer.end(c->spec_stream);
+            cudaEventRecord(c->ev_spec_done, c->spec_stream);
+            c->timer.begin("k_trace_main", s);
+            if (tp.p.enable_32_cones) k_trace_main<32, false, 8><<<grid, 128, 0, s>>>(tq);
+            else k_trace_main<16, false, 8><<<grid, 128, 0, s>>>(tq);
+            ++n;
+            c->timer.end(s);
+            if (c->mark_main_done) cudaEventRecord(c->mark_main_done, s); // the diffuse image is complete here
+            if (perSmW > beside) {      // second wave: exits at once when the list is already exhausted
+                k_trace_specular_warp<<<sms * (perSmW - beside), 128, 0, s>>>(tq); ++n;
+            }
+            cudaStreamWaitEvent(s, c->ev_spec_done, 0);
+            if (joint_b) cudaEventRecord(joint_b, s);
+            return n;
+        }
+    }
     c->timer.begin("k_trace_main", s);
     if (tp.p.enable_32_cones) k_trace_main<32, false, 8><<<grid, 128, 0, s>>>(tp);
     else k_trace_main<16, false, 8><<<grid, 128, 0, s>>>(tp);
     ++n;
     c->timer.end(s);
     if (c->mark_main_done) cudaEventRecord(c->mark_main_done, s); // the diffuse image is complete here
-    const uint32_t mode = tp.p.rendering_mode;
     if (mode == 6 || mode == 8) {
         // persistent kernels: exactly as many blocks as fit on the device at once
         static int specBlocks = 0, specWarpBlocks = 0;

@@ -190,7 +190,8 @@ def default_filter_params(filter_method=1, tonemap_enable=0):
 
 class Stats(C.Structure):
     _fields_ = [("triangles", C.c_uint64), ("clip_pairs", C.c_uint64), ("occupied_voxels", C.c_uint64),
-                ("svo_fragments", C.c_uint64), ("svo_nodes", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("svo_fragments", C.c_uint64), ("svo_nodes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("shaded_pairs", C.c_uint64)]
 
 
 def default_vct_params(region0, resolution, rendering_mode=8):
