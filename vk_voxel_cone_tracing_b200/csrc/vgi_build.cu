@@ -740,7 +740,8 @@ __global__ void __launch_bounds__(128) k_level_records(BuildParams bp, int level
 //            covers the high corner of a tri-linear footprint whose low corner lies in the brick) may be
 //            non-zero. One byte per (brick row, nz word): bit k of byte [(bz*(R/4) + by)*wpr + xw] is
 //            brick bx = 8*xw + k.
-//  footprint one byte per voxel, written only for voxels of non-empty bricks: bit c = dx + 2 dy + 4 dz is
+//  footprint one byte per voxel, written for the voxels of non-empty bricks and zeroed for those of bricks that were
+//            non-empty in the last build (zero-initialised: valid everywhere): bit c = dx + 2 dy + 4 dz is
 //            the nz bit of record (x+dx, y+dy, z+dz), i.e. which of the 8 records of the footprint whose
 //            low corner is this voxel have to be fetched.
 // One thread per brick byte: 25 rows of 33 nz bits stay in registers.
@@ -773,8 +774,11 @@ __global__ void __launch_bounds__(128) k_brick_mask(int R, int L, int logR, cons
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         if ((any >> (4 * k)) & 0x1full) out |= 1u << k;
+    // bricks that emptied since the last build get their footprint bytes zeroed (their nz rows are all zero, so the
+    // words below come out 0): the footprint byte is valid for EVERY voxel and the tracer probes it alone
+    const uint32_t touch = out | brick[i];
     brick[i] = (uint8_t)out;
-    if (!out) return;
+    if (!touch) return;
     uint8_t* fpL = footprint + (size_t)level * nvox;
 #pragma unroll
     for (int z = 0; z < 4; ++z)
@@ -783,7 +787,7 @@ __global__ void __launch_bounds__(128) k_brick_mask(int R, int L, int logR, cons
             const unsigned long long r00 = rows[z][y], r10 = rows[z][y + 1], r01 = rows[z + 1][y], r11 = rows[z + 1][y + 1];
             uint32_t* dst = reinterpret_cast<uint32_t*>(fpL + ((((size_t)(bz * 4 + z) << logR) + (size_t)(by * 4 + y)) << logR) + (size_t)xw * 32);
             for (int k = 0; k < 8; ++k) {
-                if (!((out >> k) & 1u)) continue;
+                if (!((touch >> k) & 1u)) continue;
                 const uint32_t a = (uint32_t)(r00 >> (4 * k)) & 0x1fu, b = (uint32_t)(r10 >> (4 * k)) & 0x1fu;
                 const uint32_t c = (uint32_t)(r01 >> (4 * k)) & 0x1fu, d = (uint32_t)(r11 >> (4 * k)) & 0x1fu;
                 uint32_t word = 0u;

@@ -130,6 +130,9 @@ DEVFN uint32_t rec_index(uint32_t lin, int logR)
 #endif
 }
 
+#ifndef VGI_TRACE_FP_ONLY
+#define VGI_TRACE_FP_ONLY 1     // 1: the footprint byte is the only emptiness probe; 0: brick bit + footprint byte (round 1)
+#endif
 // Where a tri-linear footprint lies: texel index of its low corner, the fractional weights and the mask of
 // the records that can be non-zero (0 = nothing to fetch).
 struct Footprint {
@@ -162,6 +165,11 @@ DEVFN void probe_level(const TraceParams& tp, const float* posV, int level, Foot
     const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
     const uint32_t bidx = (((((uint32_t)level << nbShift) + (i0[2] >> 2)) << nbShift) + (i0[1] >> 2) << wprShift) + (i0[0] >> 5);
     fp.vox = ((((((uint32_t)level << logR) + i0[2]) << logR) + i0[1]) << logR) + i0[0];
+#if VGI_TRACE_FP_ONLY
+    (void)bidx;
+    fp.mask = __ldg(tp.footprint + fp.vox);     // valid for every voxel (k_brick_mask zeroes the bytes of emptied bricks)
+    if (!fp.mask) STAT(3, 1);
+#else
     // both lookups are issued together (one memory latency instead of two in the dependent chain); the
     // footprint byte is only meaningful where the brick bit is set
     const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
@@ -170,6 +178,7 @@ DEVFN void probe_level(const TraceParams& tp, const float* posV, int level, Foot
     if (!brick) STAT(2, 1);
     else if (!m) STAT(3, 1);
     fp.mask = brick ? m : 0u;
+#endif
 }
 
 // the filtered fetch of the non-zero records of a footprint: three face-weighted tri-linear taps
@@ -539,7 +548,7 @@ DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have
 // the non-zero corners of its cell. Steps whose lanes are more scattered take the per-lane path of v1.
 // ---------------------------------------------------------------------------------------------------
 #ifndef VGI_TRACE_V2
-#define VGI_TRACE_V2 3      // measured on B200, ms per 1080p frame: 0 = round-1 march 2.845, 1 = v2 2.94, 3 = v3 (round-1 march, one-key vote + face table) 2.825
+#define VGI_TRACE_V2 3      // measured on B200, ms per 1080p frame: 0 = round-1 march 2.845, 1 = v2 2.94, 3 = v3 (round-1 march, one-key vote + face table) 2.825; with the footprint-only probe: 0 / 3 = 2.66, and a v5 (v3 + ONE fetch pass per step for both level samples, lanes 16-31 serving the high sample) 2.85 - removed
 #endif
 
 // per-cone constants of the fetch lanes, two float4 per cone in shared memory:
@@ -1582,15 +1591,8 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
 // brick bit + footprint byte of a cell (0 = every record of its footprint is zero)
 DEVFN uint32_t spec_probe_cell(const TraceParams& tp, uint32_t key)
 {
-    const int Rm = tp.R - 1, logR = tp.logR;
-    const uint32_t ix = key & (uint32_t)Rm, iy = (key >> logR) & (uint32_t)Rm, iz = (key >> (2 * logR)) & (uint32_t)Rm;
-    const uint32_t level = key >> (3 * logR);
-    const uint32_t nbShift = (uint32_t)logR - 2u, wprShift = (uint32_t)logR - 5u;
-    const uint32_t bidx = ((((level << nbShift) + (iz >> 2)) << nbShift) + (iy >> 2) << wprShift) + (ix >> 5);
-    const uint32_t bbyte = __ldg(tp.brick_mask + bidx);
-    const uint32_t m = __ldg(tp.footprint + key);   // meaningful only where the brick bit is set
     STAT(1, 1);
-    return ((bbyte >> ((ix >> 2) & 7u)) & 1u) ? m : 0u;
+    return __ldg(tp.footprint + key);   // valid for every voxel (k_brick_mask)
 }
 
 // Both level samples of the batch in ONE pass (spec_level_pass twice, merged): the run heads of both levels probe their
