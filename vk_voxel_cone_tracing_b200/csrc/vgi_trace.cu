@@ -1165,8 +1165,10 @@ DEVFN void svo_finish_pixel(const TraceParams& tp, const PixelSetup& s, size_t p
 // Resident blocks per SM the register allocation aims at. Measured on B200 (main / specular, us per 1080p frame):
 // unconstrained (96 / 86 registers, 5 blocks) 3086 / 1395; 6 blocks (80 / 85 registers, no spills) 2842 / 1372;
 // 7 blocks (72 registers, spills) 2922 for the main kernel.
+// With the footprint-only probe the clipmap march fits 72 registers with 12 bytes of spill: 7 blocks 2.58 ms against 2.66 ms
+// at 6 (8 blocks / 64 registers: 2.59). The octree march keeps 6 (its tiles need 40 KB of shared memory: 5 blocks fit anyway).
 #ifndef VGI_TRACE_MAIN_MINBLOCKS
-#define VGI_TRACE_MAIN_MINBLOCKS 6
+#define VGI_TRACE_MAIN_MINBLOCKS 7
 #endif
 #ifndef VGI_TRACE_SPEC_MINBLOCKS
 #define VGI_TRACE_SPEC_MINBLOCKS 6
@@ -1174,7 +1176,7 @@ DEVFN void svo_finish_pixel(const TraceParams& tp, const PixelSetup& s, size_t p
 // SVO = true: the same tile / compaction machinery marching the octree (voxelConeTracing_Octree.frag); the
 // per-pixel combine follows that shader (normalisation by the sum of cosines, clamps, specular cone inline).
 template <int NCONES, bool SVO, int TILE_W>
-__global__ void __launch_bounds__(128, VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(const __grid_constant__ TraceParams tp)
+__global__ void __launch_bounds__(128, SVO ? 6 : VGI_TRACE_MAIN_MINBLOCKS) k_trace_main(const __grid_constant__ TraceParams tp)
 {
     constexpr int TILE_PIX = TILE_W * TILE_H;
     __shared__ float s_pix[8][TILE_PIX];            // startPos xyz, normal xyz, minLevel, valid
@@ -1506,7 +1508,7 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
 #define VGI_TRACE_SPEC_WARP 1
 #endif
 #ifndef VGI_TRACE_SPECW_MINBLOCKS
-#define VGI_TRACE_SPECW_MINBLOCKS 6      // measured: 8 (64 registers, spills) 1.70 ms, 6 (80) 1.59 ms, 4 1.69 ms
+#define VGI_TRACE_SPECW_MINBLOCKS 7      // measured (first warp marcher): 8 (64 registers, spills) 1.70 ms, 6 (80) 1.59 ms, 4 1.69 ms; current kernel: 6 / 7 / 8 = 1.203 / 1.167 / 1.164 ms (72 registers, no spills at 7)
 #endif
 
 struct SpecWarpShared {
