@@ -376,3 +376,73 @@ def test_update_nodes_equals_a_fresh_upload():
         outs.append((gi.stats().clip_pairs, gi.export_atlas(0).cpu(), gi.export_atlas(1).cpu()))
     assert outs[0][0] == outs[1][0] and outs[0][0] > 10000
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_trace_after_the_regions_moved_equals_a_fresh_context():
+    """The tracers probe the footprint byte alone, so k_brick_mask has to zero the bytes of bricks that emptied (regions
+    that moved away): the images traced after a walk must equal, bit for bit, those of a context that only ever saw the
+    last camera position (no stale byte claims a record that is gone)."""
+    import torch
+    inp = common.cornell_inputs()
+    walked, fresh = _gi_for(inp), _gi_for(inp)
+    dgb = walked.upload_gbuffer(inp["gbuffer"])
+    cams = [(0.0, 0.0, 0.0), (1.9, -0.7, 1.3), (-2.3, 0.9, -1.7), (40.0, 0.0, 0.0), (0.37, -0.11, 0.29)]
+    for cam in cams:
+        walked.update_regions(cam)
+        walked.build_clipmap(0)
+        prm = walked.default_vct_params(8)
+        walked.cone_trace(inp["cam"], dgb, prm)
+    fresh.update_regions(cams[-1])
+    fresh.build_clipmap(0)
+    prm = fresh.default_vct_params(8)
+    a = walked.cone_trace(inp["cam"], dgb, prm)
+    b = fresh.cone_trace(inp["cam"], dgb, prm)
+    for x, y in zip(a, b):
+        assert torch.equal(x.view(torch.int32), y.view(torch.int32))
+    assert float(a[0][..., :3].abs().sum()) > 0.0
+
+
+def test_shaded_pairs_exclude_what_the_mip_overwrites(oracle):
+    """Pairs whose voxel lies in the centre half of its level, off the blend band, only set their occupancy bit: the
+    canonical pair count still equals the oracle's, the injection's work list is shorter, and the atlases stay bit-exact
+    (test_cornell64_atlases_bit_exact and the full-size tests compare them)."""
+    inp = common.cornell_inputs()
+    gi, regs, op, rad, pairs = _build_both(oracle, inp)
+    st = gi.stats()
+    assert st.clip_pairs == pairs
+    assert 0 < st.shaded_pairs < st.clip_pairs
+
+
+def test_overlapped_marches_equal_the_serial_order():
+    """vgi_set_trace_overlap: the specular march beside the diffuse one (pre-listed pixels, second stream) writes the
+    same two images as the serial order, for whole frames, row bands and interleaved tile rows."""
+    import torch
+    inp = common.cornell_inputs()
+    gi = _gi_for(inp)
+    gi.update_regions(inp["cam_pos"])
+    gi.build_clipmap(0)
+    dgb = gi.upload_gbuffer(inp["gbuffer"])
+    prm = gi.default_vct_params(8)
+    ref = [t.clone() for t in gi.cone_trace(inp["cam"], dgb, prm)]
+    assert float(ref[1][..., :3].abs().sum()) > 0.0
+    for blocks in (1, 2, 7):
+        gi.set_trace_overlap(blocks)
+        got = gi.cone_trace(inp["cam"], dgb, prm)
+        torch.cuda.synchronize()
+        for x, y in zip(got, ref):
+            assert torch.equal(x.view(torch.int32), y.view(torch.int32)), blocks
+    gi.set_trace_overlap(2)
+    out = [torch.zeros_like(t) for t in ref]
+    h = ref[0].shape[0]
+    gi.cone_trace(inp["cam"], dgb, prm, out=out, rows=(0, h // 2))       # tile-aligned bands: the same warps as the whole frame
+    gi.cone_trace(inp["cam"], dgb, prm, out=out, rows=(h // 2, h))
+    torch.cuda.synchronize()
+    for x, y in zip(out, ref):
+        assert torch.equal(x.view(torch.int32), y.view(torch.int32))
+    out = [torch.zeros_like(t) for t in ref]
+    for part in range(3):
+        gi.cone_trace(inp["cam"], dgb, prm, out=out, part=(part, 3))
+    torch.cuda.synchronize()
+    for x, y in zip(out, ref):
+        assert torch.equal(x.view(torch.int32), y.view(torch.int32))
+    gi.set_trace_overlap(0)
