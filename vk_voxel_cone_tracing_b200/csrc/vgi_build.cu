@@ -66,9 +66,15 @@ DEVFN void emit_pair(const BuildParams& bp, uint32_t* __restrict__ occ, vgi_pair
     const size_t w = (size_t)level * wordsPerLevel + (((((size_t)z << bp.logR) + y) << bp.logR) + x) / 32;
     const uint32_t bit = 1u << (x & 31u);
     if (!(occ[w] & bit)) atomicOr(&occ[w], bit);
-    if (mip_interior(bp, level, (int)x, (int)y, (int)z)) { atomicAdd(&cnt->pairs_unlisted, 1u); return; }
-    // warp-aggregated append
-    const unsigned m = __activemask();
+    // warp-aggregated: one count of the unlisted pairs and one append of the listed ones per warp
+    const bool dead = mip_interior(bp, level, (int)x, (int)y, (int)z);
+    const unsigned all = __activemask();
+    const unsigned md = __ballot_sync(all, dead);
+    if (dead) {
+        if ((int)lane_id() == __ffs(md) - 1) atomicAdd(&cnt->pairs_unlisted, (uint32_t)__popc(md));
+        return;
+    }
+    const unsigned m = all & ~md;
     const int leader = __ffs(m) - 1;
     const unsigned rank = __popc(m & ((1u << lane_id()) - 1u));
     uint32_t base = 0;
