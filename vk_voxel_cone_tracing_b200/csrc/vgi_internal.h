@@ -106,8 +106,8 @@ struct TraceParams {
     float    eye[3];
     int      R, L, logR;
     const VoxelRecord* store;
-    const uint8_t* brick_mask;    // 1 bit per 4^3 brick (dilated by one voxel on the high side), see k_brick_mask
-    const uint8_t* footprint;     // per voxel of a non-empty brick: which of the 8 footprint records may be non-zero
+    const uint8_t* brick_mask;    // 1 bit per 4^3 brick (dilated by one voxel on the high side), see k_brick_mask; read by the tracers only with VGI_TRACE_FP_ONLY = 0
+    const uint8_t* footprint;     // per voxel: which of the 8 footprint records may be non-zero (0 in empty bricks: valid everywhere)
     float    vox_scale0;          // R / (voxel_size * volume_dimension): world units -> level-0 voxels
     float    level_scale[VGI_MAX_LEVELS]; // 2^-level
     float    min_level_dd[VGI_MAX_LEVELS]; // [k]: largest dist^2 with sqrtf(dd) / minRadius <= 2^k (+inf for k >= L-1)
@@ -220,7 +220,7 @@ struct vgi_ctx {
     int       slab_phase = 0;        // 0 idle, 1 begun, 2 finalized
     uint32_t* visit_list = nullptr;  // L segments of visit_cap voxel ids (records to rewrite this frame)
     uint32_t visit_cap = 0;
-    uint8_t* footprint = nullptr;   // L * R^3 bytes, valid where the brick bit is set
+    uint8_t* footprint = nullptr;   // L * R^3 bytes, zero-initialised and kept valid for every voxel by k_brick_mask
     Counters* counters = nullptr;
     Counters* h_counters = nullptr; // pinned
     uint32_t max_pairs = 0, max_occ = 0, max_large = 0;

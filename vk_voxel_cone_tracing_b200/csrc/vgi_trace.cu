@@ -82,9 +82,9 @@ DEVFN float2 unpack2(uint32_t t, uint32_t selLo, uint32_t selHi)
 // one clipmap level, three face-weighted tri-linear taps (ref: voxelConeTracing.frag:313-327).
 // Texel coordinate = fract(p / extent) * R - 0.5, indices wrapped modulo R: the toroidal addressing
 // that the reference obtains from REPEAT + wrapped border texels.
-// Empty space is skipped in two steps: the 4^3 brick bit (k_brick_mask), then the footprint byte
-// (k_brick_mask writes, for every voxel of a non-empty brick, which of the 8 records of the footprint
-// whose low corner is that voxel may be non-zero); only those records are loaded and filtered.
+// Empty space is skipped through the footprint byte (k_brick_mask keeps, for EVERY voxel, which of the 8 records of
+// the footprint whose low corner is that voxel may be non-zero; round 1 tested a 4^3 brick bit first,
+// VGI_TRACE_FP_ONLY = 0); only those records are loaded and filtered.
 // Returns false (out = 0) when all eight records of the footprint are zero.
 // Per-cone constants of the three face taps (ref: voxelConeTracing.frag:296-303, 318-326): which face of
 // each +/- pair the cone reads and the squared direction weights (pre-divided by 255).
@@ -141,7 +141,7 @@ struct Footprint {
     float    w[3];
 };
 
-// coordinates + the two emptiness tests (4^3 brick bit, per-voxel footprint byte).
+// coordinates + the emptiness test (per-voxel footprint byte; with VGI_TRACE_FP_ONLY = 0 the 4^3 brick bit before it).
 // posV = world position in level-0 voxels (pos * R / extent0); the texel coordinate of voxelConeTracing.frag:315-317,
 // fract(pos / extent_l) * R - 0.5 = posV * 2^-level - 0.5 (mod R), is split into cell index and weight without
 // FRND / F2I (quarter-rate pipe): adding 1.5 * 2^23 rounds (t - 0.5) to the nearest integer r, which is floor(t)
@@ -1495,8 +1495,8 @@ __global__ void __launch_bounds__(128, VGI_TRACE_SPEC_MINBLOCKS) k_trace_specula
 // The step sequence does not depend on what is sampled and takes one of 256 forms (8-bit roughness): the host
 // tabulates it (TraceParams::spec_tab) and the 32 lanes of a warp evaluate 32 CONSECUTIVE steps of one cone:
 //   * every lane computes where its two level samples lie (cell key + tri-linear weights);
-//   * consecutive lanes with equal keys form runs (about four per level and batch); lane 8 r + c tests the brick bit
-//     and the footprint byte of run r's cell and fetches corner record c, blended with the cone's face weights,
+//   * consecutive lanes with equal keys form runs (about four per level and batch); lane 8 r + c tests the
+//     footprint byte of run r's cell and fetches corner record c, blended with the cone's face weights,
 //     into shared memory — once per cell instead of once per step; a batch whose cells are all empty ends here;
 //   * every lane sums the non-zero corners of its cell with its own weights;
 //   * front-to-back accumulation is a prefix product over the batch: 1 - alpha' = (1 - alpha)(1 - o) and
@@ -1521,7 +1521,7 @@ struct SpecWarpShared {
 #endif
 
 // One level sample of the batch for every lane that wants one; false when every cell is empty.
-//  A. run heads (first lane of each group of consecutive lanes with the same cell) test their cell's brick bit and
+//  A. run heads (first lane of each group of consecutive lanes with the same cell) test their cell's
 //     footprint byte: one probe per CELL, not per step; a pass whose cells are all empty ends with one ballot;
 //  B. the non-empty cells are numbered compactly; lane 8 c + corner fetches corner `corner` of compact cell c (its three
 //     face texels blended with the cone's weights) into shared memory, four cells per round;
@@ -1590,7 +1590,7 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
     return myMask != 0u;
 }
 
-// brick bit + footprint byte of a cell (0 = every record of its footprint is zero)
+// footprint byte of a cell (0 = every record of its footprint is zero)
 DEVFN uint32_t spec_probe_cell(const TraceParams& tp, uint32_t key)
 {
     STAT(1, 1);
