@@ -130,6 +130,15 @@ DEVFN uint32_t rec_index(uint32_t lin, int logR)
 #endif
 }
 
+#ifndef VGI_TRACE_GATHER_ALL
+#define VGI_TRACE_GATHER_ALL 0
+#endif
+#ifndef VGI_TRACE_SETUP_ALL
+#define VGI_TRACE_SETUP_ALL 0
+#endif
+#ifndef VGI_TRACE_SPEC_GATHER_ALL
+#define VGI_TRACE_SPEC_GATHER_ALL 0
+#endif
 #ifndef VGI_TRACE_FP_ONLY
 #define VGI_TRACE_FP_ONLY 1     // 1: the footprint byte is the only emptiness probe; 0: brick bit + footprint byte (round 1)
 #endif
@@ -416,7 +425,9 @@ DEVFN void coop_gather(const Footprint& fp, uint32_t m, const float4* s_corner, 
     float2 lo = make_float2(0.f, 0.f), hi = lo;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
+#if !VGI_TRACE_GATHER_ALL
         if (!((m >> c) & 1u)) continue;
+#endif
         const float wc = wxy[c & 3] * ((c & 4) ? w[2] : wz0);
         const float4 v = s_corner[c];
         const float2 w2 = make_float2(wc, wc);
@@ -486,7 +497,11 @@ DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have
         Footprint f0, f1;
         f0.mask = 0u; f1.mask = 0u; f0.vox = 0u; f1.vox = 0u; // the weights are read only where the mask is set
         float curLevel = 0.0f, fr = 0.0f;
+#if VGI_TRACE_SETUP_ALL
+        {   // finished lanes compute along (their indices stay in range) and drop their masks below: no divergent region
+#else
         if (alive) {
+#endif
             STAT(0, 1);
             float position[3], d[3];
 #pragma unroll
@@ -505,6 +520,9 @@ DEVFN void march_warp_table(const TraceParams& tp, const StepTable& t, bool have
             probe_level(tp, posV, (int)fl, f0);
             if (fr > 0.0f) probe_level(tp, posV, (int)fl + 1, f1); // Q17
         }
+#if VGI_TRACE_SETUP_ALL
+        if (!alive) { f0.mask = 0u; f1.mask = 0u; }
+#endif
         float smp[4] = { 0.f, 0.f, 0.f, 0.f }, up[4] = { 0.f, 0.f, 0.f, 0.f };
         const bool vote = t.lod[k] >= VGI_TRACE_COOP_MIN_LOD;
         if (s_face) {
@@ -609,6 +627,8 @@ DEVFN bool coop_fetch(const TraceParams& tp, uint32_t vox, unsigned corner, cons
 }
 
 // a lane's weighted sum over the parked non-zero corners (bits of m) of its cell
+// ALL: every one of the eight parked slots is summed (the absent corners hold zeros): no branch per corner
+template <bool ALL = false>
 DEVFN void coop_gather_w(const float* w, uint32_t m, const float4* s_corner, float* out)
 {
     const float wx0 = 1.0f - w[0], wy0 = 1.0f - w[1], wz0 = 1.0f - w[2];
@@ -616,7 +636,7 @@ DEVFN void coop_gather_w(const float* w, uint32_t m, const float4* s_corner, flo
     float2 lo = make_float2(0.f, 0.f), hi = lo;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        if (!((m >> c) & 1u)) continue;
+        if (!ALL && !((m >> c) & 1u)) continue;
         const float wc = wxy[c & 3] * ((c & 4) ? w[2] : wz0);
         const float4 v = s_corner[c];
         const float2 w2 = make_float2(wc, wc);
@@ -1564,6 +1584,9 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
         const int c = c0 + (int)(lane >> 3);
         if (c < nCells) {
             const uint2 cm = sh.cell[c];
+#if VGI_TRACE_SPEC_GATHER_ALL
+            if (!((cm.y >> corner) & 1u)) sh.val[lane] = make_float4(0.f, 0.f, 0.f, 0.f);   // every parked slot is gathered
+#endif
             if ((cm.y >> corner) & 1u) {
                 const uint32_t vox = cm.x;
                 const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
@@ -1584,7 +1607,7 @@ DEVFN bool spec_level_pass(const TraceParams& tp, bool want, uint32_t key, const
         __syncwarp();
         // ---- C
         const int q = myCell - c0;
-        if (myMask && q >= 0 && q < 4) coop_gather_w(w, myMask, sh.val + 8 * q, out);
+        if (myMask && q >= 0 && q < 4) coop_gather_w<VGI_TRACE_SPEC_GATHER_ALL != 0>(w, myMask, sh.val + 8 * q, out);
         __syncwarp();
     }
     return myMask != 0u;
@@ -1631,6 +1654,9 @@ DEVFN void spec_both_levels(const TraceParams& tp, bool wantLo, uint32_t keyLo, 
         const int c = c0 + (int)(lane >> 3);
         if (c < nCells) {
             const uint2 cm = sh.cell[c];
+#if VGI_TRACE_SPEC_GATHER_ALL
+            if (!((cm.y >> corner) & 1u)) sh.val[lane] = make_float4(0.f, 0.f, 0.f, 0.f);   // every parked slot is gathered
+#endif
             if ((cm.y >> corner) & 1u) {
                 const uint32_t vox = cm.x;
                 const uint32_t ix = vox & (uint32_t)Rm, iy = (vox >> logR) & (uint32_t)Rm, iz = (vox >> (2 * logR)) & (uint32_t)Rm;
@@ -1650,8 +1676,8 @@ DEVFN void spec_both_levels(const TraceParams& tp, bool wantLo, uint32_t keyLo, 
         }
         __syncwarp();
         const int qL = cellL - c0, qH = cellH - c0;
-        if (myL && qL >= 0 && qL < 4) coop_gather_w(wLo, myL, sh.val + 8 * qL, smpLo);
-        if (myH && qH >= 0 && qH < 4) coop_gather_w(wHi, myH, sh.val + 8 * qH, smpHi);
+        if (myL && qL >= 0 && qL < 4) coop_gather_w<VGI_TRACE_SPEC_GATHER_ALL != 0>(wLo, myL, sh.val + 8 * qL, smpLo);
+        if (myH && qH >= 0 && qH < 4) coop_gather_w<VGI_TRACE_SPEC_GATHER_ALL != 0>(wHi, myH, sh.val + 8 * qH, smpHi);
         __syncwarp();
     }
     anyLo = myL != 0u;
